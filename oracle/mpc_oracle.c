@@ -1,0 +1,825 @@
+/* mpc_oracle.c -- CPU ORACLE for the batched MPC solve path.  TEST INFRASTRUCTURE, NOT PRODUCT.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load
+ * this.  The product (libmpcgpu.so) never links or calls it.
+ *
+ * PARITY UNPINNED: the reference's arithmetic for this path lives in acados + HPIPM + BLASFEO +
+ * CasADi-generated C, none of which is vendored in /root/reference (acados is not even version
+ * pinned: pyproject.toml:18, README.md:226-234) and none of which is installable here.  The
+ * reference's tests hold no golden solve results (solver_generator/test/test_acados.py:48-77 never
+ * solves).  This file therefore RESTATES the published algorithms with every upstream-only choice
+ * written down explicitly (see DESIGN.md "Algorithm contract"); the problem definition (dynamics,
+ * cost, constraints, bounds, parameter order) IS pinned: oracle/generated/model_*.h is derived
+ * mechanically from the reference's own Python scripts (oracle/gen_model.py).
+ *
+ * What is restated, with the reference call sites:
+ *   Solver::solve() loop, early exits, res_eq rule, exit-code map
+ *                         mpc_planner_solver/src/acados_solver_interface.cpp:86-204
+ *   loadWarmstart         acados_solver_interface.cpp:274-284
+ *   stage-N parameter reuse                              acados_solver_interface.cpp:128-134
+ *   OCP formulation/options (ERK 4 stages x 3 steps, EXACT Hessian, MIRROR, FIXED_STEP, qp_tol 1e-5,
+ *   HPIPM iter_max 50, warm start 2)  solver_generator/generate_acados_solver.py:84-177
+ *   FindBestPlanner / objective post-processing
+ *                         mpc_planner_modules/src/guidance_constraints.cpp:373-420,572-590,1025-1050
+ *
+ * Written in the common subset of C and C++: compile as C for the oracle proper; compile as C++
+ * with -DREAL=<counting type> to obtain the canonical algorithmic FLOP count (oracle/flopcount.cpp).
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifndef REAL
+#define REAL double
+#endif
+
+#ifndef MODEL_HEADER
+#error "compile with -DMODEL_HEADER=\"generated/model_<config>.h\""
+#endif
+#include MODEL_HEADER
+
+#define NX MODEL_NX
+#define NU MODEL_NU
+#define NZ MODEL_NZ
+#define NP MODEL_NP
+#define NH MODEL_NH
+#define NN MODEL_N
+
+/* ---- explicit upstream-only choices (DESIGN.md "Algorithm contract") ------------------------- */
+#define SIM_STEPS 3          /* generate_acados_solver.py:150 */
+#define REG_EPS 1e-4         /* acados reg_epsilon default for MIRROR */
+#define BOUND_INF 1e10       /* |bound| >= this => bound absent */
+#define IPM_ITER_MAX 50      /* generate_acados_solver.py:172 */
+#define IPM_TOL 1e-5         /* generate_acados_solver.py:162 (all four residual tolerances) */
+#define IPM_MU0 10.0         /* HPIPM BALANCE mode */
+#define IPM_THR0 0.1         /* HPIPM init threshold for slacks */
+#define IPM_ALPHA_MIN 1e-12
+#define IPM_LAM_MIN 1e-16
+#define IPM_T_MIN 1e-16
+#define IPM_STEP_SCALE 0.995
+#define RES_EQ_MAX 1e-2      /* acados_solver_interface.cpp:177 */
+#define JACOBI_MAX_SWEEPS 30
+#define JACOBI_TOL 1e-30     /* stop when sum offdiag^2 <= tol * sum all^2 */
+
+/* compact constraint list of one path stage: [u lower NU][u upper NU][x lower NX][x upper NX][h rows] */
+#define NCB (2 * NZ)
+static int g_nc = -1;                 /* entries per stage */
+static int g_hrow[2 * NH + 1];        /* h index of general entry e-NCB */
+static REAL g_hsgn[2 * NH + 1];       /* +1 lower, -1 upper */
+static REAL g_hbnd[2 * NH + 1];       /* bound value */
+#define NCMAX (NCB + 2 * NH)
+
+static void setup_constraints(void)
+{
+    if (g_nc >= 0) return;
+    int e = 0;
+    for (int i = 0; i < NH; i++) {
+        if (model_lh[i] > -BOUND_INF) { g_hrow[e] = i; g_hsgn[e] = 1.0; g_hbnd[e] = model_lh[i]; e++; }
+        if (model_uh[i] < BOUND_INF) { g_hrow[e] = i; g_hsgn[e] = -1.0; g_hbnd[e] = model_uh[i]; e++; }
+    }
+    g_nc = NCB + e;
+}
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+int oracle_nc(void) { setup_constraints(); return g_nc; }
+int oracle_dims(int *N, int *nx, int *nu, int *np, int *nh)
+{
+    *N = NN; *nx = NX; *nu = NU; *np = NP; *nh = NH;
+    return 0;
+}
+/* doubles per problem in the persistent memory blob */
+int oracle_mem_doubles(void) { setup_constraints(); return 1 + (NN + 1) * NX + 2 * NN * g_nc + (NN + 1) * NZ; }
+#ifdef __cplusplus
+}
+#endif
+
+typedef struct {
+    /* NLP iterate and multipliers */
+    REAL x[NN + 1][NX], u[NN][NU];
+    REAL pi[NN + 1][NX];             /* pi[k]: multiplier of x_k = Phi(x_{k-1},u_{k-1}), k >= 1 */
+    REAL lam[NN][NCMAX], t[NN][NCMAX];
+    /* QP data */
+    REAL W[NN][NX * NZ], b[NN][NX];
+    REAL H[NN + 1][NZ * NZ], g[NN + 1][NZ];
+    REAL C[NN][(NH > 0 ? NH : 1) * NZ], hval[NN][NH > 0 ? NH : 1];
+    REAL d[NN][NCMAX];               /* signed bound: chat'v >= d */
+    /* QP iterate */
+    REAL v[NN + 1][NZ], qpi[NN + 1][NX];
+    /* IPM work */
+    REAL rg[NN + 1][NZ], rb[NN][NX], rd[NN][NCMAX], rm[NN][NCMAX];
+    REAL Ht[NN + 1][NZ * NZ], gt[NN + 1][NZ];
+    REAL P[NN + 1][NX * NX], pv[NN + 1][NX], K[NN][NU * NX], kff[NN][NU], Ginv[NN][NU * NU], Gxu[NN][NX * NU];
+    REAL dv[NN + 1][NZ], dpi[NN + 1][NX], dlam[NN][NCMAX], dt[NN][NCMAX];
+    REAL dva[NN + 1][NZ];
+    int qp_warm;                     /* previous QP solution available (HPIPM warm start 2) */
+    int ipm_iters_total, qp_iters_last;
+} work_t;
+
+/* ------------------------------------------------------------------------------------------------
+ * K1: ERK4 with forward sensitivities and adjoint-weighted second-order term  [upstream: acados ERK]
+ * ---------------------------------------------------------------------------------------------- */
+/* one RK4 step h from (x,u): xn, S = d xn / d[u;x] (NX x NZ); if lam != NULL also
+ * Hc (NZ x NZ) = sum_j lam_j d2 xn_j / d[u;x]^2                                               */
+static void rk4_step(const REAL *x, const REAL *u, const REAL *p, REAL h, REAL *xn, REAL *S, const REAL *lam, REAL *Hc)
+{
+    static const double ac[4] = {0.0, 0.5, 0.5, 1.0};
+    static const double bc[4] = {1.0 / 6.0, 1.0 / 3.0, 1.0 / 3.0, 1.0 / 6.0};
+    REAL X[4][NX], Kf[4][NX], Jf[4][NX * NZ], Z[4][NZ * NZ], dK[NX * NZ];
+    for (int i = 0; i < NX; i++) xn[i] = x[i];
+    for (int i = 0; i < NX * NZ; i++) S[i] = 0.0;
+    for (int i = 0; i < NX; i++) S[i * NZ + NU + i] = 1.0;
+    for (int s = 0; s < 4; s++) {
+        /* stage state and its tangent Z = d[u;X_s]/dz */
+        for (int i = 0; i < NZ * NZ; i++) Z[s][i] = 0.0;
+        for (int i = 0; i < NU; i++) Z[s][i * NZ + i] = 1.0;
+        for (int i = 0; i < NX; i++) {
+            X[s][i] = x[i];
+            Z[s][(NU + i) * NZ + NU + i] = 1.0;
+        }
+        if (s > 0) {
+            for (int i = 0; i < NX; i++) {
+                X[s][i] += ac[s] * h * Kf[s - 1][i];
+                for (int j = 0; j < NZ; j++) Z[s][(NU + i) * NZ + j] += ac[s] * h * dK[i * NZ + j];
+            }
+        }
+        model_f(X[s], u, p, Kf[s]);
+        model_f_jac(X[s], u, p, Jf[s]);
+        for (int i = 0; i < NX; i++)
+            for (int j = 0; j < NZ; j++) {
+                REAL a = 0.0;
+                for (int k = 0; k < NZ; k++) a += Jf[s][i * NZ + k] * Z[s][k * NZ + j];
+                dK[i * NZ + j] = a;
+                S[i * NZ + j] += bc[s] * h * a;
+            }
+        for (int i = 0; i < NX; i++) xn[i] += bc[s] * h * Kf[s][i];
+    }
+    if (lam) {
+        REAL nu_[4][NX], Hf[NZ * NZ], T[NZ * NZ];
+        for (int i = 0; i < NZ * NZ; i++) Hc[i] = 0.0;
+        for (int s = 3; s >= 0; s--) {
+            for (int i = 0; i < NX; i++) {
+                nu_[s][i] = bc[s] * h * lam[i];
+                if (s < 3) {
+                    REAL a = 0.0; /* a_{s+1} h Jfx_{s+1}' nu_{s+1} */
+                    for (int k = 0; k < NX; k++) a += Jf[s + 1][k * NZ + NU + i] * nu_[s + 1][k];
+                    nu_[s][i] += ac[s + 1] * h * a;
+                }
+            }
+            model_f_hess(X[s], u, p, nu_[s], Hf);
+            for (int i = 0; i < NZ; i++)
+                for (int j = 0; j < NZ; j++) {
+                    REAL a = 0.0;
+                    for (int k = 0; k < NZ; k++) a += Hf[i * NZ + k] * Z[s][k * NZ + j];
+                    T[i * NZ + j] = a;
+                }
+            for (int i = 0; i < NZ; i++)
+                for (int j = 0; j < NZ; j++) {
+                    REAL a = 0.0;
+                    for (int k = 0; k < NZ; k++) a += Z[s][k * NZ + i] * T[k * NZ + j];
+                    Hc[i * NZ + j] += a;
+                }
+        }
+    }
+}
+
+/* SIM_STEPS RK4 steps over one shooting interval: xn = Phi(x,u), W = dPhi/d[u;x];
+ * if pi != NULL, Hc = sum_j pi_j d2 Phi_j                                                        */
+static void integrate(const REAL *x, const REAL *u, const REAL *p, REAL *xn, REAL *W, const REAL *pi, REAL *Hc)
+{
+    const REAL h = MODEL_DT / SIM_STEPS;
+    REAL y[SIM_STEPS + 1][NX], S[SIM_STEPS][NX * NZ], T[SIM_STEPS + 1][NZ * NZ], dummy[NZ * NZ];
+    for (int i = 0; i < NX; i++) y[0][i] = x[i];
+    for (int i = 0; i < NZ * NZ; i++) T[0][i] = 0.0;
+    for (int i = 0; i < NZ; i++) T[0][i * NZ + i] = 1.0;
+    for (int s = 0; s < SIM_STEPS; s++) {
+        rk4_step(y[s], u, p, h, y[s + 1], S[s], NULL, dummy);
+        for (int i = 0; i < NZ * NZ; i++) T[s + 1][i] = 0.0;
+        for (int i = 0; i < NU; i++) T[s + 1][i * NZ + i] = 1.0;
+        for (int i = 0; i < NX; i++)
+            for (int j = 0; j < NZ; j++) {
+                REAL a = 0.0;
+                for (int k = 0; k < NZ; k++) a += S[s][i * NZ + k] * T[s][k * NZ + j];
+                T[s + 1][(NU + i) * NZ + j] = a;
+            }
+    }
+    for (int i = 0; i < NX; i++) xn[i] = y[SIM_STEPS][i];
+    if (W)
+        for (int i = 0; i < NX; i++)
+            for (int j = 0; j < NZ; j++) W[i * NZ + j] = T[SIM_STEPS][(NU + i) * NZ + j];
+    if (pi) {
+        REAL lam[NX], lamp[NX], Hs[NZ * NZ], tmp[NX], St[NX * NZ], M[NZ * NZ];
+        for (int i = 0; i < NX; i++) lam[i] = pi[i];
+        for (int i = 0; i < NZ * NZ; i++) Hc[i] = 0.0;
+        for (int s = SIM_STEPS - 1; s >= 0; s--) {
+            rk4_step(y[s], u, p, h, tmp, St, lam, Hs);
+            for (int i = 0; i < NZ; i++)
+                for (int j = 0; j < NZ; j++) {
+                    REAL a = 0.0;
+                    for (int k = 0; k < NZ; k++) a += Hs[i * NZ + k] * T[s][k * NZ + j];
+                    M[i * NZ + j] = a;
+                }
+            for (int i = 0; i < NZ; i++)
+                for (int j = 0; j < NZ; j++) {
+                    REAL a = 0.0;
+                    for (int k = 0; k < NZ; k++) a += T[s][k * NZ + i] * M[k * NZ + j];
+                    Hc[i * NZ + j] += a;
+                }
+            for (int i = 0; i < NX; i++) {
+                REAL a = 0.0;
+                for (int k = 0; k < NX; k++) a += St[k * NZ + NU + i] * lam[k];
+                lamp[i] = a;
+            }
+            for (int i = 0; i < NX; i++) lam[i] = lamp[i];
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * K4: MIRROR regularisation  [upstream: acados regularize_mirror; eigen-decomposition restated as
+ * cyclic Jacobi]  A (n x n, row-major, leading dimension ld) <- V max(|lambda|, eps) V'
+ * ---------------------------------------------------------------------------------------------- */
+static void mirror(REAL *A, int n, int ld)
+{
+    REAL a[NZ][NZ], V[NZ][NZ], ev[NZ];
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++) {
+            a[i][j] = 0.5 * (A[i * ld + j] + A[j * ld + i]);
+            V[i][j] = (i == j) ? 1.0 : 0.0;
+        }
+    for (int sweep = 0; sweep < JACOBI_MAX_SWEEPS; sweep++) {
+        REAL off = 0.0, tot = 0.0;
+        for (int i = 0; i < n; i++)
+            for (int j = 0; j < n; j++) {
+                tot += a[i][j] * a[i][j];
+                if (i != j) off += a[i][j] * a[i][j];
+            }
+        if (!(off > JACOBI_TOL * tot)) break;
+        for (int p = 0; p < n - 1; p++)
+            for (int q = p + 1; q < n; q++) {
+                REAL apq = a[p][q];
+                if (apq == 0.0) continue;
+                REAL theta = (a[q][q] - a[p][p]) / (2.0 * apq);
+                REAL tt = 1.0 / (fabs(theta) + sqrt(theta * theta + 1.0));
+                if (theta < 0.0) tt = -tt;
+                REAL c = 1.0 / sqrt(tt * tt + 1.0), s = tt * c;
+                for (int k = 0; k < n; k++) {
+                    if (k == p || k == q) continue;
+                    REAL akp = a[k][p], akq = a[k][q];
+                    a[k][p] = a[p][k] = c * akp - s * akq;
+                    a[k][q] = a[q][k] = s * akp + c * akq;
+                }
+                REAL app = a[p][p], aqq = a[q][q];
+                a[p][p] = app - tt * apq;
+                a[q][q] = aqq + tt * apq;
+                a[p][q] = a[q][p] = 0.0;
+                for (int k = 0; k < n; k++) {
+                    REAL vkp = V[k][p], vkq = V[k][q];
+                    V[k][p] = c * vkp - s * vkq;
+                    V[k][q] = s * vkp + c * vkq;
+                }
+            }
+    }
+    for (int i = 0; i < n; i++) {
+        REAL e = a[i][i];
+        if (e >= -REG_EPS && e <= REG_EPS) e = REG_EPS;
+        else if (e < 0.0) e = -e;
+        ev[i] = e;
+    }
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++) {
+            REAL s = 0.0;
+            for (int k = 0; k < n; k++) s += V[i][k] * ev[k] * V[j][k];
+            A[i * ld + j] = s;
+        }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * K1-K4 for all stages: build the QP at the current iterate
+ * ---------------------------------------------------------------------------------------------- */
+static const REAL *stage_params(const REAL *params, int k) { return params + (size_t)(k < NN ? k : NN - 1) * NP; }
+
+static void linearize(work_t *w, const REAL *xinit, const REAL *params)
+{
+    for (int k = 0; k < NN; k++) {
+        const REAL *p = stage_params(params, k);
+        REAL z[NZ], xn[NX], Hd[NZ * NZ], gc[NZ], Hl[NZ * NZ], Hh[NZ * NZ], m[NH > 0 ? NH : 1];
+        for (int i = 0; i < NU; i++) z[i] = w->u[k][i];
+        for (int i = 0; i < NX; i++) z[NU + i] = w->x[k][i];
+        integrate(w->x[k], w->u[k], p, xn, w->W[k], w->pi[k + 1], Hd);
+        for (int i = 0; i < NX; i++) w->b[k][i] = xn[i] - w->x[k + 1][i];
+        model_cost_grad_hess(z, p, gc, Hl);
+        for (int e = 0; e < NH; e++) m[e] = 0.0;
+        for (int e = NCB; e < g_nc; e++) m[g_hrow[e - NCB]] -= g_hsgn[e - NCB] * w->lam[k][e]; /* lam_u - lam_l */
+        model_h_hess(z, p, m, Hh);
+        for (int i = 0; i < NZ; i++) w->g[k][i] = MODEL_DT * gc[i];
+        for (int i = 0; i < NZ * NZ; i++) w->H[k][i] = MODEL_DT * Hl[i] + Hd[i] + Hh[i];
+        mirror(w->H[k], NZ, NZ);
+        model_h(z, p, w->hval[k]);
+        model_h_jac(z, p, w->C[k]);
+        /* signed bounds: box on u (all k), on x (k >= 1), general rows */
+        for (int i = 0; i < NZ; i++) {
+            w->d[k][i] = model_lbz[i] - z[i];
+            w->d[k][NZ + i] = -(model_ubz[i] - z[i]);
+        }
+        for (int e = NCB; e < g_nc; e++) {
+            int r = g_hrow[e - NCB];
+            w->d[k][e] = g_hsgn[e - NCB] * (g_hbnd[e - NCB] - w->hval[k][r]);
+        }
+    }
+    /* terminal stage: no cost, no constraints => H_N = mirror(0) = eps I, g_N = 0 */
+    for (int i = 0; i < NZ * NZ; i++) w->H[NN][i] = 0.0;
+    for (int i = 0; i < NZ; i++) w->g[NN][i] = 0.0;
+    mirror(&w->H[NN][NU * NZ + NU], NX, NZ);
+    (void)xinit;
+}
+
+/* entry e of stage k is active? (x box rows are absent at k = 0: x_0 is fixed) */
+static int active(int k, int e)
+{
+    if (k == 0 && ((e >= NU && e < NZ) || (e >= NZ + NU && e < NCB))) return 0;
+    return 1;
+}
+/* chat_e' y for a 7-vector y */
+static REAL crow_dot(const work_t *w, int k, int e, const REAL *y)
+{
+    if (e < NZ) return y[e];
+    if (e < NCB) return -y[e - NZ];
+    int r = g_hrow[e - NCB];
+    REAL s = 0.0;
+    for (int j = 0; j < NZ; j++) s += w->C[k][r * NZ + j] * y[j];
+    return g_hsgn[e - NCB] * s;
+}
+/* y += a * chat_e */
+static void crow_axpy(const work_t *w, int k, int e, REAL a, REAL *y)
+{
+    if (e < NZ) { y[e] += a; return; }
+    if (e < NCB) { y[e - NZ] -= a; return; }
+    int r = g_hrow[e - NCB];
+    for (int j = 0; j < NZ; j++) y[j] += a * g_hsgn[e - NCB] * w->C[k][r * NZ + j];
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * K5: primal-dual interior point QP with Riccati  [upstream: HPIPM ocp_qp_ipm, restated]
+ * ---------------------------------------------------------------------------------------------- */
+static void qp_init(work_t *w, const REAL *dx0)
+{
+    if (!w->qp_warm) {
+        memset(w->v, 0, sizeof(w->v));
+        memset(w->qpi, 0, sizeof(w->qpi));
+    }
+    for (int i = 0; i < NX; i++) w->v[0][NU + i] = dx0[i];
+    if (w->qp_warm) {
+        for (int k = 0; k < NN; k++)
+            for (int e = 0; e < g_nc; e++) {
+                if (!active(k, e)) continue;
+                if (w->lam[k][e] < IPM_THR0) w->lam[k][e] = IPM_THR0;
+                if (w->t[k][e] < IPM_THR0) w->t[k][e] = IPM_THR0;
+            }
+        return;
+    }
+    for (int k = 0; k < NN; k++) {
+        for (int i = 0; i < NZ; i++) {
+            if (!active(k, i)) continue;
+            REAL dl = w->d[k][i], du = -w->d[k][NZ + i];
+            REAL tl = w->v[k][i] - dl, tu = du - w->v[k][i];
+            if (tl < IPM_THR0) {
+                if (tu < IPM_THR0) { w->v[k][i] = 0.5 * (dl + du); tl = IPM_THR0; tu = IPM_THR0; }
+                else { tl = IPM_THR0; w->v[k][i] = dl + IPM_THR0; }
+            } else if (tu < IPM_THR0) { tu = IPM_THR0; w->v[k][i] = du - IPM_THR0; }
+            w->t[k][i] = tl; w->t[k][NZ + i] = tu;
+            w->lam[k][i] = IPM_MU0 / tl; w->lam[k][NZ + i] = IPM_MU0 / tu;
+        }
+        for (int e = NCB; e < g_nc; e++) {
+            REAL tt = crow_dot(w, k, e, w->v[k]) - w->d[k][e];
+            if (tt < IPM_THR0) tt = IPM_THR0;
+            w->t[k][e] = tt;
+            w->lam[k][e] = IPM_MU0 / tt;
+        }
+    }
+}
+
+static void qp_residuals(work_t *w, REAL nrm[4], REAL *mu)
+{
+    REAL ng = 0.0, nb = 0.0, nd = 0.0, nm = 0.0, sm = 0.0;
+    int cnt = 0;
+    for (int k = 0; k <= NN; k++) {
+        REAL *r = w->rg[k];
+        int j0 = (k == NN) ? NU : 0;
+        for (int i = 0; i < NZ; i++) r[i] = 0.0;
+        for (int i = j0; i < NZ; i++) {
+            REAL s = w->g[k][i];
+            for (int j = j0; j < NZ; j++) s += w->H[k][i * NZ + j] * w->v[k][j];
+            r[i] = s;
+        }
+        if (k < NN)
+            for (int j = 0; j < NZ; j++) {
+                REAL s = 0.0;
+                for (int i = 0; i < NX; i++) s += w->W[k][i * NZ + j] * w->qpi[k + 1][i];
+                r[j] += s;
+            }
+        if (k > 0)
+            for (int i = 0; i < NX; i++) r[NU + i] -= w->qpi[k][i];
+        if (k < NN)
+            for (int e = 0; e < g_nc; e++)
+                if (active(k, e)) crow_axpy(w, k, e, -w->lam[k][e], r);
+        if (k == 0)
+            for (int i = NU; i < NZ; i++) r[i] = 0.0; /* x_0 is not a variable */
+        for (int i = 0; i < NZ; i++) if (fabs(r[i]) > ng) ng = fabs(r[i]);
+    }
+    for (int k = 0; k < NN; k++) {
+        for (int i = 0; i < NX; i++) {
+            REAL s = w->b[k][i] - w->v[k + 1][NU + i];
+            for (int j = 0; j < NZ; j++) s += w->W[k][i * NZ + j] * w->v[k][j];
+            w->rb[k][i] = s;
+            if (fabs(s) > nb) nb = fabs(s);
+        }
+        for (int e = 0; e < g_nc; e++) {
+            if (!active(k, e)) { w->rd[k][e] = 0.0; w->rm[k][e] = 0.0; continue; }
+            REAL s = crow_dot(w, k, e, w->v[k]) - w->d[k][e] - w->t[k][e];
+            REAL m = w->lam[k][e] * w->t[k][e];
+            w->rd[k][e] = s; w->rm[k][e] = m;
+            if (fabs(s) > nd) nd = fabs(s);
+            if (fabs(m) > nm) nm = fabs(m);
+            sm += m; cnt++;
+        }
+    }
+    nrm[0] = ng; nrm[1] = nb; nrm[2] = nd; nrm[3] = nm;
+    *mu = sm / (REAL)cnt;
+}
+
+/* Htilde = H + sum Gamma chat chat'  (only depends on lam, t) */
+static void kkt_hessian(work_t *w)
+{
+    for (int k = 0; k <= NN; k++) {
+        memcpy(w->Ht[k], w->H[k], sizeof(w->H[k]));
+        if (k == NN) break;
+        for (int e = 0; e < g_nc; e++) {
+            if (!active(k, e)) continue;
+            REAL G = w->lam[k][e] / w->t[k][e];
+            if (e < NCB) { int i = (e < NZ) ? e : e - NZ; w->Ht[k][i * NZ + i] += G; }
+            else {
+                int r = g_hrow[e - NCB];
+                for (int i = 0; i < NZ; i++)
+                    for (int j = 0; j < NZ; j++) w->Ht[k][i * NZ + j] += G * w->C[k][r * NZ + i] * w->C[k][r * NZ + j];
+            }
+        }
+    }
+}
+/* gtilde = rg + sum chat (rm + lam rd)/t */
+static void kkt_gradient(work_t *w)
+{
+    for (int k = 0; k <= NN; k++) {
+        for (int i = 0; i < NZ; i++) w->gt[k][i] = w->rg[k][i];
+        if (k == NN) break;
+        for (int e = 0; e < g_nc; e++) {
+            if (!active(k, e)) continue;
+            REAL gam = (w->rm[k][e] + w->lam[k][e] * w->rd[k][e]) / w->t[k][e];
+            crow_axpy(w, k, e, gam, w->gt[k]);
+        }
+    }
+}
+
+/* backward Riccati factorisation on (Ht, W): P_k, K_k, Guu^{-1}, Gxu */
+static void riccati_factor(work_t *w)
+{
+    for (int i = 0; i < NX; i++)
+        for (int j = 0; j < NX; j++) w->P[NN][i * NX + j] = w->Ht[NN][(NU + i) * NZ + NU + j];
+    for (int k = NN - 1; k >= 0; k--) {
+        REAL PW[NX * NZ], G[NZ * NZ];
+        for (int i = 0; i < NX; i++)
+            for (int j = 0; j < NZ; j++) {
+                REAL s = 0.0;
+                for (int l = 0; l < NX; l++) s += w->P[k + 1][i * NX + l] * w->W[k][l * NZ + j];
+                PW[i * NZ + j] = s;
+            }
+        for (int i = 0; i < NZ; i++)
+            for (int j = 0; j < NZ; j++) {
+                REAL s = w->Ht[k][i * NZ + j];
+                for (int l = 0; l < NX; l++) s += w->W[k][l * NZ + i] * PW[l * NZ + j];
+                G[i * NZ + j] = s;
+            }
+        /* 2x2 (NU x NU) inverse of Guu via Cholesky-free symmetric formula (NU == 2) */
+#if NU != 2
+#error "riccati_factor assumes NU == 2"
+#endif
+        REAL a = G[0], bq = 0.5 * (G[1] + G[NZ]), c = G[NZ + 1];
+        REAL det = a * c - bq * bq;
+        REAL *Gi = w->Ginv[k];
+        Gi[0] = c / det; Gi[1] = -bq / det; Gi[2] = -bq / det; Gi[3] = a / det;
+        for (int i = 0; i < NX; i++)
+            for (int j = 0; j < NU; j++) w->Gxu[k][i * NU + j] = 0.5 * (G[(NU + i) * NZ + j] + G[j * NZ + NU + i]);
+        for (int i = 0; i < NU; i++)
+            for (int j = 0; j < NX; j++) {
+                REAL s = 0.0;
+                for (int l = 0; l < NU; l++) s += Gi[i * NU + l] * w->Gxu[k][j * NU + l];
+                w->K[k][i * NX + j] = -s;
+            }
+        for (int i = 0; i < NX; i++)
+            for (int j = 0; j < NX; j++) {
+                REAL s = 0.5 * (G[(NU + i) * NZ + NU + j] + G[(NU + j) * NZ + NU + i]);
+                for (int l = 0; l < NU; l++) s += w->Gxu[k][i * NU + l] * w->K[k][l * NX + j];
+                w->P[k][i * NX + j] = s;
+            }
+        for (int i = 0; i < NX; i++)
+            for (int j = 0; j < i; j++) {
+                REAL s = 0.5 * (w->P[k][i * NX + j] + w->P[k][j * NX + i]);
+                w->P[k][i * NX + j] = s; w->P[k][j * NX + i] = s;
+            }
+    }
+}
+
+/* backward vector sweep + forward sweep with rhs (gt, rb): Newton step dv, dpi */
+static void riccati_solve(work_t *w, REAL (*dv)[NZ])
+{
+    for (int i = 0; i < NX; i++) w->pv[NN][i] = w->gt[NN][NU + i];
+    for (int k = NN - 1; k >= 0; k--) {
+        REAL y[NX], q[NZ];
+        for (int i = 0; i < NX; i++) {
+            REAL s = w->pv[k + 1][i];
+            for (int l = 0; l < NX; l++) s += w->P[k + 1][i * NX + l] * w->rb[k][l];
+            y[i] = s;
+        }
+        for (int j = 0; j < NZ; j++) {
+            REAL s = w->gt[k][j];
+            for (int i = 0; i < NX; i++) s += w->W[k][i * NZ + j] * y[i];
+            q[j] = s;
+        }
+        for (int i = 0; i < NU; i++) {
+            REAL s = 0.0;
+            for (int l = 0; l < NU; l++) s += w->Ginv[k][i * NU + l] * q[l];
+            w->kff[k][i] = -s;
+        }
+        for (int i = 0; i < NX; i++) {
+            REAL s = q[NU + i];
+            for (int l = 0; l < NU; l++) s += w->Gxu[k][i * NU + l] * w->kff[k][l];
+            w->pv[k][i] = s;
+        }
+    }
+    for (int i = 0; i < NX; i++) dv[0][NU + i] = 0.0; /* dx_0 = 0: x_0 is fixed */
+    for (int k = 0; k < NN; k++) {
+        for (int i = 0; i < NU; i++) {
+            REAL s = w->kff[k][i];
+            for (int j = 0; j < NX; j++) s += w->K[k][i * NX + j] * dv[k][NU + j];
+            dv[k][i] = s;
+        }
+        for (int i = 0; i < NX; i++) {
+            REAL s = w->rb[k][i];
+            for (int j = 0; j < NZ; j++) s += w->W[k][i * NZ + j] * dv[k][j];
+            dv[k + 1][NU + i] = s;
+        }
+        for (int i = 0; i < NX; i++) {
+            REAL s = w->pv[k + 1][i];
+            for (int j = 0; j < NX; j++) s += w->P[k + 1][i * NX + j] * dv[k + 1][NU + j];
+            w->dpi[k + 1][i] = s;
+        }
+    }
+    for (int i = 0; i < NU; i++) dv[NN][i] = 0.0;
+}
+
+/* dt, dlam from dv; returns max step alpha in (0,1] keeping lam, t >= 0 */
+static REAL ipm_step_ineq(work_t *w, REAL (*dv)[NZ])
+{
+    REAL alpha = 1.0;
+    for (int k = 0; k < NN; k++)
+        for (int e = 0; e < g_nc; e++) {
+            if (!active(k, e)) { w->dt[k][e] = 0.0; w->dlam[k][e] = 0.0; continue; }
+            REAL dt = crow_dot(w, k, e, dv[k]) + w->rd[k][e];
+            REAL dl = -(w->rm[k][e] + w->lam[k][e] * dt) / w->t[k][e];
+            w->dt[k][e] = dt; w->dlam[k][e] = dl;
+            if (dl < 0.0) { REAL a = -w->lam[k][e] / dl; if (a < alpha) alpha = a; }
+            if (dt < 0.0) { REAL a = -w->t[k][e] / dt; if (a < alpha) alpha = a; }
+        }
+    return alpha;
+}
+
+/* returns HPIPM-style status: 0 ok, 1 max iter, 2 min step, 3 NaN */
+static int qp_solve(work_t *w, const REAL *dx0)
+{
+    REAL nrm[4], mu, alpha = 1.0;
+    int kk;
+    qp_init(w, dx0);
+    qp_residuals(w, nrm, &mu);
+    for (kk = 0; kk < IPM_ITER_MAX && alpha > IPM_ALPHA_MIN &&
+                 (nrm[0] > IPM_TOL || nrm[1] > IPM_TOL || nrm[2] > IPM_TOL || nrm[3] > IPM_TOL); kk++) {
+        /* predictor (affine scaling) */
+        kkt_hessian(w);
+        kkt_gradient(w);
+        riccati_factor(w);
+        riccati_solve(w, w->dva);
+        REAL alpha_aff = ipm_step_ineq(w, w->dva);
+        REAL smu = 0.0;
+        int cnt = 0;
+        for (int k = 0; k < NN; k++)
+            for (int e = 0; e < g_nc; e++)
+                if (active(k, e)) {
+                    smu += (w->lam[k][e] + alpha_aff * w->dlam[k][e]) * (w->t[k][e] + alpha_aff * w->dt[k][e]);
+                    cnt++;
+                }
+        REAL mu_aff = smu / (REAL)cnt;
+        REAL rat = mu_aff / mu, sigma = rat * rat * rat;
+        /* corrector: rm += dt_aff dlam_aff - sigma mu */
+        for (int k = 0; k < NN; k++)
+            for (int e = 0; e < g_nc; e++)
+                if (active(k, e)) w->rm[k][e] += w->dt[k][e] * w->dlam[k][e] - sigma * mu;
+        kkt_gradient(w);
+        riccati_solve(w, w->dv);
+        alpha = ipm_step_ineq(w, w->dv);
+        REAL a = alpha < 1.0 ? alpha * IPM_STEP_SCALE : alpha;
+        for (int k = 0; k <= NN; k++) {
+            for (int i = 0; i < NZ; i++) w->v[k][i] += a * w->dv[k][i];
+            if (k > 0) for (int i = 0; i < NX; i++) w->qpi[k][i] += a * w->dpi[k][i];
+            if (k < NN)
+                for (int e = 0; e < g_nc; e++) {
+                    if (!active(k, e)) continue;
+                    w->lam[k][e] += a * w->dlam[k][e];
+                    w->t[k][e] += a * w->dt[k][e];
+                    if (w->lam[k][e] < IPM_LAM_MIN) w->lam[k][e] = IPM_LAM_MIN;
+                    if (w->t[k][e] < IPM_T_MIN) w->t[k][e] = IPM_T_MIN;
+                }
+        }
+        qp_residuals(w, nrm, &mu);
+    }
+    w->qp_iters_last = kk;
+    w->ipm_iters_total += kk;
+    if (kk == IPM_ITER_MAX) return 1;
+    if (alpha <= IPM_ALPHA_MIN) return 2;
+    if (mu != mu) return 3;
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * One Solver::solve() call   (acados_solver_interface.cpp:86-204)
+ * ---------------------------------------------------------------------------------------------- */
+static void solve_one(work_t *w, const REAL *xinit, const REAL *x0, const REAL *params, int num_iter, REAL *mem,
+                      REAL *xtraj, REAL *utraj, REAL *pobj, int *exit_code, int *qp_status, REAL *res_eq, int *ipm_iters)
+{
+    /* persistent solver memory (multipliers survive between solve() calls on one capsule) */
+    memset(w->pi, 0, sizeof(w->pi));
+    memset(w->lam, 0, sizeof(w->lam));
+    memset(w->t, 0, sizeof(w->t));
+    memset(w->v, 0, sizeof(w->v));
+    w->qp_warm = 0;
+    w->ipm_iters_total = 0;
+    if (mem && mem[0] != 0.0) {
+        const REAL *m = mem + 1;
+        memcpy(w->pi, m, sizeof(REAL) * (NN + 1) * NX); m += (NN + 1) * NX;
+        for (int k = 0; k < NN; k++) { memcpy(w->lam[k], m, sizeof(REAL) * g_nc); m += g_nc; }
+        for (int k = 0; k < NN; k++) { memcpy(w->t[k], m, sizeof(REAL) * g_nc); m += g_nc; }
+        memcpy(w->v, m, sizeof(REAL) * (NN + 1) * NZ);
+        w->qp_warm = (mem[0] >= 2.0);
+        memcpy(w->qpi, w->pi, sizeof(w->pi));
+    }
+    /* loadWarmstart: x0 = [u_k, x_k] per stage  (acados_solver_interface.cpp:274-284) */
+    for (int k = 0; k <= NN; k++) {
+        if (k < NN) for (int i = 0; i < NU; i++) w->u[k][i] = x0[k * NZ + i];
+        for (int i = 0; i < NX; i++) w->x[k][i] = x0[k * NZ + NU + i];
+    }
+    int status = 0, qps = 0;
+    for (int it = 0; it < num_iter; it++) {
+        REAL dx0[NX];
+        linearize(w, xinit, params);
+        for (int i = 0; i < NX; i++) dx0[i] = xinit[i] - w->x[0][i];
+        qps = qp_solve(w, dx0);
+        if (qps != 0 && qps != 1) { status = 4; break; }       /* ACADOS_QP_FAILURE; iterate unchanged */
+        for (int k = 0; k <= NN; k++) {                        /* full step (FIXED_STEP) */
+            if (k < NN) for (int i = 0; i < NU; i++) w->u[k][i] += w->v[k][i];
+            for (int i = 0; i < NX; i++) w->x[k][i] += w->v[k][NU + i];
+        }
+        memcpy(w->pi, w->qpi, sizeof(w->pi));
+        w->qp_warm = 1;
+        status = 0;
+        if (qps != 0) break;                                   /* wrapper breaks on qp_status != 0 (:105-106) */
+    }
+    /* completeOneIteration (:162-204) */
+    REAL cost = 0.0, req = 0.0;
+    for (int k = 0; k < NN; k++) {
+        const REAL *p = stage_params(params, k);
+        REAL z[NZ], xn[NX];
+        for (int i = 0; i < NU; i++) z[i] = w->u[k][i];
+        for (int i = 0; i < NX; i++) z[NU + i] = w->x[k][i];
+        cost += MODEL_DT * model_cost(z, p);
+        integrate(w->x[k], w->u[k], p, xn, NULL, NULL, NULL);
+        for (int i = 0; i < NX; i++) { REAL r = fabs(xn[i] - w->x[k + 1][i]); if (r > req) req = r; }
+    }
+    for (int k = 0; k <= NN; k++) {
+        for (int i = 0; i < NX; i++) xtraj[k * NX + i] = w->x[k][i];
+        if (k < NN) for (int i = 0; i < NU; i++) utraj[k * NU + i] = w->u[k][i];
+    }
+    if (!(req <= RES_EQ_MAX) && status == 0) status = 4;
+    *pobj = cost; *res_eq = req; *qp_status = qps;
+    *exit_code = (status == 0) ? 1 : (status == 1 ? 0 : status);
+    if (ipm_iters) *ipm_iters = w->ipm_iters_total;
+    if (mem) {
+        if (status != 0) {
+            memset(mem, 0, sizeof(REAL) * oracle_mem_doubles()); /* Solver_acados_reset + reset_qp_memory (:187-191) */
+        } else {
+            REAL *m = mem + 1;
+            mem[0] = 2.0;
+            memcpy(m, w->pi, sizeof(REAL) * (NN + 1) * NX); m += (NN + 1) * NX;
+            for (int k = 0; k < NN; k++) { memcpy(m, w->lam[k], sizeof(REAL) * g_nc); m += g_nc; }
+            for (int k = 0; k < NN; k++) { memcpy(m, w->t[k], sizeof(REAL) * g_nc); m += g_nc; }
+            memcpy(m, w->v, sizeof(REAL) * (NN + 1) * NZ);
+        }
+    }
+}
+
+#ifndef ORACLE_NO_API
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Batched solve; OpenMP over problems mirrors guidance_constraints.cpp:304 (one capsule per thread). */
+int oracle_solve_batch(int n, const double *xinit, const double *x0, const double *params, const int *num_iter,
+                       double *mem_inout, double *xtraj, double *utraj, double *pobj, int *exit_code,
+                       int *qp_status, double *res_eq, int *ipm_iters, int num_threads)
+{
+    setup_constraints();
+    int md = oracle_mem_doubles();
+#pragma omp parallel num_threads(num_threads > 0 ? num_threads : 1)
+    {
+        work_t *w = (work_t *)malloc(sizeof(work_t));
+#pragma omp for schedule(dynamic, 1)
+        for (int i = 0; i < n; i++)
+            solve_one(w, xinit + (size_t)i * NX, x0 + (size_t)i * NZ * (NN + 1), params + (size_t)i * NN * NP, num_iter[i],
+                      mem_inout ? mem_inout + (size_t)i * md : NULL, xtraj + (size_t)i * NX * (NN + 1),
+                      utraj + (size_t)i * NU * NN, pobj + i, exit_code + i, qp_status + i, res_eq + i,
+                      ipm_iters ? ipm_iters + i : NULL);
+        free(w);
+    }
+    return 0;
+}
+
+/* K7: FindBestPlanner (guidance_constraints.cpp:572-590) with the objective post-processing of
+ * :373-420: obj = (pobj - obj_sub) * obj_scale; success = exit_code == 1; strict <, ascending.   */
+int oracle_select_best(int n_sets, const int *set_offsets, const double *pobj, const int *exit_code,
+                       const double *obj_scale, const double *obj_sub, const unsigned char *disabled, int *best_idx)
+{
+    for (int s = 0; s < n_sets; s++) {
+        double best = 1e10;
+        int bi = -1;
+        for (int i = set_offsets[s]; i < set_offsets[s + 1]; i++) {
+            if (disabled && disabled[i]) continue;
+            double obj = pobj[i];
+            if (obj_sub) obj -= obj_sub[i];
+            if (obj_scale) obj *= obj_scale[i];
+            if (exit_code[i] == 1 && obj < best) { best = obj; bi = i - set_offsets[s]; }
+        }
+        best_idx[s] = bi;
+    }
+    return 0;
+}
+
+/* ---- component entry points used by the unit tests ------------------------------------------ */
+void oracle_model_eval(const double *z, const double *p, const double *mu, const double *mh, double *f, double *Jf,
+                       double *Hf, double *cost, double *gc, double *Hc, double *h, double *Jh, double *Hh)
+{
+    model_f(z + NU, z, p, f); model_f_jac(z + NU, z, p, Jf); model_f_hess(z + NU, z, p, mu, Hf);
+    *cost = model_cost(z, p); model_cost_grad_hess(z, p, gc, Hc);
+    model_h(z, p, h); model_h_jac(z, p, Jh); model_h_hess(z, p, mh, Hh);
+}
+void oracle_integrate(const double *x, const double *u, const double *p, const double *pi, double *xn, double *W, double *Hc)
+{
+    integrate(x, u, p, xn, W, pi, Hc);
+}
+void oracle_mirror(double *A, int n) { mirror(A, n, n); }
+const double *oracle_bounds(int which)
+{
+    return which == 0 ? model_lbz : which == 1 ? model_ubz : which == 2 ? model_lh : model_uh;
+}
+const char *oracle_param_name(int i) { return model_param_names[i]; }
+const char *oracle_var_name(int i) { return model_var_names[i]; }
+
+/* Linearise at (x0 warm start, multipliers zero) and solve ONE QP; export QP data and solution so
+ * that tests can verify the KKT conditions independently (numpy).                               */
+int oracle_qp_debug(const double *xinit, const double *x0, const double *params, double *Hout, double *gout,
+                    double *Wout, double *bout, double *Cout, double *dout, double *vout, double *piout,
+                    double *lamout, double *tout, int *iters)
+{
+    setup_constraints();
+    work_t *w = (work_t *)calloc(1, sizeof(work_t));
+    for (int k = 0; k <= NN; k++) {
+        if (k < NN) for (int i = 0; i < NU; i++) w->u[k][i] = x0[k * NZ + i];
+        for (int i = 0; i < NX; i++) w->x[k][i] = x0[k * NZ + NU + i];
+    }
+    linearize(w, xinit, params);
+    double dx0[NX];
+    for (int i = 0; i < NX; i++) dx0[i] = xinit[i] - w->x[0][i];
+    int st = qp_solve(w, dx0);
+    memcpy(Hout, w->H, sizeof(w->H)); memcpy(gout, w->g, sizeof(w->g));
+    memcpy(Wout, w->W, sizeof(w->W)); memcpy(bout, w->b, sizeof(w->b));
+    memcpy(Cout, w->C, sizeof(w->C));
+    for (int k = 0; k < NN; k++)
+        for (int e = 0; e < g_nc; e++) {
+            dout[k * g_nc + e] = w->d[k][e]; lamout[k * g_nc + e] = w->lam[k][e]; tout[k * g_nc + e] = w->t[k][e];
+        }
+    memcpy(vout, w->v, sizeof(w->v)); memcpy(piout, w->qpi, sizeof(w->qpi));
+    *iters = w->qp_iters_last;
+    free(w);
+    return st;
+}
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORACLE_NO_API */

@@ -1,0 +1,217 @@
+"""Synthetic obstacle / path / warm-start data for the batched MPC solve path.
+
+Every array is laid out exactly as the reference's `AcadosParameters` block
+(mpc_planner_solver/include/mpc_planner_solver/acados_solver_interface.h:51-91):
+  xinit[nx], x0[(nu+nx)(N+1)] stage-major [u_k, x_k], all_parameters[N*npar] (index k*npar+idx).
+Parameter VALUES follow the conventions of the reference's C++ modules:
+  * weights                    mpc_planner_jackalsimulator/config/settings.yaml:78-92
+  * spline block per stage     mpc_planner_modules/src/contouring.cpp:52-126 (same for every k)
+  * ellipsoid obstacles        ellipsoid_constraints.cpp:34-90   (stage k <- prediction k-1, dummies at k=0)
+  * guidance halfspaces        linearized_constraints.cpp:49-189 (from the warm-start positions, k>=1;
+                               dummy (1,0,x+100) at k=0 and for the non-guided planner)
+  * constant-velocity predictions  mpc_planner/src/data_preparation.cpp:64-81
+  * braking roll-out           mpc_planner_solver/src/acados_solver_interface.cpp:303-342
+The guidance planner itself (external `guidance_planner` package) is replaced by a synthetic
+stand-in: planner h follows a laterally shifted corridor chosen by h, pushed out of obstacles.
+"""
+import numpy as np
+
+WEIGHTS = dict(acceleration=0.34, angular_velocity=0.85, velocity=0.55, reference_velocity=2.0,
+               contour=0.05, lag=0.75, terminal_angle=100.0, terminal_contouring=10.0,
+               consistency_weight=0.05)
+ROBOT_RADIUS = 0.325
+OBSTACLE_RADIUS = 0.325
+DECELERATION = 3.0
+NUM_SEGMENTS = 5
+_LATERAL = np.array([0.0, 1.0, -1.0, 2.0, -2.0, 3.0, -3.0, 0.5])
+
+
+def _natural_cubic(t, y):
+    """Batched natural cubic spline. t: (B,n) strictly increasing knots, y: (B,n).
+    Returns per-segment coefficients a,b,c,d (B,n-1) of a*s^3+b*s^2+c*s+d, s = t - t_i."""
+    B, n = t.shape
+    h = np.diff(t, axis=1)
+    A = np.zeros((B, n, n))
+    rhs = np.zeros((B, n))
+    A[:, 0, 0] = 1.0
+    A[:, -1, -1] = 1.0
+    idx = np.arange(1, n - 1)
+    A[:, idx, idx - 1] = h[:, :-1]
+    A[:, idx, idx] = 2.0 * (h[:, :-1] + h[:, 1:])
+    A[:, idx, idx + 1] = h[:, 1:]
+    rhs[:, 1:-1] = 3.0 * ((y[:, 2:] - y[:, 1:-1]) / h[:, 1:] - (y[:, 1:-1] - y[:, :-2]) / h[:, :-1])
+    c = np.linalg.solve(A, rhs[..., None])[..., 0]
+    b = (y[:, 1:] - y[:, :-1]) / h - h * (2.0 * c[:, :-1] + c[:, 1:]) / 3.0
+    a = (c[:, 1:] - c[:, :-1]) / (3.0 * h)
+    return a, c[:, :-1], b, y[:, :-1]
+
+
+def make_batch(pmap, dims, n_sets, planners_per_set=1, seed=1234, guided=None, gaussian=False):
+    """Build `n_sets * planners_per_set` problems.
+
+    pmap: parameter name -> index (parameter_map.yaml); dims: dict(N, nx, nu, npar, dt).
+    guided: if None, inferred from the presence of `lin_constraint_0_a1` in pmap.
+    Problems of a set share state, path and obstacles and differ in warm start + halfspaces
+    (planner index h < planners_per_set-1: guided; the last one is the non-guided planner when
+    planners_per_set > 1), matching GuidanceConstraints (guidance_constraints.cpp:304-370).
+    Returns dict of float64 arrays + `set_offsets`.
+    """
+    N, nx, nu, npar, dt = dims["N"], dims["nx"], dims["nu"], dims["npar"], dims["dt"]
+    nz = nx + nu
+    rng = np.random.default_rng(seed)
+    S, Pn = n_sets, planners_per_set
+    B = S * Pn
+    has_lin = "lin_constraint_0_a1" in pmap
+    if guided is None:
+        guided = has_lin
+    M = sum(1 for k in pmap if k.startswith("ellipsoid_obst_") and k.endswith("_x"))
+    Mg = sum(1 for k in pmap if k.startswith("gaussian_obst_") and k.endswith("_x"))
+    Md = sum(1 for k in pmap if k.startswith("disc_0_decomp_") and k.endswith("_a1"))
+    Mall = max(M, Mg)
+
+    # ---- per-set scenario ---------------------------------------------------------------------
+    st = np.stack([rng.uniform(-0.5, 0.5, S), rng.uniform(-0.5, 0.5, S), rng.uniform(-0.3, 0.3, S),
+                   rng.uniform(0.0, 2.5, S), np.zeros(S)], axis=1)
+    nw = NUM_SEGMENTS + 2
+    wx = np.concatenate([np.zeros((S, 1)), np.cumsum(rng.uniform(3.0, 6.0, (S, nw - 1)), axis=1)], axis=1)
+    wy = np.concatenate([np.zeros((S, 1)), rng.uniform(-2.0, 2.0, (S, nw - 1))], axis=1)
+    ts = np.concatenate([np.zeros((S, 1)), np.cumsum(np.hypot(np.diff(wx, axis=1), np.diff(wy, axis=1)), axis=1)], axis=1)
+    ax, bx, cx, dx = _natural_cubic(ts, wx)
+    ay, by, cy, dy = _natural_cubic(ts, wy)
+    op0 = np.stack([rng.uniform(2.0, 20.0, (S, Mall)), rng.uniform(-4.0, 4.0, (S, Mall))], axis=2)
+    ospeed = rng.uniform(0.5, 1.5, (S, Mall))
+    ohead = rng.uniform(-np.pi, np.pi, (S, Mall))
+    ovel = np.stack([ospeed * np.cos(ohead), ospeed * np.sin(ohead)], axis=2)
+    steps = np.arange(N)[None, :, None, None]
+    opred = op0[:, None] + ovel[:, None] * dt * steps          # (S, N, M, 2): prediction index i
+
+    # ---- warm starts --------------------------------------------------------------------------
+    x0 = np.zeros((S, Pn, N + 1, nz))
+    kk = np.arange(N + 1)[None, :]
+    for h in range(Pn):
+        nonguided = (Pn > 1 and h == Pn - 1) and guided
+        X = np.zeros((S, N + 1, nz))
+        if guided and not nonguided:
+            vg = np.clip(st[:, 3:4] * 0 + WEIGHTS["reference_velocity"], 0.5, 2.5)
+            lat = _LATERAL[h % len(_LATERAL)]
+            px = st[:, 0:1] + vg * dt * kk
+            py = st[:, 1:2] + lat * np.sin(np.pi * kk / N) ** 2
+            pos = np.stack([px, py], axis=2)                    # (S, N+1, 2)
+            # push out of obstacles (stand-in for projectToSafety, linearized_constraints.cpp:130-148)
+            for _ in range(3):
+                for j in range(Mall):
+                    o = np.concatenate([opred[:, :1, j], opred[:, :, j]], axis=1)  # stage k uses k-1
+                    dvec = pos - o
+                    dist = np.linalg.norm(dvec, axis=2, keepdims=True)
+                    need = ROBOT_RADIUS + OBSTACLE_RADIUS + 0.1
+                    push = np.where(dist < need, (need - dist) / np.maximum(dist, 1e-9), 0.0)
+                    pos = pos + dvec * push
+            pos[:, 0] = st[:, 0:2]
+            vel = np.gradient(pos, dt, axis=1)
+            X[:, :, nu + 0] = pos[:, :, 0]
+            X[:, :, nu + 1] = pos[:, :, 1]
+            X[:, :, nu + 2] = np.arctan2(vel[:, :, 1], vel[:, :, 0])
+            X[:, :, nu + 3] = np.linalg.norm(vel, axis=2)
+            X[:, :, nu + 4] = np.concatenate([np.zeros((S, 1)), np.cumsum(X[:, :-1, nu + 3] * dt, axis=1)], axis=1)
+            X[:, 0, nu:] = st
+        else:
+            # braking roll-out for the non-guided planner; constant-velocity cruise otherwise
+            a = -DECELERATION if nonguided else 0.0
+            x, y, psi, v, s = (st[:, i].copy() for i in range(5))
+            for k in range(N + 1):
+                X[:, k, 0] = a
+                X[:, k, nu:] = np.stack([x, y, psi, v, s], axis=1)
+                x = x + v * dt * np.cos(psi)
+                y = y + v * dt * np.sin(psi)
+                s = s + v * dt
+                v = np.maximum(v + a * dt, 0.0)
+        x0[:, h] = X
+
+    # ---- parameters ---------------------------------------------------------------------------
+    P = np.zeros((S, Pn, N, npar))
+
+    def setp(name, val):
+        if name in pmap:
+            P[..., pmap[name]] = val
+
+    for name, val in WEIGHTS.items():
+        setp(name, val)
+    for i in range(NUM_SEGMENTS):
+        for nm, arr in (("spline_x%d_a", ax), ("spline_x%d_b", bx), ("spline_x%d_c", cx), ("spline_x%d_d", dx),
+                        ("spline_y%d_a", ay), ("spline_y%d_b", by), ("spline_y%d_c", cy), ("spline_y%d_d", dy)):
+            setp(nm % i, arr[:, i][:, None, None])
+        setp("spline%d_start" % i, ts[:, i][:, None, None])
+    setp("ego_disc_radius", ROBOT_RADIUS)
+    setp("ego_disc_0_offset", 0.0)
+    if "prev_traj_x" in pmap:  # consistency reference: the planner's own warm start positions
+        P[..., pmap["prev_traj_x"]] = x0[:, :, :N, nu + 0]
+        P[..., pmap["prev_traj_y"]] = x0[:, :, :N, nu + 1]
+
+    dummy_xy = st[:, None, 0:2] + 50.0
+    for j in range(M):
+        pre = "ellipsoid_obst_%d_" % j
+        P[:, :, 1:, pmap[pre + "x"]] = opred[:, None, :N - 1, j, 0]
+        P[:, :, 1:, pmap[pre + "y"]] = opred[:, None, :N - 1, j, 1]
+        P[:, :, 1:, pmap[pre + "r"]] = OBSTACLE_RADIUS
+        P[:, :, 0, pmap[pre + "x"]] = dummy_xy[:, :, 0]
+        P[:, :, 0, pmap[pre + "y"]] = dummy_xy[:, :, 1]
+        P[:, :, 0, pmap[pre + "r"]] = 0.1
+        P[..., pmap[pre + "chi"]] = 1.0
+    for j in range(Mg):
+        pre = "gaussian_obst_%d_" % j
+        # propagatePredictionUncertainty (data_preparation.cpp:175-191): sigma grows with sqrt of the step
+        sig = np.sqrt(np.cumsum(np.full(N, (0.3 * dt) ** 2)))
+        P[:, :, 1:, pmap[pre + "x"]] = opred[:, None, :N - 1, j, 0]
+        P[:, :, 1:, pmap[pre + "y"]] = opred[:, None, :N - 1, j, 1]
+        P[:, :, 1:, pmap[pre + "major"]] = sig[None, None, :N - 1]
+        P[:, :, 1:, pmap[pre + "minor"]] = sig[None, None, :N - 1]
+        P[:, :, 1:, pmap[pre + "r"]] = OBSTACLE_RADIUS
+        P[:, :, 0, pmap[pre + "x"]] = dummy_xy[:, :, 0]
+        P[:, :, 0, pmap[pre + "y"]] = dummy_xy[:, :, 1]
+        P[:, :, 0, pmap[pre + "major"]] = 0.1
+        P[:, :, 0, pmap[pre + "minor"]] = 0.1
+        P[:, :, 0, pmap[pre + "r"]] = 0.1
+        P[..., pmap[pre + "risk"]] = 0.05
+    if Md:
+        # supporting halfspaces of a regular polygon of half-width 6 m around the reference position
+        ang = 2.0 * np.pi * np.arange(Md) / Md
+        cxk = st[:, None, 0:1] + WEIGHTS["reference_velocity"] * dt * np.arange(N)[None, :, None]   # (S,N,1)
+        cyk = st[:, None, 1:2] + 0.0 * cxk
+        for j in range(Md):
+            a1, a2 = np.cos(ang[j]), np.sin(ang[j])
+            P[..., pmap["disc_0_decomp_%d_a1" % j]] = a1
+            P[..., pmap["disc_0_decomp_%d_a2" % j]] = a2
+            P[..., pmap["disc_0_decomp_%d_b" % j]] = (a1 * cxk + a2 * cyk + 6.0)[:, None, :, 0]
+    if has_lin:
+        nlin = sum(1 for k in pmap if k.startswith("lin_constraint_") and k.endswith("_a1"))
+        dummy_b = st[:, 0] + 100.0
+        for j in range(nlin):
+            pre = "lin_constraint_%d_" % j
+            P[..., pmap[pre + "a1"]] = 1.0
+            P[..., pmap[pre + "a2"]] = 0.0
+            P[..., pmap[pre + "b"]] = dummy_b[:, None, None]
+        for h in range(Pn):
+            nonguided = (Pn > 1 and h == Pn - 1)
+            if nonguided or not guided:
+                continue
+            pos = x0[:, h, 1:N, nu:nu + 2]                       # stages 1..N-1
+            for j in range(min(nlin, M)):
+                o = opred[:, :N - 1, j]                          # stage k <- prediction k-1
+                dvec = o - pos
+                dist = np.maximum(np.linalg.norm(dvec, axis=2), 1e-9)
+                a1 = dvec[..., 0] / dist
+                a2 = dvec[..., 1] / dist
+                b = a1 * o[..., 0] + a2 * o[..., 1] - (1e-3 + ROBOT_RADIUS)
+                pre = "lin_constraint_%d_" % j
+                P[:, h, 1:, pmap[pre + "a1"]] = a1
+                P[:, h, 1:, pmap[pre + "a2"]] = a2
+                P[:, h, 1:, pmap[pre + "b"]] = b
+
+    xinit = np.repeat(st[:, None, :], Pn, axis=1)
+    return dict(
+        xinit=np.ascontiguousarray(xinit.reshape(B, nx)),
+        x0=np.ascontiguousarray(x0.reshape(B, (N + 1) * nz)),
+        params=np.ascontiguousarray(P.reshape(B, N * npar)),
+        set_offsets=np.arange(0, B + 1, Pn, dtype=np.int32),
+        n=B,
+    )

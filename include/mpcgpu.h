@@ -1,0 +1,102 @@
+/* mpcgpu.h -- C ABI of the B200 batched MPC solve engine (libmpcgpu.so).
+ *
+ * Drop-in boundary for the ONE hot path of Juleszwanen/oscar_mpc_planner_mr_modification: the SQP-RTI
+ * loop that MPCPlanner::Solver::solve() runs once per GuidanceConstraints homotopy.  Every entry
+ * point names the reference interface it replaces (paths relative to the reference root).
+ * Plain pointers and sizes only; no torch / CUDA types in the signatures (a stream is passed as
+ * void*, NULL = the engine's own stream).  All functions return 0 on success, a negative
+ * mpcgpu_status otherwise; they never throw and keep no hidden global state besides the registry
+ * of compiled problem configurations.  Callers own every array they pass.
+ */
+#ifndef MPCGPU_H
+#define MPCGPU_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mpcgpu_engine mpcgpu_engine;
+
+enum mpcgpu_status {
+    MPCGPU_OK = 0,
+    MPCGPU_ERR_ARG = -1,        /* bad argument (NULL, n > max_batch, unknown config) */
+    MPCGPU_ERR_CUDA = -2,       /* CUDA runtime error; see mpcgpu_last_error() */
+    MPCGPU_ERR_NO_DEVICE = -3   /* no usable CUDA device: there is NO CPU fallback */
+};
+
+/* Number of compiled problem configurations and their names ("c1_basic", "tmpc_shipped", ...).
+ * Replaces: the one generated solver linked at build time
+ *           (mpc_planner_solver/include/mpc_planner_solver/solver_interface.h:4-12). */
+int mpcgpu_num_configs(void);
+const char *mpcgpu_config_name(int i);
+
+/* Create / destroy an engine for one configuration on one device.
+ * Replaces: Solver_acados_create_capsule + Solver_acados_create_with_discretization and
+ *           Solver_acados_free + Solver_acados_free_capsule
+ *           (mpc_planner_solver/src/acados_solver_interface.cpp:17,33,51-65).
+ * One engine serves up to max_batch problems per call; device buffers are owned by the engine. */
+int mpcgpu_engine_create(const char *config_name, int device, int max_batch, mpcgpu_engine **out);
+int mpcgpu_engine_destroy(mpcgpu_engine *e);
+
+/* Problem dimensions. Replaces: SOLVER_N / SOLVER_NX / SOLVER_NU / SOLVER_NP / SOLVER_NH macros of
+ * the generated acados_solver_Solver.h (acados_solver_interface.h:14,20-47) and solver_settings.yaml
+ * (acados_solver_interface.cpp:13,20-24). */
+int mpcgpu_desc_query(const mpcgpu_engine *e, int *N, int *nx, int *nu, int *npar, int *nh);
+/* doubles per problem of the persistent solver memory blob (see mpcgpu_solve_batch) */
+int mpcgpu_mem_doubles(const mpcgpu_engine *e);
+
+/* Solve n independent problems; HOST arrays in, HOST arrays out (copies are inside the call).
+ * Replaces, per problem: Solver::solve() = initializeOneIteration + num_iter x solveOneIteration +
+ *           completeOneIteration (acados_solver_interface.cpp:86-204) preceded by loadWarmstart (:274-284).
+ *   xinit   [n * nx]                 AcadosParameters::xinit            (acados_solver_interface.h:53)
+ *   x0      [n * (nu+nx) * (N+1)]    AcadosParameters::x0, [u_k, x_k]   (:54)
+ *   params  [n * N * npar]           AcadosParameters::all_parameters   (:56), stage N reuses N-1 (:128-134)
+ *   num_iter[n] or NULL              SQP-RTI iterations per problem; NULL => num_iter_all for all
+ *                                    (Solver::_num_iterations; the wall-clock timeout rule of :108-116
+ *                                    is evaluated by the host shim, which passes the resulting count)
+ *   mem_inout [n * mem_doubles] or NULL   persistent capsule memory (NLP multipliers + QP warm start):
+ *                                    [flag][pi (N+1)*nx][lam N*nc][t N*nc][v (N+1)*(nu+nx)];
+ *                                    flag 0 = fresh capsule, 1 = multipliers only (after
+ *                                    ocp_nlp_solver_reset_qp_memory, :70), 2 = multipliers + QP warm start.
+ *                                    Zeroed on failure like Solver_acados_reset (:187-191).
+ *   xtraj   [n * nx * (N+1)], utraj [n * nu * N]   AcadosOutput (:129-130)
+ *   pobj[n] AcadosInfo::pobj; exit_code[n] return value of solve() (1 success, 0, 2, 3, 4: :197-203);
+ *   qp_status[n] AcadosInfo::qp_status; res_eq[n] the value tested at :177;
+ *   ipm_iters[n] or NULL: total interior-point iterations (diagnostic). */
+int mpcgpu_solve_batch(mpcgpu_engine *e, int n, const double *xinit, const double *x0, const double *params,
+                       const int *num_iter, int num_iter_all, double *mem_inout, double *xtraj, double *utraj,
+                       double *pobj, int *exit_code, int *qp_status, double *res_eq, int *ipm_iters);
+
+/* Same contract with DEVICE pointers (inputs already resident in HBM); asynchronous on `stream`
+ * (a cudaStream_t passed as void*, NULL = the engine's stream).  Use mpcgpu_sync() to wait. */
+int mpcgpu_solve_batch_device(mpcgpu_engine *e, int n, const double *xinit, const double *x0, const double *params,
+                              const int *num_iter, int num_iter_all, double *mem_inout, double *xtraj, double *utraj,
+                              double *pobj, int *exit_code, int *qp_status, double *res_eq, int *ipm_iters,
+                              void *stream);
+int mpcgpu_sync(mpcgpu_engine *e);
+
+/* Pick the best planner of each homotopy set.
+ * Replaces: the objective post-processing of GuidanceConstraints::optimize and FindBestPlanner
+ *           (mpc_planner_modules/src/guidance_constraints.cpp:373-420,572-590):
+ *   obj_i = (pobj_i - obj_sub_i) * obj_scale_i   (consistency-cost subtraction :384-388,405-408 and
+ *           selection_weight_consistency_ :418-419; either array may be NULL),
+ *   success_i = exit_code_i == 1, disabled planners skipped (:578-579), strict '<' in ascending index
+ *   order starting from 1e10 (:575-589); best_idx[s] = index within the set or -1.
+ * HOST arrays; set_offsets has n_sets+1 entries. */
+int mpcgpu_select_best(mpcgpu_engine *e, int n_sets, const int *set_offsets, const double *pobj, const int *exit_code,
+                       const double *obj_scale, const double *obj_sub, const unsigned char *disabled, int *best_idx);
+/* DEVICE-pointer variant, asynchronous on `stream`. */
+int mpcgpu_select_best_device(mpcgpu_engine *e, int n_sets, const int *set_offsets, const double *pobj,
+                              const int *exit_code, const double *obj_scale, const double *obj_sub,
+                              const unsigned char *disabled, int *best_idx, void *stream);
+
+/* Kernel launches issued by this engine so far (solve + select), for bench accounting. */
+long long mpcgpu_launch_count(const mpcgpu_engine *e);
+/* Device time in ms of the most recent mpcgpu_solve_batch[_device] solve kernel (CUDA events on the
+ * launching stream); valid after the call returned (host variant) or after mpcgpu_sync(). */
+float mpcgpu_last_kernel_ms(mpcgpu_engine *e);
+const char *mpcgpu_last_error(const mpcgpu_engine *e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPCGPU_H */

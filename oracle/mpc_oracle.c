@@ -28,6 +28,9 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#ifdef ORACLE_TRACE
+#include <stdio.h>
+#endif
 
 #ifndef REAL
 #define REAL double
@@ -108,9 +111,9 @@ typedef struct {
     /* QP iterate */
     REAL v[NN + 1][NZ], qpi[NN + 1][NX];
     /* IPM work */
-    REAL rg[NN + 1][NZ], rb[NN][NX], rd[NN][NCMAX], rm[NN][NCMAX];
+    REAL rg[NN + 1][NZ], rg0[NN + 1][NZ], rb[NN][NX], rd[NN][NCMAX], rm[NN][NCMAX];
     REAL Ht[NN + 1][NZ * NZ], gt[NN + 1][NZ];
-    REAL P[NN + 1][NX * NX], pv[NN + 1][NX], K[NN][NU * NX], kff[NN][NU], Ginv[NN][NU * NU], Gxu[NN][NX * NU];
+    REAL P[NN + 1][NX * NX], pv[NN + 1][NX], L[NN][NZ * NZ], iL[NN][NZ], lv[NN][NU];
     REAL dv[NN + 1][NZ], dpi[NN + 1][NX], dlam[NN][NCMAX], dt[NN][NCMAX];
     REAL dva[NN + 1][NZ];
     int qp_warm;                     /* previous QP solution available (HPIPM warm start 2) */
@@ -400,6 +403,9 @@ static void qp_init(work_t *w, const REAL *dx0)
     }
 }
 
+/* max that propagates NaN: a NaN anywhere must surface as QP status 3 */
+static REAL nanmax(REAL a, REAL b) { return (a != a) ? a : ((b != b) ? b : (a > b ? a : b)); }
+
 static void qp_residuals(work_t *w, REAL nrm[4], REAL *mu)
 {
     REAL ng = 0.0, nb = 0.0, nd = 0.0, nm = 0.0, sm = 0.0;
@@ -421,27 +427,28 @@ static void qp_residuals(work_t *w, REAL nrm[4], REAL *mu)
             }
         if (k > 0)
             for (int i = 0; i < NX; i++) r[NU + i] -= w->qpi[k][i];
+        for (int i = 0; i < NZ; i++) w->rg0[k][i] = r[i];
         if (k < NN)
             for (int e = 0; e < g_nc; e++)
                 if (active(k, e)) crow_axpy(w, k, e, -w->lam[k][e], r);
         if (k == 0)
             for (int i = NU; i < NZ; i++) r[i] = 0.0; /* x_0 is not a variable */
-        for (int i = 0; i < NZ; i++) if (fabs(r[i]) > ng) ng = fabs(r[i]);
+        for (int i = 0; i < NZ; i++) ng = nanmax(ng, fabs(r[i]));
     }
     for (int k = 0; k < NN; k++) {
         for (int i = 0; i < NX; i++) {
             REAL s = w->b[k][i] - w->v[k + 1][NU + i];
             for (int j = 0; j < NZ; j++) s += w->W[k][i * NZ + j] * w->v[k][j];
             w->rb[k][i] = s;
-            if (fabs(s) > nb) nb = fabs(s);
+            nb = nanmax(nb, fabs(s));
         }
         for (int e = 0; e < g_nc; e++) {
             if (!active(k, e)) { w->rd[k][e] = 0.0; w->rm[k][e] = 0.0; continue; }
             REAL s = crow_dot(w, k, e, w->v[k]) - w->d[k][e] - w->t[k][e];
             REAL m = w->lam[k][e] * w->t[k][e];
             w->rd[k][e] = s; w->rm[k][e] = m;
-            if (fabs(s) > nd) nd = fabs(s);
-            if (fabs(m) > nm) nm = fabs(m);
+            nd = nanmax(nd, fabs(s));
+            nm = nanmax(nm, fabs(m));
             sm += m; cnt++;
         }
     }
@@ -467,27 +474,34 @@ static void kkt_hessian(work_t *w)
         }
     }
 }
-/* gtilde = rg + sum chat (rm + lam rd)/t */
-static void kkt_gradient(work_t *w)
+/* gtilde = rg + sum chat gamma,  gamma = (rm + lam rd)/t.  With rm = lam t (+ corrector term) the lam
+ * part cancels against the -chat lam inside rg, so (rg0 = residual without the inequality multipliers)
+ *   gtilde = rg0 + sum chat (Gamma rd + corr),   Gamma = lam/t,
+ *   corr = 0 (predictor)  or  (dt_aff dlam_aff - sigma mu)/t (corrector).                          */
+static void kkt_gradient(work_t *w, int corrector, REAL sigmu)
 {
     for (int k = 0; k <= NN; k++) {
-        for (int i = 0; i < NZ; i++) w->gt[k][i] = w->rg[k][i];
+        for (int i = 0; i < NZ; i++) w->gt[k][i] = w->rg0[k][i];
         if (k == NN) break;
         for (int e = 0; e < g_nc; e++) {
             if (!active(k, e)) continue;
-            REAL gam = (w->rm[k][e] + w->lam[k][e] * w->rd[k][e]) / w->t[k][e];
+            REAL invt = 1.0 / w->t[k][e];
+            REAL gam = w->lam[k][e] / w->t[k][e] * w->rd[k][e];
+            if (corrector) gam += w->dt[k][e] * w->dlam[k][e] * invt - sigmu * invt;
             crow_axpy(w, k, e, gam, w->gt[k]);
         }
     }
 }
 
-/* backward Riccati factorisation on (Ht, W): P_k, K_k, Guu^{-1}, Gxu */
+/* Backward Riccati factorisation, square-root form (as HPIPM): G_k = Ht_k + W_k' P_{k+1} W_k = L L'
+ * (Cholesky), L = [Luu 0; Lxu Lxx], P_k = Lxx Lxx'.  No explicit Schur-complement subtraction.     */
 static void riccati_factor(work_t *w)
 {
     for (int i = 0; i < NX; i++)
         for (int j = 0; j < NX; j++) w->P[NN][i * NX + j] = w->Ht[NN][(NU + i) * NZ + NU + j];
     for (int k = NN - 1; k >= 0; k--) {
-        REAL PW[NX * NZ], G[NZ * NZ];
+        REAL PW[NX * NZ];
+        REAL *L = w->L[k];
         for (int i = 0; i < NX; i++)
             for (int j = 0; j < NZ; j++) {
                 REAL s = 0.0;
@@ -495,75 +509,65 @@ static void riccati_factor(work_t *w)
                 PW[i * NZ + j] = s;
             }
         for (int i = 0; i < NZ; i++)
-            for (int j = 0; j < NZ; j++) {
+            for (int j = 0; j <= i; j++) {
                 REAL s = w->Ht[k][i * NZ + j];
                 for (int l = 0; l < NX; l++) s += w->W[k][l * NZ + i] * PW[l * NZ + j];
-                G[i * NZ + j] = s;
+                L[i * NZ + j] = s;
             }
-        /* 2x2 (NU x NU) inverse of Guu via Cholesky-free symmetric formula (NU == 2) */
-#if NU != 2
-#error "riccati_factor assumes NU == 2"
-#endif
-        REAL a = G[0], bq = 0.5 * (G[1] + G[NZ]), c = G[NZ + 1];
-        REAL det = a * c - bq * bq;
-        REAL *Gi = w->Ginv[k];
-        Gi[0] = c / det; Gi[1] = -bq / det; Gi[2] = -bq / det; Gi[3] = a / det;
+        for (int j = 0; j < NZ; j++) {
+            REAL d = L[j * NZ + j];
+            for (int m = 0; m < j; m++) d -= L[j * NZ + m] * L[j * NZ + m];
+            REAL ljj = sqrt(d), inv = 1.0 / ljj;
+            L[j * NZ + j] = ljj;
+            w->iL[k][j] = inv;
+            for (int i = j + 1; i < NZ; i++) {
+                REAL a = L[i * NZ + j];
+                for (int m = 0; m < j; m++) a -= L[i * NZ + m] * L[j * NZ + m];
+                L[i * NZ + j] = a * inv;
+            }
+        }
         for (int i = 0; i < NX; i++)
-            for (int j = 0; j < NU; j++) w->Gxu[k][i * NU + j] = 0.5 * (G[(NU + i) * NZ + j] + G[j * NZ + NU + i]);
-        for (int i = 0; i < NU; i++)
-            for (int j = 0; j < NX; j++) {
+            for (int j = 0; j <= i; j++) {
                 REAL s = 0.0;
-                for (int l = 0; l < NU; l++) s += Gi[i * NU + l] * w->Gxu[k][j * NU + l];
-                w->K[k][i * NX + j] = -s;
-            }
-        for (int i = 0; i < NX; i++)
-            for (int j = 0; j < NX; j++) {
-                REAL s = 0.5 * (G[(NU + i) * NZ + NU + j] + G[(NU + j) * NZ + NU + i]);
-                for (int l = 0; l < NU; l++) s += w->Gxu[k][i * NU + l] * w->K[k][l * NX + j];
-                w->P[k][i * NX + j] = s;
-            }
-        for (int i = 0; i < NX; i++)
-            for (int j = 0; j < i; j++) {
-                REAL s = 0.5 * (w->P[k][i * NX + j] + w->P[k][j * NX + i]);
+                for (int m = 0; m <= j; m++) s += L[(NU + i) * NZ + NU + m] * L[(NU + j) * NZ + NU + m];
                 w->P[k][i * NX + j] = s; w->P[k][j * NX + i] = s;
             }
     }
 }
 
-/* backward vector sweep + forward sweep with rhs (gt, rb): Newton step dv, dpi */
+/* backward vector sweep + forward sweep with rhs (gt, rb): Newton step dv, dpi.
+ *   l = Luu^-1 q_u ; p = q_x - Lxu l ; du = -Luu^-T (Lxu' dx + l)                                  */
 static void riccati_solve(work_t *w, REAL (*dv)[NZ])
 {
+#if NU != 2
+#error "riccati_solve assumes NU == 2"
+#endif
     for (int i = 0; i < NX; i++) w->pv[NN][i] = w->gt[NN][NU + i];
     for (int k = NN - 1; k >= 0; k--) {
         REAL y[NX], q[NZ];
+        const REAL *L = w->L[k];
         for (int i = 0; i < NX; i++) {
-            REAL s = w->pv[k + 1][i];
+            REAL s = 0.0;
             for (int l = 0; l < NX; l++) s += w->P[k + 1][i * NX + l] * w->rb[k][l];
-            y[i] = s;
+            y[i] = w->pv[k + 1][i] + s;
         }
         for (int j = 0; j < NZ; j++) {
             REAL s = w->gt[k][j];
             for (int i = 0; i < NX; i++) s += w->W[k][i * NZ + j] * y[i];
             q[j] = s;
         }
-        for (int i = 0; i < NU; i++) {
-            REAL s = 0.0;
-            for (int l = 0; l < NU; l++) s += w->Ginv[k][i * NU + l] * q[l];
-            w->kff[k][i] = -s;
-        }
-        for (int i = 0; i < NX; i++) {
-            REAL s = q[NU + i];
-            for (int l = 0; l < NU; l++) s += w->Gxu[k][i * NU + l] * w->kff[k][l];
-            w->pv[k][i] = s;
-        }
+        w->lv[k][0] = q[0] * w->iL[k][0];
+        w->lv[k][1] = (q[1] - L[1 * NZ + 0] * w->lv[k][0]) * w->iL[k][1];
+        for (int i = 0; i < NX; i++)
+            w->pv[k][i] = q[NU + i] - L[(NU + i) * NZ + 0] * w->lv[k][0] - L[(NU + i) * NZ + 1] * w->lv[k][1];
     }
     for (int i = 0; i < NX; i++) dv[0][NU + i] = 0.0; /* dx_0 = 0: x_0 is fixed */
     for (int k = 0; k < NN; k++) {
-        for (int i = 0; i < NU; i++) {
-            REAL s = w->kff[k][i];
-            for (int j = 0; j < NX; j++) s += w->K[k][i * NX + j] * dv[k][NU + j];
-            dv[k][i] = s;
-        }
+        const REAL *L = w->L[k];
+        REAL r0 = w->lv[k][0], r1 = w->lv[k][1];
+        for (int j = 0; j < NX; j++) { r0 += L[(NU + j) * NZ + 0] * dv[k][NU + j]; r1 += L[(NU + j) * NZ + 1] * dv[k][NU + j]; }
+        dv[k][1] = -r1 * w->iL[k][1];
+        dv[k][0] = -(r0 + L[1 * NZ + 0] * dv[k][1]) * w->iL[k][0];
         for (int i = 0; i < NX; i++) {
             REAL s = w->rb[k][i];
             for (int j = 0; j < NZ; j++) s += w->W[k][i * NZ + j] * dv[k][j];
@@ -578,18 +582,32 @@ static void riccati_solve(work_t *w, REAL (*dv)[NZ])
     for (int i = 0; i < NU; i++) dv[NN][i] = 0.0;
 }
 
-/* dt, dlam from dv; returns max step alpha in (0,1] keeping lam, t >= 0 */
-static REAL ipm_step_ineq(work_t *w, REAL (*dv)[NZ])
+/* dt, dlam from the Newton direction; returns the max step alpha in (0,1] keeping lam, t >= 0.
+ *   dt = chat'dv + rd ;  dlam = -(rm_c + lam dt)/t  with rm_c = lam t (+ dt_aff dlam_aff - sigma mu)
+ *      = -(lam + Gamma dt [+ (dt_aff dlam_aff - sigma mu)/t])
+ * corrector != 0: w->dt/w->dlam hold the affine step on entry and are overwritten.                 */
+static void step_limit(REAL val, REAL dval, REAL *alpha)
+{
+    if (dval < 0.0 && val + *alpha * dval < 0.0) *alpha = -val / dval;
+}
+static REAL ipm_step_ineq(work_t *w, REAL (*dv)[NZ], int corrector, REAL sigmu)
 {
     REAL alpha = 1.0;
     for (int k = 0; k < NN; k++)
         for (int e = 0; e < g_nc; e++) {
             if (!active(k, e)) { w->dt[k][e] = 0.0; w->dlam[k][e] = 0.0; continue; }
+            REAL lam = w->lam[k][e], t = w->t[k][e], invt = 1.0 / t;
             REAL dt = crow_dot(w, k, e, dv[k]) + w->rd[k][e];
-            REAL dl = -(w->rm[k][e] + w->lam[k][e] * dt) / w->t[k][e];
+            REAL dl;
+            if (corrector) {
+                REAL corr = w->dt[k][e] * w->dlam[k][e] * invt;
+                dl = -(lam + lam * invt * dt + (corr - sigmu * invt));
+            } else {
+                dl = -(lam + lam * invt * dt);
+            }
             w->dt[k][e] = dt; w->dlam[k][e] = dl;
-            if (dl < 0.0) { REAL a = -w->lam[k][e] / dl; if (a < alpha) alpha = a; }
-            if (dt < 0.0) { REAL a = -w->t[k][e] / dt; if (a < alpha) alpha = a; }
+            step_limit(lam, dl, &alpha);
+            step_limit(t, dt, &alpha);
         }
     return alpha;
 }
@@ -601,31 +619,33 @@ static int qp_solve(work_t *w, const REAL *dx0)
     int kk;
     qp_init(w, dx0);
     qp_residuals(w, nrm, &mu);
-    for (kk = 0; kk < IPM_ITER_MAX && alpha > IPM_ALPHA_MIN &&
+#ifdef ORACLE_TRACE
+    printf("cpu ipm 0: rg %.3e rb %.3e rd %.3e rm %.3e mu %.3e alpha %.3e\n", (double)nrm[0], (double)nrm[1], (double)nrm[2], (double)nrm[3], (double)mu, (double)alpha);
+#endif
+#define QP_ISNAN() ((mu != mu) || (nrm[0] != nrm[0]) || (nrm[1] != nrm[1]) || (nrm[2] != nrm[2]) || (nrm[3] != nrm[3]))
+    for (kk = 0; kk < IPM_ITER_MAX && alpha > IPM_ALPHA_MIN && !QP_ISNAN() &&
                  (nrm[0] > IPM_TOL || nrm[1] > IPM_TOL || nrm[2] > IPM_TOL || nrm[3] > IPM_TOL); kk++) {
         /* predictor (affine scaling) */
         kkt_hessian(w);
-        kkt_gradient(w);
+        kkt_gradient(w, 0, 0.0);
         riccati_factor(w);
         riccati_solve(w, w->dva);
-        REAL alpha_aff = ipm_step_ineq(w, w->dva);
-        REAL smu = 0.0;
-        int cnt = 0;
+        REAL alpha_aff = ipm_step_ineq(w, w->dva, 0, 0.0);
+        /* mu_aff = sum (lam + a dlam)(t + a dt) / count, expanded in powers of a */
+        REAL S1 = 0.0, S2 = 0.0;
         for (int k = 0; k < NN; k++)
             for (int e = 0; e < g_nc; e++)
                 if (active(k, e)) {
-                    smu += (w->lam[k][e] + alpha_aff * w->dlam[k][e]) * (w->t[k][e] + alpha_aff * w->dt[k][e]);
-                    cnt++;
+                    S1 += w->lam[k][e] * w->dt[k][e] + w->t[k][e] * w->dlam[k][e];
+                    S2 += w->dt[k][e] * w->dlam[k][e];
                 }
-        REAL mu_aff = smu / (REAL)cnt;
-        REAL rat = mu_aff / mu, sigma = rat * rat * rat;
-        /* corrector: rm += dt_aff dlam_aff - sigma mu */
-        for (int k = 0; k < NN; k++)
-            for (int e = 0; e < g_nc; e++)
-                if (active(k, e)) w->rm[k][e] += w->dt[k][e] * w->dlam[k][e] - sigma * mu;
-        kkt_gradient(w);
+        REAL cnt = (REAL)(NN * (2 * NU + (g_nc - NCB)) + (NN - 1) * 2 * NX);
+        REAL mu_aff = (mu * cnt + alpha_aff * S1 + alpha_aff * alpha_aff * S2) / cnt;
+        REAL rat = mu_aff / mu, sigmu = rat * rat * rat * mu;
+        /* corrector: rm += dt_aff dlam_aff - sigma mu (folded into gtilde and dlam) */
+        kkt_gradient(w, 1, sigmu);
         riccati_solve(w, w->dv);
-        alpha = ipm_step_ineq(w, w->dv);
+        alpha = ipm_step_ineq(w, w->dv, 1, sigmu);
         REAL a = alpha < 1.0 ? alpha * IPM_STEP_SCALE : alpha;
         for (int k = 0; k <= NN; k++) {
             for (int i = 0; i < NZ; i++) w->v[k][i] += a * w->dv[k][i];
@@ -640,12 +660,15 @@ static int qp_solve(work_t *w, const REAL *dx0)
                 }
         }
         qp_residuals(w, nrm, &mu);
+#ifdef ORACLE_TRACE
+        printf("cpu ipm %d: rg %.3e rb %.3e rd %.3e rm %.3e mu %.3e alpha %.3e\n", kk + 1, (double)nrm[0], (double)nrm[1], (double)nrm[2], (double)nrm[3], (double)mu, (double)alpha);
+#endif
     }
     w->qp_iters_last = kk;
     w->ipm_iters_total += kk;
+    if (QP_ISNAN()) return 3;
     if (kk == IPM_ITER_MAX) return 1;
     if (alpha <= IPM_ALPHA_MIN) return 2;
-    if (mu != mu) return 3;
     return 0;
 }
 
@@ -701,7 +724,7 @@ static void solve_one(work_t *w, const REAL *xinit, const REAL *x0, const REAL *
         for (int i = 0; i < NX; i++) z[NU + i] = w->x[k][i];
         cost += MODEL_DT * model_cost(z, p);
         integrate(w->x[k], w->u[k], p, xn, NULL, NULL, NULL);
-        for (int i = 0; i < NX; i++) { REAL r = fabs(xn[i] - w->x[k + 1][i]); if (r > req) req = r; }
+        for (int i = 0; i < NX; i++) req = nanmax(req, fabs(xn[i] - w->x[k + 1][i]));
     }
     for (int k = 0; k <= NN; k++) {
         for (int i = 0; i < NX; i++) xtraj[k * NX + i] = w->x[k][i];

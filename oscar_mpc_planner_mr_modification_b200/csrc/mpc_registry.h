@@ -1,0 +1,15 @@
+// Internal registry of compiled problem configurations (one mpc_config_impl.cu object per config).
+#pragma once
+#include <cuda_runtime.h>
+
+struct MpcConfigOps {
+    const char* name;
+    int N, nx, nu, np, nh, nc, mem_doubles;
+    cudaError_t (*launch_solve)(int grid, cudaStream_t stream, int n, const double* xinit, const double* x0,
+                                const double* params, const int* num_iter, int num_iter_all, double* mem,
+                                double* xtraj, double* utraj, double* pobj, int* exit_code, int* qp_status,
+                                double* res_eq, int* ipm_iters, int* work_counter);
+    cudaError_t (*occupancy)(int* ctas_per_sm, int* threads_per_cta);
+};
+
+void mpc_register_config(const MpcConfigOps* ops);

@@ -1,0 +1,773 @@
+// mpc_solve_kernel.cuh -- one warp solves one N-stage MPC problem (SQP-RTI + interior-point QP), FP64.
+//
+// Replaces what `Solver::solve()` runs through acados for one GuidanceConstraints homotopy
+// (reference: mpc_planner_solver/src/acados_solver_interface.cpp:86-204).  The algorithm contract is
+// DESIGN.md "Algorithm contract"; the model-specific device functions come from the emitter
+// (solver_generator/generate_cuda_solver.py -> generated/<config>/model.cuh).
+//
+// Mapping: lane k of the warp owns stage k (k = 0..N, N <= 31).  Everything that is independent per
+// stage (RK4 roll-out with sensitivities, cost/constraint linearisation, MIRROR, the per-constraint
+// interior-point algebra, residuals) runs lane-parallel with the stage data in registers / local
+// memory; stage-to-stage coupling (x_{k+1}, pi_{k+1}, the Riccati recursion) goes through warp
+// shuffles; scalar decisions (step length, mu, residual norms, exit) are warp reductions.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#ifdef MPC_TRACE
+#include <cstdio>
+#endif
+
+#ifndef MPC_CFG_TAG
+#error "compile with -DMPC_CFG_TAG=<config> -DMPC_MODEL_HEADER='\"model.cuh\"'"
+#endif
+#define MPC_CAT2(a, b) a##b
+#define MPC_CAT(a, b) MPC_CAT2(a, b)
+#define MPC_NS MPC_CAT(mpck_, MPC_CFG_TAG)   // one namespace per compiled configuration
+
+namespace MPC_NS {
+#include MPC_MODEL_HEADER
+using namespace mpcgen;
+
+static_assert(NSTAGE + 1 <= 32, "lane-per-stage kernel needs N <= 31");
+static_assert(NU == 2, "Riccati input block elimination is written for nu == 2");
+
+constexpr int NCB = 2 * NZ;                 // box entries: lower(z_i) i<NZ, then upper(z_i)
+constexpr int NC = NCB + NCG;               // inequality entries per path stage
+constexpr int NPX = NX * (NX + 1) / 2;      // packed P
+constexpr unsigned FULL = 0xffffffffu;
+
+// ---- algorithm constants: identical to oracle/mpc_oracle.c -------------------------------------
+constexpr double REG_EPS = 1e-4;
+constexpr int IPM_ITER_MAX = 50;
+constexpr double IPM_TOL = 1e-5;
+constexpr double IPM_MU0 = 10.0;
+constexpr double IPM_THR0 = 0.1;
+constexpr double IPM_ALPHA_MIN = 1e-12;
+constexpr double IPM_LAM_MIN = 1e-16;
+constexpr double IPM_T_MIN = 1e-16;
+constexpr double IPM_STEP_SCALE = 0.995;
+constexpr double RES_EQ_MAX = 1e-2;
+constexpr int JACOBI_MAX_SWEEPS = 30;
+constexpr double JACOBI_TOL = 1e-30;
+// inequality entries over the whole horizon: u box + general on N stages, x box on stages 1..N-1
+constexpr int IPM_COUNT = NSTAGE * (2 * NU + NCG) + (NSTAGE - 1) * 2 * NX;
+
+__host__ __device__ constexpr int pk(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
+
+__device__ __forceinline__ double shfl(double v, int src) { return __shfl_sync(FULL, v, src); }
+__device__ __forceinline__ double shfl_down1(double v) { return __shfl_down_sync(FULL, v, 1); }
+// max that PROPAGATES NaN (fmax would drop it): a NaN anywhere must surface as QP status 3
+__device__ __forceinline__ double nanmax(double a, double b) { return (a != a) ? a : ((b != b) ? b : (a > b ? a : b)); }
+__device__ __forceinline__ double clamp_lo(double x, double lo) { return (x < lo) ? lo : x; }   // keeps NaN
+__device__ __forceinline__ double warp_max(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = nanmax(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+// ---- K4: MIRROR regularisation of one packed symmetric NZ x NZ block (cyclic Jacobi) -----------
+__device__ __noinline__ void mirror_packed(double* Hp)
+{
+    double a[NZ][NZ], V[NZ][NZ];
+    for (int i = 0; i < NZ; i++)
+        for (int j = 0; j < NZ; j++) {
+            a[i][j] = Hp[pk(i, j)];
+            V[i][j] = (i == j) ? 1.0 : 0.0;
+        }
+    for (int sweep = 0; sweep < JACOBI_MAX_SWEEPS; sweep++) {
+        double off = 0.0, tot = 0.0;
+        for (int i = 0; i < NZ; i++)
+            for (int j = 0; j < NZ; j++) {
+                tot += a[i][j] * a[i][j];
+                if (i != j) off += a[i][j] * a[i][j];
+            }
+        if (!(off > JACOBI_TOL * tot)) break;
+        for (int p = 0; p < NZ - 1; p++)
+            for (int q = p + 1; q < NZ; q++) {
+                const double apq = a[p][q];
+                if (apq == 0.0) continue;
+                const double theta = (a[q][q] - a[p][p]) / (2.0 * apq);
+                double tt = 1.0 / (fabs(theta) + sqrt(theta * theta + 1.0));
+                if (theta < 0.0) tt = -tt;
+                const double c = 1.0 / sqrt(tt * tt + 1.0), s = tt * c;
+                for (int k = 0; k < NZ; k++) {
+                    if (k == p || k == q) continue;
+                    const double akp = a[k][p], akq = a[k][q];
+                    const double np_ = c * akp - s * akq, nq_ = s * akp + c * akq;
+                    a[k][p] = np_; a[p][k] = np_;
+                    a[k][q] = nq_; a[q][k] = nq_;
+                }
+                const double app = a[p][p], aqq = a[q][q];
+                a[p][p] = app - tt * apq;
+                a[q][q] = aqq + tt * apq;
+                a[p][q] = 0.0; a[q][p] = 0.0;
+                for (int k = 0; k < NZ; k++) {
+                    const double vkp = V[k][p], vkq = V[k][q];
+                    V[k][p] = c * vkp - s * vkq;
+                    V[k][q] = s * vkp + c * vkq;
+                }
+            }
+    }
+    double ev[NZ];
+    for (int i = 0; i < NZ; i++) {
+        double e = a[i][i];
+        if (e >= -REG_EPS && e <= REG_EPS) e = REG_EPS;
+        else if (e < 0.0) e = -e;
+        ev[i] = e;
+    }
+    for (int i = 0; i < NZ; i++)
+        for (int j = 0; j <= i; j++) {
+            double s = 0.0;
+            for (int k = 0; k < NZ; k++) s += V[i][k] * ev[k] * V[j][k];
+            Hp[pk(i, j)] = s;
+        }
+}
+
+// chat_e' y for general entry e (y indexed by z component)
+__device__ __forceinline__ double gen_dot(const double* C, int e, const double* y)
+{
+    const int r = HROW[e];
+    double s = 0.0;
+#pragma unroll
+    for (int a = 0; a < NHS; a++) s += C[r * NHS + a] * y[HSUP[a]];
+    return HSGN[e] * s;
+}
+
+// One inequality entry of the Newton step. In: lam, t, residual rd = chat'v - d - t, chat'dva, chat'dv
+// (affine and final directions), sigma*mu (0 => affine only).  Out: dt, dlam of the requested step.
+struct IneqStep {
+    double dt, dlam, invt, corr;
+};
+__device__ __forceinline__ IneqStep ineq_affine(double lam, double t, double rd, double cdva)
+{
+    IneqStep s;
+    s.invt = 1.0 / t;
+    s.dt = cdva + rd;
+    s.dlam = -(lam + lam * s.invt * s.dt);
+    s.corr = s.dt * s.dlam * s.invt;
+    return s;
+}
+__device__ __forceinline__ IneqStep ineq_final(double lam, double t, double rd, double cdva, double cdv, double sigmu)
+{
+    IneqStep a = ineq_affine(lam, t, rd, cdva);
+    IneqStep s;
+    s.invt = a.invt;
+    s.dt = cdv + rd;
+    s.dlam = -(lam + lam * a.invt * s.dt + (a.corr - sigmu * a.invt));
+    s.corr = 0.0;
+    return s;
+}
+__device__ __forceinline__ void step_limit(double val, double dval, double& alpha)
+{
+    if (dval < 0.0 && val + alpha * dval < 0.0) alpha = -val / dval;
+}
+
+// ------------------------------------------------------------------------------------------------
+// One Solver::solve() on one warp
+// ------------------------------------------------------------------------------------------------
+__device__ void solve_problem(int prob, const double* __restrict__ xinit_g, const double* __restrict__ x0_g,
+                              const double* __restrict__ params_g, int num_iter, double* mem_g, int mem_doubles,
+                              double* xtraj_g, double* utraj_g, double* pobj_g, int* exit_g, int* qps_g,
+                              double* reseq_g, int* ipm_g)
+{
+    const int k = threadIdx.x & 31;           // stage owned by this lane
+    const bool path = k < NSTAGE;             // has inputs, cost, constraints, dynamics
+    const bool term = k == NSTAGE;
+    const bool live = k <= NSTAGE;
+    const bool xbox = path && k >= 1;         // x_0 is fixed: no state bounds at stage 0
+    const double* __restrict__ p = params_g + ((size_t)prob * NSTAGE + (path ? k : NSTAGE - 1)) * NP;
+
+    double z[NZ], pi[NX], v[NZ], qpi[NX];
+    double lamb[NCB], tb[NCB], lamg[NCG > 0 ? NCG : 1], tg[NCG > 0 ? NCG : 1];
+#pragma unroll
+    for (int i = 0; i < NZ; i++) {
+        z[i] = live ? x0_g[(size_t)prob * NZ * (NSTAGE + 1) + k * NZ + i] : 0.0;   // loadWarmstart (:274-284)
+        v[i] = 0.0;
+    }
+    if (term) { z[0] = 0.0; z[1] = 0.0; }
+    double xi[NX];
+#pragma unroll
+    for (int i = 0; i < NX; i++) { xi[i] = xinit_g[(size_t)prob * NX + i]; pi[i] = 0.0; qpi[i] = 0.0; }
+#pragma unroll
+    for (int e = 0; e < NCB; e++) { lamb[e] = 0.0; tb[e] = 0.0; }
+    for (int e = 0; e < NCG; e++) { lamg[e] = 0.0; tg[e] = 0.0; }
+    int qp_warm = 0;
+    double* mem = mem_g ? mem_g + (size_t)prob * mem_doubles : nullptr;
+    if (mem && mem[0] != 0.0) {               // persistent capsule memory: [flag][pi][lam][t][v]
+        const double* m = mem + 1;
+        if (live) for (int i = 0; i < NX; i++) pi[i] = m[k * NX + i];
+        m += (NSTAGE + 1) * NX;
+        if (path) {
+            for (int e = 0; e < NCB; e++) { lamb[e] = m[k * NC + e]; tb[e] = m[NSTAGE * NC + k * NC + e]; }
+            for (int e = 0; e < NCG; e++) { lamg[e] = m[k * NC + NCB + e]; tg[e] = m[NSTAGE * NC + k * NC + NCB + e]; }
+        }
+        m += 2 * NSTAGE * NC;
+        if (live) for (int i = 0; i < NZ; i++) v[i] = m[k * NZ + i];
+        qp_warm = (mem[0] >= 2.0);
+#pragma unroll
+        for (int i = 0; i < NX; i++) qpi[i] = pi[i];
+    }
+
+    int status = 0, qps = 0, ipm_total = 0;
+    for (int it = 0; it < num_iter; it++) {
+        // ======================= K1-K4: linearise at the current iterate ============================
+        double H[NPK], g[NZ], Wv[NWV], b[NX];
+        double C[NH > 0 ? NH * NHS : 1], dg[NCG > 0 ? NCG : 1];
+        {
+            double pin[NX], xnx[NX];
+#pragma unroll
+            for (int i = 0; i < NX; i++) { pin[i] = shfl_down1(pi[i]); xnx[i] = shfl_down1(z[NU + i]); }
+#pragma unroll
+            for (int i = 0; i < NPK; i++) H[i] = 0.0;
+#pragma unroll
+            for (int i = 0; i < NZ; i++) g[i] = 0.0;
+#pragma unroll
+            for (int i = 0; i < NX; i++) b[i] = 0.0;
+            if (path) {
+                double xn[NX];
+                cost_lin(z, p, g, H);
+                dyn_lin(z, pin, xn, Wv, H);
+#pragma unroll
+                for (int i = 0; i < NX; i++) b[i] = xn[i] - xnx[i];
+                if (NH > 0) {
+                    double mh[NH > 0 ? NH : 1], hv[NH > 0 ? NH : 1];
+                    for (int r = 0; r < NH; r++) mh[r] = 0.0;
+                    for (int e = 0; e < NCG; e++) mh[HROW[e]] -= HSGN[e] * lamg[e];   // lam_u - lam_l
+                    con_hess_add(z, p, mh, H);
+                    con_eval(z, p, hv, C);
+                    for (int e = 0; e < NCG; e++) dg[e] = HSGN[e] * (HBND[e] - hv[HROW[e]]);
+                }
+                mirror_packed(H);
+            } else if (term) {
+#pragma unroll
+                for (int i = NU; i < NZ; i++) H[pk(i, i)] = REG_EPS;   // mirror(0) = eps I; no terminal cost
+            }
+        }
+
+        // ======================= K5: interior-point QP ============================================
+        // ---- initialisation (HPIPM-style; warm start 2 keeps v, pi, lam, t and thresholds lam, t)
+        if (!qp_warm) {
+#pragma unroll
+            for (int i = 0; i < NZ; i++) v[i] = 0.0;
+#pragma unroll
+            for (int i = 0; i < NX; i++) qpi[i] = 0.0;
+        }
+        if (k == 0) {
+#pragma unroll
+            for (int i = 0; i < NX; i++) v[NU + i] = xi[i] - z[NU + i];
+        }
+        if (qp_warm) {
+#pragma unroll
+            for (int i = 0; i < NZ; i++) {
+                const bool act = (i < NU) ? path : xbox;
+                if (act) {
+                    lamb[i] = clamp_lo(lamb[i], IPM_THR0); tb[i] = clamp_lo(tb[i], IPM_THR0);
+                    lamb[NZ + i] = clamp_lo(lamb[NZ + i], IPM_THR0); tb[NZ + i] = clamp_lo(tb[NZ + i], IPM_THR0);
+                }
+            }
+            if (path) for (int e = 0; e < NCG; e++) { lamg[e] = clamp_lo(lamg[e], IPM_THR0); tg[e] = clamp_lo(tg[e], IPM_THR0); }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NZ; i++) {
+                const bool act = (i < NU) ? path : xbox;
+                if (act) {
+                    const double dl = LBZ[i] - z[i], du = UBZ[i] - z[i];
+                    double tl = v[i] - dl, tu = du - v[i];
+                    if (tl < IPM_THR0) {
+                        if (tu < IPM_THR0) { v[i] = 0.5 * (dl + du); tl = IPM_THR0; tu = IPM_THR0; }
+                        else { tl = IPM_THR0; v[i] = dl + IPM_THR0; }
+                    } else if (tu < IPM_THR0) { tu = IPM_THR0; v[i] = du - IPM_THR0; }
+                    tb[i] = tl; tb[NZ + i] = tu;
+                    lamb[i] = IPM_MU0 / tl; lamb[NZ + i] = IPM_MU0 / tu;
+                }
+            }
+            if (path) for (int e = 0; e < NCG; e++) {
+                double tt = gen_dot(C, e, v) - dg[e];
+                if (tt < IPM_THR0) tt = IPM_THR0;
+                tg[e] = tt; lamg[e] = IPM_MU0 / tt;
+            }
+        }
+
+        double alpha = 1.0, mu = 0.0;
+        double nrm_g, nrm_b, nrm_d, nrm_m;
+        int kk = 0;
+        bool isnan_ = false;
+        for (;; kk++) {
+            // ---- pass A: residuals, norms, mu; Htilde = H + sum Gamma chat chat'; gtilde (affine)
+            double Ht[NPK], gt[NZ], rb[NX];
+            double ng = 0.0, nb = 0.0, nd = 0.0, nm = 0.0, sm = 0.0;
+            {
+                double qpn[NX], vxn[NX], rg[NZ];
+#pragma unroll
+                for (int i = 0; i < NX; i++) { qpn[i] = shfl_down1(qpi[i]); vxn[i] = shfl_down1(v[NU + i]); }
+#pragma unroll
+                for (int i = 0; i < NPK; i++) Ht[i] = H[i];
+#pragma unroll
+                for (int i = 0; i < NZ; i++) {
+                    double s = g[i];
+#pragma unroll
+                    for (int j = 0; j < NZ; j++) s += H[pk(i, j)] * v[j];
+                    rg[i] = s;
+                }
+#pragma unroll
+                for (int i = 0; i < NX; i++) rb[i] = 0.0;
+                if (path) {
+                    wt_mul_add(Wv, qpn, rg);
+#pragma unroll
+                    for (int i = 0; i < NX; i++) rb[i] = b[i] - vxn[i];
+                    w_mul_add(Wv, v, rb);
+                }
+                if (k >= 1) {
+#pragma unroll
+                    for (int i = 0; i < NX; i++) rg[NU + i] -= qpi[i];
+                }
+#pragma unroll
+                for (int i = 0; i < NZ; i++) gt[i] = rg[i];
+#pragma unroll
+                for (int i = 0; i < NZ; i++) {
+                    const bool act = (i < NU) ? path : xbox;
+                    if (act) {
+                        const double dl = LBZ[i] - z[i], du = UBZ[i] - z[i];
+                        {   // lower: chat = +e_i, d = dl
+                            const double lam = lamb[i], t = tb[i];
+                            const double rd = v[i] - dl - t, G = lam / t, m = lam * t;
+                            Ht[pk(i, i)] += G; gt[i] += G * rd; rg[i] -= lam;
+                            nd = nanmax(nd, fabs(rd)); nm = nanmax(nm, fabs(m)); sm += m;
+                        }
+                        {   // upper: chat = -e_i, d = -du
+                            const double lam = lamb[NZ + i], t = tb[NZ + i];
+                            const double rd = du - v[i] - t, G = lam / t, m = lam * t;
+                            Ht[pk(i, i)] += G; gt[i] -= G * rd; rg[i] += lam;
+                            nd = nanmax(nd, fabs(rd)); nm = nanmax(nm, fabs(m)); sm += m;
+                        }
+                    }
+                }
+                if (path) {
+                    for (int e = 0; e < NCG; e++) {
+                        const int r = HROW[e];
+                        const double sg = HSGN[e], lam = lamg[e], t = tg[e];
+                        double cv = 0.0;
+#pragma unroll
+                        for (int a = 0; a < NHS; a++) cv += C[r * NHS + a] * v[HSUP[a]];
+                        const double rd = sg * cv - dg[e] - t, G = lam / t, m = lam * t;
+#pragma unroll
+                        for (int a = 0; a < NHS; a++) {
+                            const double ca = C[r * NHS + a];
+#pragma unroll
+                            for (int bb = 0; bb <= a; bb++) Ht[pk(HSUP[a], HSUP[bb])] += G * ca * C[r * NHS + bb];
+                            gt[HSUP[a]] += sg * ca * (G * rd);
+                            rg[HSUP[a]] -= sg * ca * lam;
+                        }
+                        nd = nanmax(nd, fabs(rd)); nm = nanmax(nm, fabs(m)); sm += m;
+                    }
+                }
+                if (k == 0) {
+#pragma unroll
+                    for (int i = NU; i < NZ; i++) rg[i] = 0.0;      // x_0 is not a variable
+                }
+                if (live) {
+#pragma unroll
+                    for (int i = 0; i < NZ; i++) ng = nanmax(ng, fabs(rg[i]));
+#pragma unroll
+                    for (int i = 0; i < NX; i++) nb = nanmax(nb, fabs(rb[i]));
+                }
+            }
+            nrm_g = warp_max(ng); nrm_b = warp_max(nb); nrm_d = warp_max(nd); nrm_m = warp_max(nm);
+            mu = warp_sum(sm) / (double)IPM_COUNT;
+#ifdef MPC_TRACE
+            if (k == 0 && prob == MPC_TRACE)
+                printf("gpu sqp %d ipm %d: rg %.3e rb %.3e rd %.3e rm %.3e mu %.3e alpha %.3e\n", it, kk, nrm_g, nrm_b, nrm_d, nrm_m, mu, alpha);
+#endif
+            isnan_ = (mu != mu) || (nrm_g != nrm_g) || (nrm_b != nrm_b) || (nrm_d != nrm_d) || (nrm_m != nrm_m);
+            if (!(kk < IPM_ITER_MAX && alpha > IPM_ALPHA_MIN && !isnan_ &&
+                  (nrm_g > IPM_TOL || nrm_b > IPM_TOL || nrm_d > IPM_TOL || nrm_m > IPM_TOL)))
+                break;
+
+            // ---- Riccati factorisation + predictor solve.  Stage k lives on lane k; the recursion
+            //      walks down the lanes, (P, p) of stage k+1 arrive by shuffle.  Square-root form:
+            //      G = Ht + W'P+W = L L' (Cholesky, no explicit Schur-complement subtraction),
+            //      L = [Luu 0; Lxu Lxx], P = Lxx Lxx', l = Luu^-1 q_u, p = q_x - Lxu l.
+            double P[NPX], pv[NX], Lf[NPK], Prb[NX], lv[NU], iL0 = 0.0, iL1 = 0.0;
+#pragma unroll
+            for (int i = 0; i < NPX; i++) P[i] = 0.0;
+#pragma unroll
+            for (int i = 0; i < NX; i++) { pv[i] = 0.0; Prb[i] = 0.0; }
+#pragma unroll
+            for (int i = 0; i < NPK; i++) Lf[i] = 0.0;
+            lv[0] = lv[1] = 0.0;
+            if (term) {
+#pragma unroll
+                for (int i = 0; i < NX; i++) {
+                    pv[i] = gt[NU + i];
+#pragma unroll
+                    for (int j = 0; j <= i; j++) P[pk(i, j)] = Ht[pk(NU + i, NU + j)];
+                }
+            }
+#pragma unroll 1
+            for (int s = NSTAGE - 1; s >= 0; s--) {
+                double Pn[NPX], pn[NX];
+#pragma unroll
+                for (int i = 0; i < NPX; i++) Pn[i] = shfl(P[i], s + 1);
+#pragma unroll
+                for (int i = 0; i < NX; i++) pn[i] = shfl(pv[i], s + 1);
+                if (k == s) {
+                    double q[NZ], y[NX];
+#pragma unroll
+                    for (int i = 0; i < NPK; i++) Lf[i] = Ht[i];
+                    wtpw_add(Wv, Pn, Lf);
+#pragma unroll
+                    for (int i = 0; i < NX; i++) {
+                        double a = 0.0;
+#pragma unroll
+                        for (int j = 0; j < NX; j++) a += Pn[pk(i, j)] * rb[j];
+                        Prb[i] = a;
+                        y[i] = pn[i] + a;
+                    }
+#pragma unroll
+                    for (int i = 0; i < NZ; i++) q[i] = gt[i];
+                    wt_mul_add(Wv, y, q);
+                    // in-place Cholesky of the packed NZ x NZ block
+#pragma unroll
+                    for (int j = 0; j < NZ; j++) {
+                        double d = Lf[pk(j, j)];
+#pragma unroll
+                        for (int m = 0; m < j; m++) d -= Lf[pk(j, m)] * Lf[pk(j, m)];
+                        const double ljj = sqrt(d), inv = 1.0 / ljj;
+                        Lf[pk(j, j)] = ljj;
+                        if (j == 0) iL0 = inv;
+                        if (j == 1) iL1 = inv;
+#pragma unroll
+                        for (int i = j + 1; i < NZ; i++) {
+                            double a = Lf[pk(i, j)];
+#pragma unroll
+                            for (int m = 0; m < j; m++) a -= Lf[pk(i, m)] * Lf[pk(j, m)];
+                            Lf[pk(i, j)] = a * inv;
+                        }
+                    }
+                    lv[0] = q[0] * iL0;
+                    lv[1] = (q[1] - Lf[pk(1, 0)] * lv[0]) * iL1;
+#pragma unroll
+                    for (int i = 0; i < NX; i++) pv[i] = q[NU + i] - Lf[pk(NU + i, 0)] * lv[0] - Lf[pk(NU + i, 1)] * lv[1];
+#pragma unroll
+                    for (int i = 0; i < NX; i++)
+#pragma unroll
+                        for (int j = 0; j <= i; j++) {
+                            double a = 0.0;
+#pragma unroll
+                            for (int m = 0; m <= j; m++) a += Lf[pk(NU + i, NU + m)] * Lf[pk(NU + j, NU + m)];
+                            P[pk(i, j)] = a;
+                        }
+                }
+            }
+            // forward sweep: dva
+            double dva[NZ], dpi[NX];
+#pragma unroll
+            for (int i = 0; i < NZ; i++) dva[i] = 0.0;
+#pragma unroll
+            for (int i = 0; i < NX; i++) dpi[i] = 0.0;
+#pragma unroll 1
+            for (int s = 0; s < NSTAGE; s++) {
+                double dxn[NX];
+#pragma unroll
+                for (int i = 0; i < NX; i++) dxn[i] = 0.0;
+                if (k == s) {
+                    double r0 = lv[0], r1 = lv[1];      // du = -Luu^-T (Lxu' dx + l)
+#pragma unroll
+                    for (int j = 0; j < NX; j++) { r0 += Lf[pk(NU + j, 0)] * dva[NU + j]; r1 += Lf[pk(NU + j, 1)] * dva[NU + j]; }
+                    dva[1] = -r1 * iL1;
+                    dva[0] = -(r0 + Lf[pk(1, 0)] * dva[1]) * iL0;
+#pragma unroll
+                    for (int i = 0; i < NX; i++) dxn[i] = rb[i];
+                    w_mul_add(Wv, dva, dxn);
+                }
+#pragma unroll
+                for (int i = 0; i < NX; i++) dxn[i] = shfl(dxn[i], s);
+                if (k == s + 1) {
+#pragma unroll
+                    for (int i = 0; i < NX; i++) dva[NU + i] = dxn[i];
+                }
+            }
+
+            // ---- pass B: affine step length, mu_aff sums, corrector vectors
+            double alpha_aff = 1.0, S1 = 0.0, S2 = 0.0, V1[NZ], V2[NZ];
+#pragma unroll
+            for (int i = 0; i < NZ; i++) { V1[i] = 0.0; V2[i] = 0.0; }
+#pragma unroll
+            for (int i = 0; i < NZ; i++) {
+                const bool act = (i < NU) ? path : xbox;
+                if (act) {
+                    const double dl = LBZ[i] - z[i], du = UBZ[i] - z[i];
+                    {
+                        const double lam = lamb[i], t = tb[i];
+                        const IneqStep st = ineq_affine(lam, t, v[i] - dl - t, dva[i]);
+                        step_limit(lam, st.dlam, alpha_aff); step_limit(t, st.dt, alpha_aff);
+                        S1 += lam * st.dt + t * st.dlam; S2 += st.dt * st.dlam;
+                        V1[i] += st.corr; V2[i] += st.invt;
+                    }
+                    {
+                        const double lam = lamb[NZ + i], t = tb[NZ + i];
+                        const IneqStep st = ineq_affine(lam, t, du - v[i] - t, -dva[i]);
+                        step_limit(lam, st.dlam, alpha_aff); step_limit(t, st.dt, alpha_aff);
+                        S1 += lam * st.dt + t * st.dlam; S2 += st.dt * st.dlam;
+                        V1[i] -= st.corr; V2[i] -= st.invt;
+                    }
+                }
+            }
+            if (path) {
+                for (int e = 0; e < NCG; e++) {
+                    const int r = HROW[e];
+                    const double sg = HSGN[e], lam = lamg[e], t = tg[e];
+                    double cv = 0.0, cd = 0.0;
+#pragma unroll
+                    for (int a = 0; a < NHS; a++) { cv += C[r * NHS + a] * v[HSUP[a]]; cd += C[r * NHS + a] * dva[HSUP[a]]; }
+                    const IneqStep st = ineq_affine(lam, t, sg * cv - dg[e] - t, sg * cd);
+                    step_limit(lam, st.dlam, alpha_aff); step_limit(t, st.dt, alpha_aff);
+                    S1 += lam * st.dt + t * st.dlam; S2 += st.dt * st.dlam;
+#pragma unroll
+                    for (int a = 0; a < NHS; a++) {
+                        V1[HSUP[a]] += sg * C[r * NHS + a] * st.corr;
+                        V2[HSUP[a]] += sg * C[r * NHS + a] * st.invt;
+                    }
+                }
+            }
+            alpha_aff = warp_min(alpha_aff);
+            S1 = warp_sum(S1); S2 = warp_sum(S2);
+            const double mu_aff = (mu * (double)IPM_COUNT + alpha_aff * S1 + alpha_aff * alpha_aff * S2) / (double)IPM_COUNT;
+            const double rat = mu_aff / mu, sigmu = rat * rat * rat * mu;
+#pragma unroll
+            for (int i = 0; i < NZ; i++) gt[i] += V1[i] - sigmu * V2[i];
+
+            // ---- corrector solve (factorisation reused): backward vector sweep + forward sweep
+            if (term) {
+#pragma unroll
+                for (int i = 0; i < NX; i++) pv[i] = gt[NU + i];
+            }
+#pragma unroll 1
+            for (int s = NSTAGE - 1; s >= 0; s--) {
+                double pn[NX];
+#pragma unroll
+                for (int i = 0; i < NX; i++) pn[i] = shfl(pv[i], s + 1);
+                if (k == s) {
+                    double q[NZ], y[NX];
+#pragma unroll
+                    for (int i = 0; i < NX; i++) y[i] = pn[i] + Prb[i];
+#pragma unroll
+                    for (int i = 0; i < NZ; i++) q[i] = gt[i];
+                    wt_mul_add(Wv, y, q);
+                    lv[0] = q[0] * iL0;
+                    lv[1] = (q[1] - Lf[pk(1, 0)] * lv[0]) * iL1;
+#pragma unroll
+                    for (int i = 0; i < NX; i++) pv[i] = q[NU + i] - Lf[pk(NU + i, 0)] * lv[0] - Lf[pk(NU + i, 1)] * lv[1];
+                }
+            }
+            double dv[NZ];
+#pragma unroll
+            for (int i = 0; i < NZ; i++) dv[i] = 0.0;
+#pragma unroll 1
+            for (int s = 0; s < NSTAGE; s++) {
+                double dxn[NX];
+#pragma unroll
+                for (int i = 0; i < NX; i++) dxn[i] = 0.0;
+                if (k == s) {
+                    double r0 = lv[0], r1 = lv[1];
+#pragma unroll
+                    for (int j = 0; j < NX; j++) { r0 += Lf[pk(NU + j, 0)] * dv[NU + j]; r1 += Lf[pk(NU + j, 1)] * dv[NU + j]; }
+                    dv[1] = -r1 * iL1;
+                    dv[0] = -(r0 + Lf[pk(1, 0)] * dv[1]) * iL0;
+#pragma unroll
+                    for (int i = 0; i < NX; i++) dxn[i] = rb[i];
+                    w_mul_add(Wv, dv, dxn);
+                }
+#pragma unroll
+                for (int i = 0; i < NX; i++) dxn[i] = shfl(dxn[i], s);
+                if (k == s + 1) {
+#pragma unroll
+                    for (int i = 0; i < NX; i++) {
+                        dv[NU + i] = dxn[i];
+                    }
+#pragma unroll
+                    for (int i = 0; i < NX; i++) {
+                        double a = pv[i];
+#pragma unroll
+                        for (int j = 0; j < NX; j++) a += P[pk(i, j)] * dxn[j];
+                        dpi[i] = a;
+                    }
+                }
+            }
+
+            // ---- pass C: step length of the corrected direction
+            double al = 1.0;
+#pragma unroll
+            for (int i = 0; i < NZ; i++) {
+                const bool act = (i < NU) ? path : xbox;
+                if (act) {
+                    const double dl = LBZ[i] - z[i], du = UBZ[i] - z[i];
+                    {
+                        const double lam = lamb[i], t = tb[i];
+                        const IneqStep st = ineq_final(lam, t, v[i] - dl - t, dva[i], dv[i], sigmu);
+                        step_limit(lam, st.dlam, al); step_limit(t, st.dt, al);
+                    }
+                    {
+                        const double lam = lamb[NZ + i], t = tb[NZ + i];
+                        const IneqStep st = ineq_final(lam, t, du - v[i] - t, -dva[i], -dv[i], sigmu);
+                        step_limit(lam, st.dlam, al); step_limit(t, st.dt, al);
+                    }
+                }
+            }
+            if (path) {
+                for (int e = 0; e < NCG; e++) {
+                    const int r = HROW[e];
+                    const double sg = HSGN[e], lam = lamg[e], t = tg[e];
+                    double cv = 0.0, cda = 0.0, cd = 0.0;
+#pragma unroll
+                    for (int a = 0; a < NHS; a++) {
+                        const double ca = C[r * NHS + a];
+                        cv += ca * v[HSUP[a]]; cda += ca * dva[HSUP[a]]; cd += ca * dv[HSUP[a]];
+                    }
+                    const IneqStep st = ineq_final(lam, t, sg * cv - dg[e] - t, sg * cda, sg * cd, sigmu);
+                    step_limit(lam, st.dlam, al); step_limit(t, st.dt, al);
+                }
+            }
+            alpha = warp_min(al);
+            const double a_ = alpha < 1.0 ? alpha * IPM_STEP_SCALE : alpha;
+
+            // ---- pass D: update (v, pi, lam, t)
+#pragma unroll
+            for (int i = 0; i < NZ; i++) {
+                const bool act = (i < NU) ? path : xbox;
+                if (act) {
+                    const double dl = LBZ[i] - z[i], du = UBZ[i] - z[i];
+                    {
+                        const double lam = lamb[i], t = tb[i];
+                        const IneqStep st = ineq_final(lam, t, v[i] - dl - t, dva[i], dv[i], sigmu);
+                        lamb[i] = clamp_lo(lam + a_ * st.dlam, IPM_LAM_MIN); tb[i] = clamp_lo(t + a_ * st.dt, IPM_T_MIN);
+                    }
+                    {
+                        const double lam = lamb[NZ + i], t = tb[NZ + i];
+                        const IneqStep st = ineq_final(lam, t, du - v[i] - t, -dva[i], -dv[i], sigmu);
+                        lamb[NZ + i] = clamp_lo(lam + a_ * st.dlam, IPM_LAM_MIN); tb[NZ + i] = clamp_lo(t + a_ * st.dt, IPM_T_MIN);
+                    }
+                }
+            }
+            if (path) {
+                for (int e = 0; e < NCG; e++) {
+                    const int r = HROW[e];
+                    const double sg = HSGN[e], lam = lamg[e], t = tg[e];
+                    double cv = 0.0, cda = 0.0, cd = 0.0;
+#pragma unroll
+                    for (int a = 0; a < NHS; a++) {
+                        const double ca = C[r * NHS + a];
+                        cv += ca * v[HSUP[a]]; cda += ca * dva[HSUP[a]]; cd += ca * dv[HSUP[a]];
+                    }
+                    const IneqStep st = ineq_final(lam, t, sg * cv - dg[e] - t, sg * cda, sg * cd, sigmu);
+                    lamg[e] = clamp_lo(lam + a_ * st.dlam, IPM_LAM_MIN); tg[e] = clamp_lo(t + a_ * st.dt, IPM_T_MIN);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < NZ; i++) v[i] += a_ * dv[i];
+#pragma unroll
+            for (int i = 0; i < NX; i++) qpi[i] += a_ * dpi[i];
+        }
+        ipm_total += kk;
+        qps = isnan_ ? 3 : ((kk == IPM_ITER_MAX) ? 1 : (alpha <= IPM_ALPHA_MIN ? 2 : 0));
+        (void)nrm_g; (void)nrm_b; (void)nrm_d; (void)nrm_m;
+
+        // ======================= K6: SQP-RTI full step ============================================
+        if (qps != 0 && qps != 1) { status = 4; break; }   // ACADOS_QP_FAILURE: iterate unchanged
+#pragma unroll
+        for (int i = 0; i < NZ; i++) z[i] += v[i];
+        if (term) { z[0] = 0.0; z[1] = 0.0; }
+#pragma unroll
+        for (int i = 0; i < NX; i++) pi[i] = qpi[i];
+        qp_warm = 1;
+        status = 0;
+        if (qps != 0) break;                               // wrapper breaks on qp_status != 0 (:105-106)
+    }
+
+    // ======================= completeOneIteration (:162-204) ======================================
+    double cst = 0.0, req = 0.0;
+    {
+        double xnx[NX];
+#pragma unroll
+        for (int i = 0; i < NX; i++) xnx[i] = shfl_down1(z[NU + i]);
+        if (path) {
+            double xn[NX];
+            cst = DT * cost_val(z, p);
+            dyn_phi(z, xn);
+#pragma unroll
+            for (int i = 0; i < NX; i++) req = nanmax(req, fabs(xn[i] - xnx[i]));
+        }
+    }
+    // deterministic stage-order sum (matches the oracle's sequential accumulation)
+    double cost = 0.0;
+#pragma unroll 1
+    for (int s = 0; s < NSTAGE; s++) cost += shfl(cst, s);
+    req = warp_max(req);
+    if (!(req <= RES_EQ_MAX) && status == 0) status = 4;
+    const int exit_code = (status == 0) ? 1 : (status == 1 ? 0 : status);
+    if (live) {
+#pragma unroll
+        for (int i = 0; i < NX; i++) xtraj_g[(size_t)prob * NX * (NSTAGE + 1) + k * NX + i] = z[NU + i];
+    }
+    if (path) {
+#pragma unroll
+        for (int i = 0; i < NU; i++) utraj_g[(size_t)prob * NU * NSTAGE + k * NU + i] = z[i];
+    }
+    if (k == 0) {
+        pobj_g[prob] = cost; exit_g[prob] = exit_code; qps_g[prob] = qps; reseq_g[prob] = req;
+        if (ipm_g) ipm_g[prob] = ipm_total;
+    }
+    if (mem) {
+        if (status != 0) {                                 // Solver_acados_reset + reset_qp_memory (:187-191)
+            for (int i = k; i < mem_doubles; i += 32) mem[i] = 0.0;
+        } else {
+            double* m = mem + 1;
+            if (k == 0) mem[0] = 2.0;
+            if (live) for (int i = 0; i < NX; i++) m[k * NX + i] = pi[i];
+            m += (NSTAGE + 1) * NX;
+            if (path) {
+                for (int e = 0; e < NCB; e++) { m[k * NC + e] = lamb[e]; m[NSTAGE * NC + k * NC + e] = tb[e]; }
+                for (int e = 0; e < NCG; e++) { m[k * NC + NCB + e] = lamg[e]; m[NSTAGE * NC + k * NC + NCB + e] = tg[e]; }
+            }
+            m += 2 * NSTAGE * NC;
+            if (live) for (int i = 0; i < NZ; i++) m[k * NZ + i] = v[i];
+        }
+    }
+}
+
+constexpr int WARPS_PER_CTA = 4;
+
+// Persistent grid: warps pull problem indices from a global counter (work per problem is data
+// dependent: 50-100 interior-point iterations), so late finishers do not idle a whole CTA.
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+mpc_solve_kernel(int n, const double* __restrict__ xinit, const double* __restrict__ x0, const double* __restrict__ params,
+                 const int* __restrict__ num_iter, int num_iter_all, double* mem, int mem_doubles, double* xtraj,
+                 double* utraj, double* pobj, int* exit_code, int* qp_status, double* res_eq, int* ipm_iters,
+                 int* work_counter)
+{
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        int prob = 0;
+        if (lane == 0) prob = atomicAdd(work_counter, 1);
+        prob = __shfl_sync(FULL, prob, 0);
+        if (prob >= n) return;
+        const int nit = num_iter ? num_iter[prob] : num_iter_all;
+        solve_problem(prob, xinit, x0, params, nit, mem, mem_doubles, xtraj, utraj, pobj, exit_code, qp_status, res_eq,
+                      ipm_iters);
+    }
+}
+
+}  // namespace MPC_NS

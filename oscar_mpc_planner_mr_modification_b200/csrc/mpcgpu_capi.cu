@@ -1,0 +1,255 @@
+// C ABI of the batched MPC solve engine (include/mpcgpu.h).  Host-side plumbing only: device buffers,
+// H2D/D2H staging, stream + events, the persistent-grid launch, and the best-planner selection kernel.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mpcgpu.h"
+#include "mpc_registry.h"
+
+namespace {
+std::vector<const MpcConfigOps*>& registry()
+{
+    static std::vector<const MpcConfigOps*> r;
+    return r;
+}
+
+// K7: one thread per homotopy set -- FindBestPlanner (guidance_constraints.cpp:572-590) with the
+// objective post-processing of :373-420.  Sequential, ascending, strict '<': bit-exact by construction.
+__global__ void select_best_kernel(int n_sets, const int* __restrict__ set_offsets, const double* __restrict__ pobj,
+                                   const int* __restrict__ exit_code, const double* __restrict__ obj_scale,
+                                   const double* __restrict__ obj_sub, const unsigned char* __restrict__ disabled,
+                                   int* __restrict__ best_idx)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_sets) return;
+    double best = 1e10;
+    int bi = -1;
+    for (int i = set_offsets[s]; i < set_offsets[s + 1]; i++) {
+        if (disabled && disabled[i]) continue;
+        double obj = pobj[i];
+        if (obj_sub) obj = obj - obj_sub[i];
+        if (obj_scale) obj = obj * obj_scale[i];
+        if (exit_code[i] == 1 && obj < best) { best = obj; bi = i - set_offsets[s]; }
+    }
+    best_idx[s] = bi;
+}
+}  // namespace
+
+void mpc_register_config(const MpcConfigOps* ops) { registry().push_back(ops); }
+
+struct mpcgpu_engine {
+    const MpcConfigOps* ops = nullptr;
+    int device = 0, max_batch = 0, grid = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // device staging for the host-pointer entry points
+    double *d_xinit = nullptr, *d_x0 = nullptr, *d_params = nullptr, *d_mem = nullptr, *d_xtraj = nullptr, *d_utraj = nullptr,
+           *d_pobj = nullptr, *d_res_eq = nullptr, *d_scale = nullptr, *d_sub = nullptr;
+    int *d_num_iter = nullptr, *d_exit = nullptr, *d_qps = nullptr, *d_ipm = nullptr, *d_counter = nullptr, *d_offsets = nullptr,
+        *d_best = nullptr;
+    unsigned char* d_disabled = nullptr;
+    long long launches = 0;
+    std::string err;
+};
+
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t _e = (call);                                                                      \
+        if (_e != cudaSuccess) {                                                                      \
+            e->err = std::string(#call) + ": " + cudaGetErrorString(_e);                              \
+            return MPCGPU_ERR_CUDA;                                                                   \
+        }                                                                                             \
+    } while (0)
+
+extern "C" {
+
+int mpcgpu_num_configs(void) { return (int)registry().size(); }
+const char* mpcgpu_config_name(int i) { return (i >= 0 && i < (int)registry().size()) ? registry()[i]->name : nullptr; }
+
+int mpcgpu_engine_create(const char* config_name, int device, int max_batch, mpcgpu_engine** out)
+{
+    if (!config_name || !out || max_batch <= 0) return MPCGPU_ERR_ARG;
+    *out = nullptr;
+    const MpcConfigOps* ops = nullptr;
+    for (auto* o : registry())
+        if (std::strcmp(o->name, config_name) == 0) ops = o;
+    if (!ops) return MPCGPU_ERR_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+        std::fprintf(stderr, "mpcgpu: no usable CUDA device (requested %d of %d); there is no CPU fallback\n", device, ndev);
+        return MPCGPU_ERR_NO_DEVICE;
+    }
+    mpcgpu_engine* e = new mpcgpu_engine();
+    e->ops = ops; e->device = device; e->max_batch = max_batch;
+    auto fail = [&](int code) { *out = e; return code; };   // caller can read last_error, then destroy
+    if (cudaSetDevice(device) != cudaSuccess) { e->err = "cudaSetDevice failed"; return fail(MPCGPU_ERR_CUDA); }
+    const size_t B = (size_t)max_batch;
+    const int N = ops->N, nx = ops->nx, nu = ops->nu, nz = nx + nu;
+#define AL(ptr, count) do { cudaError_t _e = cudaMalloc((void**)&(ptr), (count)); if (_e != cudaSuccess) { e->err = std::string("cudaMalloc ") + #ptr + ": " + cudaGetErrorString(_e); return fail(MPCGPU_ERR_CUDA); } } while (0)
+    AL(e->d_xinit, B * nx * 8); AL(e->d_x0, B * nz * (N + 1) * 8); AL(e->d_params, B * N * ops->np * 8);
+    AL(e->d_mem, B * ops->mem_doubles * 8); AL(e->d_xtraj, B * nx * (N + 1) * 8); AL(e->d_utraj, B * nu * N * 8);
+    AL(e->d_pobj, B * 8); AL(e->d_res_eq, B * 8); AL(e->d_scale, B * 8); AL(e->d_sub, B * 8);
+    AL(e->d_num_iter, B * 4); AL(e->d_exit, B * 4); AL(e->d_qps, B * 4); AL(e->d_ipm, B * 4); AL(e->d_counter, 4);
+    AL(e->d_offsets, (B + 1) * 4); AL(e->d_best, B * 4); AL(e->d_disabled, B);
+#undef AL
+    if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&e->ev0) != cudaSuccess || cudaEventCreate(&e->ev1) != cudaSuccess) {
+        e->err = "stream/event creation failed";
+        return fail(MPCGPU_ERR_CUDA);
+    }
+    int ctas = 0, threads = 0, sms = 0;
+    if (ops->occupancy(&ctas, &threads) != cudaSuccess || ctas <= 0 ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) {
+        e->err = "occupancy query failed";
+        return fail(MPCGPU_ERR_CUDA);
+    }
+    e->grid = sms * ctas;   // persistent grid: every SM holds its full complement of CTAs
+    *out = e;
+    return MPCGPU_OK;
+}
+
+int mpcgpu_engine_destroy(mpcgpu_engine* e)
+{
+    if (!e) return MPCGPU_ERR_ARG;
+    cudaSetDevice(e->device);
+    void* ptrs[] = {e->d_xinit, e->d_x0, e->d_params, e->d_mem, e->d_xtraj, e->d_utraj, e->d_pobj, e->d_res_eq, e->d_scale,
+                    e->d_sub, e->d_num_iter, e->d_exit, e->d_qps, e->d_ipm, e->d_counter, e->d_offsets, e->d_best, e->d_disabled};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+    return MPCGPU_OK;
+}
+
+int mpcgpu_desc_query(const mpcgpu_engine* e, int* N, int* nx, int* nu, int* npar, int* nh)
+{
+    if (!e) return MPCGPU_ERR_ARG;
+    if (N) *N = e->ops->N;
+    if (nx) *nx = e->ops->nx;
+    if (nu) *nu = e->ops->nu;
+    if (npar) *npar = e->ops->np;
+    if (nh) *nh = e->ops->nh;
+    return MPCGPU_OK;
+}
+int mpcgpu_mem_doubles(const mpcgpu_engine* e) { return e ? e->ops->mem_doubles : MPCGPU_ERR_ARG; }
+
+int mpcgpu_solve_batch_device(mpcgpu_engine* e, int n, const double* xinit, const double* x0, const double* params,
+                              const int* num_iter, int num_iter_all, double* mem_inout, double* xtraj, double* utraj,
+                              double* pobj, int* exit_code, int* qp_status, double* res_eq, int* ipm_iters, void* stream)
+{
+    if (!e || n < 0 || !xinit || !x0 || !params || !xtraj || !utraj || !pobj || !exit_code || !qp_status || !res_eq)
+        return MPCGPU_ERR_ARG;
+    if (n == 0) return MPCGPU_OK;
+    CK(cudaSetDevice(e->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+    const int warps_per_cta = 4;
+    int grid = (n + warps_per_cta - 1) / warps_per_cta;
+    if (grid > e->grid) grid = e->grid;
+    CK(cudaEventRecord(e->ev0, st));
+    CK(e->ops->launch_solve(grid, st, n, xinit, x0, params, num_iter, num_iter_all, mem_inout, xtraj, utraj, pobj, exit_code,
+                            qp_status, res_eq, ipm_iters, e->d_counter));
+    CK(cudaEventRecord(e->ev1, st));
+    e->launches += 1;
+    return MPCGPU_OK;
+}
+
+int mpcgpu_sync(mpcgpu_engine* e)
+{
+    if (!e) return MPCGPU_ERR_ARG;
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    return MPCGPU_OK;
+}
+
+int mpcgpu_solve_batch(mpcgpu_engine* e, int n, const double* xinit, const double* x0, const double* params,
+                       const int* num_iter, int num_iter_all, double* mem_inout, double* xtraj, double* utraj, double* pobj,
+                       int* exit_code, int* qp_status, double* res_eq, int* ipm_iters)
+{
+    if (!e || n < 0 || n > e->max_batch || !xinit || !x0 || !params || !xtraj || !utraj || !pobj || !exit_code ||
+        !qp_status || !res_eq)
+        return MPCGPU_ERR_ARG;
+    if (n == 0) return MPCGPU_OK;
+    CK(cudaSetDevice(e->device));
+    const MpcConfigOps* o = e->ops;
+    const size_t B = (size_t)n;
+    const int N = o->N, nx = o->nx, nu = o->nu, nz = nx + nu;
+    cudaStream_t st = e->stream;
+    CK(cudaMemcpyAsync(e->d_xinit, xinit, B * nx * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(e->d_x0, x0, B * nz * (N + 1) * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(e->d_params, params, B * N * o->np * 8, cudaMemcpyHostToDevice, st));
+    if (num_iter) CK(cudaMemcpyAsync(e->d_num_iter, num_iter, B * 4, cudaMemcpyHostToDevice, st));
+    if (mem_inout) CK(cudaMemcpyAsync(e->d_mem, mem_inout, B * o->mem_doubles * 8, cudaMemcpyHostToDevice, st));
+    int rc = mpcgpu_solve_batch_device(e, n, e->d_xinit, e->d_x0, e->d_params, num_iter ? e->d_num_iter : nullptr, num_iter_all,
+                                       mem_inout ? e->d_mem : nullptr, e->d_xtraj, e->d_utraj, e->d_pobj, e->d_exit, e->d_qps,
+                                       e->d_res_eq, e->d_ipm, st);
+    if (rc != MPCGPU_OK) return rc;
+    CK(cudaMemcpyAsync(xtraj, e->d_xtraj, B * nx * (N + 1) * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(utraj, e->d_utraj, B * nu * N * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(pobj, e->d_pobj, B * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(exit_code, e->d_exit, B * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(qp_status, e->d_qps, B * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(res_eq, e->d_res_eq, B * 8, cudaMemcpyDeviceToHost, st));
+    if (ipm_iters) CK(cudaMemcpyAsync(ipm_iters, e->d_ipm, B * 4, cudaMemcpyDeviceToHost, st));
+    if (mem_inout) CK(cudaMemcpyAsync(mem_inout, e->d_mem, B * o->mem_doubles * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return MPCGPU_OK;
+}
+
+int mpcgpu_select_best_device(mpcgpu_engine* e, int n_sets, const int* set_offsets, const double* pobj, const int* exit_code,
+                              const double* obj_scale, const double* obj_sub, const unsigned char* disabled, int* best_idx,
+                              void* stream)
+{
+    if (!e || n_sets < 0 || !set_offsets || !pobj || !exit_code || !best_idx) return MPCGPU_ERR_ARG;
+    if (n_sets == 0) return MPCGPU_OK;
+    CK(cudaSetDevice(e->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+    select_best_kernel<<<(n_sets + 127) / 128, 128, 0, st>>>(n_sets, set_offsets, pobj, exit_code, obj_scale, obj_sub, disabled,
+                                                              best_idx);
+    CK(cudaGetLastError());
+    e->launches += 1;
+    return MPCGPU_OK;
+}
+
+int mpcgpu_select_best(mpcgpu_engine* e, int n_sets, const int* set_offsets, const double* pobj, const int* exit_code,
+                       const double* obj_scale, const double* obj_sub, const unsigned char* disabled, int* best_idx)
+{
+    if (!e || n_sets < 0 || !set_offsets || !pobj || !exit_code || !best_idx) return MPCGPU_ERR_ARG;
+    if (n_sets == 0) return MPCGPU_OK;
+    const int n = set_offsets[n_sets];
+    if (n > e->max_batch || n_sets > e->max_batch) return MPCGPU_ERR_ARG;
+    CK(cudaSetDevice(e->device));
+    cudaStream_t st = e->stream;
+    CK(cudaMemcpyAsync(e->d_offsets, set_offsets, (size_t)(n_sets + 1) * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(e->d_pobj, pobj, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(e->d_exit, exit_code, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    if (obj_scale) CK(cudaMemcpyAsync(e->d_scale, obj_scale, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    if (obj_sub) CK(cudaMemcpyAsync(e->d_sub, obj_sub, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    if (disabled) CK(cudaMemcpyAsync(e->d_disabled, disabled, (size_t)n, cudaMemcpyHostToDevice, st));
+    int rc = mpcgpu_select_best_device(e, n_sets, e->d_offsets, e->d_pobj, e->d_exit, obj_scale ? e->d_scale : nullptr,
+                                       obj_sub ? e->d_sub : nullptr, disabled ? e->d_disabled : nullptr, e->d_best, st);
+    if (rc != MPCGPU_OK) return rc;
+    CK(cudaMemcpyAsync(best_idx, e->d_best, (size_t)n_sets * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return MPCGPU_OK;
+}
+
+long long mpcgpu_launch_count(const mpcgpu_engine* e) { return e ? e->launches : 0; }
+
+float mpcgpu_last_kernel_ms(mpcgpu_engine* e)
+{
+    if (!e) return -1.0f;
+    float ms = -1.0f;
+    if (cudaEventSynchronize(e->ev1) != cudaSuccess) return -1.0f;
+    if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) != cudaSuccess) return -1.0f;
+    return ms;
+}
+
+const char* mpcgpu_last_error(const mpcgpu_engine* e) { return e ? e->err.c_str() : "null engine"; }
+
+}  // extern "C"

@@ -1,0 +1,180 @@
+"""ctypes binding of libmpcgpu.so (include/mpcgpu.h) -- host-side plumbing for tests and bench.
+
+There is NO CPU fallback: if the shared library or a CUDA device is missing, construction raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+import yaml
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_PKG, "lib", "libmpcgpu.so")
+_lib = None
+
+SYMBOLS = [
+    "mpcgpu_num_configs", "mpcgpu_config_name", "mpcgpu_engine_create", "mpcgpu_engine_destroy", "mpcgpu_desc_query",
+    "mpcgpu_mem_doubles", "mpcgpu_solve_batch", "mpcgpu_solve_batch_device", "mpcgpu_sync", "mpcgpu_select_best",
+    "mpcgpu_select_best_device", "mpcgpu_launch_count", "mpcgpu_last_kernel_ms", "mpcgpu_last_error",
+]
+
+
+def load_library():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise RuntimeError("libmpcgpu.so is not built (%s); run `python __graft_entry__.py`. "
+                               "There is no CPU fallback for the solve path." % _LIB_PATH)
+        lib = ctypes.CDLL(_LIB_PATH)
+        lib.mpcgpu_config_name.restype = ctypes.c_char_p
+        lib.mpcgpu_last_error.restype = ctypes.c_char_p
+        lib.mpcgpu_last_error.argtypes = [ctypes.c_void_p]
+        lib.mpcgpu_launch_count.restype = ctypes.c_longlong
+        lib.mpcgpu_launch_count.argtypes = [ctypes.c_void_p]
+        lib.mpcgpu_last_kernel_ms.restype = ctypes.c_float
+        lib.mpcgpu_last_kernel_ms.argtypes = [ctypes.c_void_p]
+        lib.mpcgpu_engine_create.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
+        lib.mpcgpu_engine_destroy.argtypes = [ctypes.c_void_p]
+        lib.mpcgpu_desc_query.argtypes = [ctypes.c_void_p] + [ctypes.POINTER(ctypes.c_int)] * 5
+        lib.mpcgpu_mem_doubles.argtypes = [ctypes.c_void_p]
+        lib.mpcgpu_sync.argtypes = [ctypes.c_void_p]
+        vp = ctypes.c_void_p
+        lib.mpcgpu_solve_batch.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp, vp]
+        lib.mpcgpu_solve_batch_device.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+        lib.mpcgpu_select_best.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp]
+        lib.mpcgpu_select_best_device.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp, vp]
+        _lib = lib
+    return _lib
+
+
+def config_dir(config):
+    return os.path.join(_PKG, "generated", config)
+
+
+def load_maps(config):
+    d = config_dir(config)
+    with open(os.path.join(d, "parameter_map.yaml")) as f:
+        pmap = yaml.safe_load(f)
+    with open(os.path.join(d, "model_map.yaml")) as f:
+        mmap = yaml.safe_load(f)
+    with open(os.path.join(d, "solver_settings.yaml")) as f:
+        st = yaml.safe_load(f)
+    pmap = {k: v for k, v in pmap.items() if k != "num parameters"}
+    return pmap, mmap, st
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(ctypes.c_void_p)
+    return ctypes.c_void_p(int(a))   # raw device address (e.g. torch.Tensor.data_ptr())
+
+
+class MpcGpuError(RuntimeError):
+    pass
+
+
+class Engine:
+    """One engine = one problem configuration on one GPU."""
+
+    def __init__(self, config, device=0, max_batch=4096):
+        self.lib = load_library()
+        self.config = config
+        self.parameter_map, self.model_map, st = load_maps(config)
+        self.handle = ctypes.c_void_p()
+        rc = self.lib.mpcgpu_engine_create(config.encode(), device, max_batch, ctypes.byref(self.handle))
+        if rc != 0:
+            msg = self.lib.mpcgpu_last_error(self.handle).decode() if self.handle else ""
+            if self.handle:
+                self.lib.mpcgpu_engine_destroy(self.handle)
+                self.handle = ctypes.c_void_p()
+            raise MpcGpuError("mpcgpu_engine_create(%s, device %d) failed: status %d %s" % (config, device, rc, msg))
+        d = [ctypes.c_int() for _ in range(5)]
+        self.lib.mpcgpu_desc_query(self.handle, *[ctypes.byref(v) for v in d])
+        self.N, self.nx, self.nu, self.npar, self.nh = [v.value for v in d]
+        assert (self.N, self.nx, self.nu, self.npar) == (st["N"], st["nx"], st["nu"], st["npar"])
+        self.nz = self.nx + self.nu
+        self.max_batch = max_batch
+        self.mem_doubles = self.lib.mpcgpu_mem_doubles(self.handle)
+        self.dims = dict(N=self.N, nx=self.nx, nu=self.nu, npar=self.npar, dt=0.2)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.mpcgpu_engine_destroy(self.handle)
+            self.handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise MpcGpuError("%s failed: status %d %s" % (what, rc, self.lib.mpcgpu_last_error(self.handle).decode()))
+
+    def alloc_outputs(self, n):
+        return dict(xtraj=np.zeros((n, (self.N + 1) * self.nx)), utraj=np.zeros((n, self.N * self.nu)), pobj=np.zeros(n),
+                    exit_code=np.zeros(n, np.int32), qp_status=np.zeros(n, np.int32), res_eq=np.zeros(n),
+                    ipm_iters=np.zeros(n, np.int32))
+
+    def solve_batch(self, xinit, x0, params, num_iter=10, mem=None, out=None):
+        """HOST numpy arrays in/out (H2D + kernel + D2H inside the call)."""
+        n = xinit.shape[0]
+        xinit = np.ascontiguousarray(xinit, np.float64)
+        x0 = np.ascontiguousarray(x0, np.float64)
+        params = np.ascontiguousarray(params, np.float64)
+        assert x0.size == n * self.nz * (self.N + 1) and params.size == n * self.N * self.npar and xinit.size == n * self.nx
+        if out is None:
+            out = self.alloc_outputs(n)
+        ni = None
+        nall = 0
+        if np.ndim(num_iter) == 0:
+            nall = int(num_iter)
+        else:
+            ni = np.ascontiguousarray(num_iter, np.int32)
+        if mem is not None:
+            assert mem.dtype == np.float64 and mem.size == n * self.mem_doubles and mem.flags["C_CONTIGUOUS"]
+        rc = self.lib.mpcgpu_solve_batch(self.handle, n, _ptr(xinit), _ptr(x0), _ptr(params), _ptr(ni), nall, _ptr(mem),
+                                         _ptr(out["xtraj"]), _ptr(out["utraj"]), _ptr(out["pobj"]), _ptr(out["exit_code"]),
+                                         _ptr(out["qp_status"]), _ptr(out["res_eq"]), _ptr(out["ipm_iters"]))
+        self._check(rc, "mpcgpu_solve_batch")
+        return out
+
+    def solve_batch_device(self, n, xinit, x0, params, num_iter, xtraj, utraj, pobj, exit_code, qp_status, res_eq,
+                           ipm_iters=None, mem=None, num_iter_dev=None, stream=None):
+        """Raw device addresses (ints); asynchronous."""
+        rc = self.lib.mpcgpu_solve_batch_device(self.handle, n, _ptr(xinit), _ptr(x0), _ptr(params), _ptr(num_iter_dev),
+                                                int(num_iter), _ptr(mem), _ptr(xtraj), _ptr(utraj), _ptr(pobj), _ptr(exit_code),
+                                                _ptr(qp_status), _ptr(res_eq), _ptr(ipm_iters), _ptr(stream))
+        self._check(rc, "mpcgpu_solve_batch_device")
+
+    def select_best(self, set_offsets, pobj, exit_code, obj_scale=None, obj_sub=None, disabled=None):
+        set_offsets = np.ascontiguousarray(set_offsets, np.int32)
+        n_sets = set_offsets.size - 1
+        best = np.zeros(n_sets, np.int32)
+        pobj = np.ascontiguousarray(pobj, np.float64)
+        exit_code = np.ascontiguousarray(exit_code, np.int32)
+        sc = None if obj_scale is None else np.ascontiguousarray(obj_scale, np.float64)
+        sb = None if obj_sub is None else np.ascontiguousarray(obj_sub, np.float64)
+        ds = None if disabled is None else np.ascontiguousarray(disabled, np.uint8)
+        rc = self.lib.mpcgpu_select_best(self.handle, n_sets, _ptr(set_offsets), _ptr(pobj), _ptr(exit_code), _ptr(sc), _ptr(sb),
+                                         _ptr(ds), _ptr(best))
+        self._check(rc, "mpcgpu_select_best")
+        return best
+
+    def select_best_device(self, n_sets, set_offsets, pobj, exit_code, best_idx, obj_scale=None, obj_sub=None, disabled=None,
+                           stream=None):
+        rc = self.lib.mpcgpu_select_best_device(self.handle, n_sets, _ptr(set_offsets), _ptr(pobj), _ptr(exit_code),
+                                                _ptr(obj_scale), _ptr(obj_sub), _ptr(disabled), _ptr(best_idx), _ptr(stream))
+        self._check(rc, "mpcgpu_select_best_device")
+
+    def sync(self):
+        self._check(self.lib.mpcgpu_sync(self.handle), "mpcgpu_sync")
+
+    def last_kernel_ms(self):
+        return float(self.lib.mpcgpu_last_kernel_ms(self.handle))
+
+    def launch_count(self):
+        return int(self.lib.mpcgpu_launch_count(self.handle))

@@ -1,11 +1,31 @@
-"""sympy -> C statement helpers shared by the generators (generation-time tooling only)."""
+"""sympy helpers of the CUDA emitter: C++ expression printer, CSE'd statement blocks, and access to
+the sympy-backed `casadi` stand-in the module definitions are evaluated with."""
+import importlib
+import os
+import sys
+
 import sympy as sp
 from sympy.printing.c import C99CodePrinter
 
+_COMPAT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "casadi_compat")
+
+
+def symbolic_namespace():
+    """The `casadi` module the problem definition scripts import (sympy-backed stand-in)."""
+    if _COMPAT not in sys.path:
+        sys.path.insert(0, _COMPAT)
+    mod = importlib.import_module("casadi")
+    if not hasattr(mod, "to_sympy"):
+        raise RuntimeError("a real casadi is on the path; the CUDA emitter needs the sympy-backed stand-in "
+                           "(put %s first on sys.path)" % _COMPAT)
+    return mod
+
+
+def to_exprs(v):
+    return symbolic_namespace().to_sympy(v)
+
 
 class _Printer(C99CodePrinter):
-    """C99 printer: small integer powers as products, every literal a double."""
-
     def _print_Pow(self, expr):
         b, e = expr.args
         if e.is_Integer and 2 <= int(e) <= 4:
@@ -42,25 +62,17 @@ def ccode(expr):
     return _printer.doprint(sp.sympify(expr))
 
 
-def emit_block(outputs, subs_map, tmp_prefix="t", indent="    ", decl="const double"):
-    """C statements assigning `outputs` = [(lhs_string, sympy_expr), ...].
-
-    subs_map maps model symbols to C lvalue strings (e.g. x_0 -> "z[2]").
-    Common subexpressions are hoisted into `const double tN` temporaries.
-    """
+def emit_block(outputs, subs_map, tmp_prefix="t", indent="    "):
+    """Statements for outputs = [(lhs, expr)] ; an lhs ending in '+' accumulates (lhs += expr)."""
     exprs = [sp.sympify(e) for _, e in outputs]
-    tmp_syms = sp.numbered_symbols(tmp_prefix)
-    rep, red = sp.cse(exprs, symbols=tmp_syms, order="none")
+    rep, red = sp.cse(exprs, symbols=sp.numbered_symbols(tmp_prefix), order="none")
     ren = {s: sp.Symbol(c) for s, c in subs_map.items()}
     lines = []
     for s, e in rep:
-        lines.append("%s%s %s = %s;" % (indent, decl, s, ccode(e.xreplace(ren))))
+        lines.append("%sconst double %s = %s;" % (indent, s, ccode(e.xreplace(ren))))
     for (lhs, _), e in zip(outputs, red):
-        lines.append("%s%s = %s;" % (indent, lhs, ccode(e.xreplace(ren))))
+        op = "="
+        if lhs.endswith("+"):
+            lhs, op = lhs[:-1].strip(), "+="
+        lines.append("%s%s %s %s;" % (indent, lhs, op, ccode(e.xreplace(ren))))
     return "\n".join(lines)
-
-
-def count_ops(outputs):
-    exprs = [sp.sympify(e) for _, e in outputs]
-    rep, red = sp.cse(exprs, order="none")
-    return sum(sp.count_ops(e) for _, e in rep) + sum(sp.count_ops(e) for e in red)

@@ -1,7 +1,7 @@
 """Load the REFERENCE's own symbolic problem definition (generation-time tooling, container only).
 
 Imports the unmodified reference scripts from /root/reference through the sympy-backed `casadi`
-stand-in (tools/casadi_shim) and returns plain sympy expressions for the dynamics, the stage cost and
+stand-in (oscar_mpc_planner_mr_modification_b200/solver_generator/casadi_compat) and returns plain sympy expressions for the dynamics, the stage cost and
 the constraints of a named configuration.  /root/reference does not exist on the GPU box, so nothing
 here is used at run time: the oracle model code (oracle/generated/*.c) and the golden vectors
 (tests/golden/*.npz) are produced from it ONCE and committed.
@@ -25,7 +25,7 @@ def reference_available():
 
 
 def _prepare_imports():
-    shim = os.path.join(_HERE, "casadi_shim")
+    shim = os.path.join(_HERE, "..", "oscar_mpc_planner_mr_modification_b200", "solver_generator", "casadi_compat")
     gen = os.path.join(REFERENCE_ROOT, "solver_generator")
     mods = os.path.join(REFERENCE_ROOT, "mpc_planner_modules", "scripts")
     for p in (mods, gen, shim):
@@ -53,8 +53,9 @@ def load_settings(max_obstacles, N):
     return settings
 
 
-def build(config_name):
-    """Returns dict with sympy symbols/expressions taken from the reference scripts."""
+def build_modules(config_name):
+    """(modules, model, settings) built from the reference's own module classes -- the three objects
+    the reference passes to generate_acados_solver()."""
     _prepare_imports()
     import contextlib
     import io
@@ -72,10 +73,6 @@ def build(config_name):
         from guidance_constraints import GuidanceConstraintModule
         from decomp_constraints import DecompConstraintModule
         from solver_model import ContouringSecondOrderUnicycleModel
-        from solver_definition import (define_parameters, objective, constraints,
-                                       constraint_lower_bounds, constraint_upper_bounds)
-        from util.parameters import AcadosParameters
-        import casadi as cd
 
     # generate_jackalsimulator_solver.py:37-58 (configuration_no_obstacles)
     modules = ModuleManager()
@@ -100,6 +97,21 @@ def build(config_name):
         modules.add_module(DecompConstraintModule(settings))
     else:
         raise KeyError(kind)
+    return modules, model, settings
+
+
+def build(config_name):
+    """Returns dict with sympy symbols/expressions taken from the reference scripts."""
+    import contextlib
+    import io
+
+    cfg = CONFIGS[config_name]
+    modules, model, settings = build_modules(config_name)
+    with contextlib.redirect_stdout(io.StringIO()):
+        from solver_definition import (define_parameters, objective, constraints,
+                                       constraint_lower_bounds, constraint_upper_bounds)
+        from util.parameters import AcadosParameters
+        import casadi as cd
 
     # generate_acados_solver.py:68-75, 27-65
     with contextlib.redirect_stdout(io.StringIO()):

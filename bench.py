@@ -1,0 +1,329 @@
+#!/usr/bin/env python3
+"""bench.py -- throughput of the batched MPC solve path (BASELINE.json metric) on N B200s.
+
+A step = one pass of the hot path over one batch of synthetic homotopy sets: every problem runs
+`num_iter` SQP-RTI iterations (one `Solver::solve()` of the reference,
+mpc_planner_solver/src/acados_solver_interface.cpp:86-204) and the best planner of every set is
+picked (guidance_constraints.cpp:572-590).  Workload = BASELINE.json configs[1]: T-MPC++ with
+8 guided + 1 non-guided planner, 12 dynamic obstacles, N=30 (generated config `c2_tmpc12`).
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
+  python bench.py --impl reference ...                     CPU arm: the oracle port on the host cores
+
+`value`   device-resident inputs, CUDA-event timed, max over ranks.
+`e2e`     same metric through the C ABI with pinned HOST buffers (H2D + kernel + D2H inside).
+`roofline`  FP64 pipe: algorithmic FLOPs (oracle/flops.json, counted by the oracle built
+          with a counting scalar type) / measured solve-kernel time, against the DFMA peak measured
+          here (MEASURED_PEAKS.json has no FP64 entry); HBM streaming reported beside it.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "MPC solves/sec (N=30 SQP-RTI batch)"
+PLANNERS = {"c1_basic": 1, "tmpc_shipped": 5, "c2_tmpc12": 9}
+
+
+def load_json(path, default=None):
+    try:
+        with open(path) as f:
+            return json.load(f)
+    except Exception:
+        return default
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return None
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 7:
+                continue
+            try:
+                sm.append(float(c[0])); mx.append(float(c[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, c[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def bytes_per_solve(d):
+    """in 8(nx + nvar(N+1) + N npar) + out 8(nx(N+1) + nu N + 3) + 8"""
+    nz = d["nx"] + d["nu"]
+    return 8 * (d["nx"] + nz * (d["N"] + 1) + d["N"] * d["npar"]) + 8 * (d["nx"] * (d["N"] + 1) + d["nu"] * d["N"] + 3) + 8
+
+
+def cpu_oracle_rate(cfg, planners, num_iter, n_sets, threads, seed=4321):
+    from oracle_binding import Oracle
+    from oscar_mpc_planner_mr_modification_b200 import synthetic
+    orc = Oracle(cfg)
+    b = synthetic.make_batch(orc.parameter_map, orc.dims, n_sets, planners, seed=seed)
+    t0 = time.perf_counter()
+    out = orc.solve_batch(b["xinit"], b["x0"], b["params"], num_iter=num_iter, threads=threads)
+    orc.select_best(b["set_offsets"], out["pobj"], out["exit_code"])
+    dt = time.perf_counter() - t0
+    return b["n"] / dt, dt, b["n"]
+
+
+def run_reference(args):
+    """CPU arm.  The reference's own implementation of the path (acados/HPIPM generated solver) cannot
+    be built here (not vendored, no network): this times the oracle port -- the only other place
+    bench.py executes oracle/ -- OpenMP over problems like guidance_constraints.cpp:304."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg, planners = args.config, PLANNERS[args.config]
+    threads = os.cpu_count() or 1
+    n_sets = args.ref_sets
+    for _ in range(min(args.warmup, 1)):
+        cpu_oracle_rate(cfg, planners, args.num_iter, max(1, n_sets // 8), threads)
+    rates, times = [], []
+    for s in range(args.steps):
+        r, dt, n = cpu_oracle_rate(cfg, planners, args.num_iter, n_sets, threads, seed=4321 + s)
+        rates.append(r); times.append(dt)
+    value = float(n * len(times) / sum(times))
+    sample = "%d homotopy sets x %d planners per step (bounded sample of the %s workload), %d SQP-RTI iterations" % (
+        n_sets, planners, cfg, args.num_iter)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(cfg, planners, args.num_iter), "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "solves/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_name(cfg, planners, num_iter):
+    return "%s: T-MPC++ homotopy sets, %d planners/set, N=30, dt=0.2, %d SQP-RTI iterations/solve" % (cfg, planners, num_iter)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2_tmpc12", choices=sorted(PLANNERS))
+    ap.add_argument("--sets", type=int, default=4096, help="homotopy sets per GPU per step")
+    ap.add_argument("--num-iter", type=int, default=10, help="SQP-RTI iterations per solve (settings.yaml:18)")
+    ap.add_argument("--ref-sets", type=int, default=48, help="homotopy sets per step of the CPU arm")
+    ap.add_argument("--cpu-sets", type=int, default=48, help="homotopy sets of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    from oscar_mpc_planner_mr_modification_b200 import engine, synthetic
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the solve path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    cfg, planners = args.config, PLANNERS[args.config]
+    n_sets = args.sets
+    n = n_sets * planners
+    eng = engine.Engine(cfg, device=local_rank, max_batch=n)
+    d = eng.dims
+    N, nx, nu, npar = d["N"], d["nx"], d["nu"], d["npar"]
+    nz = nx + nu
+
+    # ---- synthetic batch of this rank's shard (independent homotopy sets; no data-path collective)
+    t_gen = time.perf_counter()
+    batch = synthetic.make_batch(eng.parameter_map, d, n_sets, planners, seed=1234 + 7919 * rank)
+    t_gen = time.perf_counter() - t_gen
+
+    def pinned(a):
+        t = torch.empty(a.shape, dtype=torch.float64 if a.dtype == np.float64 else torch.int32, pin_memory=True)
+        t.numpy()[...] = a
+        return t
+
+    h_xinit, h_x0, h_params = pinned(batch["xinit"]), pinned(batch["x0"]), pinned(batch["params"])
+    h_offsets = pinned(batch["set_offsets"])
+    d_xinit, d_x0, d_params = h_xinit.to(dev), h_x0.to(dev), h_params.to(dev)
+    d_offsets = h_offsets.to(dev)
+    d_xtraj = torch.empty((n, (N + 1) * nx), dtype=torch.float64, device=dev)
+    d_utraj = torch.empty((n, N * nu), dtype=torch.float64, device=dev)
+    d_pobj = torch.empty(n, dtype=torch.float64, device=dev)
+    d_res = torch.empty(n, dtype=torch.float64, device=dev)
+    d_exit = torch.empty(n, dtype=torch.int32, device=dev)
+    d_qps = torch.empty(n, dtype=torch.int32, device=dev)
+    d_ipm = torch.empty(n, dtype=torch.int32, device=dev)
+    d_best = torch.empty(n_sets, dtype=torch.int32, device=dev)
+    stream = torch.cuda.Stream(device=dev)      # a real (non-default) stream: the engine launches on it, events record on it
+    torch.cuda.synchronize()
+
+    def step_device():
+        eng.solve_batch_device(n, d_xinit.data_ptr(), d_x0.data_ptr(), d_params.data_ptr(), args.num_iter, d_xtraj.data_ptr(),
+                               d_utraj.data_ptr(), d_pobj.data_ptr(), d_exit.data_ptr(), d_qps.data_ptr(), d_res.data_ptr(),
+                               ipm_iters=d_ipm.data_ptr(), stream=stream.cuda_stream)
+        eng.select_best_device(n_sets, d_offsets.data_ptr(), d_pobj.data_ptr(), d_exit.data_ptr(), d_best.data_ptr(),
+                               stream=stream.cuda_stream)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    fp64_peak = engine.measure_fp64_peak(local_rank)
+
+    # ---- value: device-resident, CUDA events on the launching stream, max over ranks
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    launches0 = eng.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ms = []
+    assert stream.cuda_stream != 0
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    total_ms = ev0.elapsed_time(ev1)
+    launches = eng.launch_count() - launches0
+    # solve-kernel duration (events recorded by the engine around the kernel, same stream): one more pass
+    for _ in range(3):
+        step_device()
+        torch.cuda.synchronize()
+        kernel_ms.append(eng.last_kernel_ms())
+    barrier()
+    clocks = sampler.stop()
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    value = world * n * args.steps / (total_ms_max * 1e-3)
+
+    exit_codes = d_exit.cpu().numpy()
+    ipm_mean = float(d_ipm.cpu().numpy().mean())
+    best = d_best.cpu().numpy()
+
+    # ---- e2e: the C-ABI call a user makes, pinned host buffers, H2D + kernel + D2H + select inside
+    out = eng.alloc_outputs(n)
+    h_out = {k: pinned(v) for k, v in out.items()}
+    np_out = {k: v.numpy() for k, v in h_out.items()}
+    xi_np, x0_np, p_np = h_xinit.numpy(), h_x0.numpy(), h_params.numpy()
+    off_np = h_offsets.numpy()
+
+    def step_e2e():
+        eng.solve_batch(xi_np, x0_np, p_np, num_iter=args.num_iter, out=np_out)
+        return eng.select_best(off_np, np_out["pobj"], np_out["exit_code"])
+
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        best_e2e = step_e2e()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * args.steps / float(t.item())
+    h2d = (h_xinit.numel() + h_x0.numel() + h_params.numel()) * 8 + (n_sets + 1) * 4 + n * 12
+    d2h = (n * ((N + 1) * nx + N * nu + 2)) * 8 + n * 12 + n_sets * 4
+    assert (best_e2e == best).all(), "device-resident and host-API paths disagree on the selected planners"
+
+    # ---- roofline of the dominant kernel (mpc_solve_kernel)
+    flops = load_json(os.path.join(ROOT, "oracle", "flops.json"), {})
+    fkey = "%s/iter%d" % (cfg, args.num_iter)
+    kms = float(np.mean(kernel_ms))
+    roofline = None
+    if fkey in flops:
+        fl = flops[fkey]
+        # scale the canonical sample figure to this batch's measured interior-point iteration count
+        fps = fl["flops_fixed_part"] + fl["flops_per_ipm_iter"] * ipm_mean
+        achieved = fps * n / (kms * 1e-3) / 1e12
+        peaks = load_json(os.path.join(ROOT, "MEASURED_PEAKS.json"), {})
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        hbm_ach = bytes_per_solve(d) * n / (kms * 1e-3) / 1e9
+        roofline = {"bound": "fp64", "kernel": "mpc_solve_kernel", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                    "frac": achieved / fp64_peak, "traffic": None,
+                    "peak_source": "DFMA micro-kernel measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
+                    "flops_per_solve": fps, "kernel_ms": kms,
+                    "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
+                            "bytes_per_solve": bytes_per_solve(d),
+                            "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"}}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only): the oracle port on the box's host cores
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = min(8, os.cpu_count() or 1)       # mirrors `omp parallel for num_threads(8)` (guidance_constraints.cpp:304)
+        rate, dt, cnt = cpu_oracle_rate(cfg, planners, args.num_iter, args.cpu_sets, threads)
+        cpu_baseline = {"value": rate, "unit": "solves/s", "cores": threads, "kind": "port",
+                        "sample": "%d homotopy sets x %d planners (%d solves, %.1f s wall) of the same workload" % (
+                            args.cpu_sets, planners, cnt, dt),
+                        "reference_measured": "20-25 ms per planner solve on the reference's own traces (BASELINE.md), i.e. 40-50 solves/s/core"}
+
+    if dist is not None:
+        lt = torch.tensor([launches], dtype=torch.float64, device=dev)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt.item())
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload_name(cfg, planners, args.num_iter), "homotopy_sets_per_gpu": n_sets,
+                           "solves_per_gpu_per_step": n, "l2": "inputs (%.2f GB/GPU) larger than L2" % (h2d / 1e9),
+                           "parallelism": "sets sharded over %d GPU(s), no collective on the solve path" % world,
+                           "success_frac": float((exit_codes == 1).mean()), "ipm_iters_mean": ipm_mean,
+                           "host_generation_s": t_gen},
+                "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks}
+        print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -89,6 +89,10 @@ int mpcgpu_select_best_device(mpcgpu_engine *e, int n_sets, const int *set_offse
                               const int *exit_code, const double *obj_scale, const double *obj_sub,
                               const unsigned char *disabled, int *best_idx, void *stream);
 
+/* Measurement helper (no reference counterpart): FP64 FMA peak of `device` in TFLOP/s from a register-
+ * resident DFMA kernel (best of 5 after warm-up).  The FP64 roofline denominator of bench.py. */
+int mpcgpu_measure_fp64_peak(int device, double *tflops);
+
 /* Kernel launches issued by this engine so far (solve + select), for bench accounting. */
 long long mpcgpu_launch_count(const mpcgpu_engine *e);
 /* Device time in ms of the most recent mpcgpu_solve_batch[_device] solve kernel (CUDA events on the

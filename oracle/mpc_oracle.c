@@ -113,7 +113,7 @@ typedef struct {
     /* IPM work */
     REAL rg[NN + 1][NZ], rg0[NN + 1][NZ], rb[NN][NX], rd[NN][NCMAX], rm[NN][NCMAX];
     REAL Ht[NN + 1][NZ * NZ], gt[NN + 1][NZ];
-    REAL P[NN + 1][NX * NX], pv[NN + 1][NX], L[NN][NZ * NZ], iL[NN][NZ], lv[NN][NU];
+    REAL P[NN + 1][NX * NX], pv[NN + 1][NX], Lx0[NN][NX], Lx1[NN][NX], L10[NN], iL[NN][NU], lv[NN][NU];
     REAL dv[NN + 1][NZ], dpi[NN + 1][NX], dlam[NN][NCMAX], dt[NN][NCMAX];
     REAL dva[NN + 1][NZ];
     int qp_warm;                     /* previous QP solution available (HPIPM warm start 2) */
@@ -464,7 +464,7 @@ static void kkt_hessian(work_t *w)
         if (k == NN) break;
         for (int e = 0; e < g_nc; e++) {
             if (!active(k, e)) continue;
-            REAL G = w->lam[k][e] / w->t[k][e];
+            REAL G = w->lam[k][e] * (1.0 / w->t[k][e]);
             if (e < NCB) { int i = (e < NZ) ? e : e - NZ; w->Ht[k][i * NZ + i] += G; }
             else {
                 int r = g_hrow[e - NCB];
@@ -486,22 +486,25 @@ static void kkt_gradient(work_t *w, int corrector, REAL sigmu)
         for (int e = 0; e < g_nc; e++) {
             if (!active(k, e)) continue;
             REAL invt = 1.0 / w->t[k][e];
-            REAL gam = w->lam[k][e] / w->t[k][e] * w->rd[k][e];
+            REAL gam = w->lam[k][e] * invt * w->rd[k][e];
             if (corrector) gam += w->dt[k][e] * w->dlam[k][e] * invt - sigmu * invt;
             crow_axpy(w, k, e, gam, w->gt[k]);
         }
     }
 }
 
-/* Backward Riccati factorisation, square-root form (as HPIPM): G_k = Ht_k + W_k' P_{k+1} W_k = L L'
- * (Cholesky), L = [Luu 0; Lxu Lxx], P_k = Lxx Lxx'.  No explicit Schur-complement subtraction.     */
+/* Backward Riccati factorisation, square-root form on the input block: G_k = Ht_k + W_k' P_{k+1} W_k,
+ * two Cholesky pivots give [Luu 0; Lxu I], and P_k = Gxx - Lxu Lxu' is the trailing update of the
+ * Cholesky factorisation (backward stable; no explicit inverse of Guu).                          */
 static void riccati_factor(work_t *w)
 {
+#if NU != 2
+#error "riccati_factor assumes NU == 2"
+#endif
     for (int i = 0; i < NX; i++)
         for (int j = 0; j < NX; j++) w->P[NN][i * NX + j] = w->Ht[NN][(NU + i) * NZ + NU + j];
     for (int k = NN - 1; k >= 0; k--) {
-        REAL PW[NX * NZ];
-        REAL *L = w->L[k];
+        REAL PW[NX * NZ], G[NZ * NZ];
         for (int i = 0; i < NX; i++)
             for (int j = 0; j < NZ; j++) {
                 REAL s = 0.0;
@@ -512,24 +515,19 @@ static void riccati_factor(work_t *w)
             for (int j = 0; j <= i; j++) {
                 REAL s = w->Ht[k][i * NZ + j];
                 for (int l = 0; l < NX; l++) s += w->W[k][l * NZ + i] * PW[l * NZ + j];
-                L[i * NZ + j] = s;
+                G[i * NZ + j] = s;
             }
-        for (int j = 0; j < NZ; j++) {
-            REAL d = L[j * NZ + j];
-            for (int m = 0; m < j; m++) d -= L[j * NZ + m] * L[j * NZ + m];
-            REAL ljj = sqrt(d), inv = 1.0 / ljj;
-            L[j * NZ + j] = ljj;
-            w->iL[k][j] = inv;
-            for (int i = j + 1; i < NZ; i++) {
-                REAL a = L[i * NZ + j];
-                for (int m = 0; m < j; m++) a -= L[i * NZ + m] * L[j * NZ + m];
-                L[i * NZ + j] = a * inv;
-            }
+        REAL i0 = 1.0 / sqrt(G[0]);
+        REAL l10 = G[NZ] * i0;
+        REAL i1 = 1.0 / sqrt(G[NZ + 1] - l10 * l10);
+        w->iL[k][0] = i0; w->iL[k][1] = i1; w->L10[k] = l10;
+        for (int i = 0; i < NX; i++) {
+            w->Lx0[k][i] = G[(NU + i) * NZ] * i0;
+            w->Lx1[k][i] = (G[(NU + i) * NZ + 1] - w->Lx0[k][i] * l10) * i1;
         }
         for (int i = 0; i < NX; i++)
             for (int j = 0; j <= i; j++) {
-                REAL s = 0.0;
-                for (int m = 0; m <= j; m++) s += L[(NU + i) * NZ + NU + m] * L[(NU + j) * NZ + NU + m];
+                REAL s = G[(NU + i) * NZ + NU + j] - w->Lx0[k][i] * w->Lx0[k][j] - w->Lx1[k][i] * w->Lx1[k][j];
                 w->P[k][i * NX + j] = s; w->P[k][j * NX + i] = s;
             }
     }
@@ -545,7 +543,6 @@ static void riccati_solve(work_t *w, REAL (*dv)[NZ])
     for (int i = 0; i < NX; i++) w->pv[NN][i] = w->gt[NN][NU + i];
     for (int k = NN - 1; k >= 0; k--) {
         REAL y[NX], q[NZ];
-        const REAL *L = w->L[k];
         for (int i = 0; i < NX; i++) {
             REAL s = 0.0;
             for (int l = 0; l < NX; l++) s += w->P[k + 1][i * NX + l] * w->rb[k][l];
@@ -557,17 +554,16 @@ static void riccati_solve(work_t *w, REAL (*dv)[NZ])
             q[j] = s;
         }
         w->lv[k][0] = q[0] * w->iL[k][0];
-        w->lv[k][1] = (q[1] - L[1 * NZ + 0] * w->lv[k][0]) * w->iL[k][1];
+        w->lv[k][1] = (q[1] - w->L10[k] * w->lv[k][0]) * w->iL[k][1];
         for (int i = 0; i < NX; i++)
-            w->pv[k][i] = q[NU + i] - L[(NU + i) * NZ + 0] * w->lv[k][0] - L[(NU + i) * NZ + 1] * w->lv[k][1];
+            w->pv[k][i] = q[NU + i] - w->Lx0[k][i] * w->lv[k][0] - w->Lx1[k][i] * w->lv[k][1];
     }
     for (int i = 0; i < NX; i++) dv[0][NU + i] = 0.0; /* dx_0 = 0: x_0 is fixed */
     for (int k = 0; k < NN; k++) {
-        const REAL *L = w->L[k];
         REAL r0 = w->lv[k][0], r1 = w->lv[k][1];
-        for (int j = 0; j < NX; j++) { r0 += L[(NU + j) * NZ + 0] * dv[k][NU + j]; r1 += L[(NU + j) * NZ + 1] * dv[k][NU + j]; }
+        for (int j = 0; j < NX; j++) { r0 += w->Lx0[k][j] * dv[k][NU + j]; r1 += w->Lx1[k][j] * dv[k][NU + j]; }
         dv[k][1] = -r1 * w->iL[k][1];
-        dv[k][0] = -(r0 + L[1 * NZ + 0] * dv[k][1]) * w->iL[k][0];
+        dv[k][0] = -(r0 + w->L10[k] * dv[k][1]) * w->iL[k][0];
         for (int i = 0; i < NX; i++) {
             REAL s = w->rb[k][i];
             for (int j = 0; j < NZ; j++) s += w->W[k][i * NZ + j] * dv[k][j];
@@ -586,14 +582,17 @@ static void riccati_solve(work_t *w, REAL (*dv)[NZ])
  *   dt = chat'dv + rd ;  dlam = -(rm_c + lam dt)/t  with rm_c = lam t (+ dt_aff dlam_aff - sigma mu)
  *      = -(lam + Gamma dt [+ (dt_aff dlam_aff - sigma mu)/t])
  * corrector != 0: w->dt/w->dlam hold the affine step on entry and are overwritten.                 */
-static void step_limit(REAL val, REAL dval, REAL *alpha)
+/* ratio test without a division per entry: the running minimum of val/(-dval) over entries with
+ * dval < 0 is kept as a fraction bn/bd (bd > 0) and compared by cross-multiplication */
+static void step_limit(REAL val, REAL dval, REAL *bn, REAL *bd)
 {
-    if (dval < 0.0 && val + *alpha * dval < 0.0) *alpha = -val / dval;
+    if (dval < 0.0 && val * *bd < *bn * (-dval)) { *bn = val; *bd = -dval; }
 }
 static REAL ipm_step_ineq(work_t *w, REAL (*dv)[NZ], int corrector, REAL sigmu)
 {
     REAL alpha = 1.0;
-    for (int k = 0; k < NN; k++)
+    for (int k = 0; k < NN; k++) {       /* per-stage fraction, then min over stages (as the warp does) */
+        REAL bn = 1.0, bd = 1.0;
         for (int e = 0; e < g_nc; e++) {
             if (!active(k, e)) { w->dt[k][e] = 0.0; w->dlam[k][e] = 0.0; continue; }
             REAL lam = w->lam[k][e], t = w->t[k][e], invt = 1.0 / t;
@@ -606,9 +605,12 @@ static REAL ipm_step_ineq(work_t *w, REAL (*dv)[NZ], int corrector, REAL sigmu)
                 dl = -(lam + lam * invt * dt);
             }
             w->dt[k][e] = dt; w->dlam[k][e] = dl;
-            step_limit(lam, dl, &alpha);
-            step_limit(t, dt, &alpha);
+            step_limit(lam, dl, &bn, &bd);
+            step_limit(t, dt, &bn, &bd);
         }
+        REAL a = bn / bd;
+        if (a < alpha) alpha = a;
+    }
     return alpha;
 }
 

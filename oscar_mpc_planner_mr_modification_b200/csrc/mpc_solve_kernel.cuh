@@ -146,33 +146,34 @@ __device__ __forceinline__ double gen_dot(const double* C, int e, const double* 
     return HSGN[e] * s;
 }
 
-// One inequality entry of the Newton step. In: lam, t, residual rd = chat'v - d - t, chat'dva, chat'dv
-// (affine and final directions), sigma*mu (0 => affine only).  Out: dt, dlam of the requested step.
+// One inequality entry of the Newton step.  lam, t, invt = 1/t, rd = chat'v - d - t, chat'dva / chat'dv =
+// entry row times the affine / final direction, sigmu = sigma*mu.
+//   dt = chat'dv + rd ;  dlam = -(lam + Gamma dt [+ (dt_aff dlam_aff - sigma mu)/t]),  Gamma = lam/t
 struct IneqStep {
-    double dt, dlam, invt, corr;
+    double dt, dlam, corr;
 };
-__device__ __forceinline__ IneqStep ineq_affine(double lam, double t, double rd, double cdva)
+__device__ __forceinline__ IneqStep ineq_affine(double lam, double invt, double rd, double cdva)
 {
     IneqStep s;
-    s.invt = 1.0 / t;
     s.dt = cdva + rd;
-    s.dlam = -(lam + lam * s.invt * s.dt);
-    s.corr = s.dt * s.dlam * s.invt;
+    s.dlam = -(lam + lam * invt * s.dt);
+    s.corr = s.dt * s.dlam * invt;
     return s;
 }
-__device__ __forceinline__ IneqStep ineq_final(double lam, double t, double rd, double cdva, double cdv, double sigmu)
+__device__ __forceinline__ IneqStep ineq_final(double lam, double invt, double rd, double cdva, double cdv, double sigmu)
 {
-    IneqStep a = ineq_affine(lam, t, rd, cdva);
+    const IneqStep a = ineq_affine(lam, invt, rd, cdva);
     IneqStep s;
-    s.invt = a.invt;
     s.dt = cdv + rd;
-    s.dlam = -(lam + lam * a.invt * s.dt + (a.corr - sigmu * a.invt));
+    s.dlam = -(lam + lam * invt * s.dt + (a.corr - sigmu * invt));
     s.corr = 0.0;
     return s;
 }
-__device__ __forceinline__ void step_limit(double val, double dval, double& alpha)
+// Step-length ratio test without a division per entry: the running minimum of val/(-dval) over the
+// entries with dval < 0 is kept as a fraction bn/bd (bd > 0) and compared by cross-multiplication.
+__device__ __forceinline__ void step_limit(double val, double dval, double& bn, double& bd)
 {
-    if (dval < 0.0 && val + alpha * dval < 0.0) alpha = -val / dval;
+    if (dval < 0.0 && val * bd < bn * (-dval)) { bn = val; bd = -dval; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -308,7 +309,10 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
         for (;; kk++) {
             // ---- pass A: residuals, norms, mu; Htilde = H + sum Gamma chat chat'; gtilde (affine)
             double Ht[NPK], gt[NZ], rb[NX];
+            double itb[NCB], itg[NCG > 0 ? NCG : 1];     // 1/t of every entry, reused by passes B-D
             double ng = 0.0, nb = 0.0, nd = 0.0, nm = 0.0, sm = 0.0;
+#pragma unroll
+            for (int e = 0; e < NCB; e++) itb[e] = 0.0;
             {
                 double qpn[NX], vxn[NX], rg[NZ];
 #pragma unroll
@@ -342,14 +346,16 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                     if (act) {
                         const double dl = LBZ[i] - z[i], du = UBZ[i] - z[i];
                         {   // lower: chat = +e_i, d = dl
-                            const double lam = lamb[i], t = tb[i];
-                            const double rd = v[i] - dl - t, G = lam / t, m = lam * t;
+                            const double lam = lamb[i], t = tb[i], it_ = 1.0 / t;
+                            const double rd = v[i] - dl - t, G = lam * it_, m = lam * t;
+                            itb[i] = it_;
                             Ht[pk(i, i)] += G; gt[i] += G * rd; rg[i] -= lam;
                             nd = nanmax(nd, fabs(rd)); nm = nanmax(nm, fabs(m)); sm += m;
                         }
                         {   // upper: chat = -e_i, d = -du
-                            const double lam = lamb[NZ + i], t = tb[NZ + i];
-                            const double rd = du - v[i] - t, G = lam / t, m = lam * t;
+                            const double lam = lamb[NZ + i], t = tb[NZ + i], it_ = 1.0 / t;
+                            const double rd = du - v[i] - t, G = lam * it_, m = lam * t;
+                            itb[NZ + i] = it_;
                             Ht[pk(i, i)] += G; gt[i] -= G * rd; rg[i] += lam;
                             nd = nanmax(nd, fabs(rd)); nm = nanmax(nm, fabs(m)); sm += m;
                         }
@@ -362,7 +368,9 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                         double cv = 0.0;
 #pragma unroll
                         for (int a = 0; a < NHS; a++) cv += C[r * NHS + a] * v[HSUP[a]];
-                        const double rd = sg * cv - dg[e] - t, G = lam / t, m = lam * t;
+                        const double it_ = 1.0 / t;
+                        const double rd = sg * cv - dg[e] - t, G = lam * it_, m = lam * t;
+                        itg[e] = it_;
 #pragma unroll
                         for (int a = 0; a < NHS; a++) {
                             const double ca = C[r * NHS + a];
@@ -397,16 +405,15 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                 break;
 
             // ---- Riccati factorisation + predictor solve.  Stage k lives on lane k; the recursion
-            //      walks down the lanes, (P, p) of stage k+1 arrive by shuffle.  Square-root form:
-            //      G = Ht + W'P+W = L L' (Cholesky, no explicit Schur-complement subtraction),
-            //      L = [Luu 0; Lxu Lxx], P = Lxx Lxx', l = Luu^-1 q_u, p = q_x - Lxu l.
-            double P[NPX], pv[NX], Lf[NPK], Prb[NX], lv[NU], iL0 = 0.0, iL1 = 0.0;
+            //      walks down the lanes, (P, p) of stage k+1 arrive by shuffle.  Square-root form on the
+            //      input block: G = Ht + W'P+W, [Luu 0; Lxu I] from two Cholesky pivots, P = Gxx - Lxu Lxu'
+            //      (the trailing update of the Cholesky factorisation: backward stable, no explicit
+            //      inverse), l = Luu^-1 q_u, p = q_x - Lxu l.
+            double P[NPX], pv[NX], Lx0[NX], Lx1[NX], Prb[NX], lv[NU], L10 = 0.0, iL0 = 0.0, iL1 = 0.0;
 #pragma unroll
             for (int i = 0; i < NPX; i++) P[i] = 0.0;
 #pragma unroll
-            for (int i = 0; i < NX; i++) { pv[i] = 0.0; Prb[i] = 0.0; }
-#pragma unroll
-            for (int i = 0; i < NPK; i++) Lf[i] = 0.0;
+            for (int i = 0; i < NX; i++) { pv[i] = 0.0; Prb[i] = 0.0; Lx0[i] = 0.0; Lx1[i] = 0.0; }
             lv[0] = lv[1] = 0.0;
             if (term) {
 #pragma unroll
@@ -424,10 +431,10 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
 #pragma unroll
                 for (int i = 0; i < NX; i++) pn[i] = shfl(pv[i], s + 1);
                 if (k == s) {
-                    double q[NZ], y[NX];
+                    double G[NPK], q[NZ], y[NX];
 #pragma unroll
-                    for (int i = 0; i < NPK; i++) Lf[i] = Ht[i];
-                    wtpw_add(Wv, Pn, Lf);
+                    for (int i = 0; i < NPK; i++) G[i] = Ht[i];
+                    wtpw_add(Wv, Pn, G);
 #pragma unroll
                     for (int i = 0; i < NX; i++) {
                         double a = 0.0;
@@ -439,37 +446,22 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
 #pragma unroll
                     for (int i = 0; i < NZ; i++) q[i] = gt[i];
                     wt_mul_add(Wv, y, q);
-                    // in-place Cholesky of the packed NZ x NZ block
+                    iL0 = rsqrt(G[pk(0, 0)]);
+                    L10 = G[pk(1, 0)] * iL0;
+                    iL1 = rsqrt(G[pk(1, 1)] - L10 * L10);
 #pragma unroll
-                    for (int j = 0; j < NZ; j++) {
-                        double d = Lf[pk(j, j)];
-#pragma unroll
-                        for (int m = 0; m < j; m++) d -= Lf[pk(j, m)] * Lf[pk(j, m)];
-                        const double ljj = sqrt(d), inv = 1.0 / ljj;
-                        Lf[pk(j, j)] = ljj;
-                        if (j == 0) iL0 = inv;
-                        if (j == 1) iL1 = inv;
-#pragma unroll
-                        for (int i = j + 1; i < NZ; i++) {
-                            double a = Lf[pk(i, j)];
-#pragma unroll
-                            for (int m = 0; m < j; m++) a -= Lf[pk(i, m)] * Lf[pk(j, m)];
-                            Lf[pk(i, j)] = a * inv;
-                        }
+                    for (int i = 0; i < NX; i++) {
+                        Lx0[i] = G[pk(NU + i, 0)] * iL0;
+                        Lx1[i] = (G[pk(NU + i, 1)] - Lx0[i] * L10) * iL1;
                     }
-                    lv[0] = q[0] * iL0;
-                    lv[1] = (q[1] - Lf[pk(1, 0)] * lv[0]) * iL1;
-#pragma unroll
-                    for (int i = 0; i < NX; i++) pv[i] = q[NU + i] - Lf[pk(NU + i, 0)] * lv[0] - Lf[pk(NU + i, 1)] * lv[1];
 #pragma unroll
                     for (int i = 0; i < NX; i++)
 #pragma unroll
-                        for (int j = 0; j <= i; j++) {
-                            double a = 0.0;
+                        for (int j = 0; j <= i; j++) P[pk(i, j)] = G[pk(NU + i, NU + j)] - Lx0[i] * Lx0[j] - Lx1[i] * Lx1[j];
+                    lv[0] = q[0] * iL0;
+                    lv[1] = (q[1] - L10 * lv[0]) * iL1;
 #pragma unroll
-                            for (int m = 0; m <= j; m++) a += Lf[pk(NU + i, NU + m)] * Lf[pk(NU + j, NU + m)];
-                            P[pk(i, j)] = a;
-                        }
+                    for (int i = 0; i < NX; i++) pv[i] = q[NU + i] - Lx0[i] * lv[0] - Lx1[i] * lv[1];
                 }
             }
             // forward sweep: dva
@@ -486,9 +478,9 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                 if (k == s) {
                     double r0 = lv[0], r1 = lv[1];      // du = -Luu^-T (Lxu' dx + l)
 #pragma unroll
-                    for (int j = 0; j < NX; j++) { r0 += Lf[pk(NU + j, 0)] * dva[NU + j]; r1 += Lf[pk(NU + j, 1)] * dva[NU + j]; }
+                    for (int j = 0; j < NX; j++) { r0 += Lx0[j] * dva[NU + j]; r1 += Lx1[j] * dva[NU + j]; }
                     dva[1] = -r1 * iL1;
-                    dva[0] = -(r0 + Lf[pk(1, 0)] * dva[1]) * iL0;
+                    dva[0] = -(r0 + L10 * dva[1]) * iL0;
 #pragma unroll
                     for (int i = 0; i < NX; i++) dxn[i] = rb[i];
                     w_mul_add(Wv, dva, dxn);
@@ -502,7 +494,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
             }
 
             // ---- pass B: affine step length, mu_aff sums, corrector vectors
-            double alpha_aff = 1.0, S1 = 0.0, S2 = 0.0, V1[NZ], V2[NZ];
+            double abn = 1.0, abd = 1.0, S1 = 0.0, S2 = 0.0, V1[NZ], V2[NZ];   // alpha_aff = abn/abd
 #pragma unroll
             for (int i = 0; i < NZ; i++) { V1[i] = 0.0; V2[i] = 0.0; }
 #pragma unroll
@@ -512,17 +504,19 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                     const double dl = LBZ[i] - z[i], du = UBZ[i] - z[i];
                     {
                         const double lam = lamb[i], t = tb[i];
-                        const IneqStep st = ineq_affine(lam, t, v[i] - dl - t, dva[i]);
-                        step_limit(lam, st.dlam, alpha_aff); step_limit(t, st.dt, alpha_aff);
+                        const double it_ = itb[i];
+                        const IneqStep st = ineq_affine(lam, it_, v[i] - dl - t, dva[i]);
+                        step_limit(lam, st.dlam, abn, abd); step_limit(t, st.dt, abn, abd);
                         S1 += lam * st.dt + t * st.dlam; S2 += st.dt * st.dlam;
-                        V1[i] += st.corr; V2[i] += st.invt;
+                        V1[i] += st.corr; V2[i] += it_;
                     }
                     {
                         const double lam = lamb[NZ + i], t = tb[NZ + i];
-                        const IneqStep st = ineq_affine(lam, t, du - v[i] - t, -dva[i]);
-                        step_limit(lam, st.dlam, alpha_aff); step_limit(t, st.dt, alpha_aff);
+                        const double it_ = itb[NZ + i];
+                        const IneqStep st = ineq_affine(lam, it_, du - v[i] - t, -dva[i]);
+                        step_limit(lam, st.dlam, abn, abd); step_limit(t, st.dt, abn, abd);
                         S1 += lam * st.dt + t * st.dlam; S2 += st.dt * st.dlam;
-                        V1[i] -= st.corr; V2[i] -= st.invt;
+                        V1[i] -= st.corr; V2[i] -= it_;
                     }
                 }
             }
@@ -533,17 +527,18 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                     double cv = 0.0, cd = 0.0;
 #pragma unroll
                     for (int a = 0; a < NHS; a++) { cv += C[r * NHS + a] * v[HSUP[a]]; cd += C[r * NHS + a] * dva[HSUP[a]]; }
-                    const IneqStep st = ineq_affine(lam, t, sg * cv - dg[e] - t, sg * cd);
-                    step_limit(lam, st.dlam, alpha_aff); step_limit(t, st.dt, alpha_aff);
+                    const double it_ = itg[e];
+                    const IneqStep st = ineq_affine(lam, it_, sg * cv - dg[e] - t, sg * cd);
+                    step_limit(lam, st.dlam, abn, abd); step_limit(t, st.dt, abn, abd);
                     S1 += lam * st.dt + t * st.dlam; S2 += st.dt * st.dlam;
 #pragma unroll
                     for (int a = 0; a < NHS; a++) {
                         V1[HSUP[a]] += sg * C[r * NHS + a] * st.corr;
-                        V2[HSUP[a]] += sg * C[r * NHS + a] * st.invt;
+                        V2[HSUP[a]] += sg * C[r * NHS + a] * it_;
                     }
                 }
             }
-            alpha_aff = warp_min(alpha_aff);
+            const double alpha_aff = warp_min(abn / abd);
             S1 = warp_sum(S1); S2 = warp_sum(S2);
             const double mu_aff = (mu * (double)IPM_COUNT + alpha_aff * S1 + alpha_aff * alpha_aff * S2) / (double)IPM_COUNT;
             const double rat = mu_aff / mu, sigmu = rat * rat * rat * mu;
@@ -568,9 +563,9 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                     for (int i = 0; i < NZ; i++) q[i] = gt[i];
                     wt_mul_add(Wv, y, q);
                     lv[0] = q[0] * iL0;
-                    lv[1] = (q[1] - Lf[pk(1, 0)] * lv[0]) * iL1;
+                    lv[1] = (q[1] - L10 * lv[0]) * iL1;
 #pragma unroll
-                    for (int i = 0; i < NX; i++) pv[i] = q[NU + i] - Lf[pk(NU + i, 0)] * lv[0] - Lf[pk(NU + i, 1)] * lv[1];
+                    for (int i = 0; i < NX; i++) pv[i] = q[NU + i] - Lx0[i] * lv[0] - Lx1[i] * lv[1];
                 }
             }
             double dv[NZ];
@@ -582,11 +577,11 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
 #pragma unroll
                 for (int i = 0; i < NX; i++) dxn[i] = 0.0;
                 if (k == s) {
-                    double r0 = lv[0], r1 = lv[1];
+                    double r0 = lv[0], r1 = lv[1];      // du = -Luu^-T (Lxu' dx + l)
 #pragma unroll
-                    for (int j = 0; j < NX; j++) { r0 += Lf[pk(NU + j, 0)] * dv[NU + j]; r1 += Lf[pk(NU + j, 1)] * dv[NU + j]; }
+                    for (int j = 0; j < NX; j++) { r0 += Lx0[j] * dv[NU + j]; r1 += Lx1[j] * dv[NU + j]; }
                     dv[1] = -r1 * iL1;
-                    dv[0] = -(r0 + Lf[pk(1, 0)] * dv[1]) * iL0;
+                    dv[0] = -(r0 + L10 * dv[1]) * iL0;
 #pragma unroll
                     for (int i = 0; i < NX; i++) dxn[i] = rb[i];
                     w_mul_add(Wv, dv, dxn);
@@ -595,21 +590,21 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                 for (int i = 0; i < NX; i++) dxn[i] = shfl(dxn[i], s);
                 if (k == s + 1) {
 #pragma unroll
-                    for (int i = 0; i < NX; i++) {
-                        dv[NU + i] = dxn[i];
-                    }
+                    for (int i = 0; i < NX; i++) dv[NU + i] = dxn[i];
+                }
+            }
+            if (k >= 1 && live) {                       // dpi_k = P_k dx_k + p_k (lane-parallel)
 #pragma unroll
-                    for (int i = 0; i < NX; i++) {
-                        double a = pv[i];
+                for (int i = 0; i < NX; i++) {
+                    double a = pv[i];
 #pragma unroll
-                        for (int j = 0; j < NX; j++) a += P[pk(i, j)] * dxn[j];
-                        dpi[i] = a;
-                    }
+                    for (int j = 0; j < NX; j++) a += P[pk(i, j)] * dv[NU + j];
+                    dpi[i] = a;
                 }
             }
 
             // ---- pass C: step length of the corrected direction
-            double al = 1.0;
+            double bn = 1.0, bd = 1.0;                  // alpha = bn/bd
 #pragma unroll
             for (int i = 0; i < NZ; i++) {
                 const bool act = (i < NU) ? path : xbox;
@@ -617,13 +612,13 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                     const double dl = LBZ[i] - z[i], du = UBZ[i] - z[i];
                     {
                         const double lam = lamb[i], t = tb[i];
-                        const IneqStep st = ineq_final(lam, t, v[i] - dl - t, dva[i], dv[i], sigmu);
-                        step_limit(lam, st.dlam, al); step_limit(t, st.dt, al);
+                        const IneqStep st = ineq_final(lam, itb[i], v[i] - dl - t, dva[i], dv[i], sigmu);
+                        step_limit(lam, st.dlam, bn, bd); step_limit(t, st.dt, bn, bd);
                     }
                     {
                         const double lam = lamb[NZ + i], t = tb[NZ + i];
-                        const IneqStep st = ineq_final(lam, t, du - v[i] - t, -dva[i], -dv[i], sigmu);
-                        step_limit(lam, st.dlam, al); step_limit(t, st.dt, al);
+                        const IneqStep st = ineq_final(lam, itb[NZ + i], du - v[i] - t, -dva[i], -dv[i], sigmu);
+                        step_limit(lam, st.dlam, bn, bd); step_limit(t, st.dt, bn, bd);
                     }
                 }
             }
@@ -637,11 +632,11 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                         const double ca = C[r * NHS + a];
                         cv += ca * v[HSUP[a]]; cda += ca * dva[HSUP[a]]; cd += ca * dv[HSUP[a]];
                     }
-                    const IneqStep st = ineq_final(lam, t, sg * cv - dg[e] - t, sg * cda, sg * cd, sigmu);
-                    step_limit(lam, st.dlam, al); step_limit(t, st.dt, al);
+                    const IneqStep st = ineq_final(lam, itg[e], sg * cv - dg[e] - t, sg * cda, sg * cd, sigmu);
+                    step_limit(lam, st.dlam, bn, bd); step_limit(t, st.dt, bn, bd);
                 }
             }
-            alpha = warp_min(al);
+            alpha = warp_min(bn / bd);
             const double a_ = alpha < 1.0 ? alpha * IPM_STEP_SCALE : alpha;
 
             // ---- pass D: update (v, pi, lam, t)
@@ -652,12 +647,12 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                     const double dl = LBZ[i] - z[i], du = UBZ[i] - z[i];
                     {
                         const double lam = lamb[i], t = tb[i];
-                        const IneqStep st = ineq_final(lam, t, v[i] - dl - t, dva[i], dv[i], sigmu);
+                        const IneqStep st = ineq_final(lam, itb[i], v[i] - dl - t, dva[i], dv[i], sigmu);
                         lamb[i] = clamp_lo(lam + a_ * st.dlam, IPM_LAM_MIN); tb[i] = clamp_lo(t + a_ * st.dt, IPM_T_MIN);
                     }
                     {
                         const double lam = lamb[NZ + i], t = tb[NZ + i];
-                        const IneqStep st = ineq_final(lam, t, du - v[i] - t, -dva[i], -dv[i], sigmu);
+                        const IneqStep st = ineq_final(lam, itb[NZ + i], du - v[i] - t, -dva[i], -dv[i], sigmu);
                         lamb[NZ + i] = clamp_lo(lam + a_ * st.dlam, IPM_LAM_MIN); tb[NZ + i] = clamp_lo(t + a_ * st.dt, IPM_T_MIN);
                     }
                 }
@@ -672,7 +667,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                         const double ca = C[r * NHS + a];
                         cv += ca * v[HSUP[a]]; cda += ca * dva[HSUP[a]]; cd += ca * dv[HSUP[a]];
                     }
-                    const IneqStep st = ineq_final(lam, t, sg * cv - dg[e] - t, sg * cda, sg * cd, sigmu);
+                    const IneqStep st = ineq_final(lam, itg[e], sg * cv - dg[e] - t, sg * cda, sg * cd, sigmu);
                     lamg[e] = clamp_lo(lam + a_ * st.dlam, IPM_LAM_MIN); tg[e] = clamp_lo(t + a_ * st.dt, IPM_T_MIN);
                 }
             }

@@ -37,6 +37,23 @@ __global__ void select_best_kernel(int n_sets, const int* __restrict__ set_offse
     }
     best_idx[s] = bi;
 }
+
+// FP64 roofline denominator: MEASURED_PEAKS.json has no FP64 entry, so bench.py measures the DFMA peak
+// with this kernel: 8 independent FMA chains per thread, 2 flops per FMA.
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double seed)
+{
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 0.999999, c = 1e-9;
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+            a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
 }  // namespace
 
 void mpc_register_config(const MpcConfigOps* ops) { registry().push_back(ops); }
@@ -236,6 +253,35 @@ int mpcgpu_select_best(mpcgpu_engine* e, int n_sets, const int* set_offsets, con
     if (rc != MPCGPU_OK) return rc;
     CK(cudaMemcpyAsync(best_idx, e->d_best, (size_t)n_sets * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    return MPCGPU_OK;
+}
+
+int mpcgpu_measure_fp64_peak(int device, double* tflops)
+{
+    if (!tflops) return MPCGPU_ERR_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return MPCGPU_ERR_NO_DEVICE;
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const int blocks = sms * 8, threads = 256, iters = 4096;
+    double* out = nullptr;
+    if (cudaMalloc((void**)&out, (size_t)blocks * threads * 8) != cudaSuccess) return MPCGPU_ERR_CUDA;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 6; rep++) {
+        cudaEventRecord(e0);
+        dfma_peak_kernel<<<blocks, threads>>>(out, iters, 1.0 + rep);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(out); return MPCGPU_ERR_CUDA; }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flops = 2.0 * 64.0 * (double)iters * (double)blocks * (double)threads;
+        const double tf = flops / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(out);
+    *tflops = best;
     return MPCGPU_OK;
 }
 

@@ -15,7 +15,7 @@ _lib = None
 SYMBOLS = [
     "mpcgpu_num_configs", "mpcgpu_config_name", "mpcgpu_engine_create", "mpcgpu_engine_destroy", "mpcgpu_desc_query",
     "mpcgpu_mem_doubles", "mpcgpu_solve_batch", "mpcgpu_solve_batch_device", "mpcgpu_sync", "mpcgpu_select_best",
-    "mpcgpu_select_best_device", "mpcgpu_launch_count", "mpcgpu_last_kernel_ms", "mpcgpu_last_error",
+    "mpcgpu_select_best_device", "mpcgpu_measure_fp64_peak", "mpcgpu_launch_count", "mpcgpu_last_kernel_ms", "mpcgpu_last_error",
 ]
 
 
@@ -69,6 +69,15 @@ def _ptr(a):
     if isinstance(a, np.ndarray):
         return a.ctypes.data_as(ctypes.c_void_p)
     return ctypes.c_void_p(int(a))   # raw device address (e.g. torch.Tensor.data_ptr())
+
+
+def measure_fp64_peak(device=0):
+    lib = load_library()
+    v = ctypes.c_double()
+    rc = lib.mpcgpu_measure_fp64_peak(int(device), ctypes.byref(v))
+    if rc != 0:
+        raise RuntimeError("mpcgpu_measure_fp64_peak failed: %d" % rc)
+    return v.value
 
 
 class MpcGpuError(RuntimeError):

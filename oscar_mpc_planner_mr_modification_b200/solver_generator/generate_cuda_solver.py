@@ -220,12 +220,18 @@ def emit_model_header(pb, name, sim_steps=3):
     Ps = sp.symbols("P0:%d" % npx)
     Pm = sp.Matrix(nx, nx, lambda i, j: Ps[_idx(i, j)])
     Pmap = {Ps[i]: "P[%d]" % i for i in range(npx)}
-    G = Wsym.T * Pm * Wsym
+    # two-step product T = P W, G += W' T: both steps only touch the structural non-zeros of W
+    Ts = sp.Matrix(nx, nz, lambda i, j: sp.Symbol("T%d_%d" % (i, j)))
+    Tm = Pm * Wsym
     mm = dict(wmap)
     mm.update(Pmap)
-    w("\n// G(packed NZ) += W' P W   (P packed NX)")
+    G = Wsym.T * Ts
+    w("\n// G(packed NZ) += W' P W   (P packed NX); T = P W first, then W' T")
     w("__device__ __forceinline__ void wtpw_add(const double* Wv, const double* P, double* G)\n{")
-    w(emit_block([("G[%d] +" % _idx(i, j), sp.expand(G[i, j])) for i in range(nz) for j in range(i + 1) if G[i, j] != 0], mm))
+    w(emit_block([("const double T%d_%d" % (i, j), Tm[i, j]) for i in range(nx) for j in range(nz)], mm, tmp_prefix="a"))
+    mt = dict(wmap)
+    mt.update({Ts[i, j]: "T%d_%d" % (i, j) for i in range(nx) for j in range(nz)})
+    w(emit_block([("G[%d] +" % _idx(i, j), G[i, j]) for i in range(nz) for j in range(i + 1) if G[i, j] != 0], mt, tmp_prefix="b"))
     w("}")
     vs = sp.symbols("v0:%d" % nz)
     ys = sp.symbols("y0:%d" % nx)

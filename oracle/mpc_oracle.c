@@ -62,7 +62,7 @@
 #define IPM_STEP_SCALE 0.995
 #define RES_EQ_MAX 1e-2      /* acados_solver_interface.cpp:177 */
 #define JACOBI_MAX_SWEEPS 30
-#define JACOBI_TOL 1e-30     /* stop when sum offdiag^2 <= tol * sum all^2 */
+#define JACOBI_TOL 1e-24     /* stop when sum offdiag^2 <= tol * sum all^2 */
 
 /* compact constraint list of one path stage: [u lower NU][u upper NU][x lower NX][x upper NX][h rows] */
 #define NCB (2 * NZ)
@@ -263,9 +263,10 @@ static void mirror(REAL *A, int n, int ld)
             for (int q = p + 1; q < n; q++) {
                 REAL apq = a[p][q];
                 if (apq == 0.0) continue;
-                REAL theta = (a[q][q] - a[p][p]) / (2.0 * apq);
-                REAL tt = 1.0 / (fabs(theta) + sqrt(theta * theta + 1.0));
-                if (theta < 0.0) tt = -tt;
+                /* t = 2 a_pq / (tau + sign(tau) sqrt(tau^2 + 4 a_pq^2)), tau = a_qq - a_pp */
+                REAL tau = a[q][q] - a[p][p];
+                REAL r = sqrt(tau * tau + 4.0 * apq * apq);
+                REAL tt = 2.0 * apq / (tau + (tau >= 0.0 ? r : -r));
                 REAL c = 1.0 / sqrt(tt * tt + 1.0), s = tt * c;
                 for (int k = 0; k < n; k++) {
                     if (k == p || k == q) continue;

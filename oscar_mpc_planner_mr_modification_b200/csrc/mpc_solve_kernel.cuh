@@ -48,7 +48,7 @@ constexpr double IPM_T_MIN = 1e-16;
 constexpr double IPM_STEP_SCALE = 0.995;
 constexpr double RES_EQ_MAX = 1e-2;
 constexpr int JACOBI_MAX_SWEEPS = 30;
-constexpr double JACOBI_TOL = 1e-30;
+constexpr double JACOBI_TOL = 1e-24;   // stop when sum offdiag^2 <= tol * sum all^2
 // inequality entries over the whole horizon: u box + general on N stages, x box on stages 1..N-1
 constexpr int IPM_COUNT = NSTAGE * (2 * NU + NCG) + (NSTAGE - 1) * 2 * NX;
 
@@ -79,58 +79,74 @@ __device__ __forceinline__ double warp_sum(double v)
 }
 
 // ---- K4: MIRROR regularisation of one packed symmetric NZ x NZ block (cyclic Jacobi) -----------
+// Register-resident: the 21 rotations of a sweep are fully unrolled so that the matrix (packed) and the
+// eigenvector matrix are indexed statically.  Rotation: t = 2 a_pq / (tau + sign(tau) sqrt(tau^2 + 4 a_pq^2)),
+// tau = a_qq - a_pp, c = 1/sqrt(t^2+1), s = t c  (one sqrt, one division, one rsqrt).
 __device__ __noinline__ void mirror_packed(double* Hp)
 {
-    double a[NZ][NZ], V[NZ][NZ];
+    double a[NPK], V[NZ][NZ];
+#pragma unroll
+    for (int i = 0; i < NPK; i++) a[i] = Hp[i];
+#pragma unroll
     for (int i = 0; i < NZ; i++)
-        for (int j = 0; j < NZ; j++) {
-            a[i][j] = Hp[pk(i, j)];
-            V[i][j] = (i == j) ? 1.0 : 0.0;
-        }
+#pragma unroll
+        for (int j = 0; j < NZ; j++) V[i][j] = (i == j) ? 1.0 : 0.0;
+#pragma unroll 1
     for (int sweep = 0; sweep < JACOBI_MAX_SWEEPS; sweep++) {
-        double off = 0.0, tot = 0.0;
+        double off = 0.0, dia = 0.0;
+#pragma unroll
         for (int i = 0; i < NZ; i++)
-            for (int j = 0; j < NZ; j++) {
-                tot += a[i][j] * a[i][j];
-                if (i != j) off += a[i][j] * a[i][j];
+#pragma unroll
+            for (int j = 0; j <= i; j++) {
+                if (i == j) dia += a[pk(i, j)] * a[pk(i, j)];
+                else off += a[pk(i, j)] * a[pk(i, j)];
             }
-        if (!(off > JACOBI_TOL * tot)) break;
+        off *= 2.0;
+        if (!(off > JACOBI_TOL * (off + dia))) break;
+#pragma unroll
         for (int p = 0; p < NZ - 1; p++)
+#pragma unroll
             for (int q = p + 1; q < NZ; q++) {
-                const double apq = a[p][q];
-                if (apq == 0.0) continue;
-                const double theta = (a[q][q] - a[p][p]) / (2.0 * apq);
-                double tt = 1.0 / (fabs(theta) + sqrt(theta * theta + 1.0));
-                if (theta < 0.0) tt = -tt;
-                const double c = 1.0 / sqrt(tt * tt + 1.0), s = tt * c;
-                for (int k = 0; k < NZ; k++) {
-                    if (k == p || k == q) continue;
-                    const double akp = a[k][p], akq = a[k][q];
-                    const double np_ = c * akp - s * akq, nq_ = s * akp + c * akq;
-                    a[k][p] = np_; a[p][k] = np_;
-                    a[k][q] = nq_; a[q][k] = nq_;
-                }
-                const double app = a[p][p], aqq = a[q][q];
-                a[p][p] = app - tt * apq;
-                a[q][q] = aqq + tt * apq;
-                a[p][q] = 0.0; a[q][p] = 0.0;
-                for (int k = 0; k < NZ; k++) {
-                    const double vkp = V[k][p], vkq = V[k][q];
-                    V[k][p] = c * vkp - s * vkq;
-                    V[k][q] = s * vkp + c * vkq;
+                const double apq = a[pk(q, p)];
+                if (apq != 0.0) {
+                    const double tau = a[pk(q, q)] - a[pk(p, p)];
+                    const double r = sqrt(tau * tau + 4.0 * apq * apq);
+                    const double tt = 2.0 * apq / (tau + (tau >= 0.0 ? r : -r));
+                    const double c = rsqrt(tt * tt + 1.0), sn = tt * c;
+#pragma unroll
+                    for (int k = 0; k < NZ; k++) {
+                        if (k != p && k != q) {
+                            const double akp = a[pk(k, p)], akq = a[pk(k, q)];
+                            a[pk(k, p)] = c * akp - sn * akq;
+                            a[pk(k, q)] = sn * akp + c * akq;
+                        }
+                    }
+                    a[pk(p, p)] -= tt * apq;
+                    a[pk(q, q)] += tt * apq;
+                    a[pk(q, p)] = 0.0;
+#pragma unroll
+                    for (int k = 0; k < NZ; k++) {
+                        const double vkp = V[k][p], vkq = V[k][q];
+                        V[k][p] = c * vkp - sn * vkq;
+                        V[k][q] = sn * vkp + c * vkq;
+                    }
                 }
             }
     }
     double ev[NZ];
+#pragma unroll
     for (int i = 0; i < NZ; i++) {
-        double e = a[i][i];
+        double e = a[pk(i, i)];
         if (e >= -REG_EPS && e <= REG_EPS) e = REG_EPS;
         else if (e < 0.0) e = -e;
         ev[i] = e;
     }
+#pragma unroll
     for (int i = 0; i < NZ; i++)
+#pragma unroll
         for (int j = 0; j <= i; j++) {
             double s = 0.0;
+#pragma unroll
             for (int k = 0; k < NZ; k++) s += V[i][k] * ev[k] * V[j][k];
             Hp[pk(i, j)] = s;
         }
@@ -743,11 +759,17 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
     }
 }
 
-constexpr int WARPS_PER_CTA = 4;
+#ifndef MPC_WARPS_PER_CTA
+#define MPC_WARPS_PER_CTA 4
+#endif
+#ifndef MPC_MIN_CTAS
+#define MPC_MIN_CTAS 2
+#endif
+constexpr int WARPS_PER_CTA = MPC_WARPS_PER_CTA;
 
 // Persistent grid: warps pull problem indices from a global counter (work per problem is data
 // dependent: 50-100 interior-point iterations), so late finishers do not idle a whole CTA.
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, MPC_MIN_CTAS)
 mpc_solve_kernel(int n, const double* __restrict__ xinit, const double* __restrict__ x0, const double* __restrict__ params,
                  const int* __restrict__ num_iter, int num_iter_all, double* mem, int mem_doubles, double* xtraj,
                  double* utraj, double* pobj, int* exit_code, int* qp_status, double* res_eq, int* ipm_iters,

@@ -165,7 +165,9 @@ int mpcgpu_solve_batch_device(mpcgpu_engine* e, int n, const double* xinit, cons
     if (n == 0) return MPCGPU_OK;
     CK(cudaSetDevice(e->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
-    const int warps_per_cta = 4;
+    int ctas_ = 0, threads_ = 128;
+    e->ops->occupancy(&ctas_, &threads_);
+    const int warps_per_cta = threads_ / 32;
     int grid = (n + warps_per_cta - 1) / warps_per_cta;
     if (grid > e->grid) grid = e->grid;
     CK(cudaEventRecord(e->ev0, st));

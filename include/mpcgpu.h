@@ -89,6 +89,17 @@ int mpcgpu_select_best_device(mpcgpu_engine *e, int n_sets, const int *set_offse
                               const int *exit_code, const double *obj_scale, const double *obj_sub,
                               const unsigned char *disabled, int *best_idx, void *stream);
 
+/* Diagnostic (tests): evaluate the emitted model device functions at n points (HOST arrays).
+ * Replaces nothing at run time; it is the hook that pins the CasADi-generated functions' counterparts
+ * (Solver_model / Solver_cost / Solver_constraints of the generated acados solver) to golden vectors.
+ *   z [n*(nu+nx)], p [n*npar], pi [n*nx] (multipliers weighting d2Phi), mh [n*nh] (weights of d2h)
+ *   out[n*D], D = mpcgpu_model_eval_doubles(): xn[nx] | W[nx*nz] | Hdyn[pk] | cost | g[nz] (dt-scaled) |
+ *   Hcost[pk] (dt-scaled) | h[nh] | C[nh*nhs] | Hcon[pk];  pk = nz(nz+1)/2 packed lower triangle,
+ *   nhs = number of variables h depends on (returned through *nhs). */
+int mpcgpu_model_eval_doubles(const mpcgpu_engine *e, int *nhs);
+int mpcgpu_model_eval(mpcgpu_engine *e, int n, const double *z, const double *p, const double *pi, const double *mh,
+                      double *out);
+
 /* Measurement helper (no reference counterpart): FP64 FMA peak of `device` in TFLOP/s from a register-
  * resident DFMA kernel (best of 5 after warm-up).  The FP64 roofline denominator of bench.py. */
 int mpcgpu_measure_fp64_peak(int device, double *tflops);

@@ -24,7 +24,15 @@ static cudaError_t occupancy(int* ctas_per_sm, int* threads_per_cta)
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, mpc_solve_kernel, WARPS_PER_CTA * 32, 0);
 }
 
-static const MpcConfigOps ops = {MPCGEN_CONFIG_NAME, NSTAGE, NX, NU, NP, NH, NC, MEM_DOUBLES, launch_solve, occupancy};
+static cudaError_t launch_model_eval(cudaStream_t stream, int n, const double* z, const double* p, const double* pi,
+                                     const double* mh, double* out)
+{
+    model_eval_kernel<<<(n + 63) / 64, 64, 0, stream>>>(n, z, p, pi, mh, out);
+    return cudaGetLastError();
+}
+
+static const MpcConfigOps ops = {MPCGEN_CONFIG_NAME, NSTAGE, NX, NU, NP, NH, NC, MEM_DOUBLES, launch_solve, occupancy,
+                                 NHS, MODEL_EVAL_DOUBLES, launch_model_eval};
 
 static struct Registrar {
     Registrar() { mpc_register_config(&ops); }

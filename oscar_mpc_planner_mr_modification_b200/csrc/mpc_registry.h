@@ -10,6 +10,9 @@ struct MpcConfigOps {
                                 double* xtraj, double* utraj, double* pobj, int* exit_code, int* qp_status,
                                 double* res_eq, int* ipm_iters, int* work_counter);
     cudaError_t (*occupancy)(int* ctas_per_sm, int* threads_per_cta);
+    int nhs, model_eval_doubles;
+    cudaError_t (*launch_model_eval)(cudaStream_t stream, int n, const double* z, const double* p, const double* pi,
+                                     const double* mh, double* out);
 };
 
 void mpc_register_config(const MpcConfigOps* ops);

@@ -787,4 +787,36 @@ mpc_solve_kernel(int n, const double* __restrict__ xinit, const double* __restri
     }
 }
 
+// Diagnostic kernel (tests): evaluates the emitted model functions at n points, one thread per point.
+// out layout per point: xn[NX] | W[NX*NZ] | Hdyn[NPK] | cost | g[NZ] | Hcost[NPK] | h[NH] | C[NH*NHS] | Hcon[NPK]
+constexpr int MODEL_EVAL_DOUBLES = NX + NX * NZ + NPK + 1 + NZ + NPK + NH + NH * NHS + NPK;
+__global__ void model_eval_kernel(int n, const double* __restrict__ z_g, const double* __restrict__ p_g,
+                                  const double* __restrict__ pi_g, const double* __restrict__ mh_g, double* __restrict__ out_g)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double z[NZ], pi[NX], mh[NH > 0 ? NH : 1], xn[NX], Wv[NWV], Wd[NX * NZ], H[NPK], g[NZ], hv[NH > 0 ? NH : 1], C[NH > 0 ? NH * NHS : 1];
+    const double* p = p_g + (size_t)i * NP;
+    for (int j = 0; j < NZ; j++) z[j] = z_g[(size_t)i * NZ + j];
+    for (int j = 0; j < NX; j++) pi[j] = pi_g[(size_t)i * NX + j];
+    for (int j = 0; j < NH; j++) mh[j] = mh_g[(size_t)i * NH + j];
+    double* o = out_g + (size_t)i * MODEL_EVAL_DOUBLES;
+    for (int j = 0; j < NPK; j++) H[j] = 0.0;
+    dyn_lin(z, pi, xn, Wv, H);
+    w_to_dense(Wv, Wd);
+    for (int j = 0; j < NX; j++) *o++ = xn[j];
+    for (int j = 0; j < NX * NZ; j++) *o++ = Wd[j];
+    for (int j = 0; j < NPK; j++) *o++ = H[j];
+    *o++ = cost_val(z, p);
+    cost_lin(z, p, g, H);
+    for (int j = 0; j < NZ; j++) *o++ = g[j];
+    for (int j = 0; j < NPK; j++) *o++ = H[j];
+    con_eval(z, p, hv, C);
+    for (int j = 0; j < NH; j++) *o++ = hv[j];
+    for (int j = 0; j < NH * NHS; j++) *o++ = C[j];
+    for (int j = 0; j < NPK; j++) H[j] = 0.0;
+    con_hess_add(z, p, mh, H);
+    for (int j = 0; j < NPK; j++) *o++ = H[j];
+}
+
 }  // namespace MPC_NS

@@ -258,6 +258,33 @@ int mpcgpu_select_best(mpcgpu_engine* e, int n_sets, const int* set_offsets, con
     return MPCGPU_OK;
 }
 
+int mpcgpu_model_eval_doubles(const mpcgpu_engine* e, int* nhs) { if (!e) return MPCGPU_ERR_ARG; if (nhs) *nhs = e->ops->nhs; return e->ops->model_eval_doubles; }
+
+int mpcgpu_model_eval(mpcgpu_engine* e, int n, const double* z, const double* p, const double* pi, const double* mh, double* out)
+{
+    if (!e || n <= 0 || !z || !p || !pi || !mh || !out) return MPCGPU_ERR_ARG;
+    CK(cudaSetDevice(e->device));
+    const MpcConfigOps* o = e->ops;
+    const size_t sz[5] = {(size_t)n * (o->nx + o->nu) * 8, (size_t)n * o->np * 8, (size_t)n * o->nx * 8,
+                          (size_t)n * (o->nh > 0 ? o->nh : 1) * 8, (size_t)n * o->model_eval_doubles * 8};
+    const void* src[4] = {z, p, pi, mh};
+    void* d[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    int rc = MPCGPU_OK;
+    for (int i = 0; i < 5 && rc == MPCGPU_OK; i++)
+        if (cudaMalloc(&d[i], sz[i]) != cudaSuccess) rc = MPCGPU_ERR_CUDA;
+    for (int i = 0; i < 4 && rc == MPCGPU_OK; i++)
+        if (cudaMemcpy(d[i], src[i], i == 3 ? (size_t)n * o->nh * 8 : sz[i], cudaMemcpyHostToDevice) != cudaSuccess) rc = MPCGPU_ERR_CUDA;
+    if (rc == MPCGPU_OK) {
+        if (o->launch_model_eval(e->stream, n, (double*)d[0], (double*)d[1], (double*)d[2], (double*)d[3], (double*)d[4]) != cudaSuccess ||
+            cudaStreamSynchronize(e->stream) != cudaSuccess || cudaMemcpy(out, d[4], sz[4], cudaMemcpyDeviceToHost) != cudaSuccess)
+            rc = MPCGPU_ERR_CUDA;
+    }
+    if (rc != MPCGPU_OK) e->err = std::string("mpcgpu_model_eval: ") + cudaGetErrorString(cudaGetLastError());
+    for (void* q : d)
+        if (q) cudaFree(q);
+    return rc;
+}
+
 int mpcgpu_measure_fp64_peak(int device, double* tflops)
 {
     if (!tflops) return MPCGPU_ERR_ARG;

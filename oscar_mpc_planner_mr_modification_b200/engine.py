@@ -15,7 +15,7 @@ _lib = None
 SYMBOLS = [
     "mpcgpu_num_configs", "mpcgpu_config_name", "mpcgpu_engine_create", "mpcgpu_engine_destroy", "mpcgpu_desc_query",
     "mpcgpu_mem_doubles", "mpcgpu_solve_batch", "mpcgpu_solve_batch_device", "mpcgpu_sync", "mpcgpu_select_best",
-    "mpcgpu_select_best_device", "mpcgpu_measure_fp64_peak", "mpcgpu_launch_count", "mpcgpu_last_kernel_ms", "mpcgpu_last_error",
+    "mpcgpu_select_best_device", "mpcgpu_model_eval_doubles", "mpcgpu_model_eval", "mpcgpu_measure_fp64_peak", "mpcgpu_launch_count", "mpcgpu_last_kernel_ms", "mpcgpu_last_error",
 ]
 
 
@@ -178,6 +178,26 @@ class Engine:
         rc = self.lib.mpcgpu_select_best_device(self.handle, n_sets, _ptr(set_offsets), _ptr(pobj), _ptr(exit_code),
                                                 _ptr(obj_scale), _ptr(obj_sub), _ptr(disabled), _ptr(best_idx), _ptr(stream))
         self._check(rc, "mpcgpu_select_best_device")
+
+    def model_eval(self, z, p, pi, mh):
+        """Evaluate the emitted device model functions at n points; returns a dict of arrays."""
+        n = z.shape[0]
+        nhs = ctypes.c_int()
+        self.lib.mpcgpu_model_eval_doubles.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int)]
+        D = self.lib.mpcgpu_model_eval_doubles(self.handle, ctypes.byref(nhs))
+        nhs = nhs.value
+        out = np.zeros((n, D))
+        self.lib.mpcgpu_model_eval.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 5
+        zz, pp, pi_, mh_ = (np.ascontiguousarray(a, np.float64) for a in (z, p, pi, mh))
+        self._check(self.lib.mpcgpu_model_eval(self.handle, n, _ptr(zz), _ptr(pp), _ptr(pi_), _ptr(mh_), _ptr(out)), "mpcgpu_model_eval")
+        nx, nz, nh = self.nx, self.nz, self.nh
+        pk = nz * (nz + 1) // 2
+        sizes = [("xn", nx), ("W", nx * nz), ("Hdyn", pk), ("cost", 1), ("g", nz), ("Hcost", pk), ("h", nh), ("C", nh * nhs), ("Hcon", pk)]
+        res, o = {"nhs": nhs}, 0
+        for name, sz in sizes:
+            res[name] = out[:, o:o + sz]
+            o += sz
+        return res
 
     def sync(self):
         self._check(self.lib.mpcgpu_sync(self.handle), "mpcgpu_sync")

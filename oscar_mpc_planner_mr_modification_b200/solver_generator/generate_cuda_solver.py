@@ -233,6 +233,10 @@ def emit_model_header(pb, name, sim_steps=3):
     mt.update({Ts[i, j]: "T%d_%d" % (i, j) for i in range(nx) for j in range(nz)})
     w(emit_block([("G[%d] +" % _idx(i, j), G[i, j]) for i in range(nz) for j in range(i + 1) if G[i, j] != 0], mt, tmp_prefix="b"))
     w("}")
+    w("\n// dense row-major NX x NZ sensitivity matrix from its varying entries (diagnostics / tests)")
+    w("__device__ __forceinline__ void w_to_dense(const double* Wv, double* Wd)\n{")
+    w(emit_block([("Wd[%d]" % (i * nz + j), Wsym[i, j]) for i in range(nx) for j in range(nz)], dict(wmap), tmp_prefix="c"))
+    w("}")
     vs = sp.symbols("v0:%d" % nz)
     ys = sp.symbols("y0:%d" % nx)
     Wv_ = Wsym * sp.Matrix(vs)

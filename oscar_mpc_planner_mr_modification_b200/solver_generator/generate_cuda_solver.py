@@ -321,6 +321,10 @@ def generate_cuda_solver(modules, settings, model, name, out_dir):
         f.write(emit_model_header(pb, name))
     with open(os.path.join(out_dir, "mpc_planner_parameters.h"), "w") as f:
         f.write(emit_parameter_header(pb))
+    with open(os.path.join(out_dir, "solver_dims.h"), "w") as f:      # the SOLVER_* macros of acados_solver_Solver.h
+        f.write("// GENERATED -- dimensions the reference takes from Solver/acados_solver_Solver.h\n#pragma once\n"
+                "#define SOLVER_N %d\n#define SOLVER_NX %d\n#define SOLVER_NU %d\n#define SOLVER_NP %d\n#define SOLVER_NH %d\n"
+                "#define MPCGPU_CONFIG_NAME \"%s\"\n" % (pb["N"], pb["nx"], pb["nu"], len(pb["p"]), len(pb["h"]), name))
     pmap = {n: i for i, n in enumerate(pb["param_names"])}
     pmap["num parameters"] = len(pb["param_names"])       # util/parameters.py:72
     with open(os.path.join(out_dir, "parameter_map.yaml"), "w") as f:

@@ -245,45 +245,60 @@ static void integrate(const REAL *x, const REAL *u, const REAL *p, REAL *xn, REA
  * ---------------------------------------------------------------------------------------------- */
 static void mirror(REAL *A, int n, int ld)
 {
-    REAL a[NZ][NZ], V[NZ][NZ], ev[NZ];
+    /* Pair order: round-robin tournament on np = n + (n odd) positions (an odd n gets a decoupled dummy
+     * position): every round rotates the position pairs (0,np-1) (1,np-2) ... and then shifts positions
+     * 1..np-1 cyclically; after np-1 rounds (one sweep) the arrangement is back to the identity.
+     * Rotation: ir = 1/sqrt(tau^2 + 4 a_pq^2), cos^2 = (1 + |tau| ir)/2, c = sqrt(cos^2),
+     * s = sign(tau) a_pq ir / c, t = s / c  (tau = a_qq - a_pp).                                    */
+    enum { MAXP = NZ + 1 };
+    const int np = n + (n & 1);
+    REAL a[MAXP][MAXP], V[NZ][MAXP], ev[NZ];
+    int pos[MAXP];                       /* pos[j] = variable sitting at position j (np-1 may be the dummy) */
+    for (int i = 0; i < np; i++) {
+        pos[i] = i;
+        for (int j = 0; j < np; j++) a[i][j] = (i < n && j < n) ? 0.5 * (A[i * ld + j] + A[j * ld + i]) : 0.0;
+    }
     for (int i = 0; i < n; i++)
-        for (int j = 0; j < n; j++) {
-            a[i][j] = 0.5 * (A[i * ld + j] + A[j * ld + i]);
-            V[i][j] = (i == j) ? 1.0 : 0.0;
-        }
+        for (int j = 0; j < np; j++) V[i][j] = (i == j) ? 1.0 : 0.0;
     for (int sweep = 0; sweep < JACOBI_MAX_SWEEPS; sweep++) {
-        REAL off = 0.0, tot = 0.0;
+        REAL off = 0.0, dia = 0.0;
         for (int i = 0; i < n; i++)
-            for (int j = 0; j < n; j++) {
-                tot += a[i][j] * a[i][j];
-                if (i != j) off += a[i][j] * a[i][j];
+            for (int j = 0; j <= i; j++) {
+                if (i == j) dia += a[i][j] * a[i][j];
+                else off += a[i][j] * a[i][j];
             }
-        if (!(off > JACOBI_TOL * tot)) break;
-        for (int p = 0; p < n - 1; p++)
-            for (int q = p + 1; q < n; q++) {
-                REAL apq = a[p][q];
-                if (apq == 0.0) continue;
-                /* t = 2 a_pq / (tau + sign(tau) sqrt(tau^2 + 4 a_pq^2)), tau = a_qq - a_pp */
+        off *= 2.0;
+        if (!(off > JACOBI_TOL * (off + dia))) break;
+        for (int round = 0; round < np - 1; round++) {
+            for (int pr = 0; pr < np / 2; pr++) {
+                const int p = pos[pr], q = pos[np - 1 - pr];   /* variables (matrix kept in variable order) */
+                REAL apq = a[q][p], q2 = apq * apq;
+                if (!(q2 > 0.0)) continue;
+                /* orientation as in the kernel: "p" is the lower position, "q" the higher one */
                 REAL tau = a[q][q] - a[p][p];
-                REAL r = sqrt(tau * tau + 4.0 * apq * apq);
-                REAL tt = 2.0 * apq / (tau + (tau >= 0.0 ? r : -r));
-                REAL c = 1.0 / sqrt(tt * tt + 1.0), s = tt * c;
-                for (int k = 0; k < n; k++) {
+                REAL ir = 1.0 / sqrt(tau * tau + 4.0 * q2);
+                REAL c2 = 0.5 + 0.5 * fabs(tau) * ir;
+                REAL ic = 1.0 / sqrt(c2), c = c2 * ic;
+                REAL sn = (tau >= 0.0 ? apq : -apq) * ir * ic, tt = sn * ic;
+                for (int k = 0; k < np; k++) {
                     if (k == p || k == q) continue;
                     REAL akp = a[k][p], akq = a[k][q];
-                    a[k][p] = a[p][k] = c * akp - s * akq;
-                    a[k][q] = a[q][k] = s * akp + c * akq;
+                    a[k][p] = a[p][k] = c * akp - sn * akq;
+                    a[k][q] = a[q][k] = sn * akp + c * akq;
                 }
-                REAL app = a[p][p], aqq = a[q][q];
-                a[p][p] = app - tt * apq;
-                a[q][q] = aqq + tt * apq;
+                a[p][p] -= tt * apq;
+                a[q][q] += tt * apq;
                 a[p][q] = a[q][p] = 0.0;
                 for (int k = 0; k < n; k++) {
                     REAL vkp = V[k][p], vkq = V[k][q];
-                    V[k][p] = c * vkp - s * vkq;
-                    V[k][q] = s * vkp + c * vkq;
+                    V[k][p] = c * vkp - sn * vkq;
+                    V[k][q] = sn * vkp + c * vkq;
                 }
             }
+            int last = pos[np - 1];
+            for (int j = np - 1; j >= 2; j--) pos[j] = pos[j - 1];
+            pos[1] = last;
+        }
     }
     for (int i = 0; i < n; i++) {
         REAL e = a[i][i];

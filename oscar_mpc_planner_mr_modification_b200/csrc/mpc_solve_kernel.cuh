@@ -31,6 +31,7 @@ using namespace mpcgen;
 static_assert(NSTAGE + 1 <= 32, "lane-per-stage kernel needs N <= 31");
 static_assert(NU == 2, "Riccati input block elimination is written for nu == 2");
 
+constexpr int GEN_UNROLL = MPC_GEN_UNROLL;
 constexpr int NCB = 2 * NZ;                 // box entries: lower(z_i) i<NZ, then upper(z_i)
 constexpr int NC = NCB + NCG;               // inequality entries per path stage
 constexpr int NPX = NX * (NX + 1) / 2;      // packed P
@@ -79,18 +80,27 @@ __device__ __forceinline__ double warp_sum(double v)
 }
 
 // ---- K4: MIRROR regularisation of one packed symmetric NZ x NZ block (cyclic Jacobi) -----------
-// Register-resident: the 21 rotations of a sweep are fully unrolled so that the matrix (packed) and the
-// eigenvector matrix are indexed statically.  Rotation: t = 2 a_pq / (tau + sign(tau) sqrt(tau^2 + 4 a_pq^2)),
-// tau = a_qq - a_pp, c = 1/sqrt(t^2+1), s = t c  (one sqrt, one division, one rsqrt).
+// Register-resident AND compact: the pair order is the round-robin tournament on NZ+1 = 8 positions
+// (position 7 is a decoupled dummy), i.e. every round rotates the FIXED position pairs (0,7)(1,6)(2,5)(3,4)
+// and then shifts positions 1..7 cyclically, so that one rolled loop body (4 rotations + a register
+// permutation) serves all 7 rounds of a sweep -- ~10 KB of code instead of >100 KB fully unrolled.
+// Rotation without a division: ir = rsqrt(tau^2 + 4 a_pq^2), cos^2 = (1 + |tau| ir)/2, ic = rsqrt(cos^2),
+// c = cos^2 ic, s = sign(tau) a_pq ir ic, t = s ic   (tau = a_qq - a_pp).
+constexpr int JP = NZ + 1;                       // positions
+constexpr int JPK = JP * (JP + 1) / 2;
+__host__ __device__ constexpr int jsigma(int j) { return j == 0 ? 0 : (j == 1 ? JP - 1 : j - 1); }   // new position j <- old position
 __device__ __noinline__ void mirror_packed(double* Hp)
 {
-    double a[NPK], V[NZ][NZ];
+    static_assert(NZ == 7, "tournament table is written for 7 variables + 1 dummy");
+    double a[JPK], V[NZ][JP];
 #pragma unroll
-    for (int i = 0; i < NPK; i++) a[i] = Hp[i];
+    for (int i = 0; i < JP; i++)
+#pragma unroll
+        for (int j = 0; j <= i; j++) a[pk(i, j)] = (i < NZ) ? Hp[pk(i, j)] : 0.0;
 #pragma unroll
     for (int i = 0; i < NZ; i++)
 #pragma unroll
-        for (int j = 0; j < NZ; j++) V[i][j] = (i == j) ? 1.0 : 0.0;
+        for (int j = 0; j < JP; j++) V[i][j] = (i == j) ? 1.0 : 0.0;
 #pragma unroll 1
     for (int sweep = 0; sweep < JACOBI_MAX_SWEEPS; sweep++) {
         double off = 0.0, dia = 0.0;
@@ -103,18 +113,20 @@ __device__ __noinline__ void mirror_packed(double* Hp)
             }
         off *= 2.0;
         if (!(off > JACOBI_TOL * (off + dia))) break;
+#pragma unroll 1
+        for (int round = 0; round < JP - 1; round++) {
 #pragma unroll
-        for (int p = 0; p < NZ - 1; p++)
-#pragma unroll
-            for (int q = p + 1; q < NZ; q++) {
-                const double apq = a[pk(q, p)];
-                if (apq != 0.0) {
+            for (int pr = 0; pr < JP / 2; pr++) {
+                const int p = pr, q = JP - 1 - pr;
+                const double apq = a[pk(q, p)], q2 = apq * apq;
+                if (q2 > 0.0) {
                     const double tau = a[pk(q, q)] - a[pk(p, p)];
-                    const double r = sqrt(tau * tau + 4.0 * apq * apq);
-                    const double tt = 2.0 * apq / (tau + (tau >= 0.0 ? r : -r));
-                    const double c = rsqrt(tt * tt + 1.0), sn = tt * c;
+                    const double ir = rsqrt(tau * tau + 4.0 * q2);
+                    const double c2 = 0.5 + 0.5 * fabs(tau) * ir;
+                    const double ic = rsqrt(c2), c = c2 * ic;
+                    const double sn = (tau >= 0.0 ? apq : -apq) * ir * ic, tt = sn * ic;
 #pragma unroll
-                    for (int k = 0; k < NZ; k++) {
+                    for (int k = 0; k < JP; k++) {
                         if (k != p && k != q) {
                             const double akp = a[pk(k, p)], akq = a[pk(k, q)];
                             a[pk(k, p)] = c * akp - sn * akq;
@@ -132,6 +144,23 @@ __device__ __noinline__ void mirror_packed(double* Hp)
                     }
                 }
             }
+            // shift positions 1..7 by one (position j now holds what position jsigma(j) held)
+            double an[JPK], Vn[NZ][JP];
+#pragma unroll
+            for (int i = 0; i < JP; i++)
+#pragma unroll
+                for (int j = 0; j <= i; j++) an[pk(i, j)] = a[pk(jsigma(i), jsigma(j))];
+#pragma unroll
+            for (int i = 0; i < NZ; i++)
+#pragma unroll
+                for (int j = 0; j < JP; j++) Vn[i][j] = V[i][jsigma(j)];
+#pragma unroll
+            for (int i = 0; i < JPK; i++) a[i] = an[i];
+#pragma unroll
+            for (int i = 0; i < NZ; i++)
+#pragma unroll
+                for (int j = 0; j < JP; j++) V[i][j] = Vn[i][j];
+        }
     }
     double ev[NZ];
 #pragma unroll
@@ -378,6 +407,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                     }
                 }
                 if (path) {
+#pragma unroll GEN_UNROLL
                     for (int e = 0; e < NCG; e++) {
                         const int r = HROW[e];
                         const double sg = HSGN[e], lam = lamg[e], t = tg[e];
@@ -537,6 +567,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                 }
             }
             if (path) {
+#pragma unroll GEN_UNROLL
                 for (int e = 0; e < NCG; e++) {
                     const int r = HROW[e];
                     const double sg = HSGN[e], lam = lamg[e], t = tg[e];
@@ -639,6 +670,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                 }
             }
             if (path) {
+#pragma unroll GEN_UNROLL
                 for (int e = 0; e < NCG; e++) {
                     const int r = HROW[e];
                     const double sg = HSGN[e], lam = lamg[e], t = tg[e];
@@ -674,6 +706,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                 }
             }
             if (path) {
+#pragma unroll GEN_UNROLL
                 for (int e = 0; e < NCG; e++) {
                     const int r = HROW[e];
                     const double sg = HSGN[e], lam = lamg[e], t = tg[e];
@@ -759,6 +792,9 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
     }
 }
 
+#ifndef MPC_GEN_UNROLL
+#define MPC_GEN_UNROLL 2   // general-constraint loops: entries in flight together (hides local-memory latency)
+#endif
 #ifndef MPC_WARPS_PER_CTA
 #define MPC_WARPS_PER_CTA 4
 #endif

@@ -140,6 +140,37 @@ def _interval_map(pb, sim_steps=3):
     return y
 
 
+def _group_rows(h, p, min_len=3):
+    """Find runs of consecutive constraint rows that are the SAME expression with a block of parameters
+    shifted by a constant stride (the reference defines obstacles / halfspaces in a Python loop, so the
+    parameter blocks are contiguous: ellipsoid_constraints.py:41-49, guidance_constraints.py:76-81).
+    Returns [(first_row, count, stride, fixed_param_indices)], rows outside any run are emitted flat."""
+    pidx = {sym: i for i, sym in enumerate(p)}
+    par = [sorted(pidx[q] for q in e.free_symbols if q in pidx) for e in h]
+    groups, i = [], 0
+    while i < len(h) - 1:
+        fixed = sorted(set(par[i]) & set(par[i + 1]))
+        s0 = [q for q in par[i] if q not in fixed]
+        s1 = [q for q in par[i + 1] if q not in fixed]
+        ok = len(s0) == len(s1) and len(s0) > 0 and len({b - a for a, b in zip(s0, s1)}) == 1 and s1[0] > s0[0]
+        if not ok:
+            i += 1
+            continue
+        stride = s1[0] - s0[0]
+        cnt = 1
+        while i + cnt < len(h):
+            shift = {p[q]: p[q + cnt * stride] for q in s0 if q + cnt * stride < len(p)}
+            if len(shift) != len(s0) or h[i].xreplace(shift) != h[i + cnt]:      # structural equality (no simplify: can be very slow)
+                break
+            cnt += 1
+        if cnt >= min_len:
+            groups.append((i, cnt, stride, fixed))
+            i += cnt
+        else:
+            i += 1
+    return groups
+
+
 def emit_model_header(pb, name, sim_steps=3):
     z, p, cost, h = pb["z"], pb["p"], pb["cost"], pb["h"]
     nu, nx = pb["nu"], pb["nx"]
@@ -266,29 +297,65 @@ def emit_model_header(pb, name, sim_steps=3):
     w("}")
 
     # ---- constraints ------------------------------------------------------------------------------
+    groups = _group_rows(h, p) if nh else []
+    in_group = set()
+    for (r0, cnt, stride, fixed) in groups:
+        in_group.update(range(r0, r0 + cnt))
+    flat = [i for i in range(nh) if i not in in_group]
+    w("// constraint rows emitted as loops over parameter blocks (first row, count, parameter stride): %s"
+      % [(g[0], g[1], g[2]) for g in groups])
+
+    def qmap(r0, fixed):
+        """row r0 of a group: shifting parameters are read through q = p + r*stride"""
+        mq = dict(zmap)
+        for i, sym in enumerate(p):
+            mq[sym] = ("p[%d]" if i in fixed else "q[%d]") % i
+        return mq
+
     w("\n// hv[NH] = h(z,p);  C[r*NHS + s] = d h_r / d z_HSUP[s]")
     w("__device__ __forceinline__ void con_eval(const double* z, const double* __restrict__ p, double* hv, double* C)\n{")
-    if nh:
-        w(emit_block([("hv[%d]" % i, h[i]) for i in range(nh)] +
-                     [("C[%d]" % (i * nhs + s), sp.diff(h[i], z[sup[s]])) for i in range(nh) for s in range(nhs)], m))
+    if flat:
+        w(emit_block([("hv[%d]" % i, h[i]) for i in flat] +
+                     [("C[%d]" % (i * nhs + s_), sp.diff(h[i], z[sup[s_]])) for i in flat for s_ in range(nhs)], m))
+    for gi, (r0, cnt, stride, fixed) in enumerate(groups):
+        w("#pragma unroll 1\n    for (int r = 0; r < %d; r++) {\n        const double* __restrict__ q = p + r * %d;" % (cnt, stride))
+        w(emit_block([("hv[%d + r]" % r0, h[r0])] +
+                     [("C[(%d + r) * %d + %d]" % (r0, nhs, s_), sp.diff(h[r0], z[sup[s_]])) for s_ in range(nhs)],
+                     qmap(r0, fixed), tmp_prefix="g%d_" % gi, indent="        "))
+        w("    }")
     w("}")
     w("\n// H(packed NZ) += sum_r mh[r] d2 h_r / dz2")
     w("__device__ __forceinline__ void con_hess_add(const double* z, const double* __restrict__ p, const double* mh, double* H)\n{")
     if nh:
         mhs = sp.symbols("mh0:%d" % nh)
-        Lh = sum(mhs[i] * h[i] for i in range(nh))
-        gh = {s: sp.diff(Lh, z[s]) for s in sup}
-        outs = []
-        for a in sup:
-            for b in sup:
-                if b <= a:
-                    e = sp.diff(gh[a], z[b])
-                    if e != 0:
-                        outs.append(("H[%d] +" % _idx(a, b), e))
-        m3 = dict(m)
-        m3.update({mhs[i]: "mh[%d]" % i for i in range(nh)})
-        if outs:
-            w(emit_block(outs, m3))
+
+        def hess_outputs(rows, msyms):
+            Lh = sum(msyms[i] * h[i] for i in rows)
+            gh = {s_: sp.diff(Lh, z[s_]) for s_ in sup}
+            outs = []
+            for a_ in sup:
+                for b_ in sup:
+                    if b_ <= a_:
+                        e = sp.diff(gh[a_], z[b_])
+                        if e != 0:
+                            outs.append(("H[%d] +" % _idx(a_, b_), e))
+            return outs
+
+        if flat:
+            outs = hess_outputs(flat, mhs)
+            m3 = dict(m)
+            m3.update({mhs[i]: "mh[%d]" % i for i in range(nh)})
+            if outs:
+                w(emit_block(outs, m3))
+        for gi, (r0, cnt, stride, fixed) in enumerate(groups):
+            outs = hess_outputs([r0], mhs)
+            if not outs:
+                continue
+            mq = qmap(r0, fixed)
+            mq[mhs[r0]] = "mh[%d + r]" % r0
+            w("#pragma unroll 1\n    for (int r = 0; r < %d; r++) {\n        const double* __restrict__ q = p + r * %d;" % (cnt, stride))
+            w(emit_block(outs, mq, tmp_prefix="k%d_" % gi, indent="        "))
+            w("    }")
     w("}")
     w("}  // namespace mpcgen")
     return "\n".join(out) + "\n"

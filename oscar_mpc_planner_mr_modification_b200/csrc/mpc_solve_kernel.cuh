@@ -17,6 +17,9 @@
 #include <cstdio>
 #endif
 
+#ifndef MPC_GEN_UNROLL
+#define MPC_GEN_UNROLL 2   // general-constraint loops: entries in flight together (hides local-memory latency)
+#endif
 #ifndef MPC_CFG_TAG
 #error "compile with -DMPC_CFG_TAG=<config> -DMPC_MODEL_HEADER='\"model.cuh\"'"
 #endif
@@ -792,9 +795,6 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
     }
 }
 
-#ifndef MPC_GEN_UNROLL
-#define MPC_GEN_UNROLL 2   // general-constraint loops: entries in flight together (hides local-memory latency)
-#endif
 #ifndef MPC_WARPS_PER_CTA
 #define MPC_WARPS_PER_CTA 4
 #endif

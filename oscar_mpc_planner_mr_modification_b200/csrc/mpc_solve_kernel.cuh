@@ -354,13 +354,28 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
         double nrm_g, nrm_b, nrm_d, nrm_m;
         int kk = 0;
         bool isnan_ = false;
-        for (;; kk++) {
-            // ---- pass A: residuals, norms, mu; Htilde = H + sum Gamma chat chat'; gtilde (affine)
-            double Ht[NPK], gt[NZ], rb[NX];
-            double itb[NCB], itg[NCG > 0 ? NCG : 1];     // 1/t of every entry, reused by passes B-D
-            double ng = 0.0, nb = 0.0, nd = 0.0, nm = 0.0, sm = 0.0;
+        // state of the previous iteration's step, applied at the top of the next pass (fused update):
+        double itb[NCB], itg[NCG > 0 ? NCG : 1];     // 1/t of every entry, reused by passes B, C and the update
+        double dva[NZ], dv[NZ], dpi[NX], sigmu = 0.0, a_ = 0.0;
 #pragma unroll
-            for (int e = 0; e < NCB; e++) itb[e] = 0.0;
+        for (int e = 0; e < NCB; e++) itb[e] = 0.0;
+#pragma unroll
+        for (int i = 0; i < NZ; i++) { dva[i] = 0.0; dv[i] = 0.0; }
+#pragma unroll
+        for (int i = 0; i < NX; i++) dpi[i] = 0.0;
+        for (;; kk++) {
+            // ---- pass DA (one traversal of the inequality entries): apply the step of the previous iteration
+            //      (v, pi, lam, t), then residuals, norms, mu, Htilde = H + sum Gamma chat chat', gtilde (affine)
+            double Ht[NPK], gt[NZ], rb[NX];
+            double ng = 0.0, nb = 0.0, nd = 0.0, nm = 0.0, sm = 0.0;
+            const bool upd = kk > 0;
+            double vo[NZ];                           // v before the update (the step's residuals refer to it)
+#pragma unroll
+            for (int i = 0; i < NZ; i++) { vo[i] = v[i]; if (upd) v[i] += a_ * dv[i]; }
+            if (upd) {
+#pragma unroll
+                for (int i = 0; i < NX; i++) qpi[i] += a_ * dpi[i];
+            }
             {
                 double qpn[NX], vxn[NX], rg[NZ];
 #pragma unroll
@@ -394,14 +409,26 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                     if (act) {
                         const double dl = LBZ[i] - z[i], du = UBZ[i] - z[i];
                         {   // lower: chat = +e_i, d = dl
-                            const double lam = lamb[i], t = tb[i], it_ = 1.0 / t;
+                            double lam = lamb[i], t = tb[i];
+                            if (upd) {
+                                const IneqStep st = ineq_final(lam, itb[i], vo[i] - dl - t, dva[i], dv[i], sigmu);
+                                lam = clamp_lo(lam + a_ * st.dlam, IPM_LAM_MIN); t = clamp_lo(t + a_ * st.dt, IPM_T_MIN);
+                                lamb[i] = lam; tb[i] = t;
+                            }
+                            const double it_ = 1.0 / t;
                             const double rd = v[i] - dl - t, G = lam * it_, m = lam * t;
                             itb[i] = it_;
                             Ht[pk(i, i)] += G; gt[i] += G * rd; rg[i] -= lam;
                             nd = nanmax(nd, fabs(rd)); nm = nanmax(nm, fabs(m)); sm += m;
                         }
                         {   // upper: chat = -e_i, d = -du
-                            const double lam = lamb[NZ + i], t = tb[NZ + i], it_ = 1.0 / t;
+                            double lam = lamb[NZ + i], t = tb[NZ + i];
+                            if (upd) {
+                                const IneqStep st = ineq_final(lam, itb[NZ + i], du - vo[i] - t, -dva[i], -dv[i], sigmu);
+                                lam = clamp_lo(lam + a_ * st.dlam, IPM_LAM_MIN); t = clamp_lo(t + a_ * st.dt, IPM_T_MIN);
+                                lamb[NZ + i] = lam; tb[NZ + i] = t;
+                            }
+                            const double it_ = 1.0 / t;
                             const double rd = du - v[i] - t, G = lam * it_, m = lam * t;
                             itb[NZ + i] = it_;
                             Ht[pk(i, i)] += G; gt[i] -= G * rd; rg[i] += lam;
@@ -413,8 +440,20 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
 #pragma unroll GEN_UNROLL
                     for (int e = 0; e < NCG; e++) {
                         const int r = HROW[e];
-                        const double sg = HSGN[e], lam = lamg[e], t = tg[e];
+                        const double sg = HSGN[e];
+                        double lam = lamg[e], t = tg[e];
                         double cv = 0.0;
+                        if (upd) {
+                            double cvo = 0.0, cda = 0.0, cd = 0.0;
+#pragma unroll
+                            for (int a = 0; a < NHS; a++) {
+                                const double ca = C[r * NHS + a];
+                                cvo += ca * vo[HSUP[a]]; cda += ca * dva[HSUP[a]]; cd += ca * dv[HSUP[a]];
+                            }
+                            const IneqStep st = ineq_final(lam, itg[e], sg * cvo - dg[e] - t, sg * cda, sg * cd, sigmu);
+                            lam = clamp_lo(lam + a_ * st.dlam, IPM_LAM_MIN); t = clamp_lo(t + a_ * st.dt, IPM_T_MIN);
+                            lamg[e] = lam; tg[e] = t;
+                        }
 #pragma unroll
                         for (int a = 0; a < NHS; a++) cv += C[r * NHS + a] * v[HSUP[a]];
                         const double it_ = 1.0 / t;
@@ -514,7 +553,6 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                 }
             }
             // forward sweep: dva
-            double dva[NZ], dpi[NX];
 #pragma unroll
             for (int i = 0; i < NZ; i++) dva[i] = 0.0;
 #pragma unroll
@@ -591,7 +629,8 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
             const double alpha_aff = warp_min(abn / abd);
             S1 = warp_sum(S1); S2 = warp_sum(S2);
             const double mu_aff = (mu * (double)IPM_COUNT + alpha_aff * S1 + alpha_aff * alpha_aff * S2) / (double)IPM_COUNT;
-            const double rat = mu_aff / mu, sigmu = rat * rat * rat * mu;
+            const double rat = mu_aff / mu;
+            sigmu = rat * rat * rat * mu;
 #pragma unroll
             for (int i = 0; i < NZ; i++) gt[i] += V1[i] - sigmu * V2[i];
 
@@ -618,7 +657,6 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                     for (int i = 0; i < NX; i++) pv[i] = q[NU + i] - Lx0[i] * lv[0] - Lx1[i] * lv[1];
                 }
             }
-            double dv[NZ];
 #pragma unroll
             for (int i = 0; i < NZ; i++) dv[i] = 0.0;
 #pragma unroll 1
@@ -688,45 +726,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                 }
             }
             alpha = warp_min(bn / bd);
-            const double a_ = alpha < 1.0 ? alpha * IPM_STEP_SCALE : alpha;
-
-            // ---- pass D: update (v, pi, lam, t)
-#pragma unroll
-            for (int i = 0; i < NZ; i++) {
-                const bool act = (i < NU) ? path : xbox;
-                if (act) {
-                    const double dl = LBZ[i] - z[i], du = UBZ[i] - z[i];
-                    {
-                        const double lam = lamb[i], t = tb[i];
-                        const IneqStep st = ineq_final(lam, itb[i], v[i] - dl - t, dva[i], dv[i], sigmu);
-                        lamb[i] = clamp_lo(lam + a_ * st.dlam, IPM_LAM_MIN); tb[i] = clamp_lo(t + a_ * st.dt, IPM_T_MIN);
-                    }
-                    {
-                        const double lam = lamb[NZ + i], t = tb[NZ + i];
-                        const IneqStep st = ineq_final(lam, itb[NZ + i], du - v[i] - t, -dva[i], -dv[i], sigmu);
-                        lamb[NZ + i] = clamp_lo(lam + a_ * st.dlam, IPM_LAM_MIN); tb[NZ + i] = clamp_lo(t + a_ * st.dt, IPM_T_MIN);
-                    }
-                }
-            }
-            if (path) {
-#pragma unroll GEN_UNROLL
-                for (int e = 0; e < NCG; e++) {
-                    const int r = HROW[e];
-                    const double sg = HSGN[e], lam = lamg[e], t = tg[e];
-                    double cv = 0.0, cda = 0.0, cd = 0.0;
-#pragma unroll
-                    for (int a = 0; a < NHS; a++) {
-                        const double ca = C[r * NHS + a];
-                        cv += ca * v[HSUP[a]]; cda += ca * dva[HSUP[a]]; cd += ca * dv[HSUP[a]];
-                    }
-                    const IneqStep st = ineq_final(lam, itg[e], sg * cv - dg[e] - t, sg * cda, sg * cd, sigmu);
-                    lamg[e] = clamp_lo(lam + a_ * st.dlam, IPM_LAM_MIN); tg[e] = clamp_lo(t + a_ * st.dt, IPM_T_MIN);
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < NZ; i++) v[i] += a_ * dv[i];
-#pragma unroll
-            for (int i = 0; i < NX; i++) qpi[i] += a_ * dpi[i];
+            a_ = alpha < 1.0 ? alpha * IPM_STEP_SCALE : alpha;      // applied by the next pass DA
         }
         ipm_total += kk;
         qps = isnan_ ? 3 : ((kk == IPM_ITER_MAX) ? 1 : (alpha <= IPM_ALPHA_MIN ? 2 : 0));
@@ -796,10 +796,10 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
 }
 
 #ifndef MPC_WARPS_PER_CTA
-#define MPC_WARPS_PER_CTA 4
+#define MPC_WARPS_PER_CTA 8
 #endif
 #ifndef MPC_MIN_CTAS
-#define MPC_MIN_CTAS 2
+#define MPC_MIN_CTAS 1
 #endif
 constexpr int WARPS_PER_CTA = MPC_WARPS_PER_CTA;
 

@@ -144,9 +144,10 @@ def main():
     ap.add_argument("--config", default="c2_tmpc12", choices=sorted(PLANNERS))
     ap.add_argument("--sets", type=int, default=4096, help="homotopy sets per GPU per step")
     ap.add_argument("--num-iter", type=int, default=10, help="SQP-RTI iterations per solve (settings.yaml:18)")
-    ap.add_argument("--ref-sets", type=int, default=48, help="homotopy sets per step of the CPU arm")
-    ap.add_argument("--cpu-sets", type=int, default=48, help="homotopy sets of the cpu_baseline sample")
+    ap.add_argument("--ref-sets", type=int, default=128, help="homotopy sets per step of the CPU arm")
+    ap.add_argument("--cpu-sets", type=int, default=96, help="homotopy sets of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--latency-reps", type=int, default=100, help="single-set latency repetitions (0 = skip)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
@@ -274,6 +275,24 @@ def main():
     d2h = (n * ((N + 1) * nx + N * nu + 2)) * 8 + n * 12 + n_sets * 4
     assert (best_e2e == best).all(), "device-resident and host-API paths disagree on the selected planners"
 
+    # ---- latency of ONE homotopy set end to end (H2D -> solve -> select -> D2H), BASELINE.json's second metric
+    latency = None
+    if rank == 0 and args.latency_reps > 0:
+        eng1 = engine.Engine(cfg, device=local_rank, max_batch=planners)
+        lat = []
+        o1 = None
+        for rep in range(args.latency_reps + 5):
+            s0 = (rep * 37) % n_sets
+            sl = slice(s0 * planners, (s0 + 1) * planners)
+            t0 = time.perf_counter()
+            o1 = eng1.solve_batch(xi_np[sl], x0_np[sl], p_np[sl], num_iter=args.num_iter, out=o1)
+            eng1.select_best(np.array([0, planners], np.int32), o1["pobj"], o1["exit_code"])
+            lat.append((time.perf_counter() - t0) * 1e3)
+        lat = np.array(lat[5:])
+        latency = {"unit": "ms", "what": "one homotopy set (%d planners) through the C ABI, host buffers" % planners,
+                   "p50": float(np.percentile(lat, 50)), "p95": float(np.percentile(lat, 95)), "reps": int(args.latency_reps)}
+        eng1.close()
+
     # ---- roofline of the dominant kernel (mpc_solve_kernel)
     flops = load_json(os.path.join(ROOT, "oracle", "flops.json"), {})
     fkey = "%s/iter%d" % (cfg, args.num_iter)
@@ -300,6 +319,19 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = min(8, os.cpu_count() or 1)       # mirrors `omp parallel for num_threads(8)` (guidance_constraints.cpp:304)
         rate, dt, cnt = cpu_oracle_rate(cfg, planners, args.num_iter, args.cpu_sets, threads)
+        if latency is not None:      # the same single-set latency on the host cores (OpenMP over the planners)
+            from oracle_binding import Oracle
+            orc = Oracle(cfg)
+            cl = []
+            for rep in range(12):
+                sl = slice(rep * planners, (rep + 1) * planners)
+                t0 = time.perf_counter()
+                r = orc.solve_batch(xi_np[sl], x0_np[sl], p_np[sl], num_iter=args.num_iter, threads=threads)
+                orc.select_best(np.array([0, planners], np.int32), r["pobj"], r["exit_code"])
+                cl.append((time.perf_counter() - t0) * 1e3)
+            latency["cpu_port_p50"] = float(np.percentile(cl[2:], 50))
+            latency["cpu_cores"] = threads
+            latency["reference_measured_ms"] = "35.3 mean / 34.6 p50 ('Optimization' scope, 5 planners, reference traces, BASELINE.md)"
         cpu_baseline = {"value": rate, "unit": "solves/s", "cores": threads, "kind": "port",
                         "sample": "%d homotopy sets x %d planners (%d solves, %.1f s wall) of the same workload" % (
                             args.cpu_sets, planners, cnt, dt),
@@ -321,7 +353,8 @@ def main():
                            "success_frac": float((exit_codes == 1).mean()), "ipm_iters_mean": ipm_mean,
                            "host_generation_s": t_gen},
                 "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks}
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
+                "latency": latency}
         print(json.dumps(line))
 
 

@@ -230,7 +230,7 @@ __device__ __forceinline__ void step_limit(double val, double dval, double& bn, 
 __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, const double* __restrict__ x0_g,
                               const double* __restrict__ params_g, int num_iter, double* mem_g, int mem_doubles,
                               double* xtraj_g, double* utraj_g, double* pobj_g, int* exit_g, int* qps_g,
-                              double* reseq_g, int* ipm_g)
+                              double* reseq_g, int* ipm_g, double* hb)
 {
     const int k = threadIdx.x & 31;           // stage owned by this lane
     const bool path = k < NSTAGE;             // has inputs, cost, constraints, dynamics
@@ -510,15 +510,20 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
 #pragma unroll
                     for (int j = 0; j <= i; j++) P[pk(i, j)] = Ht[pk(NU + i, NU + j)];
                 }
+#pragma unroll
+                for (int i = 0; i < NPX; i++) hb[i] = P[i];
+#pragma unroll
+                for (int i = 0; i < NX; i++) hb[NPX + i] = pv[i];
             }
 #pragma unroll 1
             for (int s = NSTAGE - 1; s >= 0; s--) {
-                double Pn[NPX], pn[NX];
-#pragma unroll
-                for (int i = 0; i < NPX; i++) Pn[i] = shfl(P[i], s + 1);
-#pragma unroll
-                for (int i = 0; i < NX; i++) pn[i] = shfl(pv[i], s + 1);
+                __syncwarp();
                 if (k == s) {
+                    double Pn[NPX], pn[NX];
+#pragma unroll
+                    for (int i = 0; i < NPX; i++) Pn[i] = hb[i];
+#pragma unroll
+                    for (int i = 0; i < NX; i++) pn[i] = hb[NPX + i];
                     double G[NPK], q[NZ], y[NX];
 #pragma unroll
                     for (int i = 0; i < NPK; i++) G[i] = Ht[i];
@@ -550,6 +555,10 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                     lv[1] = (q[1] - L10 * lv[0]) * iL1;
 #pragma unroll
                     for (int i = 0; i < NX; i++) pv[i] = q[NU + i] - Lx0[i] * lv[0] - Lx1[i] * lv[1];
+#pragma unroll
+                    for (int i = 0; i < NPX; i++) hb[i] = P[i];
+#pragma unroll
+                    for (int i = 0; i < NX; i++) hb[NPX + i] = pv[i];
                 }
             }
             // forward sweep: dva
@@ -559,10 +568,13 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
             for (int i = 0; i < NX; i++) dpi[i] = 0.0;
 #pragma unroll 1
             for (int s = 0; s < NSTAGE; s++) {
-                double dxn[NX];
-#pragma unroll
-                for (int i = 0; i < NX; i++) dxn[i] = 0.0;
+                __syncwarp();
                 if (k == s) {
+                    if (s > 0) {
+#pragma unroll
+                        for (int i = 0; i < NX; i++) dva[NU + i] = hb[i];
+                    }
+                    double dxn[NX];
                     double r0 = lv[0], r1 = lv[1];      // du = -Luu^-T (Lxu' dx + l)
 #pragma unroll
                     for (int j = 0; j < NX; j++) { r0 += Lx0[j] * dva[NU + j]; r1 += Lx1[j] * dva[NU + j]; }
@@ -571,13 +583,14 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
 #pragma unroll
                     for (int i = 0; i < NX; i++) dxn[i] = rb[i];
                     w_mul_add(Wv, dva, dxn);
-                }
 #pragma unroll
-                for (int i = 0; i < NX; i++) dxn[i] = shfl(dxn[i], s);
-                if (k == s + 1) {
-#pragma unroll
-                    for (int i = 0; i < NX; i++) dva[NU + i] = dxn[i];
+                    for (int i = 0; i < NX; i++) hb[i] = dxn[i];
                 }
+            }
+            __syncwarp();
+            if (term) {
+#pragma unroll
+                for (int i = 0; i < NX; i++) dva[NU + i] = hb[i];
             }
 
             // ---- pass B: affine step length, mu_aff sums, corrector vectors
@@ -635,16 +648,18 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
             for (int i = 0; i < NZ; i++) gt[i] += V1[i] - sigmu * V2[i];
 
             // ---- corrector solve (factorisation reused): backward vector sweep + forward sweep
+            __syncwarp();
             if (term) {
 #pragma unroll
-                for (int i = 0; i < NX; i++) pv[i] = gt[NU + i];
+                for (int i = 0; i < NX; i++) { pv[i] = gt[NU + i]; hb[NPX + i] = pv[i]; }
             }
 #pragma unroll 1
             for (int s = NSTAGE - 1; s >= 0; s--) {
-                double pn[NX];
-#pragma unroll
-                for (int i = 0; i < NX; i++) pn[i] = shfl(pv[i], s + 1);
+                __syncwarp();
                 if (k == s) {
+                    double pn[NX];
+#pragma unroll
+                    for (int i = 0; i < NX; i++) pn[i] = hb[NPX + i];
                     double q[NZ], y[NX];
 #pragma unroll
                     for (int i = 0; i < NX; i++) y[i] = pn[i] + Prb[i];
@@ -654,17 +669,20 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                     lv[0] = q[0] * iL0;
                     lv[1] = (q[1] - L10 * lv[0]) * iL1;
 #pragma unroll
-                    for (int i = 0; i < NX; i++) pv[i] = q[NU + i] - Lx0[i] * lv[0] - Lx1[i] * lv[1];
+                    for (int i = 0; i < NX; i++) { pv[i] = q[NU + i] - Lx0[i] * lv[0] - Lx1[i] * lv[1]; hb[NPX + i] = pv[i]; }
                 }
             }
 #pragma unroll
             for (int i = 0; i < NZ; i++) dv[i] = 0.0;
 #pragma unroll 1
             for (int s = 0; s < NSTAGE; s++) {
-                double dxn[NX];
-#pragma unroll
-                for (int i = 0; i < NX; i++) dxn[i] = 0.0;
+                __syncwarp();
                 if (k == s) {
+                    if (s > 0) {
+#pragma unroll
+                        for (int i = 0; i < NX; i++) dv[NU + i] = hb[i];
+                    }
+                    double dxn[NX];
                     double r0 = lv[0], r1 = lv[1];      // du = -Luu^-T (Lxu' dx + l)
 #pragma unroll
                     for (int j = 0; j < NX; j++) { r0 += Lx0[j] * dv[NU + j]; r1 += Lx1[j] * dv[NU + j]; }
@@ -673,13 +691,14 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
 #pragma unroll
                     for (int i = 0; i < NX; i++) dxn[i] = rb[i];
                     w_mul_add(Wv, dv, dxn);
-                }
 #pragma unroll
-                for (int i = 0; i < NX; i++) dxn[i] = shfl(dxn[i], s);
-                if (k == s + 1) {
-#pragma unroll
-                    for (int i = 0; i < NX; i++) dv[NU + i] = dxn[i];
+                    for (int i = 0; i < NX; i++) hb[i] = dxn[i];
                 }
+            }
+            __syncwarp();
+            if (term) {
+#pragma unroll
+                for (int i = 0; i < NX; i++) dv[NU + i] = hb[i];
             }
             if (k >= 1 && live) {                       // dpi_k = P_k dx_k + p_k (lane-parallel)
 #pragma unroll
@@ -811,6 +830,8 @@ mpc_solve_kernel(int n, const double* __restrict__ xinit, const double* __restri
                  double* utraj, double* pobj, int* exit_code, int* qp_status, double* res_eq, int* ipm_iters,
                  int* work_counter)
 {
+    // per-warp hand-off buffer of the Riccati sweeps: (P, p) of stage k+1 -> lane k, dx_k+1 -> lane k+1
+    __shared__ double s_hand[WARPS_PER_CTA][NPX + NX + 4];
     const int lane = threadIdx.x & 31;
     for (;;) {
         int prob = 0;
@@ -819,7 +840,7 @@ mpc_solve_kernel(int n, const double* __restrict__ xinit, const double* __restri
         if (prob >= n) return;
         const int nit = num_iter ? num_iter[prob] : num_iter_all;
         solve_problem(prob, xinit, x0, params, nit, mem, mem_doubles, xtraj, utraj, pobj, exit_code, qp_status, res_eq,
-                      ipm_iters);
+                      ipm_iters, s_hand[threadIdx.x >> 5]);
     }
 }
 

@@ -61,7 +61,14 @@ __host__ __device__ constexpr int pk(int i, int j) { return i >= j ? i * (i + 1)
 __device__ __forceinline__ double shfl(double v, int src) { return __shfl_sync(FULL, v, src); }
 __device__ __forceinline__ double shfl_down1(double v) { return __shfl_down_sync(FULL, v, 1); }
 // max that PROPAGATES NaN (fmax would drop it): a NaN anywhere must surface as QP status 3
-__device__ __forceinline__ double nanmax(double a, double b) { return (a != a) ? a : ((b != b) ? b : (a > b ? a : b)); }
+// for NON-NEGATIVE arguments (|x|): IEEE-754 doubles order like unsigned integers and every NaN pattern is
+// larger than +inf, so an integer max is a NaN-propagating max -- on the ALU pipe, not the FP64 pipe.
+__device__ __forceinline__ double nanmax(double a, double b)
+{
+    const unsigned long long ua = (unsigned long long)__double_as_longlong(a) & 0x7fffffffffffffffull;
+    const unsigned long long ub = (unsigned long long)__double_as_longlong(b) & 0x7fffffffffffffffull;
+    return __longlong_as_double((long long)(ua > ub ? ua : ub));
+}
 __device__ __forceinline__ double clamp_lo(double x, double lo) { return (x < lo) ? lo : x; }   // keeps NaN
 __device__ __forceinline__ double warp_max(double v)
 {
@@ -351,7 +358,9 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
         }
 
         double alpha = 1.0, mu = 0.0;
+#ifdef MPC_TRACE
         double nrm_g, nrm_b, nrm_d, nrm_m;
+#endif
         int kk = 0;
         bool isnan_ = false;
         // state of the previous iteration's step, applied at the top of the next pass (fused update):
@@ -481,15 +490,21 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                     for (int i = 0; i < NX; i++) nb = nanmax(nb, fabs(rb[i]));
                 }
             }
-            nrm_g = warp_max(ng); nrm_b = warp_max(nb); nrm_d = warp_max(nd); nrm_m = warp_max(nm);
+            // convergence / NaN decisions by warp votes (max-norm <= tol  <=>  every lane's maximum <= tol)
+            const bool lane_nan = (ng != ng) || (nb != nb) || (nd != nd) || (nm != nm);
+            const bool lane_ok = (ng <= IPM_TOL) && (nb <= IPM_TOL) && (nd <= IPM_TOL) && (nm <= IPM_TOL);
+            const bool any_nan = __any_sync(FULL, lane_nan);
+            const bool all_ok = __all_sync(FULL, lane_ok);
             mu = warp_sum(sm) / (double)IPM_COUNT;
+#ifdef MPC_TRACE
+            nrm_g = warp_max(ng); nrm_b = warp_max(nb); nrm_d = warp_max(nd); nrm_m = warp_max(nm);
+#endif
 #ifdef MPC_TRACE
             if (k == 0 && prob == MPC_TRACE)
                 printf("gpu sqp %d ipm %d: rg %.3e rb %.3e rd %.3e rm %.3e mu %.3e alpha %.3e\n", it, kk, nrm_g, nrm_b, nrm_d, nrm_m, mu, alpha);
 #endif
-            isnan_ = (mu != mu) || (nrm_g != nrm_g) || (nrm_b != nrm_b) || (nrm_d != nrm_d) || (nrm_m != nrm_m);
-            if (!(kk < IPM_ITER_MAX && alpha > IPM_ALPHA_MIN && !isnan_ &&
-                  (nrm_g > IPM_TOL || nrm_b > IPM_TOL || nrm_d > IPM_TOL || nrm_m > IPM_TOL)))
+            isnan_ = (mu != mu) || any_nan;
+            if (!(kk < IPM_ITER_MAX && alpha > IPM_ALPHA_MIN && !isnan_ && !all_ok))
                 break;
 
             // ---- Riccati factorisation + predictor solve.  Stage k lives on lane k; the recursion
@@ -749,7 +764,6 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
         }
         ipm_total += kk;
         qps = isnan_ ? 3 : ((kk == IPM_ITER_MAX) ? 1 : (alpha <= IPM_ALPHA_MIN ? 2 : 0));
-        (void)nrm_g; (void)nrm_b; (void)nrm_d; (void)nrm_m;
 
         // ======================= K6: SQP-RTI full step ============================================
         if (qps != 0 && qps != 1) { status = 4; break; }   // ACADOS_QP_FAILURE: iterate unchanged

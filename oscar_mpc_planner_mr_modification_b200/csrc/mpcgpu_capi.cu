@@ -61,12 +61,12 @@ void mpc_register_config(const MpcConfigOps* ops) { registry().push_back(ops); }
 struct mpcgpu_engine {
     const MpcConfigOps* ops = nullptr;
     int device = 0, max_batch = 0, grid = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr;   // stream2: second lane of the chunked host pipeline
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // device staging for the host-pointer entry points
     double *d_xinit = nullptr, *d_x0 = nullptr, *d_params = nullptr, *d_mem = nullptr, *d_xtraj = nullptr, *d_utraj = nullptr,
            *d_pobj = nullptr, *d_res_eq = nullptr, *d_scale = nullptr, *d_sub = nullptr;
-    int *d_num_iter = nullptr, *d_exit = nullptr, *d_qps = nullptr, *d_ipm = nullptr, *d_counter = nullptr, *d_offsets = nullptr,
+    int *d_num_iter = nullptr, *d_exit = nullptr, *d_qps = nullptr, *d_ipm = nullptr, *d_counter = nullptr, *d_counter2 = nullptr, *d_offsets = nullptr,
         *d_best = nullptr;
     unsigned char* d_disabled = nullptr;
     long long launches = 0;
@@ -110,10 +110,11 @@ int mpcgpu_engine_create(const char* config_name, int device, int max_batch, mpc
     AL(e->d_xinit, B * nx * 8); AL(e->d_x0, B * nz * (N + 1) * 8); AL(e->d_params, B * N * ops->np * 8);
     AL(e->d_mem, B * ops->mem_doubles * 8); AL(e->d_xtraj, B * nx * (N + 1) * 8); AL(e->d_utraj, B * nu * N * 8);
     AL(e->d_pobj, B * 8); AL(e->d_res_eq, B * 8); AL(e->d_scale, B * 8); AL(e->d_sub, B * 8);
-    AL(e->d_num_iter, B * 4); AL(e->d_exit, B * 4); AL(e->d_qps, B * 4); AL(e->d_ipm, B * 4); AL(e->d_counter, 4);
+    AL(e->d_num_iter, B * 4); AL(e->d_exit, B * 4); AL(e->d_qps, B * 4); AL(e->d_ipm, B * 4); AL(e->d_counter, 4); AL(e->d_counter2, 4);
     AL(e->d_offsets, (B + 1) * 4); AL(e->d_best, B * 4); AL(e->d_disabled, B);
 #undef AL
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&e->ev0) != cudaSuccess || cudaEventCreate(&e->ev1) != cudaSuccess) {
         e->err = "stream/event creation failed";
         return fail(MPCGPU_ERR_CUDA);
@@ -134,12 +135,13 @@ int mpcgpu_engine_destroy(mpcgpu_engine* e)
     if (!e) return MPCGPU_ERR_ARG;
     cudaSetDevice(e->device);
     void* ptrs[] = {e->d_xinit, e->d_x0, e->d_params, e->d_mem, e->d_xtraj, e->d_utraj, e->d_pobj, e->d_res_eq, e->d_scale,
-                    e->d_sub, e->d_num_iter, e->d_exit, e->d_qps, e->d_ipm, e->d_counter, e->d_offsets, e->d_best, e->d_disabled};
+                    e->d_sub, e->d_num_iter, e->d_exit, e->d_qps, e->d_ipm, e->d_counter, e->d_counter2, e->d_offsets, e->d_best, e->d_disabled};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->stream) cudaStreamDestroy(e->stream);
+    if (e->stream2) cudaStreamDestroy(e->stream2);
     delete e;
     return MPCGPU_OK;
 }
@@ -156,6 +158,10 @@ int mpcgpu_desc_query(const mpcgpu_engine* e, int* N, int* nx, int* nu, int* npa
 }
 int mpcgpu_mem_doubles(const mpcgpu_engine* e) { return e ? e->ops->mem_doubles : MPCGPU_ERR_ARG; }
 
+static int launch_solve_on(mpcgpu_engine* e, cudaStream_t st, int* counter, int n, const double* xinit, const double* x0,
+                           const double* params, const int* num_iter, int num_iter_all, double* mem_inout, double* xtraj,
+                           double* utraj, double* pobj, int* exit_code, int* qp_status, double* res_eq, int* ipm_iters);
+
 int mpcgpu_solve_batch_device(mpcgpu_engine* e, int n, const double* xinit, const double* x0, const double* params,
                               const int* num_iter, int num_iter_all, double* mem_inout, double* xtraj, double* utraj,
                               double* pobj, int* exit_code, int* qp_status, double* res_eq, int* ipm_iters, void* stream)
@@ -165,6 +171,14 @@ int mpcgpu_solve_batch_device(mpcgpu_engine* e, int n, const double* xinit, cons
     if (n == 0) return MPCGPU_OK;
     CK(cudaSetDevice(e->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+    return launch_solve_on(e, st, e->d_counter, n, xinit, x0, params, num_iter, num_iter_all, mem_inout, xtraj, utraj, pobj,
+                           exit_code, qp_status, res_eq, ipm_iters);
+}
+
+static int launch_solve_on(mpcgpu_engine* e, cudaStream_t st, int* counter, int n, const double* xinit, const double* x0,
+                           const double* params, const int* num_iter, int num_iter_all, double* mem_inout, double* xtraj,
+                           double* utraj, double* pobj, int* exit_code, int* qp_status, double* res_eq, int* ipm_iters)
+{
     int ctas_ = 0, threads_ = 128;
     e->ops->occupancy(&ctas_, &threads_);
     const int warps_per_cta = threads_ / 32;
@@ -172,7 +186,7 @@ int mpcgpu_solve_batch_device(mpcgpu_engine* e, int n, const double* xinit, cons
     if (grid > e->grid) grid = e->grid;
     CK(cudaEventRecord(e->ev0, st));
     CK(e->ops->launch_solve(grid, st, n, xinit, x0, params, num_iter, num_iter_all, mem_inout, xtraj, utraj, pobj, exit_code,
-                            qp_status, res_eq, ipm_iters, e->d_counter));
+                            qp_status, res_eq, ipm_iters, counter));
     CK(cudaEventRecord(e->ev1, st));
     e->launches += 1;
     return MPCGPU_OK;
@@ -198,25 +212,42 @@ int mpcgpu_solve_batch(mpcgpu_engine* e, int n, const double* xinit, const doubl
     const MpcConfigOps* o = e->ops;
     const size_t B = (size_t)n;
     const int N = o->N, nx = o->nx, nu = o->nu, nz = nx + nu;
-    cudaStream_t st = e->stream;
-    CK(cudaMemcpyAsync(e->d_xinit, xinit, B * nx * 8, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(e->d_x0, x0, B * nz * (N + 1) * 8, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(e->d_params, params, B * N * o->np * 8, cudaMemcpyHostToDevice, st));
-    if (num_iter) CK(cudaMemcpyAsync(e->d_num_iter, num_iter, B * 4, cudaMemcpyHostToDevice, st));
-    if (mem_inout) CK(cudaMemcpyAsync(e->d_mem, mem_inout, B * o->mem_doubles * 8, cudaMemcpyHostToDevice, st));
-    int rc = mpcgpu_solve_batch_device(e, n, e->d_xinit, e->d_x0, e->d_params, num_iter ? e->d_num_iter : nullptr, num_iter_all,
-                                       mem_inout ? e->d_mem : nullptr, e->d_xtraj, e->d_utraj, e->d_pobj, e->d_exit, e->d_qps,
-                                       e->d_res_eq, e->d_ipm, st);
-    if (rc != MPCGPU_OK) return rc;
-    CK(cudaMemcpyAsync(xtraj, e->d_xtraj, B * nx * (N + 1) * 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(utraj, e->d_utraj, B * nu * N * 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(pobj, e->d_pobj, B * 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(exit_code, e->d_exit, B * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(qp_status, e->d_qps, B * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(res_eq, e->d_res_eq, B * 8, cudaMemcpyDeviceToHost, st));
-    if (ipm_iters) CK(cudaMemcpyAsync(ipm_iters, e->d_ipm, B * 4, cudaMemcpyDeviceToHost, st));
-    if (mem_inout) CK(cudaMemcpyAsync(mem_inout, e->d_mem, B * o->mem_doubles * 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    // Chunked two-stream pipeline: the H2D copy of chunk c+1 and the D2H copy of chunk c-1 overlap the solve
+    // kernel of chunk c (pinned host memory makes the copies truly asynchronous).  Chunks stay >= 8192
+    // problems so that the persistent grid keeps several waves per launch.
+    int nchunk = n / 8192;
+    if (nchunk < 1) nchunk = 1;
+    if (nchunk > 4) nchunk = 4;
+    const int per = (n + nchunk - 1) / nchunk;
+    const size_t sx0 = (size_t)nz * (N + 1), spar = (size_t)N * o->np, sxt = (size_t)nx * (N + 1), sut = (size_t)nu * N,
+                 smem_ = (size_t)o->mem_doubles;
+    for (int c = 0; c < nchunk; c++) {
+        const size_t b0 = (size_t)c * per;
+        if (b0 >= B) break;
+        const size_t m = (b0 + per <= B) ? (size_t)per : B - b0;
+        cudaStream_t st = (c & 1) ? e->stream2 : e->stream;
+        int* counter = (c & 1) ? e->d_counter2 : e->d_counter;
+        CK(cudaMemcpyAsync(e->d_xinit + b0 * nx, xinit + b0 * nx, m * nx * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(e->d_x0 + b0 * sx0, x0 + b0 * sx0, m * sx0 * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(e->d_params + b0 * spar, params + b0 * spar, m * spar * 8, cudaMemcpyHostToDevice, st));
+        if (num_iter) CK(cudaMemcpyAsync(e->d_num_iter + b0, num_iter + b0, m * 4, cudaMemcpyHostToDevice, st));
+        if (mem_inout) CK(cudaMemcpyAsync(e->d_mem + b0 * smem_, mem_inout + b0 * smem_, m * smem_ * 8, cudaMemcpyHostToDevice, st));
+        int rc = launch_solve_on(e, st, counter, (int)m, e->d_xinit + b0 * nx, e->d_x0 + b0 * sx0, e->d_params + b0 * spar,
+                                 num_iter ? e->d_num_iter + b0 : nullptr, num_iter_all, mem_inout ? e->d_mem + b0 * smem_ : nullptr,
+                                 e->d_xtraj + b0 * sxt, e->d_utraj + b0 * sut, e->d_pobj + b0, e->d_exit + b0, e->d_qps + b0,
+                                 e->d_res_eq + b0, e->d_ipm + b0);
+        if (rc != MPCGPU_OK) return rc;
+        CK(cudaMemcpyAsync(xtraj + b0 * sxt, e->d_xtraj + b0 * sxt, m * sxt * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(utraj + b0 * sut, e->d_utraj + b0 * sut, m * sut * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(pobj + b0, e->d_pobj + b0, m * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(exit_code + b0, e->d_exit + b0, m * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(qp_status + b0, e->d_qps + b0, m * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(res_eq + b0, e->d_res_eq + b0, m * 8, cudaMemcpyDeviceToHost, st));
+        if (ipm_iters) CK(cudaMemcpyAsync(ipm_iters + b0, e->d_ipm + b0, m * 4, cudaMemcpyDeviceToHost, st));
+        if (mem_inout) CK(cudaMemcpyAsync(mem_inout + b0 * smem_, e->d_mem + b0 * smem_, m * smem_ * 8, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaStreamSynchronize(e->stream2));
     return MPCGPU_OK;
 }
 

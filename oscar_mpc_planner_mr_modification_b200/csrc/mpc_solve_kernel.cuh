@@ -20,6 +20,12 @@
 #ifndef MPC_GEN_UNROLL
 #define MPC_GEN_UNROLL 2   // general-constraint loops: entries in flight together (hides local-memory latency)
 #endif
+#ifndef MPC_WARPS_PER_CTA
+#define MPC_WARPS_PER_CTA 8
+#endif
+#ifndef MPC_MIN_CTAS
+#define MPC_MIN_CTAS 1
+#endif
 #ifndef MPC_CFG_TAG
 #error "compile with -DMPC_CFG_TAG=<config> -DMPC_MODEL_HEADER='\"model.cuh\"'"
 #endif
@@ -31,7 +37,11 @@ namespace MPC_NS {
 #include MPC_MODEL_HEADER
 using namespace mpcgen;
 
-static_assert(NSTAGE + 1 <= 32, "lane-per-stage kernel needs N <= 31");
+// One thread per stage: a problem is solved by a GROUP of GW consecutive warps of one CTA (GW = 1 for
+// N <= 31, GW = 2 for N <= 63, e.g. the N = 50 CC-MPC configuration).  Stage k = warp-in-group * 32 + lane.
+constexpr int GW = (NSTAGE + 1 + 31) / 32;
+static_assert(GW == 1 || GW == 2, "thread-per-stage kernel needs N <= 63");
+static_assert(MPC_WARPS_PER_CTA % ((NSTAGE + 1 + 31) / 32) == 0, "warps per CTA must be a multiple of the group size");
 static_assert(NU == 2, "Riccati input block elimination is written for nu == 2");
 
 constexpr int GEN_UNROLL = MPC_GEN_UNROLL;
@@ -88,6 +98,73 @@ __device__ __forceinline__ double warp_sum(double v)
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
     return v;
 }
+
+// ---- group primitives: warp shuffles inside a warp, shared-memory exchange + named barrier across the
+//      GW warps of a problem.  For GW == 1 every function reduces to the plain warp intrinsic.
+constexpr int XCH = 16;                          // exchange doubles per warp
+struct Grp {
+    double* xch;                                 // [GW][XCH] shared-memory exchange area of this group
+    int gid, wig;                                // group index inside the CTA, warp index inside the group
+    __device__ __forceinline__ void sync() const
+    {
+        if constexpr (GW == 1) __syncwarp();
+        else asm volatile("bar.sync %0, %1;" ::"r"(gid + 1), "r"(GW * 32) : "memory");
+    }
+    // out[i] <- in[i] of the thread owning stage k+1 (undefined for the last stage)
+    template <int n> __device__ __forceinline__ void shift_down(const double (&in)[n], double (&out)[n]) const
+    {
+#pragma unroll
+        for (int i = 0; i < n; i++) out[i] = __shfl_down_sync(FULL, in[i], 1);
+        if constexpr (GW > 1) {
+            const int lane = threadIdx.x & 31;
+            if (wig == 1 && lane == 0) {
+#pragma unroll
+                for (int i = 0; i < n; i++) xch[i] = in[i];
+            }
+            sync();
+            if (wig == 0 && lane == 31) {
+#pragma unroll
+                for (int i = 0; i < n; i++) out[i] = xch[i];
+            }
+            sync();
+        }
+    }
+    // cross-warp stage of a reduction: v is already warp-reduced (identical in all lanes of a warp)
+    template <int OP> __device__ __forceinline__ double across(double v) const      // OP 0 sum, 1 min, 2 nan-max
+    {
+        if constexpr (GW > 1) {
+            if ((threadIdx.x & 31) == 0) xch[wig * XCH] = v;
+            sync();
+            const double a = xch[0], b = xch[XCH];
+            sync();
+            v = (OP == 0) ? a + b : ((OP == 1) ? fmin(a, b) : nanmax(a, b));
+        }
+        return v;
+    }
+    __device__ __forceinline__ double sum(double v) const { return across<0>(warp_sum(v)); }
+    __device__ __forceinline__ double min(double v) const { return across<1>(warp_min(v)); }
+    __device__ __forceinline__ double max(double v) const { return across<2>(warp_max(v)); }
+    __device__ __forceinline__ bool any(bool p) const
+    {
+        bool r = __any_sync(FULL, p);
+        if constexpr (GW > 1) r = across<2>(r ? 1.0 : 0.0) > 0.5;
+        return r;
+    }
+    __device__ __forceinline__ bool all(bool p) const
+    {
+        bool r = __all_sync(FULL, p);
+        if constexpr (GW > 1) r = across<1>(r ? 1.0 : 0.0) > 0.5;
+        return r;
+    }
+    // sum of one value per stage in stage order (warp-local stage order, then warp 0 + warp 1)
+    __device__ __forceinline__ double ordered_sum(double v) const
+    {
+        double acc = 0.0;
+#pragma unroll 1
+        for (int l = 0; l < 32; l++) acc += __shfl_sync(FULL, v, l);
+        return across<0>(acc);
+    }
+};
 
 // ---- K4: MIRROR regularisation of one packed symmetric NZ x NZ block (cyclic Jacobi) -----------
 // Register-resident AND compact: the pair order is the round-robin tournament on NZ+1 = 8 positions
@@ -237,9 +314,9 @@ __device__ __forceinline__ void step_limit(double val, double dval, double& bn, 
 __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, const double* __restrict__ x0_g,
                               const double* __restrict__ params_g, int num_iter, double* mem_g, int mem_doubles,
                               double* xtraj_g, double* utraj_g, double* pobj_g, int* exit_g, int* qps_g,
-                              double* reseq_g, int* ipm_g, double* hb)
+                              double* reseq_g, int* ipm_g, double* hb, const Grp grp)
 {
-    const int k = threadIdx.x & 31;           // stage owned by this lane
+    const int k = grp.wig * 32 + (threadIdx.x & 31);   // stage owned by this thread
     const bool path = k < NSTAGE;             // has inputs, cost, constraints, dynamics
     const bool term = k == NSTAGE;
     const bool live = k <= NSTAGE;
@@ -283,9 +360,11 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
         double H[NPK], g[NZ], Wv[NWV], b[NX];
         double C[NH > 0 ? NH * NHS : 1], dg[NCG > 0 ? NCG : 1];
         {
-            double pin[NX], xnx[NX];
+            double pin[NX], xnx[NX], zx_[NX];
 #pragma unroll
-            for (int i = 0; i < NX; i++) { pin[i] = shfl_down1(pi[i]); xnx[i] = shfl_down1(z[NU + i]); }
+            for (int i = 0; i < NX; i++) zx_[i] = z[NU + i];
+            grp.shift_down(pi, pin);
+            grp.shift_down(zx_, xnx);
 #pragma unroll
             for (int i = 0; i < NPK; i++) H[i] = 0.0;
 #pragma unroll
@@ -386,9 +465,11 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                 for (int i = 0; i < NX; i++) qpi[i] += a_ * dpi[i];
             }
             {
-                double qpn[NX], vxn[NX], rg[NZ];
+                double qpn[NX], vxn[NX], rg[NZ], vx_[NX];
 #pragma unroll
-                for (int i = 0; i < NX; i++) { qpn[i] = shfl_down1(qpi[i]); vxn[i] = shfl_down1(v[NU + i]); }
+                for (int i = 0; i < NX; i++) vx_[i] = v[NU + i];
+                grp.shift_down(qpi, qpn);
+                grp.shift_down(vx_, vxn);
 #pragma unroll
                 for (int i = 0; i < NPK; i++) Ht[i] = H[i];
 #pragma unroll
@@ -493,11 +574,11 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
             // convergence / NaN decisions by warp votes (max-norm <= tol  <=>  every lane's maximum <= tol)
             const bool lane_nan = (ng != ng) || (nb != nb) || (nd != nd) || (nm != nm);
             const bool lane_ok = (ng <= IPM_TOL) && (nb <= IPM_TOL) && (nd <= IPM_TOL) && (nm <= IPM_TOL);
-            const bool any_nan = __any_sync(FULL, lane_nan);
-            const bool all_ok = __all_sync(FULL, lane_ok);
-            mu = warp_sum(sm) / (double)IPM_COUNT;
+            const bool any_nan = grp.any(lane_nan);
+            const bool all_ok = grp.all(lane_ok);
+            mu = grp.sum(sm) / (double)IPM_COUNT;
 #ifdef MPC_TRACE
-            nrm_g = warp_max(ng); nrm_b = warp_max(nb); nrm_d = warp_max(nd); nrm_m = warp_max(nm);
+            nrm_g = grp.max(ng); nrm_b = grp.max(nb); nrm_d = grp.max(nd); nrm_m = grp.max(nm);
 #endif
 #ifdef MPC_TRACE
             if (k == 0 && prob == MPC_TRACE)
@@ -532,7 +613,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
             }
 #pragma unroll 1
             for (int s = NSTAGE - 1; s >= 0; s--) {
-                __syncwarp();
+                grp.sync();
                 if (k == s) {
                     double Pn[NPX], pn[NX];
 #pragma unroll
@@ -583,7 +664,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
             for (int i = 0; i < NX; i++) dpi[i] = 0.0;
 #pragma unroll 1
             for (int s = 0; s < NSTAGE; s++) {
-                __syncwarp();
+                grp.sync();
                 if (k == s) {
                     if (s > 0) {
 #pragma unroll
@@ -602,7 +683,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                     for (int i = 0; i < NX; i++) hb[i] = dxn[i];
                 }
             }
-            __syncwarp();
+            grp.sync();
             if (term) {
 #pragma unroll
                 for (int i = 0; i < NX; i++) dva[NU + i] = hb[i];
@@ -654,8 +735,8 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                     }
                 }
             }
-            const double alpha_aff = warp_min(abn / abd);
-            S1 = warp_sum(S1); S2 = warp_sum(S2);
+            const double alpha_aff = grp.min(abn / abd);
+            S1 = grp.sum(S1); S2 = grp.sum(S2);
             const double mu_aff = (mu * (double)IPM_COUNT + alpha_aff * S1 + alpha_aff * alpha_aff * S2) / (double)IPM_COUNT;
             const double rat = mu_aff / mu;
             sigmu = rat * rat * rat * mu;
@@ -663,14 +744,14 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
             for (int i = 0; i < NZ; i++) gt[i] += V1[i] - sigmu * V2[i];
 
             // ---- corrector solve (factorisation reused): backward vector sweep + forward sweep
-            __syncwarp();
+            grp.sync();
             if (term) {
 #pragma unroll
                 for (int i = 0; i < NX; i++) { pv[i] = gt[NU + i]; hb[NPX + i] = pv[i]; }
             }
 #pragma unroll 1
             for (int s = NSTAGE - 1; s >= 0; s--) {
-                __syncwarp();
+                grp.sync();
                 if (k == s) {
                     double pn[NX];
 #pragma unroll
@@ -691,7 +772,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
             for (int i = 0; i < NZ; i++) dv[i] = 0.0;
 #pragma unroll 1
             for (int s = 0; s < NSTAGE; s++) {
-                __syncwarp();
+                grp.sync();
                 if (k == s) {
                     if (s > 0) {
 #pragma unroll
@@ -710,7 +791,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                     for (int i = 0; i < NX; i++) hb[i] = dxn[i];
                 }
             }
-            __syncwarp();
+            grp.sync();
             if (term) {
 #pragma unroll
                 for (int i = 0; i < NX; i++) dv[NU + i] = hb[i];
@@ -759,7 +840,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                     step_limit(lam, st.dlam, bn, bd); step_limit(t, st.dt, bn, bd);
                 }
             }
-            alpha = warp_min(bn / bd);
+            alpha = grp.min(bn / bd);
             a_ = alpha < 1.0 ? alpha * IPM_STEP_SCALE : alpha;      // applied by the next pass DA
         }
         ipm_total += kk;
@@ -780,9 +861,10 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
     // ======================= completeOneIteration (:162-204) ======================================
     double cst = 0.0, req = 0.0;
     {
-        double xnx[NX];
+        double xnx[NX], zx_[NX];
 #pragma unroll
-        for (int i = 0; i < NX; i++) xnx[i] = shfl_down1(z[NU + i]);
+        for (int i = 0; i < NX; i++) zx_[i] = z[NU + i];
+        grp.shift_down(zx_, xnx);
         if (path) {
             double xn[NX];
             cst = DT * cost_val(z, p);
@@ -792,10 +874,8 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
         }
     }
     // deterministic stage-order sum (matches the oracle's sequential accumulation)
-    double cost = 0.0;
-#pragma unroll 1
-    for (int s = 0; s < NSTAGE; s++) cost += shfl(cst, s);
-    req = warp_max(req);
+    const double cost = grp.ordered_sum(cst);
+    req = grp.max(req);
     if (!(req <= RES_EQ_MAX) && status == 0) status = 4;
     const int exit_code = (status == 0) ? 1 : (status == 1 ? 0 : status);
     if (live) {
@@ -812,7 +892,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
     }
     if (mem) {
         if (status != 0) {                                 // Solver_acados_reset + reset_qp_memory (:187-191)
-            for (int i = k; i < mem_doubles; i += 32) mem[i] = 0.0;
+            for (int i = k; i < mem_doubles; i += 32 * GW) mem[i] = 0.0;
         } else {
             double* m = mem + 1;
             if (k == 0) mem[0] = 2.0;
@@ -828,12 +908,6 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
     }
 }
 
-#ifndef MPC_WARPS_PER_CTA
-#define MPC_WARPS_PER_CTA 8
-#endif
-#ifndef MPC_MIN_CTAS
-#define MPC_MIN_CTAS 1
-#endif
 constexpr int WARPS_PER_CTA = MPC_WARPS_PER_CTA;
 
 // Persistent grid: warps pull problem indices from a global counter (work per problem is data
@@ -844,17 +918,32 @@ mpc_solve_kernel(int n, const double* __restrict__ xinit, const double* __restri
                  double* utraj, double* pobj, int* exit_code, int* qp_status, double* res_eq, int* ipm_iters,
                  int* work_counter)
 {
-    // per-warp hand-off buffer of the Riccati sweeps: (P, p) of stage k+1 -> lane k, dx_k+1 -> lane k+1
-    __shared__ double s_hand[WARPS_PER_CTA][NPX + NX + 4];
-    const int lane = threadIdx.x & 31;
+    // per-group shared memory: hand-off buffer of the Riccati sweeps ((P, p) of stage k+1 -> stage k,
+    // dx_k+1 -> stage k+1), the cross-warp exchange area, and the fetched problem index
+    constexpr int GROUPS = WARPS_PER_CTA / GW;
+    __shared__ double s_hand[GROUPS][NPX + NX + 4];
+    __shared__ double s_xch[GROUPS][GW * XCH];
+    __shared__ int s_prob[GROUPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    Grp grp;
+    grp.gid = warp / GW;
+    grp.wig = warp % GW;
+    grp.xch = s_xch[grp.gid];
     for (;;) {
         int prob = 0;
-        if (lane == 0) prob = atomicAdd(work_counter, 1);
-        prob = __shfl_sync(FULL, prob, 0);
+        if (grp.wig == 0 && lane == 0) prob = atomicAdd(work_counter, 1);
+        if constexpr (GW == 1) {
+            prob = __shfl_sync(FULL, prob, 0);
+        } else {
+            if (grp.wig == 0 && lane == 0) s_prob[grp.gid] = prob;
+            grp.sync();
+            prob = s_prob[grp.gid];
+            grp.sync();
+        }
         if (prob >= n) return;
         const int nit = num_iter ? num_iter[prob] : num_iter_all;
         solve_problem(prob, xinit, x0, params, nit, mem, mem_doubles, xtraj, utraj, pobj, exit_code, qp_status, res_eq,
-                      ipm_iters, s_hand[threadIdx.x >> 5]);
+                      ipm_iters, s_hand[grp.gid], grp);
     }
 }
 

@@ -63,6 +63,8 @@ struct mpcgpu_engine {
     int device = 0, max_batch = 0, grid = 0;
     cudaStream_t stream = nullptr, stream2 = nullptr;   // stream2: second lane of the chunked host pipeline
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t cev0[4] = {nullptr, nullptr, nullptr, nullptr}, cev1[4] = {nullptr, nullptr, nullptr, nullptr};   // per chunk (host path)
+    int chunks_timed = 0;      // > 0: last_kernel_ms sums the chunk kernels of the last host call
     // device staging for the host-pointer entry points
     double *d_xinit = nullptr, *d_x0 = nullptr, *d_params = nullptr, *d_mem = nullptr, *d_xtraj = nullptr, *d_utraj = nullptr,
            *d_pobj = nullptr, *d_res_eq = nullptr, *d_scale = nullptr, *d_sub = nullptr;
@@ -115,7 +117,8 @@ int mpcgpu_engine_create(const char* config_name, int device, int max_batch, mpc
 #undef AL
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreate(&e->ev0) != cudaSuccess || cudaEventCreate(&e->ev1) != cudaSuccess) {
+        cudaEventCreate(&e->ev0) != cudaSuccess || cudaEventCreate(&e->ev1) != cudaSuccess ||
+        [&] { for (int i = 0; i < 4; i++) if (cudaEventCreate(&e->cev0[i]) != cudaSuccess || cudaEventCreate(&e->cev1[i]) != cudaSuccess) return true; return false; }()) {
         e->err = "stream/event creation failed";
         return fail(MPCGPU_ERR_CUDA);
     }
@@ -140,6 +143,7 @@ int mpcgpu_engine_destroy(mpcgpu_engine* e)
         if (p) cudaFree(p);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
+    for (int i = 0; i < 4; i++) { if (e->cev0[i]) cudaEventDestroy(e->cev0[i]); if (e->cev1[i]) cudaEventDestroy(e->cev1[i]); }
     if (e->stream) cudaStreamDestroy(e->stream);
     if (e->stream2) cudaStreamDestroy(e->stream2);
     delete e;
@@ -158,9 +162,9 @@ int mpcgpu_desc_query(const mpcgpu_engine* e, int* N, int* nx, int* nu, int* npa
 }
 int mpcgpu_mem_doubles(const mpcgpu_engine* e) { return e ? e->ops->mem_doubles : MPCGPU_ERR_ARG; }
 
-static int launch_solve_on(mpcgpu_engine* e, cudaStream_t st, int* counter, int n, const double* xinit, const double* x0,
-                           const double* params, const int* num_iter, int num_iter_all, double* mem_inout, double* xtraj,
-                           double* utraj, double* pobj, int* exit_code, int* qp_status, double* res_eq, int* ipm_iters);
+static int launch_solve_on(mpcgpu_engine* e, cudaStream_t st, int* counter, cudaEvent_t t0, cudaEvent_t t1, int n, const double* xinit,
+                           const double* x0, const double* params, const int* num_iter, int num_iter_all, double* mem_inout,
+                           double* xtraj, double* utraj, double* pobj, int* exit_code, int* qp_status, double* res_eq, int* ipm_iters);
 
 int mpcgpu_solve_batch_device(mpcgpu_engine* e, int n, const double* xinit, const double* x0, const double* params,
                               const int* num_iter, int num_iter_all, double* mem_inout, double* xtraj, double* utraj,
@@ -171,23 +175,24 @@ int mpcgpu_solve_batch_device(mpcgpu_engine* e, int n, const double* xinit, cons
     if (n == 0) return MPCGPU_OK;
     CK(cudaSetDevice(e->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
-    return launch_solve_on(e, st, e->d_counter, n, xinit, x0, params, num_iter, num_iter_all, mem_inout, xtraj, utraj, pobj,
-                           exit_code, qp_status, res_eq, ipm_iters);
+    e->chunks_timed = 0;
+    return launch_solve_on(e, st, e->d_counter, e->ev0, e->ev1, n, xinit, x0, params, num_iter, num_iter_all, mem_inout, xtraj, utraj,
+                           pobj, exit_code, qp_status, res_eq, ipm_iters);
 }
 
-static int launch_solve_on(mpcgpu_engine* e, cudaStream_t st, int* counter, int n, const double* xinit, const double* x0,
-                           const double* params, const int* num_iter, int num_iter_all, double* mem_inout, double* xtraj,
-                           double* utraj, double* pobj, int* exit_code, int* qp_status, double* res_eq, int* ipm_iters)
+static int launch_solve_on(mpcgpu_engine* e, cudaStream_t st, int* counter, cudaEvent_t t0, cudaEvent_t t1, int n, const double* xinit,
+                           const double* x0, const double* params, const int* num_iter, int num_iter_all, double* mem_inout,
+                           double* xtraj, double* utraj, double* pobj, int* exit_code, int* qp_status, double* res_eq, int* ipm_iters)
 {
     int ctas_ = 0, threads_ = 128;
     e->ops->occupancy(&ctas_, &threads_);
     const int warps_per_cta = threads_ / 32;
     int grid = (n + warps_per_cta - 1) / warps_per_cta;
     if (grid > e->grid) grid = e->grid;
-    CK(cudaEventRecord(e->ev0, st));
+    CK(cudaEventRecord(t0, st));
     CK(e->ops->launch_solve(grid, st, n, xinit, x0, params, num_iter, num_iter_all, mem_inout, xtraj, utraj, pobj, exit_code,
                             qp_status, res_eq, ipm_iters, counter));
-    CK(cudaEventRecord(e->ev1, st));
+    CK(cudaEventRecord(t1, st));
     e->launches += 1;
     return MPCGPU_OK;
 }
@@ -197,6 +202,7 @@ int mpcgpu_sync(mpcgpu_engine* e)
     if (!e) return MPCGPU_ERR_ARG;
     CK(cudaSetDevice(e->device));
     CK(cudaStreamSynchronize(e->stream));
+    CK(cudaStreamSynchronize(e->stream2));
     return MPCGPU_OK;
 }
 
@@ -232,7 +238,7 @@ int mpcgpu_solve_batch(mpcgpu_engine* e, int n, const double* xinit, const doubl
         CK(cudaMemcpyAsync(e->d_params + b0 * spar, params + b0 * spar, m * spar * 8, cudaMemcpyHostToDevice, st));
         if (num_iter) CK(cudaMemcpyAsync(e->d_num_iter + b0, num_iter + b0, m * 4, cudaMemcpyHostToDevice, st));
         if (mem_inout) CK(cudaMemcpyAsync(e->d_mem + b0 * smem_, mem_inout + b0 * smem_, m * smem_ * 8, cudaMemcpyHostToDevice, st));
-        int rc = launch_solve_on(e, st, counter, (int)m, e->d_xinit + b0 * nx, e->d_x0 + b0 * sx0, e->d_params + b0 * spar,
+        int rc = launch_solve_on(e, st, counter, e->cev0[c], e->cev1[c], (int)m, e->d_xinit + b0 * nx, e->d_x0 + b0 * sx0, e->d_params + b0 * spar,
                                  num_iter ? e->d_num_iter + b0 : nullptr, num_iter_all, mem_inout ? e->d_mem + b0 * smem_ : nullptr,
                                  e->d_xtraj + b0 * sxt, e->d_utraj + b0 * sut, e->d_pobj + b0, e->d_exit + b0, e->d_qps + b0,
                                  e->d_res_eq + b0, e->d_ipm + b0);
@@ -248,6 +254,7 @@ int mpcgpu_solve_batch(mpcgpu_engine* e, int n, const double* xinit, const doubl
     }
     CK(cudaStreamSynchronize(e->stream));
     CK(cudaStreamSynchronize(e->stream2));
+    e->chunks_timed = nchunk;
     return MPCGPU_OK;
 }
 
@@ -351,6 +358,14 @@ float mpcgpu_last_kernel_ms(mpcgpu_engine* e)
 {
     if (!e) return -1.0f;
     float ms = -1.0f;
+    if (e->chunks_timed > 0) {      // host call: sum of the chunk kernels
+        float tot = 0.0f;
+        for (int c = 0; c < e->chunks_timed; c++) {
+            if (cudaEventSynchronize(e->cev1[c]) != cudaSuccess || cudaEventElapsedTime(&ms, e->cev0[c], e->cev1[c]) != cudaSuccess) return -1.0f;
+            tot += ms;
+        }
+        return tot;
+    }
     if (cudaEventSynchronize(e->ev1) != cudaSuccess) return -1.0f;
     if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) != cudaSuccess) return -1.0f;
     return ms;

@@ -76,6 +76,5 @@ def solve_golden(cfg, n_sets, seed=2024):
 if __name__ == "__main__":
     for cfg in PLANNERS:
         model_golden(cfg)
-        if cfg != "c5_ccmpc":
-            solve_golden(cfg, 8 if PLANNERS[cfg] > 1 else 32)
+        solve_golden(cfg, 8 if PLANNERS[cfg] > 1 else 32)
         print("golden", cfg)

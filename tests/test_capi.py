@@ -29,11 +29,11 @@ def test_library_exports_every_declared_symbol():
 def test_registered_configurations_and_maps():
     lib = engine.load_library()
     names = [lib.mpcgpu_config_name(i).decode() for i in range(lib.mpcgpu_num_configs())]
-    assert set(names) == {"c1_basic", "tmpc_shipped", "c2_tmpc12"}
-    expect = {"c1_basic": (83, 4), "tmpc_shipped": (98, 8), "c2_tmpc12": (175, 24)}
+    assert set(names) == {"c1_basic", "tmpc_shipped", "c2_tmpc12", "c5_ccmpc"}
+    expect = {"c1_basic": (83, 4, 30), "tmpc_shipped": (98, 8, 30), "c2_tmpc12": (175, 24, 30), "c5_ccmpc": (115, 16, 50)}
     for n in names:
         pmap, mmap, st = engine.load_maps(n)
-        assert st == dict(N=30, nx=5, nu=2, nvar=7, npar=expect[n][0])
+        assert st == dict(N=expect[n][2], nx=5, nu=2, nvar=7, npar=expect[n][0])
         assert len(pmap) == expect[n][0] and sorted(pmap.values()) == list(range(expect[n][0]))
         assert mmap["a"][:2] == ["u", 0] and mmap["spline"][:2] == ["x", 6] and mmap["v"][2:] == [-0.01, 3.0]
     pm = engine.load_maps("c2_tmpc12")[0]

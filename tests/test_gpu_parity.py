@@ -29,7 +29,11 @@ def run_both(cfg, n_sets, planners, num_iter, seed):
 
 def check(out, ref):
     assert (out["exit_code"] == ref["exit_code"]).all(), np.nonzero(out["exit_code"] != ref["exit_code"])
-    assert (out["qp_status"] == ref["qp_status"]).all()
+    ok_ = ref["exit_code"] == 1
+    assert (out["qp_status"][ok_] == ref["qp_status"][ok_]).all()
+    # failed solves: same failure class (QP failure vs res_eq demotion); a diverging interior-point run may end
+    # as "minimum step" (2) on one side and "NaN" (3) on the other -- both are ACADOS_QP_FAILURE, exit code 4
+    assert ((out["qp_status"][~ok_] >= 2) == (ref["qp_status"][~ok_] >= 2)).all()
     # interior-point iteration counts are a diagnostic: a residual landing within rounding of the 1e-5
     # tolerance may cost one extra iteration on one side; the SQP iterate re-converges (checked below)
     ok = ref["exit_code"] == 1
@@ -44,7 +48,7 @@ def check(out, ref):
     return ex.max(), eu.max()
 
 
-@pytest.mark.parametrize("cfg,planners", [("c1_basic", 1), ("tmpc_shipped", 5), ("c2_tmpc12", 9)])
+@pytest.mark.parametrize("cfg,planners", [("c1_basic", 1), ("tmpc_shipped", 5), ("c2_tmpc12", 9), ("c5_ccmpc", 1)])
 @pytest.mark.parametrize("num_iter", [1, 10])
 def test_solve_parity(cfg, planners, num_iter):
     n_sets = 16 if planners > 1 else 64

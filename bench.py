@@ -306,8 +306,11 @@ def main():
         peaks = load_json(os.path.join(ROOT, "MEASURED_PEAKS.json"), {})
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         hbm_ach = bytes_per_solve(d) * n / (kms * 1e-3) / 1e9
+        tr = load_json(os.path.join(ROOT, "profiles", "traffic.json"), {}).get(fkey)
+        traffic = tr["dram_bytes_per_solve"] * n if tr else None     # per launch, from the committed ncu --set full capture
         roofline = {"bound": "fp64", "kernel": "mpc_solve_kernel", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                    "frac": achieved / fp64_peak, "traffic": None,
+                    "frac": achieved / fp64_peak, "traffic": traffic,
+                    "traffic_note": "DRAM bytes per launch (ncu) vs %d algorithmic: thread-local arrays / spills written back through L2" % (bytes_per_solve(d) * n),
                     "peak_source": "DFMA micro-kernel measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                     "flops_per_solve": fps, "kernel_ms": kms,
                     "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,

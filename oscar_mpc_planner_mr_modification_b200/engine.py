@@ -9,7 +9,7 @@ import numpy as np
 import yaml
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_PKG, "lib", "libmpcgpu.so")
+_LIB_PATH = os.environ.get("MPCGPU_LIB") or os.path.join(_PKG, "lib", "libmpcgpu.so")
 _lib = None
 
 SYMBOLS = [

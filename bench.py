@@ -275,6 +275,30 @@ def main():
     d2h = (n * ((N + 1) * nx + N * nu + 2)) * 8 + n * 12 + n_sets * 4
     assert (best_e2e == best).all(), "device-resident and host-API paths disagree on the selected planners"
 
+    # ---- e2e through the compact homotopy-set entry (mpcgpu_solve_sets): shared parameter block per set
+    e2e_sets = None
+    if planners > 1:
+        Pv = p_np.reshape(n_sets, planners, N, npar)
+        differs = np.nonzero((Pv[:64] != Pv[:64, :1]).any(axis=(0, 1, 2)))[0].astype(np.int32)
+        h_shared = pinned(np.ascontiguousarray(Pv[:, 0]))
+        h_vals = pinned(np.ascontiguousarray(Pv[..., differs]))
+        h_xs = pinned(np.ascontiguousarray(xi_np.reshape(n_sets, planners, nx)[:, 0]))
+        so = dict(np_out)
+        so["best"] = pinned(np.zeros(n_sets, np.int32)).numpy()
+        eng.solve_sets(n_sets, planners, h_xs.numpy(), h_shared.numpy(), x0_np, differs, h_vals.numpy(), num_iter=args.num_iter, out=so)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            eng.solve_sets(n_sets, planners, h_xs.numpy(), h_shared.numpy(), x0_np, differs, h_vals.numpy(), num_iter=args.num_iter, out=so)
+        torch.cuda.synchronize()
+        ts_ = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(ts_, op=dist.ReduceOp.MAX)
+        assert (so["best"] == best).all()
+        e2e_sets = {"value": world * n * args.steps / float(ts_.item()), "unit": "solves/s",
+                    "h2d_bytes_per_step": int((h_shared.numel() + h_vals.numel() + h_xs.numel() + h_x0.numel()) * 8 + differs.size * 4),
+                    "what": "mpcgpu_solve_sets: shared parameter block per set + %d per-planner parameters, selection fused" % differs.size}
+
     # ---- latency of ONE homotopy set end to end (H2D -> solve -> select -> D2H), BASELINE.json's second metric
     latency = None
     if rank == 0 and args.latency_reps > 0:
@@ -357,7 +381,7 @@ def main():
                            "host_generation_s": t_gen},
                 "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
-                "latency": latency}
+                "latency": latency, "e2e_sets": e2e_sets}
         print(json.dumps(line))
 
 

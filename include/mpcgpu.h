@@ -74,6 +74,22 @@ int mpcgpu_solve_batch_device(mpcgpu_engine *e, int n, const double *xinit, cons
                               void *stream);
 int mpcgpu_sync(mpcgpu_engine *e);
 
+/* Homotopy-SET entry: what GuidanceConstraints::optimize does for one robot --
+ * `*solver = *_solver` for every planner (guidance_constraints.cpp:323: all planners start from the main
+ * solver's parameter block), planner-specific parameters on top (guidance halfspaces
+ * linearized_constraints.cpp:150-189, consistency reference), one solve() each (:369) and FindBestPlanner
+ * (:572-590) -- as ONE call for n_sets sets of `planners` planners.  The shared block travels once per
+ * set: host->device bytes drop from P*N*npar to N*npar + P*N*nidx doubles per set.
+ *   xinit_sets [n_sets*nx]; shared_params [n_sets*N*npar]; x0 [n*(nu+nx)*(N+1)], n = n_sets*planners,
+ *   problem index = set*planners + planner; param_idx [nidx] flat parameter indices that differ per planner;
+ *   planner_params [n*N*nidx] their values (stage-major); outputs as mpcgpu_solve_batch plus
+ *   best_idx [n_sets] with the semantics of mpcgpu_select_best (obj_scale / obj_sub / disabled may be NULL). */
+int mpcgpu_solve_sets(mpcgpu_engine *e, int n_sets, int planners, const double *xinit_sets, const double *shared_params,
+                      const double *x0, int nidx, const int *param_idx, const double *planner_params, const int *num_iter,
+                      int num_iter_all, double *xtraj, double *utraj, double *pobj, int *exit_code, int *qp_status,
+                      double *res_eq, const double *obj_scale, const double *obj_sub, const unsigned char *disabled,
+                      int *best_idx);
+
 /* Pick the best planner of each homotopy set.
  * Replaces: the objective post-processing of GuidanceConstraints::optimize and FindBestPlanner
  *           (mpc_planner_modules/src/guidance_constraints.cpp:373-420,572-590):

@@ -38,6 +38,37 @@ __global__ void select_best_kernel(int n_sets, const int* __restrict__ set_offse
     best_idx[s] = bi;
 }
 
+// Compact parameter path: params[prob][k][:] <- shared[set][k][:], then the per-planner
+// parameters (guidance halfspaces, consistency reference, ...) are scattered over it.  One thread per
+// (problem, stage, parameter); coalesced in the parameter index.
+__global__ void expand_params_kernel(int n, int planners, int N, int npar, int nidx, const double* __restrict__ shared,
+                                     const int* __restrict__ idx, const double* __restrict__ vals, double* __restrict__ params)
+{
+    const size_t total = (size_t)n * N * npar;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int j = (int)(t % npar);
+        const size_t pk_ = t / npar;               // prob * N + k
+        const size_t prob = pk_ / N;
+        const int k = (int)(pk_ % N);
+        params[t] = shared[((prob / planners) * N + k) * npar + j];
+    }
+}
+__global__ void scatter_params_kernel(int n, int N, int npar, int nidx, const int* __restrict__ idx, const double* __restrict__ vals,
+                                      double* __restrict__ params)
+{
+    const size_t total = (size_t)n * N * nidx;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int j = (int)(t % nidx);
+        const size_t pk_ = t / nidx;
+        params[pk_ * npar + idx[j]] = vals[t];
+    }
+}
+__global__ void repeat_xinit_kernel(int n, int planners, int nx, const double* __restrict__ xs, double* __restrict__ xinit)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n * nx) xinit[t] = xs[(size_t)(t / nx / planners) * nx + t % nx];
+}
+
 // FP64 roofline denominator: MEASURED_PEAKS.json has no FP64 entry, so bench.py measures the DFMA peak
 // with this kernel: 8 independent FMA chains per thread, 2 flops per FMA.
 __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double seed)
@@ -71,6 +102,9 @@ struct mpcgpu_engine {
     int *d_num_iter = nullptr, *d_exit = nullptr, *d_qps = nullptr, *d_ipm = nullptr, *d_counter = nullptr, *d_counter2 = nullptr, *d_offsets = nullptr,
         *d_best = nullptr;
     unsigned char* d_disabled = nullptr;
+    double *d_shared = nullptr, *d_pvals = nullptr, *d_xs = nullptr;   // compact (per-set) inputs, allocated on first use
+    int* d_pidx = nullptr;
+    size_t cap_shared = 0, cap_pvals = 0;
     long long launches = 0;
     std::string err;
 };
@@ -137,7 +171,7 @@ int mpcgpu_engine_destroy(mpcgpu_engine* e)
 {
     if (!e) return MPCGPU_ERR_ARG;
     cudaSetDevice(e->device);
-    void* ptrs[] = {e->d_xinit, e->d_x0, e->d_params, e->d_mem, e->d_xtraj, e->d_utraj, e->d_pobj, e->d_res_eq, e->d_scale,
+    void* ptrs[] = {e->d_shared, e->d_pvals, e->d_xs, e->d_pidx, e->d_xinit, e->d_x0, e->d_params, e->d_mem, e->d_xtraj, e->d_utraj, e->d_pobj, e->d_res_eq, e->d_scale,
                     e->d_sub, e->d_num_iter, e->d_exit, e->d_qps, e->d_ipm, e->d_counter, e->d_counter2, e->d_offsets, e->d_best, e->d_disabled};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -270,6 +304,79 @@ int mpcgpu_select_best_device(mpcgpu_engine* e, int n_sets, const int* set_offse
                                                               best_idx);
     CK(cudaGetLastError());
     e->launches += 1;
+    return MPCGPU_OK;
+}
+
+int mpcgpu_solve_sets(mpcgpu_engine* e, int n_sets, int planners, const double* xinit_sets, const double* shared_params,
+                      const double* x0, int nidx, const int* param_idx, const double* planner_params, const int* num_iter,
+                      int num_iter_all, double* xtraj, double* utraj, double* pobj, int* exit_code, int* qp_status, double* res_eq,
+                      const double* obj_scale, const double* obj_sub, const unsigned char* disabled, int* best_idx)
+{
+    if (!e || n_sets < 0 || planners <= 0 || !xinit_sets || !shared_params || !x0 || nidx < 0 || (nidx > 0 && (!param_idx || !planner_params)) ||
+        !xtraj || !utraj || !pobj || !exit_code || !qp_status || !res_eq || !best_idx)
+        return MPCGPU_ERR_ARG;
+    const long long nll = (long long)n_sets * planners;
+    if (nll > e->max_batch) return MPCGPU_ERR_ARG;
+    const int n = (int)nll;
+    if (n == 0) return MPCGPU_OK;
+    CK(cudaSetDevice(e->device));
+    const MpcConfigOps* o = e->ops;
+    const int N = o->N, nx = o->nx, nu = o->nu, nz = nx + nu, np = o->np;
+    for (int j = 0; j < nidx; j++)
+        if (param_idx[j] < 0 || param_idx[j] >= np) return MPCGPU_ERR_ARG;
+    cudaStream_t st = e->stream;
+    const size_t need_sh = (size_t)n_sets * N * np, need_pv = (size_t)n * N * (nidx > 0 ? nidx : 1);
+    if (need_sh > e->cap_shared) {
+        if (e->d_shared) cudaFree(e->d_shared);
+        if (e->d_xs) cudaFree(e->d_xs);
+        e->d_shared = nullptr; e->d_xs = nullptr; e->cap_shared = 0;
+        CK(cudaMalloc((void**)&e->d_shared, need_sh * 8));
+        CK(cudaMalloc((void**)&e->d_xs, (size_t)n_sets * nx * 8));
+        e->cap_shared = need_sh;
+    }
+    if (need_pv > e->cap_pvals) {
+        if (e->d_pvals) cudaFree(e->d_pvals);
+        e->d_pvals = nullptr; e->cap_pvals = 0;
+        CK(cudaMalloc((void**)&e->d_pvals, need_pv * 8));
+        e->cap_pvals = need_pv;
+    }
+    if (!e->d_pidx) CK(cudaMalloc((void**)&e->d_pidx, (size_t)np * 4));
+    CK(cudaMemcpyAsync(e->d_xs, xinit_sets, (size_t)n_sets * nx * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(e->d_shared, shared_params, need_sh * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(e->d_x0, x0, (size_t)n * nz * (N + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (nidx > 0) {
+        if (nidx > np) return MPCGPU_ERR_ARG;
+        CK(cudaMemcpyAsync(e->d_pidx, param_idx, (size_t)nidx * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(e->d_pvals, planner_params, (size_t)n * N * nidx * 8, cudaMemcpyHostToDevice, st));
+    }
+    if (num_iter) CK(cudaMemcpyAsync(e->d_num_iter, num_iter, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    repeat_xinit_kernel<<<(n * nx + 255) / 256, 256, 0, st>>>(n, planners, nx, e->d_xs, e->d_xinit);
+    expand_params_kernel<<<1184, 256, 0, st>>>(n, planners, N, np, nidx, e->d_shared, e->d_pidx, e->d_pvals, e->d_params);
+    if (nidx > 0) scatter_params_kernel<<<592, 256, 0, st>>>(n, N, np, nidx, e->d_pidx, e->d_pvals, e->d_params);
+    CK(cudaGetLastError());
+    e->launches += (nidx > 0) ? 3 : 2;
+    e->chunks_timed = 0;
+    int rc = launch_solve_on(e, st, e->d_counter, e->ev0, e->ev1, n, e->d_xinit, e->d_x0, e->d_params, num_iter ? e->d_num_iter : nullptr,
+                             num_iter_all, nullptr, e->d_xtraj, e->d_utraj, e->d_pobj, e->d_exit, e->d_qps, e->d_res_eq, e->d_ipm);
+    if (rc != MPCGPU_OK) return rc;
+    // selection on the device, then everything back
+    std::vector<int> off((size_t)n_sets + 1);
+    for (int s_ = 0; s_ <= n_sets; s_++) off[s_] = s_ * planners;
+    CK(cudaMemcpyAsync(e->d_offsets, off.data(), (size_t)(n_sets + 1) * 4, cudaMemcpyHostToDevice, st));
+    if (obj_scale) CK(cudaMemcpyAsync(e->d_scale, obj_scale, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    if (obj_sub) CK(cudaMemcpyAsync(e->d_sub, obj_sub, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    if (disabled) CK(cudaMemcpyAsync(e->d_disabled, disabled, (size_t)n, cudaMemcpyHostToDevice, st));
+    rc = mpcgpu_select_best_device(e, n_sets, e->d_offsets, e->d_pobj, e->d_exit, obj_scale ? e->d_scale : nullptr,
+                                   obj_sub ? e->d_sub : nullptr, disabled ? e->d_disabled : nullptr, e->d_best, st);
+    if (rc != MPCGPU_OK) return rc;
+    CK(cudaMemcpyAsync(xtraj, e->d_xtraj, (size_t)n * nx * (N + 1) * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(utraj, e->d_utraj, (size_t)n * nu * N * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(pobj, e->d_pobj, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(exit_code, e->d_exit, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(qp_status, e->d_qps, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(res_eq, e->d_res_eq, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(best_idx, e->d_best, (size_t)n_sets * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     return MPCGPU_OK;
 }
 

@@ -14,7 +14,7 @@ _lib = None
 
 SYMBOLS = [
     "mpcgpu_num_configs", "mpcgpu_config_name", "mpcgpu_engine_create", "mpcgpu_engine_destroy", "mpcgpu_desc_query",
-    "mpcgpu_mem_doubles", "mpcgpu_solve_batch", "mpcgpu_solve_batch_device", "mpcgpu_sync", "mpcgpu_select_best",
+    "mpcgpu_mem_doubles", "mpcgpu_solve_batch", "mpcgpu_solve_batch_device", "mpcgpu_sync", "mpcgpu_solve_sets", "mpcgpu_select_best",
     "mpcgpu_select_best_device", "mpcgpu_model_eval_doubles", "mpcgpu_model_eval", "mpcgpu_measure_fp64_peak", "mpcgpu_launch_count", "mpcgpu_last_kernel_ms", "mpcgpu_last_error",
 ]
 
@@ -158,6 +158,24 @@ class Engine:
                                                 int(num_iter), _ptr(mem), _ptr(xtraj), _ptr(utraj), _ptr(pobj), _ptr(exit_code),
                                                 _ptr(qp_status), _ptr(res_eq), _ptr(ipm_iters), _ptr(stream))
         self._check(rc, "mpcgpu_solve_batch_device")
+
+    def solve_sets(self, n_sets, planners, xinit_sets, shared_params, x0, param_idx, planner_params, num_iter=10, out=None):
+        """Compact homotopy-set entry: shared parameter block per set + per-planner overrides; returns the
+        per-problem outputs and `best` (selected planner per set)."""
+        n = n_sets * planners
+        if out is None:
+            out = self.alloc_outputs(n)
+            out["best"] = np.zeros(n_sets, np.int32)
+        idx = np.ascontiguousarray(param_idx, np.int32)
+        vp = ctypes.c_void_p
+        self.lib.mpcgpu_solve_sets.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, ctypes.c_int, vp, vp, vp, ctypes.c_int] + [vp] * 10
+        xs, sh, x0_, pv = (np.ascontiguousarray(a, np.float64) for a in (xinit_sets, shared_params, x0, planner_params))
+        assert sh.size == n_sets * self.N * self.npar and x0_.size == n * self.nz * (self.N + 1) and pv.size == n * self.N * idx.size
+        rc = self.lib.mpcgpu_solve_sets(self.handle, n_sets, planners, _ptr(xs), _ptr(sh), _ptr(x0_), int(idx.size), _ptr(idx), _ptr(pv), None,
+                                        int(num_iter), _ptr(out["xtraj"]), _ptr(out["utraj"]), _ptr(out["pobj"]), _ptr(out["exit_code"]),
+                                        _ptr(out["qp_status"]), _ptr(out["res_eq"]), None, None, None, _ptr(out["best"]))
+        self._check(rc, "mpcgpu_solve_sets")
+        return out
 
     def select_best(self, set_offsets, pobj, exit_code, obj_scale=None, obj_sub=None, disabled=None):
         set_offsets = np.ascontiguousarray(set_offsets, np.int32)

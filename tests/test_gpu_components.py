@@ -184,3 +184,32 @@ def test_full_size_batch_properties():
     okr = ref["exit_code"] == 1
     scale = np.maximum(1.0, np.abs(ref["xtraj"][okr]).max(axis=1))
     assert (np.abs(out["xtraj"][idx][okr] - ref["xtraj"][okr]).max(axis=1) / scale).max() < REL_TOL
+
+
+def compact_sets(batch, eng, planners):
+    """Split a flat synthetic batch into (shared block per set, indices that differ between the planners
+    of a set, their per-planner values) -- the inputs of mpcgpu_solve_sets."""
+    n = batch["n"]
+    n_sets = n // planners
+    P = batch["params"].reshape(n_sets, planners, eng.N, eng.npar)
+    differs = np.nonzero((P != P[:, :1]).any(axis=(0, 1, 2)))[0].astype(np.int32)
+    shared = np.ascontiguousarray(P[:, 0])
+    vals = np.ascontiguousarray(P[..., differs])
+    xs = np.ascontiguousarray(batch["xinit"].reshape(n_sets, planners, eng.nx)[:, 0])
+    return n_sets, xs, shared, differs, vals
+
+
+@pytest.mark.parametrize("cfg,planners", [("tmpc_shipped", 5), ("c2_tmpc12", 9)])
+def test_compact_set_entry_equals_flat_entry(cfg, planners):
+    """mpcgpu_solve_sets (shared parameter block per set + per-planner overrides + fused selection) gives
+    bit-identical results to mpcgpu_solve_batch + mpcgpu_select_best on the expanded inputs."""
+    eng = engine.Engine(cfg, 0, 512)
+    b = synthetic.make_batch(eng.parameter_map, eng.dims, 12, planners, seed=17)
+    n_sets, xs, shared, idx, vals = compact_sets(b, eng, planners)
+    assert 0 < idx.size < eng.npar // 2                       # only the guidance halfspaces (+ consistency reference) differ
+    flat = eng.solve_batch(b["xinit"], b["x0"], b["params"], num_iter=4)
+    best = eng.select_best(b["set_offsets"], flat["pobj"], flat["exit_code"])
+    out = eng.solve_sets(n_sets, planners, xs, shared, b["x0"], idx, vals, num_iter=4)
+    for k in ("xtraj", "utraj", "pobj", "exit_code", "qp_status", "res_eq"):
+        np.testing.assert_array_equal(out[k], flat[k])
+    np.testing.assert_array_equal(out["best"], best)

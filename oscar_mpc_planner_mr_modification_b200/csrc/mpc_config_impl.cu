@@ -12,16 +12,20 @@ static cudaError_t launch_solve(int grid, cudaStream_t stream, int n, const doub
 {
     cudaError_t err = cudaMemsetAsync(work_counter, 0, sizeof(int), stream);
     if (err != cudaSuccess) return err;
-    mpc_solve_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(n, xinit, x0, params, num_iter, num_iter_all, mem, MEM_DOUBLES,
-                                                               xtraj, utraj, pobj, exit_code, qp_status, res_eq, ipm_iters,
-                                                               work_counter);
+    if (grid < 0)      // latency mode: one problem per CTA, -grid CTAs
+        mpc_solve_kernel<GW><<<-grid, GW * 32, 0, stream>>>(n, xinit, x0, params, num_iter, num_iter_all, mem, MEM_DOUBLES, xtraj, utraj,
+                                                             pobj, exit_code, qp_status, res_eq, ipm_iters, work_counter);
+    else
+        mpc_solve_kernel<WARPS_PER_CTA><<<grid, WARPS_PER_CTA * 32, 0, stream>>>(n, xinit, x0, params, num_iter, num_iter_all, mem,
+                                                                                  MEM_DOUBLES, xtraj, utraj, pobj, exit_code, qp_status,
+                                                                                  res_eq, ipm_iters, work_counter);
     return cudaGetLastError();
 }
 
 static cudaError_t occupancy(int* ctas_per_sm, int* threads_per_cta)
 {
     *threads_per_cta = WARPS_PER_CTA * 32;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, mpc_solve_kernel, WARPS_PER_CTA * 32, 0);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, mpc_solve_kernel<WARPS_PER_CTA>, WARPS_PER_CTA * 32, 0);
 }
 
 static cudaError_t launch_model_eval(cudaStream_t stream, int n, const double* z, const double* p, const double* pi,
@@ -32,7 +36,7 @@ static cudaError_t launch_model_eval(cudaStream_t stream, int n, const double* z
 }
 
 static const MpcConfigOps ops = {MPCGEN_CONFIG_NAME, NSTAGE, NX, NU, NP, NH, NC, MEM_DOUBLES, launch_solve, occupancy,
-                                 NHS, MODEL_EVAL_DOUBLES, launch_model_eval};
+                                 NHS, MODEL_EVAL_DOUBLES, launch_model_eval, GW};
 
 static struct Registrar {
     Registrar() { mpc_register_config(&ops); }

@@ -910,9 +910,12 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
 
 constexpr int WARPS_PER_CTA = MPC_WARPS_PER_CTA;
 
-// Persistent grid: warps pull problem indices from a global counter (work per problem is data
+// Persistent grid: warp groups pull problem indices from a global counter (work per problem is data
 // dependent: 50-100 interior-point iterations), so late finishers do not idle a whole CTA.
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, MPC_MIN_CTAS)
+// Two instantiations: WPC = WARPS_PER_CTA (throughput: 8 warps share an SM) and WPC = GW (latency: one
+// problem per CTA, so a small batch -- one homotopy set -- spreads over as many SMs as it has problems).
+template <int WPC>
+__global__ void __launch_bounds__(WPC * 32, (WPC == WARPS_PER_CTA) ? MPC_MIN_CTAS : 1)
 mpc_solve_kernel(int n, const double* __restrict__ xinit, const double* __restrict__ x0, const double* __restrict__ params,
                  const int* __restrict__ num_iter, int num_iter_all, double* mem, int mem_doubles, double* xtraj,
                  double* utraj, double* pobj, int* exit_code, int* qp_status, double* res_eq, int* ipm_iters,
@@ -920,7 +923,7 @@ mpc_solve_kernel(int n, const double* __restrict__ xinit, const double* __restri
 {
     // per-group shared memory: hand-off buffer of the Riccati sweeps ((P, p) of stage k+1 -> stage k,
     // dx_k+1 -> stage k+1), the cross-warp exchange area, and the fetched problem index
-    constexpr int GROUPS = WARPS_PER_CTA / GW;
+    constexpr int GROUPS = WPC / GW;
     __shared__ double s_hand[GROUPS][NPX + NX + 4];
     __shared__ double s_xch[GROUPS][GW * XCH];
     __shared__ int s_prob[GROUPS];

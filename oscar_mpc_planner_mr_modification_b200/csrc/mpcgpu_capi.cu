@@ -91,7 +91,7 @@ void mpc_register_config(const MpcConfigOps* ops) { registry().push_back(ops); }
 
 struct mpcgpu_engine {
     const MpcConfigOps* ops = nullptr;
-    int device = 0, max_batch = 0, grid = 0;
+    int device = 0, max_batch = 0, grid = 0, sms = 0, threads_per_cta = 0;
     cudaStream_t stream = nullptr, stream2 = nullptr;   // stream2: second lane of the chunked host pipeline
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t cev0[4] = {nullptr, nullptr, nullptr, nullptr}, cev1[4] = {nullptr, nullptr, nullptr, nullptr};   // per chunk (host path)
@@ -163,6 +163,8 @@ int mpcgpu_engine_create(const char* config_name, int device, int max_batch, mpc
         return fail(MPCGPU_ERR_CUDA);
     }
     e->grid = sms * ctas;   // persistent grid: every SM holds its full complement of CTAs
+    e->sms = sms;
+    e->threads_per_cta = threads;
     *out = e;
     return MPCGPU_OK;
 }
@@ -218,11 +220,16 @@ static int launch_solve_on(mpcgpu_engine* e, cudaStream_t st, int* counter, cuda
                            const double* x0, const double* params, const int* num_iter, int num_iter_all, double* mem_inout,
                            double* xtraj, double* utraj, double* pobj, int* exit_code, int* qp_status, double* res_eq, int* ipm_iters)
 {
-    int ctas_ = 0, threads_ = 128;
-    e->ops->occupancy(&ctas_, &threads_);
-    const int warps_per_cta = threads_ / 32;
-    int grid = (n + warps_per_cta - 1) / warps_per_cta;
-    if (grid > e->grid) grid = e->grid;
+    // small batches (one or a few homotopy sets): one problem per CTA so every problem gets its own SM;
+    // otherwise the persistent throughput grid
+    int grid;
+    if (n <= 2 * e->sms) {
+        grid = -n;
+    } else {
+        const int groups_per_cta = e->threads_per_cta / 32 / e->ops->group_warps;
+        grid = (n + groups_per_cta - 1) / groups_per_cta;
+        if (grid > e->grid) grid = e->grid;
+    }
     CK(cudaEventRecord(t0, st));
     CK(e->ops->launch_solve(grid, st, n, xinit, x0, params, num_iter, num_iter_all, mem_inout, xtraj, utraj, pobj, exit_code,
                             qp_status, res_eq, ipm_iters, counter));

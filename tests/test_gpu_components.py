@@ -213,3 +213,23 @@ def test_compact_set_entry_equals_flat_entry(cfg, planners):
     for k in ("xtraj", "utraj", "pobj", "exit_code", "qp_status", "res_eq"):
         np.testing.assert_array_equal(out[k], flat[k])
     np.testing.assert_array_equal(out["best"], best)
+
+
+def test_gpu_converged_iterate_is_a_kkt_point_of_the_reference_nlp():
+    """Same algorithm-independent NLP-level check as tests/test_nlp_optimality.py, on the GPU result."""
+    from test_nlp_optimality import nlp_kkt
+    cfg, planners = "c2_tmpc12", 9
+    eng = engine.Engine(cfg, 0, 64)
+    orc = Oracle(cfg)               # model functions only (pinned to the reference by the golden tests)
+    b = synthetic.make_batch(eng.parameter_map, eng.dims, 1, planners, seed=41)
+    mem = np.zeros((b["n"], eng.mem_doubles))
+    r = eng.solve_batch(b["xinit"], b["x0"], b["params"], num_iter=40, mem=mem)
+    checked = 0
+    for i in np.nonzero(r["exit_code"] == 1)[0]:
+        x = r["xtraj"][i].reshape(eng.N + 1, eng.nx); u = r["utraj"][i].reshape(eng.N, eng.nu)
+        stat, dyn, feas, comp, x0err = nlp_kkt(orc, b["xinit"][i], b["params"][i], x, u, mem[i])
+        if dyn > 1e-6:
+            continue
+        checked += 1
+        assert stat < 5e-4 and feas < 1e-5 and comp < 1e-3 and x0err < 1e-9, (i, stat, feas, comp)
+    assert checked >= 5

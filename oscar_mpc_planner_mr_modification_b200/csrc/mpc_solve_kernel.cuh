@@ -176,7 +176,7 @@ struct Grp {
 constexpr int JP = NZ + 1;                       // positions
 constexpr int JPK = JP * (JP + 1) / 2;
 __host__ __device__ constexpr int jsigma(int j) { return j == 0 ? 0 : (j == 1 ? JP - 1 : j - 1); }   // new position j <- old position
-__device__ __noinline__ void mirror_packed(double* Hp)
+__device__ __noinline__ void mirror_generic(double* Hp)
 {
     static_assert(NZ == 7, "tournament table is written for 7 variables + 1 dummy");
     double a[JPK], V[NZ][JP];
@@ -266,6 +266,114 @@ __device__ __noinline__ void mirror_packed(double* Hp)
             for (int k = 0; k < NZ; k++) s += V[i][k] * ev[k] * V[j][k];
             Hp[pk(i, j)] = s;
         }
+}
+
+// Block path: when the entries that couple the emitter's Hessian blocks (HBLK_*) are exactly zero in every lane
+// of the warp (e.g. zero disc offset: the constraints do not depend on psi), MIRROR acts on each diagonal block
+// separately -- a 4x4 and a 3x3 Jacobi instead of a 7x7 one.  Row-cyclic order, same rotation and stopping rule.
+template <int B>
+__device__ __forceinline__ void mirror_block(double* Hp)
+{
+    constexpr int n = HBLK_SIZE[B];
+    double a[n][n], V[n][n];
+#pragma unroll
+    for (int i = 0; i < n; i++)
+#pragma unroll
+        for (int j = 0; j < n; j++) {
+            a[i][j] = Hp[pk(HBLK_IDX[B][i], HBLK_IDX[B][j])];
+            V[i][j] = (i == j) ? 1.0 : 0.0;
+        }
+#pragma unroll 1
+    for (int sweep = 0; sweep < JACOBI_MAX_SWEEPS; sweep++) {
+        double off = 0.0, dia = 0.0;
+#pragma unroll
+        for (int i = 0; i < n; i++)
+#pragma unroll
+            for (int j = 0; j <= i; j++) {
+                if (i == j) dia += a[i][j] * a[i][j];
+                else off += a[i][j] * a[i][j];
+            }
+        off *= 2.0;
+        if (!(off > JACOBI_TOL * (off + dia))) break;
+#pragma unroll
+        for (int p = 0; p < n - 1; p++)
+#pragma unroll
+            for (int q = p + 1; q < n; q++) {
+                const double apq = a[q][p], q2 = apq * apq;
+                if (q2 > 0.0) {
+                    const double tau = a[q][q] - a[p][p];
+                    const double ir = rsqrt(tau * tau + 4.0 * q2);
+                    const double c2 = 0.5 + 0.5 * fabs(tau) * ir;
+                    const double ic = rsqrt(c2), c = c2 * ic;
+                    const double sn = (tau >= 0.0 ? apq : -apq) * ir * ic, tt = sn * ic;
+#pragma unroll
+                    for (int k = 0; k < n; k++) {
+                        if (k != p && k != q) {
+                            const double akp = a[k][p], akq = a[k][q];
+                            const double np_ = c * akp - sn * akq, nq_ = sn * akp + c * akq;
+                            a[k][p] = np_; a[p][k] = np_;
+                            a[k][q] = nq_; a[q][k] = nq_;
+                        }
+                    }
+                    a[p][p] -= tt * apq;
+                    a[q][q] += tt * apq;
+                    a[q][p] = 0.0; a[p][q] = 0.0;
+#pragma unroll
+                    for (int k = 0; k < n; k++) {
+                        const double vkp = V[k][p], vkq = V[k][q];
+                        V[k][p] = c * vkp - sn * vkq;
+                        V[k][q] = sn * vkp + c * vkq;
+                    }
+                }
+            }
+    }
+#pragma unroll
+    for (int i = 0; i < n; i++) {
+        double e = a[i][i];
+        if (e >= -REG_EPS && e <= REG_EPS) e = REG_EPS;
+        else if (e < 0.0) e = -e;
+        a[i][i] = e;
+    }
+#pragma unroll
+    for (int i = 0; i < n; i++)
+#pragma unroll
+        for (int j = 0; j <= i; j++) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < n; k++) s += V[i][k] * a[k][k] * V[j][k];
+            Hp[pk(HBLK_IDX[B][i], HBLK_IDX[B][j])] = s;
+        }
+}
+template <int B>
+__device__ __forceinline__ void mirror_blocks_from(double* Hp)
+{
+    if constexpr (B < HBLK_N) {
+        mirror_block<B>(Hp);
+        mirror_blocks_from<B + 1>(Hp);
+    }
+}
+__host__ __device__ constexpr int hblk_of(int v)
+{
+    for (int b = 0; b < HBLK_N; b++)
+        for (int i = 0; i < HBLK_SIZE[b]; i++)
+            if (HBLK_IDX[b][i] == v) return b;
+    return -1;
+}
+__device__ __noinline__ void mirror_packed(double* Hp)
+{
+    if constexpr (HBLK_N > 1) {
+        bool coupled = false;
+#pragma unroll
+        for (int i = 0; i < NZ; i++)
+#pragma unroll
+            for (int j = 0; j < i; j++)
+                if (hblk_of(i) != hblk_of(j)) coupled = coupled || (Hp[pk(i, j)] != 0.0);
+        if (!__any_sync(__activemask(), coupled)) {
+            mirror_blocks_from<0>(Hp);
+            return;
+        }
+    }
+    mirror_generic(Hp);
 }
 
 // chat_e' y for general entry e (y indexed by z component)

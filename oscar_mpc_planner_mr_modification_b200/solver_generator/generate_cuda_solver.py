@@ -290,6 +290,29 @@ def emit_model_header(pb, name, sim_steps=3):
     w("    return l;\n}")
     g = [sp.diff(cost, v) for v in z]
     Hc = {(i, j): sp.diff(g[i], z[j]) for i in range(nz) for j in range(i + 1)}
+    # Diagonal blocks of the stage Hessian when the constraints add no coupling (e.g. zero disc offset: h does not
+    # depend on psi): connected components of the sparsity of (cost Hessian + dynamics second-order term).  The
+    # kernel checks the coupling entries at run time and then mirrors the blocks separately.
+    adj = {i: {i} for i in range(nz)}
+    for (i, j), e in list(Hc.items()) + list(Hd.items()):
+        if e != 0:
+            adj[i].add(j); adj[j].add(i)
+    comp, seen = [], set()
+    for i in range(nz):
+        if i in seen:
+            continue
+        stack, c = [i], []
+        while stack:
+            q_ = stack.pop()
+            if q_ in seen:
+                continue
+            seen.add(q_); c.append(q_); stack.extend(adj[q_] - seen)
+        comp.append(sorted(c))
+    bmax = max(len(c) for c in comp)
+    w("constexpr int HBLK_N = %d, HBLK_MAX = %d;   // Hessian blocks without constraint coupling: %s" % (len(comp), bmax, comp))
+    w("__device__ constexpr int HBLK_SIZE[%d] = {%s};" % (len(comp), ", ".join(str(len(c)) for c in comp)))
+    w("__device__ constexpr int HBLK_IDX[%d][%d] = {%s};" % (len(comp), bmax, ", ".join(
+        "{" + ", ".join(str(v) for v in c + [-1] * (bmax - len(c))) + "}" for c in comp)))
     w("\n// g = DT * grad l ; H(packed) = DT * hess l   (all NPK entries written)")
     w("__device__ __forceinline__ void cost_lin(const double* z, const double* __restrict__ p, double* g, double* H)\n{")
     w(emit_block([("g[%d]" % i, pb["dt"] * g[i]) for i in range(nz)] +

@@ -57,3 +57,17 @@ def test_solve_parity(cfg, planners, num_iter):
     best = eng.select_best(batch["set_offsets"], out["pobj"], out["exit_code"])
     ref_best = orc.select_best(batch["set_offsets"], ref["pobj"], ref["exit_code"])
     assert (best == ref_best).all()
+
+
+@pytest.mark.parametrize("cfg,planners", [("c1_basic", 1), ("c2_tmpc12", 9)])
+def test_solve_parity_with_disc_offset(cfg, planners):
+    """A non-zero ego disc offset makes the constraints depend on psi, which couples the two Hessian blocks:
+    the kernel must then take the generic 7x7 MIRROR path instead of the block-wise one."""
+    eng = engine.Engine(cfg, device=0, max_batch=256)
+    orc = Oracle(cfg)
+    batch = synthetic.make_batch(eng.parameter_map, eng.dims, 12 if planners > 1 else 48, planners, seed=77)
+    P = batch["params"].reshape(batch["n"], eng.N, eng.npar)
+    P[:, :, eng.parameter_map["ego_disc_0_offset"]] = 0.2
+    out = eng.solve_batch(batch["xinit"], batch["x0"], batch["params"], num_iter=10)
+    ref = orc.solve_batch(batch["xinit"], batch["x0"], batch["params"], num_iter=10)
+    check(out, ref)

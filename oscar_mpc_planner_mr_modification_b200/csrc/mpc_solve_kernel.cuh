@@ -101,7 +101,7 @@ __device__ __forceinline__ double warp_sum(double v)
 
 // ---- group primitives: warp shuffles inside a warp, shared-memory exchange + named barrier across the
 //      GW warps of a problem.  For GW == 1 every function reduces to the plain warp intrinsic.
-constexpr int XCH = 16;                          // exchange doubles per warp
+constexpr int XCH = 32;                          // exchange doubles per warp (an affine map: 30)
 struct Grp {
     double* xch;                                 // [GW][XCH] shared-memory exchange area of this group
     int gid, wig;                                // group index inside the CTA, warp index inside the group
@@ -123,6 +123,28 @@ struct Grp {
             }
             sync();
             if (wig == 0 && lane == 31) {
+#pragma unroll
+                for (int i = 0; i < n; i++) out[i] = xch[i];
+            }
+            sync();
+        }
+    }
+    // out[i] <- in[i] of the thread owning stage k-1 (zero for stage 0)
+    template <int n> __device__ __forceinline__ void shift_up(const double (&in)[n], double (&out)[n]) const
+    {
+        const int lane = threadIdx.x & 31;
+#pragma unroll
+        for (int i = 0; i < n; i++) {
+            const double t = __shfl_up_sync(FULL, in[i], 1);
+            out[i] = (lane == 0) ? 0.0 : t;
+        }
+        if constexpr (GW > 1) {
+            if (wig == 0 && lane == 31) {
+#pragma unroll
+                for (int i = 0; i < n; i++) xch[i] = in[i];
+            }
+            sync();
+            if (wig == 1 && lane == 0) {
 #pragma unroll
                 for (int i = 0; i < n; i++) out[i] = xch[i];
             }
@@ -165,6 +187,127 @@ struct Grp {
         return across<0>(acc);
     }
 };
+
+// ---- Parallel-in-stage substitution sweeps.  With the factorisation in hand both the forward sweep
+//      dx_{k+1} = Acl_k dx_k + bcl_k  and the backward vector sweep  p_k = Acl_k' p_{k+1} + c_k  are affine
+//      recurrences with the closed-loop matrices Acl_k = A_k + B_k K_k, K_k = -Luu^-T Lxu'.  Affine maps compose
+//      associatively, so the recurrences are evaluated as a Hillis-Steele scan over the lanes (log2(32) levels of
+//      5x5 products with all lanes busy) instead of 30 dependent single-lane steps.
+struct Aff {
+    double M[NX * NX], c[NX];                    // x -> M x + c
+};
+// a <- a o r  (apply r first):  M = a.M r.M,  c = a.M r.c + a.c ; row by row, in place
+__device__ __forceinline__ void aff_compose(Aff& a, const Aff& r, bool with_matrix)
+{
+#pragma unroll
+    for (int i = 0; i < NX; i++) {
+        double row[NX], ci = a.c[i];
+#pragma unroll
+        for (int l = 0; l < NX; l++) ci += a.M[i * NX + l] * r.c[l];
+        a.c[i] = ci;
+        if (with_matrix) {
+#pragma unroll
+            for (int j = 0; j < NX; j++) {
+                double m = 0.0;
+#pragma unroll
+                for (int l = 0; l < NX; l++) m += a.M[i * NX + l] * r.M[l * NX + j];
+                row[j] = m;
+            }
+#pragma unroll
+            for (int j = 0; j < NX; j++) a.M[i * NX + j] = row[j];
+        }
+    }
+}
+// Inclusive scan over the stages.  UP: lane k ends with a_k o a_{k-1} o ... o a_0 (forward sweep);
+// !UP: lane k ends with a_k o a_{k+1} o ... (backward sweep).  Only the vector part is needed afterwards.
+template <bool UP>
+__device__ __noinline__ void aff_scan(Aff* ap, const Grp grp)      // ONE copy of the scan per direction: code size matters
+{
+    Aff a = *ap;
+    const int lane = threadIdx.x & 31;
+#pragma unroll 1
+    for (int d = 1; d < 32; d <<= 1) {
+        Aff r;
+#pragma unroll
+        for (int i = 0; i < NX * NX; i++) r.M[i] = UP ? __shfl_up_sync(FULL, a.M[i], d) : __shfl_down_sync(FULL, a.M[i], d);
+#pragma unroll
+        for (int i = 0; i < NX; i++) r.c[i] = UP ? __shfl_up_sync(FULL, a.c[i], d) : __shfl_down_sync(FULL, a.c[i], d);
+        const bool valid = UP ? (lane >= d) : (lane + d < 32);
+        if (valid) aff_compose(a, r, GW > 1 || d < 16);
+    }
+    if constexpr (GW > 1) {
+        // second warp (UP) / first warp (!UP) continues from the other warp's total
+        const bool src = UP ? (grp.wig == 0 && lane == 31) : (grp.wig == 1 && lane == 0);
+        double* x = grp.xch;                     // needs NX*NX + NX <= GW * XCH doubles
+        static_assert(NX * NX + NX <= GW * XCH, "exchange area too small for an affine map");
+        if (src) {
+#pragma unroll
+            for (int i = 0; i < NX * NX; i++) x[i] = a.M[i];
+#pragma unroll
+            for (int i = 0; i < NX; i++) x[NX * NX + i] = a.c[i];
+        }
+        grp.sync();
+        if (UP ? (grp.wig == 1) : (grp.wig == 0)) {
+            Aff r;
+#pragma unroll
+            for (int i = 0; i < NX * NX; i++) r.M[i] = x[i];
+#pragma unroll
+            for (int i = 0; i < NX; i++) r.c[i] = x[NX * NX + i];
+            aff_compose(a, r, false);
+        }
+        grp.sync();
+    }
+#pragma unroll
+    for (int i = 0; i < NX; i++) ap->c[i] = a.c[i];      // only the vector part is used by the callers
+}
+// closed-loop matrix of one stage from the factorisation: Acl = A + B K, K = -Luu^-T Lxu'
+__device__ __forceinline__ void closed_loop(const double* Wv, const double* Lx0, const double* Lx1, double L10, double iL0, double iL1,
+                                            double* Acl /*NX*NX*/, double* Bd /*NX*NU*/)
+{
+    double Wd[NX * NZ], K0[NX], K1[NX];
+    w_to_dense(Wv, Wd);
+#pragma unroll
+    for (int j = 0; j < NX; j++) {
+        K1[j] = -Lx1[j] * iL1;
+        K0[j] = -(Lx0[j] + L10 * K1[j]) * iL0;
+    }
+#pragma unroll
+    for (int i = 0; i < NX; i++) {
+        Bd[i * NU] = Wd[i * NZ]; Bd[i * NU + 1] = Wd[i * NZ + 1];
+#pragma unroll
+        for (int j = 0; j < NX; j++) Acl[i * NX + j] = Wd[i * NZ + NU + j] + Wd[i * NZ] * K0[j] + Wd[i * NZ + 1] * K1[j];
+    }
+}
+// forward sweep by scan: returns du (2) and dx (NX) of this lane's stage in dvec = [du; dx]
+__device__ __noinline__ void forward_scan(const double* Wv, const double* Lx0, const double* Lx1, double L10, double iL0, double iL1,
+                                             const double* lv, const double* rb, bool path, double* dvec, const Grp grp)
+{
+    Aff a;
+    double Bd[NX * NU];
+    if (path) {
+        closed_loop(Wv, Lx0, Lx1, L10, iL0, iL1, a.M, Bd);
+        const double k1 = -lv[1] * iL1, k0 = -(lv[0] + L10 * k1) * iL0;      // kff = -Luu^-T l
+#pragma unroll
+        for (int i = 0; i < NX; i++) a.c[i] = rb[i] + Bd[i * NU] * k0 + Bd[i * NU + 1] * k1;
+    } else {                                     // terminal / idle lanes: identity
+#pragma unroll
+        for (int i = 0; i < NX * NX; i++) a.M[i] = (i / NX == i % NX) ? 1.0 : 0.0;
+#pragma unroll
+        for (int i = 0; i < NX; i++) a.c[i] = 0.0;
+    }
+    aff_scan<true>(&a, grp);                     // lane k: a.c = dx_{k+1}   (dx_0 = 0)
+    double dxn[NX], dx[NX];
+#pragma unroll
+    for (int i = 0; i < NX; i++) dxn[i] = a.c[i];
+    grp.shift_up(dxn, dx);                       // dx_k from lane k-1 (stage 0: zero)
+#pragma unroll
+    for (int i = 0; i < NX; i++) dvec[NU + i] = dx[i];
+    double r0 = lv[0], r1 = lv[1];               // du = -Luu^-T (Lxu' dx + l)
+#pragma unroll
+    for (int j = 0; j < NX; j++) { r0 += Lx0[j] * dx[j]; r1 += Lx1[j] * dx[j]; }
+    dvec[1] = path ? -r1 * iL1 : 0.0;
+    dvec[0] = path ? -(r0 + L10 * dvec[1]) * iL0 : 0.0;
+}
 
 // ---- K4: MIRROR regularisation of one packed symmetric NZ x NZ block (cyclic Jacobi) -----------
 // Register-resident AND compact: the pair order is the round-robin tournament on NZ+1 = 8 positions
@@ -419,6 +562,9 @@ __device__ __forceinline__ void step_limit(double val, double dval, double& bn, 
 // ------------------------------------------------------------------------------------------------
 // One Solver::solve() on one warp
 // ------------------------------------------------------------------------------------------------
+// SCAN: substitution sweeps as a parallel prefix scan over the stages (lowest latency: the latency-mode kernel)
+// or lane-serial (fewest instructions: the throughput kernel).
+template <bool SCAN>
 __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, const double* __restrict__ x0_g,
                               const double* __restrict__ params_g, int num_iter, double* mem_g, int mem_doubles,
                               double* xtraj_g, double* utraj_g, double* pobj_g, int* exit_g, int* qps_g,
@@ -767,9 +913,12 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
             }
             // forward sweep: dva
 #pragma unroll
-            for (int i = 0; i < NZ; i++) dva[i] = 0.0;
-#pragma unroll
             for (int i = 0; i < NX; i++) dpi[i] = 0.0;
+            if constexpr (SCAN) {
+            forward_scan(Wv, Lx0, Lx1, L10, iL0, iL1, lv, rb, path, dva, grp);
+            } else {
+#pragma unroll
+            for (int i = 0; i < NZ; i++) dva[i] = 0.0;
 #pragma unroll 1
             for (int s = 0; s < NSTAGE; s++) {
                 grp.sync();
@@ -795,6 +944,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
             if (term) {
 #pragma unroll
                 for (int i = 0; i < NX; i++) dva[NU + i] = hb[i];
+            }
             }
 
             // ---- pass B: affine step length, mu_aff sums, corrector vectors
@@ -852,6 +1002,50 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
             for (int i = 0; i < NZ; i++) gt[i] += V1[i] - sigmu * V2[i];
 
             // ---- corrector solve (factorisation reused): backward vector sweep + forward sweep
+            if constexpr (SCAN) {
+            {   // backward vector sweep as a scan: p_k = Acl_k' (p_{k+1} + P_{k+1} rb_k) + (gt_x - Lxu Luu^-1 gt_u)
+                Aff am;
+                double Bd[NX * NU];
+                if (path) {
+                    double Acl[NX * NX];
+                    closed_loop(Wv, Lx0, Lx1, L10, iL0, iL1, Acl, Bd);
+                    const double lg0 = gt[0] * iL0, lg1 = (gt[1] - L10 * lg0) * iL1;
+#pragma unroll
+                    for (int i = 0; i < NX; i++) {
+                        double c_ = gt[NU + i] - Lx0[i] * lg0 - Lx1[i] * lg1;
+#pragma unroll
+                        for (int j = 0; j < NX; j++) {
+                            am.M[i * NX + j] = Acl[j * NX + i];
+                            c_ += Acl[j * NX + i] * Prb[j];
+                        }
+                        am.c[i] = c_;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < NX * NX; i++) am.M[i] = (!term && i / NX == i % NX) ? 1.0 : 0.0;   // terminal: absorbing
+#pragma unroll
+                    for (int i = 0; i < NX; i++) am.c[i] = term ? gt[NU + i] : 0.0;
+#pragma unroll
+                    for (int i = 0; i < NX * NU; i++) Bd[i] = 0.0;
+                }
+                aff_scan<false>(&am, grp);
+                double pn[NX];
+#pragma unroll
+                for (int i = 0; i < NX; i++) pv[i] = am.c[i];
+                grp.shift_down(pv, pn);
+                if (path) {
+                    double q0 = gt[0], q1 = gt[1];
+#pragma unroll
+                    for (int i = 0; i < NX; i++) {
+                        const double y = pn[i] + Prb[i];
+                        q0 += Bd[i * NU] * y; q1 += Bd[i * NU + 1] * y;
+                    }
+                    lv[0] = q0 * iL0;
+                    lv[1] = (q1 - L10 * lv[0]) * iL1;
+                }
+            }
+            forward_scan(Wv, Lx0, Lx1, L10, iL0, iL1, lv, rb, path, dv, grp);
+            } else {
             grp.sync();
             if (term) {
 #pragma unroll
@@ -903,6 +1097,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
             if (term) {
 #pragma unroll
                 for (int i = 0; i < NX; i++) dv[NU + i] = hb[i];
+            }
             }
             if (k >= 1 && live) {                       // dpi_k = P_k dx_k + p_k (lane-parallel)
 #pragma unroll
@@ -1053,7 +1248,7 @@ mpc_solve_kernel(int n, const double* __restrict__ xinit, const double* __restri
         }
         if (prob >= n) return;
         const int nit = num_iter ? num_iter[prob] : num_iter_all;
-        solve_problem(prob, xinit, x0, params, nit, mem, mem_doubles, xtraj, utraj, pobj, exit_code, qp_status, res_eq,
+        solve_problem<(WPC != WARPS_PER_CTA)>(prob, xinit, x0, params, nit, mem, mem_doubles, xtraj, utraj, pobj, exit_code, qp_status, res_eq,
                       ipm_iters, s_hand[grp.gid], grp);
     }
 }

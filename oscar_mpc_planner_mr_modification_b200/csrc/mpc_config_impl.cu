@@ -4,7 +4,32 @@
 
 namespace MPC_NS {
 
+constexpr size_t SMEM_THR = COOP ? (size_t)(WARPS_PER_CTA / GW) * RS_DOUBLES * sizeof(double) : 0;   // cooperative Riccati workspace
+constexpr size_t SMEM_LAT = COOP ? (size_t)RS_DOUBLES * sizeof(double) : 0;
+#ifndef MPC_SPLIT
+#define MPC_SPLIT 1
+#endif
+// Role-split kernel (one CTA of several warps per problem, mpc_solve_split.cuh) for SMALL batches -- one or a few homotopy
+// sets, where latency is what counts -- when the configuration has enough general constraints to share out.  Large
+// batches use the thread-per-stage kernel (8 problems per SM; higher throughput).  MPC_SPLIT=2 forces it for every batch.
+constexpr bool USE_SPLIT = (MPC_SPLIT != 0) && SPLIT_OK;
+constexpr bool SPLIT_ALWAYS = (MPC_SPLIT == 2) && SPLIT_OK;
+constexpr size_t SMEM_SPLIT = (size_t)SP_DOUBLES * sizeof(double);
 constexpr int MEM_DOUBLES = 1 + (NSTAGE + 1) * NX + 2 * NSTAGE * NC + (NSTAGE + 1) * NZ;
+
+// dynamic shared memory beyond 48 KB is an opt-in per kernel (and per device context: set on every call, it is cheap)
+static cudaError_t set_smem_attributes()
+{
+    cudaError_t err = cudaSuccess;
+    if (USE_SPLIT) {
+        err = cudaFuncSetAttribute(mpc_solve_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_SPLIT);
+        if (err != cudaSuccess || SPLIT_ALWAYS) return err;
+    }
+    err = cudaFuncSetAttribute(mpc_solve_kernel<GW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LAT);
+    if (err == cudaSuccess && GW != WARPS_PER_CTA)
+        err = cudaFuncSetAttribute(mpc_solve_kernel<WARPS_PER_CTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_THR);
+    return err;
+}
 
 static cudaError_t launch_solve(int grid, cudaStream_t stream, int n, const double* xinit, const double* x0, const double* params,
                          const int* num_iter, int num_iter_all, double* mem, double* xtraj, double* utraj, double* pobj,
@@ -12,11 +37,17 @@ static cudaError_t launch_solve(int grid, cudaStream_t stream, int n, const doub
 {
     cudaError_t err = cudaMemsetAsync(work_counter, 0, sizeof(int), stream);
     if (err != cudaSuccess) return err;
-    if (grid < 0)      // latency mode: one problem per CTA, -grid CTAs
-        mpc_solve_kernel<GW><<<-grid, GW * 32, 0, stream>>>(n, xinit, x0, params, num_iter, num_iter_all, mem, MEM_DOUBLES, xtraj, utraj,
+    err = set_smem_attributes();
+    if (err != cudaSuccess) return err;
+    if (USE_SPLIT && (grid < 0 || SPLIT_ALWAYS))
+        mpc_solve_split_kernel<<<grid < 0 ? -grid : grid, SPLIT_THREADS, SMEM_SPLIT, stream>>>(n, xinit, x0, params, num_iter, num_iter_all, mem,
+                                                                                          MEM_DOUBLES, xtraj, utraj, pobj, exit_code,
+                                                                                          qp_status, res_eq, ipm_iters, work_counter);
+    else if (grid < 0)      // latency mode: one problem per CTA, -grid CTAs
+        mpc_solve_kernel<GW><<<-grid, GW * 32, SMEM_LAT, stream>>>(n, xinit, x0, params, num_iter, num_iter_all, mem, MEM_DOUBLES, xtraj, utraj,
                                                              pobj, exit_code, qp_status, res_eq, ipm_iters, work_counter);
     else
-        mpc_solve_kernel<WARPS_PER_CTA><<<grid, WARPS_PER_CTA * 32, 0, stream>>>(n, xinit, x0, params, num_iter, num_iter_all, mem,
+        mpc_solve_kernel<WARPS_PER_CTA><<<grid, WARPS_PER_CTA * 32, SMEM_THR, stream>>>(n, xinit, x0, params, num_iter, num_iter_all, mem,
                                                                                   MEM_DOUBLES, xtraj, utraj, pobj, exit_code, qp_status,
                                                                                   res_eq, ipm_iters, work_counter);
     return cudaGetLastError();
@@ -24,8 +55,14 @@ static cudaError_t launch_solve(int grid, cudaStream_t stream, int n, const doub
 
 static cudaError_t occupancy(int* ctas_per_sm, int* threads_per_cta)
 {
+    cudaError_t err = set_smem_attributes();
+    if (err != cudaSuccess) return err;
+    if (SPLIT_ALWAYS) {
+        *threads_per_cta = SPLIT_THREADS;
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, mpc_solve_split_kernel, SPLIT_THREADS, SMEM_SPLIT);
+    }
     *threads_per_cta = WARPS_PER_CTA * 32;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, mpc_solve_kernel<WARPS_PER_CTA>, WARPS_PER_CTA * 32, 0);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, mpc_solve_kernel<WARPS_PER_CTA>, WARPS_PER_CTA * 32, SMEM_THR);
 }
 
 static cudaError_t launch_model_eval(cudaStream_t stream, int n, const double* z, const double* p, const double* pi,
@@ -36,7 +73,7 @@ static cudaError_t launch_model_eval(cudaStream_t stream, int n, const double* z
 }
 
 static const MpcConfigOps ops = {MPCGEN_CONFIG_NAME, NSTAGE, NX, NU, NP, NH, NC, MEM_DOUBLES, launch_solve, occupancy,
-                                 NHS, MODEL_EVAL_DOUBLES, launch_model_eval, GW};
+                                 NHS, MODEL_EVAL_DOUBLES, launch_model_eval, SPLIT_ALWAYS ? SPLIT_WARPS : GW};
 
 static struct Registrar {
     Registrar() { mpc_register_config(&ops); }

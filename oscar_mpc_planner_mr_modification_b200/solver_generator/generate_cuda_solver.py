@@ -380,6 +380,46 @@ def emit_model_header(pb, name, sim_steps=3):
             w(emit_block(outs, mq, tmp_prefix="k%d_" % gi, indent="        "))
             w("    }")
     w("}")
+
+    # ---- the same two functions restricted to the rows [r_lo, r_hi): outputs are indexed by (row - r_lo).  Used by the
+    #      role-split kernel, where the general constraints of a stage are shared out over several warps.
+    w("\n// rows [r_lo, r_hi) only: hv[r - r_lo], C[(r - r_lo)*NHS + s]")
+    w("__device__ __forceinline__ void con_eval_rows(const double* z, const double* __restrict__ p, int r_lo, int r_hi, double* hv, double* C)\n{")
+    for i in flat:
+        w("    if (r_lo <= %d && %d < r_hi) {\n        const int o = %d - r_lo;" % (i, i, i))
+        w(emit_block([("hv[o]", h[i])] + [("C[o * %d + %d]" % (nhs, s_), sp.diff(h[i], z[sup[s_]])) for s_ in range(nhs)],
+                     m, tmp_prefix="f%d_" % i, indent="        "))
+        w("    }")
+    for gi, (r0, cnt, stride, fixed) in enumerate(groups):
+        w("#pragma unroll 1\n    for (int r = (r_lo > %d ? r_lo - %d : 0); r < (r_hi - %d < %d ? r_hi - %d : %d); r++) {" % (r0, r0, r0, cnt, r0, cnt))
+        w("        const double* __restrict__ q = p + r * %d;\n        const int o = %d + r - r_lo;" % (stride, r0))
+        w(emit_block([("hv[o]", h[r0])] + [("C[o * %d + %d]" % (nhs, s_), sp.diff(h[r0], z[sup[s_]])) for s_ in range(nhs)],
+                     qmap(r0, fixed), tmp_prefix="g%d_" % gi, indent="        "))
+        w("    }")
+    w("}")
+    w("\n// rows [r_lo, r_hi) only: H(packed NZ) += sum_r mh[r - r_lo] d2 h_r / dz2")
+    w("__device__ __forceinline__ void con_hess_add_rows(const double* z, const double* __restrict__ p, int r_lo, int r_hi, const double* mh, double* H)\n{")
+    if nh:
+        for i in flat:
+            outs = hess_outputs([i], mhs)
+            if not outs:
+                continue
+            m3 = dict(m)
+            m3[mhs[i]] = "mh[%d - r_lo]" % i
+            w("    if (r_lo <= %d && %d < r_hi) {" % (i, i))
+            w(emit_block(outs, m3, tmp_prefix="e%d_" % i, indent="        "))
+            w("    }")
+        for gi, (r0, cnt, stride, fixed) in enumerate(groups):
+            outs = hess_outputs([r0], mhs)
+            if not outs:
+                continue
+            mq = qmap(r0, fixed)
+            mq[mhs[r0]] = "mh[%d + r - r_lo]" % r0
+            w("#pragma unroll 1\n    for (int r = (r_lo > %d ? r_lo - %d : 0); r < (r_hi - %d < %d ? r_hi - %d : %d); r++) {" % (r0, r0, r0, cnt, r0, cnt))
+            w("        const double* __restrict__ q = p + r * %d;" % stride)
+            w(emit_block(outs, mq, tmp_prefix="k%d_" % gi, indent="        "))
+            w("    }")
+    w("}")
     w("}  // namespace mpcgen")
     return "\n".join(out) + "\n"
 

@@ -120,6 +120,16 @@ int mpcgpu_model_eval(mpcgpu_engine *e, int n, const double *z, const double *p,
  * resident DFMA kernel (best of 5 after warm-up).  The FP64 roofline denominator of bench.py. */
 int mpcgpu_measure_fp64_peak(int device, double *tflops);
 
+/* Kernel choice (no reference counterpart).  Two kernels implement the same solve: the thread-per-stage kernel
+ * (one warp per problem, 8 problems per SM: throughput) and the role-split kernel (one CTA of 4 warps per
+ * problem: latency; compiled for configurations with enough general constraints).  AUTO takes the role-split
+ * kernel for batches of at most 2 x SM-count problems.  Returns 1 if the configuration has a role-split kernel,
+ * 0 if not (SPLIT then falls back to the thread-per-stage kernel), negative on bad arguments. */
+#define MPCGPU_KERNEL_AUTO 0
+#define MPCGPU_KERNEL_STAGE 1
+#define MPCGPU_KERNEL_SPLIT 2
+int mpcgpu_set_kernel_mode(mpcgpu_engine *e, int mode);
+
 /* Kernel launches issued by this engine so far (solve + select), for bench accounting. */
 long long mpcgpu_launch_count(const mpcgpu_engine *e);
 /* Device time in ms of the most recent mpcgpu_solve_batch[_device] solve kernel (CUDA events on the

@@ -31,7 +31,7 @@ static cudaError_t set_smem_attributes()
     return err;
 }
 
-static cudaError_t launch_solve(int grid, cudaStream_t stream, int n, const double* xinit, const double* x0, const double* params,
+static cudaError_t launch_solve(int grid, int mode, cudaStream_t stream, int n, const double* xinit, const double* x0, const double* params,
                          const int* num_iter, int num_iter_all, double* mem, double* xtraj, double* utraj, double* pobj,
                          int* exit_code, int* qp_status, double* res_eq, int* ipm_iters, int* work_counter)
 {
@@ -39,8 +39,10 @@ static cudaError_t launch_solve(int grid, cudaStream_t stream, int n, const doub
     if (err != cudaSuccess) return err;
     err = set_smem_attributes();
     if (err != cudaSuccess) return err;
-    if (USE_SPLIT && (grid < 0 || SPLIT_ALWAYS))
-        mpc_solve_split_kernel<<<grid < 0 ? -grid : grid, SPLIT_THREADS, SMEM_SPLIT, stream>>>(n, xinit, x0, params, num_iter, num_iter_all, mem,
+    // small batches (grid < 0) -> role-split kernel unless the caller pins a kernel
+    const bool split = USE_SPLIT && (mode == 2 || SPLIT_ALWAYS || (mode == 0 && grid < 0));
+    if (split)
+        mpc_solve_split_kernel<<<grid < 0 ? -grid : (n < 148 * 8 ? n : 148 * 8), SPLIT_THREADS, SMEM_SPLIT, stream>>>(n, xinit, x0, params, num_iter, num_iter_all, mem,
                                                                                           MEM_DOUBLES, xtraj, utraj, pobj, exit_code,
                                                                                           qp_status, res_eq, ipm_iters, work_counter);
     else if (grid < 0)      // latency mode: one problem per CTA, -grid CTAs
@@ -73,7 +75,7 @@ static cudaError_t launch_model_eval(cudaStream_t stream, int n, const double* z
 }
 
 static const MpcConfigOps ops = {MPCGEN_CONFIG_NAME, NSTAGE, NX, NU, NP, NH, NC, MEM_DOUBLES, launch_solve, occupancy,
-                                 NHS, MODEL_EVAL_DOUBLES, launch_model_eval, SPLIT_ALWAYS ? SPLIT_WARPS : GW};
+                                 NHS, MODEL_EVAL_DOUBLES, launch_model_eval, SPLIT_ALWAYS ? SPLIT_WARPS : GW, USE_SPLIT ? 1 : 0};
 
 static struct Registrar {
     Registrar() { mpc_register_config(&ops); }

@@ -6,7 +6,8 @@ struct MpcConfigOps {
     const char* name;
     int N, nx, nu, np, nh, nc, mem_doubles;
     // grid > 0: throughput kernel with `grid` CTAs; grid < 0: latency kernel, one problem per CTA, -grid CTAs
-    cudaError_t (*launch_solve)(int grid, cudaStream_t stream, int n, const double* xinit, const double* x0,
+    // mode: MPCGPU_KERNEL_AUTO / _STAGE / _SPLIT (include/mpcgpu.h); a configuration without a role-split kernel ignores _SPLIT
+    cudaError_t (*launch_solve)(int grid, int mode, cudaStream_t stream, int n, const double* xinit, const double* x0,
                                 const double* params, const int* num_iter, int num_iter_all, double* mem,
                                 double* xtraj, double* utraj, double* pobj, int* exit_code, int* qp_status,
                                 double* res_eq, int* ipm_iters, int* work_counter);
@@ -15,6 +16,7 @@ struct MpcConfigOps {
     cudaError_t (*launch_model_eval)(cudaStream_t stream, int n, const double* z, const double* p, const double* pi,
                                      const double* mh, double* out);
     int group_warps;   // warps cooperating on one problem (1 for N <= 31, 2 for N <= 63)
+    int has_split;     // 1 when the role-split kernel exists for this configuration
 };
 
 void mpc_register_config(const MpcConfigOps* ops);

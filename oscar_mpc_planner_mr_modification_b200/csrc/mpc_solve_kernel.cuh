@@ -329,7 +329,9 @@ constexpr int RO_Q = RO_G + NPK;                 // row 7 of the packed augmente
 constexpr int RO_B = RO_Q + NZ;
 constexpr int RO_PRB = RO_B + NX * NB;
 constexpr int RO_DZ = RO_PRB + NX;
-constexpr int RO_END = RO_DZ + NZ;
+constexpr int RO_ACL = RO_DZ + NZ;               // closed-loop matrix A + B K of the stage (role-split kernel: serial sweeps)
+constexpr int RO_BCL = RO_ACL + NX * NX;         // affine term of the sweep in progress
+constexpr int RO_END = RO_BCL + NX;
 constexpr int RSTRIDE = RO_END | 1;              // odd stride: lane-parallel accesses (lane = stage) are conflict-free
 constexpr int RS_DOUBLES = (NSTAGE + 1) * RSTRIDE + NX * NB;   // per problem, incl. the T = P+ [W | rb] scratch
 static_assert(pk(NZ, 0) == NPK, "augmented row must follow the packed Hessian");
@@ -616,6 +618,56 @@ __device__ __noinline__ void riccati_backvec_coop(double* __restrict__ rs, const
         else if (lane < NZ) blk[RO_Q + lane] = pvi;
         __syncwarp();
     }
+}
+
+// ---- Substitution sweeps in closed-loop form (role-split kernel).  With Acl_k = A_k + B_k K_k parked per stage, both sweeps
+//      are x+ = Acl x + b (forward) / p = Acl' p+ + c (backward): lanes 0..4 own one component each, the five components are
+//      exchanged by shuffles (no shared-memory round trip on the dependency chain), the matrix row / column of the NEXT stage
+//      is loaded while the current one is combined.  The chain of a stage is one shuffle + a depth-3 FMA tree.
+template <bool FWD>
+__device__ __noinline__ void riccati_sweep_cl(double* __restrict__ rs, const int oz)
+{
+    const int lane = threadIdx.x & 31;
+    const int i = lane < NX ? lane : NX - 1;
+    double x = 0.0;                                  // forward: dx_0 = 0
+    if (!FWD) x = rs[NSTAGE * RSTRIDE + RO_Q + NU + i];      // backward: p_N
+    else if (lane < NX) rs[RO_DZ + NU + i] = 0.0;
+    const int s0 = FWD ? 0 : NSTAGE - 1, ds = FWD ? 1 : -1;
+    double a[NX], c;
+    {
+        const double* __restrict__ blk = rs + s0 * RSTRIDE;
+#pragma unroll
+        for (int j = 0; j < NX; j++) a[j] = FWD ? blk[RO_ACL + i * NX + j] : blk[RO_ACL + j * NX + i];
+        c = blk[RO_BCL + i];
+    }
+#pragma unroll 1
+    for (int n = 0, s = s0; n < NSTAGE; n++, s += ds) {
+        double an[NX], cn = 0.0;
+        if (n + 1 < NSTAGE) {                        // next stage's operands: independent of the recursion
+            const double* __restrict__ nb = rs + (s + ds) * RSTRIDE;
+#pragma unroll
+            for (int j = 0; j < NX; j++) an[j] = FWD ? nb[RO_ACL + i * NX + j] : nb[RO_ACL + j * NX + i];
+            cn = nb[RO_BCL + i];
+        } else {
+#pragma unroll
+            for (int j = 0; j < NX; j++) an[j] = 0.0;
+        }
+        double xs[NX];
+#pragma unroll
+        for (int j = 0; j < NX; j++) xs[j] = __shfl_sync(FULL, x, j);
+        static_assert(NX == 5, "FMA tree written for nx = 5");
+        (void)oz;                                        // (gating the shuffles like the loads of the factorisation measured slower)
+        const double t0 = a[0] * xs[0] + c, t1 = a[1] * xs[1], t2 = a[4] * xs[4];
+        x = ((a[2] * xs[2] + t0) + (a[3] * xs[3] + t1)) + t2;
+        if (lane < NX) {
+            if (FWD) rs[(s + 1) * RSTRIDE + RO_DZ + NU + i] = x;      // dx_{s+1}
+            else rs[s * RSTRIDE + RO_Q + NU + i] = x;                 // p_s
+        }
+#pragma unroll
+        for (int j = 0; j < NX; j++) a[j] = an[j];
+        c = cn;
+    }
+    __syncwarp();
 }
 
 // ---- K4: MIRROR regularisation of one packed symmetric NZ x NZ block (cyclic Jacobi) -----------

@@ -519,10 +519,12 @@ __device__ __noinline__ void split_role_a(const int prob, const double* __restri
             __syncwarp();
             riccati_factor_coop2(rs, oz);
             PROF(8)
-            // substitution sweeps as affine-map prefix scans over the lanes (log2(32) levels instead of 30 dependent steps)
-            double Lx0[NX], Lx1[NX], Prb[NX], lv[NU], pv[NX], L10 = 0.0, iL0 = 0.0, iL1 = 0.0;
+            // closed-loop matrices of every stage (lane-parallel), then the predictor sweep
+            double Lx0[NX], Lx1[NX], Prb[NX], lv[NU], Bd[NX * NU], L10 = 0.0, iL0 = 0.0, iL1 = 0.0;
 #pragma unroll
-            for (int i = 0; i < NX; i++) { Lx0[i] = 0.0; Lx1[i] = 0.0; Prb[i] = 0.0; pv[i] = 0.0; }
+            for (int i = 0; i < NX; i++) { Lx0[i] = 0.0; Lx1[i] = 0.0; Prb[i] = 0.0; }
+#pragma unroll
+            for (int i = 0; i < NX * NU; i++) Bd[i] = 0.0;
             lv[0] = lv[1] = 0.0;
             if (path) {
                 iL0 = blk[RO_G + pk(0, 0)]; L10 = blk[RO_G + pk(1, 0)]; iL1 = blk[RO_G + pk(1, 1)];
@@ -531,11 +533,32 @@ __device__ __noinline__ void split_role_a(const int prob, const double* __restri
                 for (int i = 0; i < NX; i++) {
                     Lx0[i] = blk[RO_G + pk(NU + i, 0)]; Lx1[i] = blk[RO_G + pk(NU + i, 1)]; Prb[i] = blk[RO_PRB + i];
                 }
+                double Acl[NX * NX];
+                closed_loop(Wv, Lx0, Lx1, L10, iL0, iL1, Acl, Bd);
+                const double k1 = -lv[1] * iL1, k0 = -(lv[0] + L10 * k1) * iL0;      // kff = -Luu^-T l
+#pragma unroll
+                for (int i = 0; i < NX * NX; i++) blk[RO_ACL + i] = Acl[i];
+#pragma unroll
+                for (int i = 0; i < NX; i++) blk[RO_BCL + i] = rb[i] + Bd[i * NU] * k0 + Bd[i * NU + 1] * k1;
             }
-            forward_scan(Wv, Lx0, Lx1, L10, iL0, iL1, lv, rb, path, dva, grp);
+            __syncwarp();
+            PROF(22)
+            riccati_sweep_cl<true>(rs, oz);
+            PROF(23)
+            if (live) {
+#pragma unroll
+                for (int i = 0; i < NX; i++) dva[NU + i] = blk[RO_DZ + NU + i];
+            }
+            {
+                double r0 = lv[0], r1 = lv[1];           // du = -Luu^-T (Lxu' dx + l)
+#pragma unroll
+                for (int j = 0; j < NX; j++) { r0 += Lx0[j] * dva[NU + j]; r1 += Lx1[j] * dva[NU + j]; }
+                dva[1] = path ? -r1 * iL1 : 0.0;
+                dva[0] = path ? -(r0 + L10 * dva[1]) * iL0 : 0.0;
+            }
             if (path) {                                              // the B roles read the step on the support of h
 #pragma unroll
-                for (int a = 0; a < NHS; a++) blk[RO_DZ + HSUP[a]] = dva[HSUP[a]];
+                for (int a = 0; a < NHS; a++) if (HSUP[a] < NU) blk[RO_DZ + HSUP[a]] = dva[HSUP[a]];
             }
             PROF(9)
             split_barrier();                                         // 3
@@ -593,36 +616,26 @@ __device__ __noinline__ void split_role_a(const int prob, const double* __restri
             PROF(13)
             split_barrier();                                         // 5
             PROF(14)
-            {   // backward vector sweep as a scan: p_k = Acl_k' (p_{k+1} + P_{k+1} rb_k) + (gt_x - Lxu Luu^-1 gt_u)
-                Aff am;
-                double Bd[NX * NU];
+            double pv[NX];
+            {   // backward vector sweep: p_k = Acl_k' (p_{k+1} + P_{k+1} rb_k) + (gt_x - Lxu Luu^-1 gt_u)
                 if (path) {
-                    double Acl[NX * NX];
-                    closed_loop(Wv, Lx0, Lx1, L10, iL0, iL1, Acl, Bd);
                     const double lg0 = gt[0] * iL0, lg1 = (gt[1] - L10 * lg0) * iL1;
 #pragma unroll
                     for (int i = 0; i < NX; i++) {
                         double c_ = gt[NU + i] - Lx0[i] * lg0 - Lx1[i] * lg1;
 #pragma unroll
-                        for (int j = 0; j < NX; j++) {
-                            am.M[i * NX + j] = Acl[j * NX + i];
-                            c_ += Acl[j * NX + i] * Prb[j];
-                        }
-                        am.c[i] = c_;
+                        for (int j = 0; j < NX; j++) c_ += blk[RO_ACL + j * NX + i] * Prb[j];
+                        blk[RO_BCL + i] = c_;
                     }
-                } else {
+                } else if (term) {
 #pragma unroll
-                    for (int i = 0; i < NX * NX; i++) am.M[i] = (!term && i / NX == i % NX) ? 1.0 : 0.0;   // terminal: absorbing
-#pragma unroll
-                    for (int i = 0; i < NX; i++) am.c[i] = term ? gt[NU + i] : 0.0;
-#pragma unroll
-                    for (int i = 0; i < NX * NU; i++) Bd[i] = 0.0;
+                    for (int i = 0; i < NX; i++) blk[RO_Q + NU + i] = gt[NU + i];      // p_N
                 }
-                aff_scan<false>(&am, grp);
+                __syncwarp();
+                riccati_sweep_cl<false>(rs, oz);
                 double pn[NX];
 #pragma unroll
-                for (int i = 0; i < NX; i++) pv[i] = am.c[i];
-                grp.shift_down(pv, pn);
+                for (int i = 0; i < NX; i++) { pv[i] = live ? blk[RO_Q + NU + i] : 0.0; pn[i] = path ? blk[RSTRIDE + RO_Q + NU + i] : 0.0; }
                 if (path) {
                     double q0 = gt[0], q1 = gt[1];
 #pragma unroll
@@ -632,13 +645,28 @@ __device__ __noinline__ void split_role_a(const int prob, const double* __restri
                     }
                     lv[0] = q0 * iL0;
                     lv[1] = (q1 - L10 * lv[0]) * iL1;
+                    const double k1 = -lv[1] * iL1, k0 = -(lv[0] + L10 * k1) * iL0;
+#pragma unroll
+                    for (int i = 0; i < NX; i++) blk[RO_BCL + i] = rb[i] + Bd[i * NU] * k0 + Bd[i * NU + 1] * k1;
                 }
+                __syncwarp();
             }
             PROF(15)
-            forward_scan(Wv, Lx0, Lx1, L10, iL0, iL1, lv, rb, path, dv, grp);
+            riccati_sweep_cl<true>(rs, oz);
+            if (live) {
+#pragma unroll
+                for (int i = 0; i < NX; i++) dv[NU + i] = blk[RO_DZ + NU + i];
+            }
+            {
+                double r0 = lv[0], r1 = lv[1];
+#pragma unroll
+                for (int j = 0; j < NX; j++) { r0 += Lx0[j] * dv[NU + j]; r1 += Lx1[j] * dv[NU + j]; }
+                dv[1] = path ? -r1 * iL1 : 0.0;
+                dv[0] = path ? -(r0 + L10 * dv[1]) * iL0 : 0.0;
+            }
             if (path) {
 #pragma unroll
-                for (int a = 0; a < NHS; a++) blk[RO_DZ + HSUP[a]] = dv[HSUP[a]];
+                for (int a = 0; a < NHS; a++) if (HSUP[a] < NU) blk[RO_DZ + HSUP[a]] = dv[HSUP[a]];
             }
             PROF(16)
             split_barrier();                                         // 6
@@ -739,7 +767,7 @@ __device__ __noinline__ void split_role_a(const int prob, const double* __restri
 #ifdef MPC_PROF
     if (k == 0 && prob == 0) {
         printf("PROF ipm %d:", ipm_total);
-        for (int i = 0; i < 22; i++) printf(" %d:%lld", i, pt_[i]);
+        for (int i = 0; i < 24; i++) printf(" %d:%lld", i, pt_[i]);
         printf("\n");
     }
 #endif

@@ -91,7 +91,7 @@ void mpc_register_config(const MpcConfigOps* ops) { registry().push_back(ops); }
 
 struct mpcgpu_engine {
     const MpcConfigOps* ops = nullptr;
-    int device = 0, max_batch = 0, grid = 0, sms = 0, threads_per_cta = 0;
+    int device = 0, max_batch = 0, grid = 0, sms = 0, threads_per_cta = 0, kernel_mode = 0;
     cudaStream_t stream = nullptr, stream2 = nullptr;   // stream2: second lane of the chunked host pipeline
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t cev0[4] = {nullptr, nullptr, nullptr, nullptr}, cev1[4] = {nullptr, nullptr, nullptr, nullptr};   // per chunk (host path)
@@ -231,7 +231,7 @@ static int launch_solve_on(mpcgpu_engine* e, cudaStream_t st, int* counter, cuda
         if (grid > e->grid) grid = e->grid;
     }
     CK(cudaEventRecord(t0, st));
-    CK(e->ops->launch_solve(grid, st, n, xinit, x0, params, num_iter, num_iter_all, mem_inout, xtraj, utraj, pobj, exit_code,
+    CK(e->ops->launch_solve(grid, e->kernel_mode, st, n, xinit, x0, params, num_iter, num_iter_all, mem_inout, xtraj, utraj, pobj, exit_code,
                             qp_status, res_eq, ipm_iters, counter));
     CK(cudaEventRecord(t1, st));
     e->launches += 1;
@@ -464,6 +464,13 @@ int mpcgpu_measure_fp64_peak(int device, double* tflops)
     cudaFree(out);
     *tflops = best;
     return MPCGPU_OK;
+}
+
+int mpcgpu_set_kernel_mode(mpcgpu_engine* e, int mode)
+{
+    if (!e || mode < MPCGPU_KERNEL_AUTO || mode > MPCGPU_KERNEL_SPLIT) return MPCGPU_ERR_ARG;
+    e->kernel_mode = mode;
+    return e->ops->has_split ? 1 : 0;
 }
 
 long long mpcgpu_launch_count(const mpcgpu_engine* e) { return e ? e->launches : 0; }

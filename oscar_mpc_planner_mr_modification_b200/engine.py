@@ -15,8 +15,11 @@ _lib = None
 SYMBOLS = [
     "mpcgpu_num_configs", "mpcgpu_config_name", "mpcgpu_engine_create", "mpcgpu_engine_destroy", "mpcgpu_desc_query",
     "mpcgpu_mem_doubles", "mpcgpu_solve_batch", "mpcgpu_solve_batch_device", "mpcgpu_sync", "mpcgpu_solve_sets", "mpcgpu_select_best",
-    "mpcgpu_select_best_device", "mpcgpu_model_eval_doubles", "mpcgpu_model_eval", "mpcgpu_measure_fp64_peak", "mpcgpu_launch_count", "mpcgpu_last_kernel_ms", "mpcgpu_last_error",
+    "mpcgpu_select_best_device", "mpcgpu_model_eval_doubles", "mpcgpu_model_eval", "mpcgpu_measure_fp64_peak", "mpcgpu_launch_count", "mpcgpu_last_kernel_ms", "mpcgpu_last_error", "mpcgpu_set_kernel_mode",
 ]
+
+
+KERNEL_AUTO, KERNEL_STAGE, KERNEL_SPLIT = 0, 1, 2      # mpcgpu_set_kernel_mode (include/mpcgpu.h)
 
 
 def load_library():
@@ -222,6 +225,13 @@ class Engine:
 
     def last_kernel_ms(self):
         return float(self.lib.mpcgpu_last_kernel_ms(self.handle))
+
+    def set_kernel_mode(self, mode):
+        """0 auto, 1 thread-per-stage kernel, 2 role-split kernel; returns True if the configuration has a role-split kernel"""
+        self.lib.mpcgpu_set_kernel_mode.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        rc = self.lib.mpcgpu_set_kernel_mode(self.handle, int(mode))
+        self._check(min(rc, 0), "mpcgpu_set_kernel_mode")
+        return rc == 1
 
     def launch_count(self):
         return int(self.lib.mpcgpu_launch_count(self.handle))

@@ -71,3 +71,65 @@ def test_solve_parity_with_disc_offset(cfg, planners):
     out = eng.solve_batch(batch["xinit"], batch["x0"], batch["params"], num_iter=10)
     ref = orc.solve_batch(batch["xinit"], batch["x0"], batch["params"], num_iter=10)
     check(out, ref)
+
+
+@pytest.mark.parametrize("cfg,planners", [("tmpc_shipped", 5), ("c2_tmpc12", 9)])
+@pytest.mark.parametrize("num_iter", [1, 10])
+def test_both_kernels_against_the_oracle(cfg, planners, num_iter):
+    """The thread-per-stage kernel and the role-split kernel (one CTA of 4 warps per problem, chosen automatically
+    for small batches) implement the same solve: each is pinned explicitly, both must meet the parity bar against
+    the oracle and agree with each other, with and without the persistent capsule memory."""
+    eng = engine.Engine(cfg, device=0, max_batch=512)
+    orc = Oracle(cfg)
+    batch = synthetic.make_batch(eng.parameter_map, eng.dims, 40, planners, seed=4242)
+    ref = orc.solve_batch(batch["xinit"], batch["x0"], batch["params"], num_iter=num_iter)
+    outs = {}
+    for mode in (engine.KERNEL_STAGE, engine.KERNEL_SPLIT):
+        assert eng.set_kernel_mode(mode), "configuration %s should have a role-split kernel" % cfg
+        outs[mode] = eng.solve_batch(batch["xinit"], batch["x0"], batch["params"], num_iter=num_iter)
+        check(outs[mode], ref)
+    a, b = outs[engine.KERNEL_STAGE], outs[engine.KERNEL_SPLIT]
+    assert (a["exit_code"] == b["exit_code"]).all()
+    ok = a["exit_code"] == 1
+    assert rel_err(a["xtraj"][ok], b["xtraj"][ok]).max() < REL_TOL
+    # persistent capsule memory: both kernels write the oracle's blob (same layout), and both continue from the SAME
+    # blob (x0 = the previous output, like loadWarmstart after a solve) to the same result
+    rmem = np.zeros((batch["n"], eng.mem_doubles))
+    r1 = orc.solve_batch(batch["xinit"], batch["x0"], batch["params"], num_iter=num_iter, mem=rmem)
+    okm = r1["exit_code"] == 1
+    for mode in (engine.KERNEL_STAGE, engine.KERNEL_SPLIT):
+        eng.set_kernel_mode(mode)
+        mem = np.zeros((batch["n"], eng.mem_doubles))
+        eng.solve_batch(batch["xinit"], batch["x0"], batch["params"], num_iter=num_iter, mem=mem)
+        np.testing.assert_array_equal(mem[:, 0], rmem[:, 0])
+        assert (mem[~okm] == 0).all()
+        assert np.abs(mem[okm] - rmem[okm]).max() < 1e-6 * max(1.0, np.abs(rmem[okm]).max())
+    n = batch["n"]
+    x0b = np.zeros((n, eng.N + 1, eng.nz))
+    x0b[:, :, eng.nu:] = r1["xtraj"].reshape(n, eng.N + 1, eng.nx)
+    x0b[:, :eng.N, :eng.nu] = r1["utraj"].reshape(n, eng.N, eng.nu)
+    x0b = x0b.reshape(n, -1)
+    ref2 = orc.solve_batch(batch["xinit"], x0b, batch["params"], num_iter=2, mem=rmem.copy())
+    ok2 = ref2["exit_code"] == 1
+    for mode in (engine.KERNEL_STAGE, engine.KERNEL_SPLIT):
+        eng.set_kernel_mode(mode)
+        o2 = eng.solve_batch(batch["xinit"], x0b, batch["params"], num_iter=2, mem=rmem.copy())
+        np.testing.assert_array_equal(o2["exit_code"], ref2["exit_code"])
+        assert rel_err(o2["xtraj"][ok2], ref2["xtraj"][ok2]).max() < REL_TOL
+    eng.set_kernel_mode(engine.KERNEL_AUTO)
+
+
+def test_split_kernel_large_batch_matches_stage_kernel():
+    """Role-split kernel pinned on a batch far larger than the grid (persistent CTAs pulling problems)."""
+    eng = engine.Engine("c2_tmpc12", device=0, max_batch=4096)
+    batch = synthetic.make_batch(eng.parameter_map, eng.dims, 400, 9, seed=99)
+    eng.set_kernel_mode(engine.KERNEL_STAGE)
+    a = eng.solve_batch(batch["xinit"], batch["x0"], batch["params"], num_iter=3)
+    eng.set_kernel_mode(engine.KERNEL_SPLIT)
+    b = eng.solve_batch(batch["xinit"], batch["x0"], batch["params"], num_iter=3)
+    eng.set_kernel_mode(engine.KERNEL_AUTO)
+    assert (a["exit_code"] == b["exit_code"]).all()
+    ok = a["exit_code"] == 1
+    assert ok.sum() > 1000
+    assert rel_err(a["xtraj"][ok], b["xtraj"][ok]).max() < REL_TOL
+    assert rel_err(a["utraj"][ok], b["utraj"][ok]).max() < REL_TOL

@@ -299,6 +299,29 @@ def main():
                     "h2d_bytes_per_step": int((h_shared.numel() + h_vals.numel() + h_xs.numel() + h_x0.numel()) * 8 + differs.size * 4),
                     "what": "mpcgpu_solve_sets: shared parameter block per set + %d per-planner parameters, selection fused" % differs.size}
 
+        # ---- the same with the guidance halfspaces built on the device (mpcgpu_solve_sets_guided)
+        lin_base, lin_count = eng.lin_constraint_block()
+        if lin_count > 0 and set(differs.tolist()) <= set(range(lin_base, lin_base + 3 * lin_count)):
+            h_ob, h_g = pinned(batch["obst_pred"]), torch.from_numpy(batch["guided"]).pin_memory()
+            go = dict(np_out)
+            go["best"] = pinned(np.zeros(n_sets, np.int32)).numpy()
+            run = lambda: eng.solve_sets_guided(n_sets, planners, h_xs.numpy(), h_shared.numpy(), x0_np, h_ob.numpy(), h_g.numpy(),
+                                                batch["robot_radius"], num_iter=args.num_iter, out=go)
+            run()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                run()
+            torch.cuda.synchronize()
+            tg_ = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if dist is not None:
+                dist.all_reduce(tg_, op=dist.ReduceOp.MAX)
+            assert (go["best"] == best).all()
+            e2e_sets["guided"] = {"value": world * n * args.steps / float(tg_.item()), "unit": "solves/s",
+                                  "h2d_bytes_per_step": int((h_shared.numel() + h_xs.numel() + h_x0.numel() + h_ob.numel()) * 8 + h_g.numel()),
+                                  "what": "mpcgpu_solve_sets_guided: halfspaces built on the device from %d obstacle predictions per set "
+                                          "and the warm starts (linearized_constraints.cpp:49-189), nothing per planner uploaded but x0" % batch["obst_pred"].shape[2]}
+
     # ---- latency of ONE homotopy set end to end (H2D -> solve -> select -> D2H), BASELINE.json's second metric
     latency = None
     if rank == 0 and args.latency_reps > 0:

@@ -90,6 +90,35 @@ int mpcgpu_solve_sets(mpcgpu_engine *e, int n_sets, int planners, const double *
                       double *res_eq, const double *obj_scale, const double *obj_sub, const unsigned char *disabled,
                       int *best_idx);
 
+/* Guidance halfspaces built ON THE DEVICE.
+ * Replaces: LinearizedConstraints::update + projectToSafety + setParameters for the topology constraints of
+ *           GuidanceConstraints (mpc_planner_modules/src/linearized_constraints.cpp:43-189 with _use_guidance = true, one
+ *           disc, radius 1e-3; called per planner at guidance_constraints.cpp:321-352), i.e. the host loop that fills
+ *           3 * (max_obstacles + add_halfspaces) parameters per planner and stage right before solve().
+ * Writes the parameter slots lin_base + 3 j + {0,1,2} = (a1, a2, b) of constraint j < lin_count for every stage of every
+ * problem (problem = set * planners + planner):
+ *   stage 0 and non-guided planners (guided[q] == 0: update(state, empty_data_)): dummies (1, 0, xinit_x + 100);
+ *   guided planners, k >= 1: pos = warm start (x0) position of stage k, pushed out of the obstacles (3 sweeps of the
+ *   Douglas-Rachford step, radius 1e-3 + robot_radius), a = (o - pos)/|o - pos|, b = a.o - (1e-3 + robot_radius) with
+ *   o = obst_pred[set][k-1][j] (prediction.modes[0][k-1].position); slots j >= n_obs are dummies.
+ * The Douglas-Rachford step itself lives in the un-vendored `ros_tools` package: restated (oracle/mpc_oracle.c), parity
+ * unpinned for that sub-step.  DEVICE pointers; xinit_sets [n_sets*nx], x0 [n*(nu+nx)*(N+1)], obst_pred
+ * [n_sets*N*n_obs*2], guided [n], params [n*N*npar] in/out; asynchronous on `stream`. */
+int mpcgpu_guidance_halfspaces_device(mpcgpu_engine *e, int n_sets, int planners, const double *xinit_sets, const double *x0,
+                                      const double *obst_pred, int n_obs, const unsigned char *guided, int lin_base,
+                                      int lin_count, double robot_radius, double *params, void *stream);
+
+/* mpcgpu_solve_sets with the guidance halfspaces built on the device (HOST arrays): the per-planner halfspace block is
+ * no longer uploaded -- obstacle predictions travel once per set (N * n_obs * 2 doubles) and the warm starts are needed
+ * anyway.  Other per-planner parameters (e.g. the consistency reference) still go through param_idx / planner_params
+ * (nidx may be 0); they are applied before the halfspaces are written. */
+int mpcgpu_solve_sets_guided(mpcgpu_engine *e, int n_sets, int planners, const double *xinit_sets, const double *shared_params,
+                             const double *x0, int n_obs, const double *obst_pred, const unsigned char *guided, int lin_base,
+                             int lin_count, double robot_radius, int nidx, const int *param_idx, const double *planner_params,
+                             const int *num_iter, int num_iter_all, double *xtraj, double *utraj, double *pobj, int *exit_code,
+                             int *qp_status, double *res_eq, const double *obj_scale, const double *obj_sub,
+                             const unsigned char *disabled, int *best_idx);
+
 /* Pick the best planner of each homotopy set.
  * Replaces: the objective post-processing of GuidanceConstraints::optimize and FindBestPlanner
  *           (mpc_planner_modules/src/guidance_constraints.cpp:373-420,572-590):

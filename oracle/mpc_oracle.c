@@ -794,6 +794,65 @@ int oracle_solve_batch(int n, const double *xinit, const double *x0, const doubl
 
 /* K7: FindBestPlanner (guidance_constraints.cpp:572-590) with the objective post-processing of
  * :373-420: obj = (pobj - obj_sub) * obj_scale; success = exit_code == 1; strict <, ascending.   */
+/* ---- guidance halfspaces -------------------------------------------------------------------------
+ * Restates what GuidanceConstraints::optimize does per planner right before solve() for its topology constraints:
+ * LinearizedConstraints::update + projectToSafety + setParameters with _use_guidance = true, one disc, radius 1e-3
+ * (mpc_planner_modules/src/linearized_constraints.cpp:43-189; guidance_constraints.cpp:321-352).
+ *   stage 0:           every slot is the dummy (1, 0, state.x + 100)                              (:155-166, :54)
+ *   guided planner:    position = the warm start getEgoPrediction(k, x|y) (:63), pushed out of the obstacles by
+ *                      projectToSafety (:130-148), a = (o - pos)/|o - pos|, b = a.o - (1e-3 + robot_radius) (:84-105)
+ *                      with o = prediction.modes[0][k-1] of obstacle j; remaining slots dummies (:181-187)
+ *   non-guided planner (update(state, empty_data_): no obstacles): dummies in every slot            (:326-329, :181-187)
+ * projectToSafety calls RosTools::DouglasRachford::douglasRachfordProjection, which lives in the un-vendored, unpinned
+ * `ros_tools` package (not in the repository): restated here as the published Douglas-Rachford step
+ * p <- (p + R_obstacle(R_anchor(p))) / 2 with R = 2 Proj - I and Proj = radial projection onto the circle of radius r
+ * around the centre (identity outside it), applied only when p is inside the obstacle's circle.  PARITY UNPINNED for
+ * this sub-step; the halfspace formulas are the reference's own lines.  xinit_sets / obst_pred are per homotopy set. */
+static void dr_proj(const double *p, const double *c, double r, const double *toward, double *out)
+{
+    const double dx = p[0] - c[0], dy = p[1] - c[1];
+    if (sqrt(dx * dx + dy * dy) < r) {
+        const double sx = toward[0] - c[0], sy = toward[1] - c[1], n = sqrt(sx * sx + sy * sy);
+        out[0] = c[0] + sx / n * r; out[1] = c[1] + sy / n * r;
+    } else { out[0] = p[0]; out[1] = p[1]; }
+}
+void oracle_guidance_halfspaces(int n_sets, int planners, int N, int nx, int nu, int npar, int lin_base, int lin_count,
+                                int n_obs, const double *xinit_sets, const double *x0, const double *obst_pred,
+                                const unsigned char *guided, double robot_radius, double *params)
+{
+    const int nz = nx + nu;
+    const double r = 1e-3 + robot_radius;
+    for (int q = 0; q < n_sets * planners; q++) {
+        const int s = q / planners;
+        const double dummy_b = xinit_sets[(size_t)s * nx] + 100.0;
+        for (int k = 0; k < N; k++) {
+            double *P = params + ((size_t)q * N + k) * npar + lin_base;
+            for (int j = 0; j < lin_count; j++) { P[3 * j] = 1.0; P[3 * j + 1] = 0.0; P[3 * j + 2] = dummy_b; }
+            if (k == 0 || !guided[q]) continue;
+            const double *ob = obst_pred + ((size_t)s * N + (k - 1)) * n_obs * 2;
+            double pos[2] = {x0[((size_t)q * (N + 1) + k) * nz + nu], x0[((size_t)q * (N + 1) + k) * nz + nu + 1]};
+            if (n_obs > 0)
+                for (int it = 0; it < 3; it++)
+                    for (int j = 0; j < n_obs; j++) {
+                        const double dx = pos[0] - ob[2 * j], dy = pos[1] - ob[2 * j + 1];
+                        if (sqrt(dx * dx + dy * dy) < r) {
+                            double pa[2], ra[2], pb[2];
+                            dr_proj(pos, ob, r, pos, pa);                       /* anchor = obstacle 0 (:143) */
+                            ra[0] = 2.0 * pa[0] - pos[0]; ra[1] = 2.0 * pa[1] - pos[1];
+                            dr_proj(ra, ob + 2 * j, r, pos, pb);
+                            pos[0] = 0.5 * (pos[0] + 2.0 * pb[0] - ra[0]); pos[1] = 0.5 * (pos[1] + 2.0 * pb[1] - ra[1]);
+                        }
+                    }
+            for (int j = 0; j < n_obs && j < lin_count; j++) {
+                const double ox = ob[2 * j], oy = ob[2 * j + 1];
+                const double dx = ox - pos[0], dy = oy - pos[1], dist = sqrt(dx * dx + dy * dy);
+                const double a1 = dx / dist, a2 = dy / dist;
+                P[3 * j] = a1; P[3 * j + 1] = a2; P[3 * j + 2] = a1 * ox + a2 * oy - r;
+            }
+        }
+    }
+}
+
 int oracle_select_best(int n_sets, const int *set_offsets, const double *pobj, const int *exit_code,
                        const double *obj_scale, const double *obj_sub, const unsigned char *disabled, int *best_idx)
 {

@@ -92,6 +92,7 @@ void mpc_register_config(const MpcConfigOps* ops) { registry().push_back(ops); }
 struct mpcgpu_engine {
     const MpcConfigOps* ops = nullptr;
     int device = 0, max_batch = 0, grid = 0, sms = 0, threads_per_cta = 0, kernel_mode = 0;
+    void* d_obst = nullptr; size_t cap_obst = 0;   // obstacle predictions + guided flags of mpcgpu_solve_sets_guided
     cudaStream_t stream = nullptr, stream2 = nullptr;   // stream2: second lane of the chunked host pipeline
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t cev0[4] = {nullptr, nullptr, nullptr, nullptr}, cev1[4] = {nullptr, nullptr, nullptr, nullptr};   // per chunk (host path)
@@ -173,7 +174,7 @@ int mpcgpu_engine_destroy(mpcgpu_engine* e)
 {
     if (!e) return MPCGPU_ERR_ARG;
     cudaSetDevice(e->device);
-    void* ptrs[] = {e->d_shared, e->d_pvals, e->d_xs, e->d_pidx, e->d_xinit, e->d_x0, e->d_params, e->d_mem, e->d_xtraj, e->d_utraj, e->d_pobj, e->d_res_eq, e->d_scale,
+    void* ptrs[] = {e->d_obst, e->d_shared, e->d_pvals, e->d_xs, e->d_pidx, e->d_xinit, e->d_x0, e->d_params, e->d_mem, e->d_xtraj, e->d_utraj, e->d_pobj, e->d_res_eq, e->d_scale,
                     e->d_sub, e->d_num_iter, e->d_exit, e->d_qps, e->d_ipm, e->d_counter, e->d_counter2, e->d_offsets, e->d_best, e->d_disabled};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -314,10 +315,121 @@ int mpcgpu_select_best_device(mpcgpu_engine* e, int n_sets, const int* set_offse
     return MPCGPU_OK;
 }
 
+// ---- guidance halfspaces on the device (contract: include/mpcgpu.h, restated in oracle/mpc_oracle.c) ----
+// One thread per (problem, stage): the work GuidanceConstraints::optimize does per planner before solve()
+// (linearized_constraints.cpp:49-189) -- instead of uploading 3 * max_obstacles doubles per planner and stage.
+// products and sums are kept unfused (__dmul_rn / __dadd_rn) so that the result is bit-identical to the host restatement
+__device__ __forceinline__ double norm2_dev(double dx, double dy) { return sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy))); }
+__device__ __forceinline__ void dr_proj_dev(const double* p, const double* c, double r, const double* toward, double* out)
+{
+    const double dx = p[0] - c[0], dy = p[1] - c[1];
+    if (norm2_dev(dx, dy) < r) {
+        const double sx = toward[0] - c[0], sy = toward[1] - c[1], n = norm2_dev(sx, sy);
+        out[0] = __dadd_rn(c[0], __dmul_rn(sx / n, r)); out[1] = __dadd_rn(c[1], __dmul_rn(sy / n, r));
+    } else { out[0] = p[0]; out[1] = p[1]; }
+}
+__global__ void guidance_halfspaces_kernel(int n, int planners, int N, int nx, int nu, int npar, int lin_base, int lin_count, int n_obs,
+                                           const double* __restrict__ xinit_sets, const double* __restrict__ x0,
+                                           const double* __restrict__ obst_pred, const unsigned char* __restrict__ guided,
+                                           double robot_radius, double* __restrict__ params)
+{
+    const long long total = (long long)n * N;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int q = (int)(t / N), k = (int)(t % N), s = q / planners, nz = nx + nu;
+        const double r = 1e-3 + robot_radius;
+        const double dummy_b = xinit_sets[(size_t)s * nx] + 100.0;
+        double* P = params + ((size_t)q * N + k) * npar + lin_base;
+        const bool act = k > 0 && guided[q];
+        double pos[2] = {0.0, 0.0};
+        const double* ob = obst_pred + ((size_t)s * N + (k > 0 ? k - 1 : 0)) * n_obs * 2;
+        if (act) {
+            pos[0] = x0[((size_t)q * (N + 1) + k) * nz + nu]; pos[1] = x0[((size_t)q * (N + 1) + k) * nz + nu + 1];
+            for (int it = 0; it < 3; it++)
+                for (int j = 0; j < n_obs; j++) {
+                    const double dx = pos[0] - ob[2 * j], dy = pos[1] - ob[2 * j + 1];
+                    if (norm2_dev(dx, dy) < r) {
+                        double pa[2], ra[2], pb[2];
+                        dr_proj_dev(pos, ob, r, pos, pa);
+                        ra[0] = 2.0 * pa[0] - pos[0]; ra[1] = 2.0 * pa[1] - pos[1];
+                        dr_proj_dev(ra, ob + 2 * j, r, pos, pb);
+                        pos[0] = 0.5 * (pos[0] + 2.0 * pb[0] - ra[0]); pos[1] = 0.5 * (pos[1] + 2.0 * pb[1] - ra[1]);
+                    }
+                }
+        }
+        for (int j = 0; j < lin_count; j++) {
+            double a1 = 1.0, a2 = 0.0, b = dummy_b;
+            if (act && j < n_obs) {
+                const double ox = ob[2 * j], oy = ob[2 * j + 1];
+                const double dx = ox - pos[0], dy = oy - pos[1], dist = norm2_dev(dx, dy);
+                a1 = dx / dist; a2 = dy / dist;
+                b = __dsub_rn(__dadd_rn(__dmul_rn(a1, ox), __dmul_rn(a2, oy)), r);      // no FMA contraction: bit-identical to the host restatement
+            }
+            P[3 * j] = a1; P[3 * j + 1] = a2; P[3 * j + 2] = b;
+        }
+    }
+}
+
+int mpcgpu_guidance_halfspaces_device(mpcgpu_engine* e, int n_sets, int planners, const double* xinit_sets, const double* x0,
+                                      const double* obst_pred, int n_obs, const unsigned char* guided, int lin_base, int lin_count,
+                                      double robot_radius, double* params, void* stream)
+{
+    if (!e || n_sets < 0 || planners <= 0 || !xinit_sets || !x0 || (n_obs > 0 && !obst_pred) || n_obs < 0 || !guided || !params || lin_count < 0 ||
+        lin_base < 0 || lin_base + 3 * lin_count > e->ops->np)
+        return MPCGPU_ERR_ARG;
+    const long long n = (long long)n_sets * planners;
+    if (n == 0 || lin_count == 0) return MPCGPU_OK;
+    CK(cudaSetDevice(e->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+    const MpcConfigOps* o = e->ops;
+    const long long total = n * o->N;
+    const int blocks = (int)((total + 127) / 128 < 148 * 16 ? (total + 127) / 128 : 148 * 16);
+    guidance_halfspaces_kernel<<<blocks, 128, 0, st>>>((int)n, planners, o->N, o->nx, o->nu, o->np, lin_base, lin_count, n_obs, xinit_sets, x0,
+                                                        obst_pred, guided, robot_radius, params);
+    CK(cudaGetLastError());
+    e->launches += 1;
+    return MPCGPU_OK;
+}
+
+struct GuidedArgs {
+    int n_obs, lin_base, lin_count;
+    const double* obst_pred;
+    const unsigned char* guided;
+    double robot_radius;
+};
+static int solve_sets_impl(mpcgpu_engine* e, int n_sets, int planners, const double* xinit_sets, const double* shared_params,
+                           const double* x0, int nidx, const int* param_idx, const double* planner_params, const GuidedArgs* ga,
+                           const int* num_iter, int num_iter_all, double* xtraj, double* utraj, double* pobj, int* exit_code,
+                           int* qp_status, double* res_eq, const double* obj_scale, const double* obj_sub, const unsigned char* disabled,
+                           int* best_idx);
+
 int mpcgpu_solve_sets(mpcgpu_engine* e, int n_sets, int planners, const double* xinit_sets, const double* shared_params,
                       const double* x0, int nidx, const int* param_idx, const double* planner_params, const int* num_iter,
                       int num_iter_all, double* xtraj, double* utraj, double* pobj, int* exit_code, int* qp_status, double* res_eq,
                       const double* obj_scale, const double* obj_sub, const unsigned char* disabled, int* best_idx)
+{
+    return solve_sets_impl(e, n_sets, planners, xinit_sets, shared_params, x0, nidx, param_idx, planner_params, nullptr, num_iter,
+                           num_iter_all, xtraj, utraj, pobj, exit_code, qp_status, res_eq, obj_scale, obj_sub, disabled, best_idx);
+}
+
+int mpcgpu_solve_sets_guided(mpcgpu_engine* e, int n_sets, int planners, const double* xinit_sets, const double* shared_params,
+                             const double* x0, int n_obs, const double* obst_pred, const unsigned char* guided, int lin_base,
+                             int lin_count, double robot_radius, int nidx, const int* param_idx, const double* planner_params,
+                             const int* num_iter, int num_iter_all, double* xtraj, double* utraj, double* pobj, int* exit_code,
+                             int* qp_status, double* res_eq, const double* obj_scale, const double* obj_sub,
+                             const unsigned char* disabled, int* best_idx)
+{
+    if (!e || n_obs < 0 || (n_obs > 0 && !obst_pred) || !guided || lin_base < 0 || lin_count < 0 || lin_base + 3 * lin_count > e->ops->np)
+        return MPCGPU_ERR_ARG;
+    const GuidedArgs ga = {n_obs, lin_base, lin_count, obst_pred, guided, robot_radius};
+    return solve_sets_impl(e, n_sets, planners, xinit_sets, shared_params, x0, nidx, param_idx, planner_params, &ga, num_iter, num_iter_all,
+                           xtraj, utraj, pobj, exit_code, qp_status, res_eq, obj_scale, obj_sub, disabled, best_idx);
+}
+
+static int solve_sets_impl(mpcgpu_engine* e, int n_sets, int planners, const double* xinit_sets, const double* shared_params,
+                           const double* x0, int nidx, const int* param_idx, const double* planner_params, const GuidedArgs* ga,
+                           const int* num_iter, int num_iter_all, double* xtraj, double* utraj, double* pobj, int* exit_code,
+                           int* qp_status, double* res_eq, const double* obj_scale, const double* obj_sub, const unsigned char* disabled,
+                           int* best_idx)
 {
     if (!e || n_sets < 0 || planners <= 0 || !xinit_sets || !shared_params || !x0 || nidx < 0 || (nidx > 0 && (!param_idx || !planner_params)) ||
         !xtraj || !utraj || !pobj || !exit_code || !qp_status || !res_eq || !best_idx)
@@ -362,6 +474,21 @@ int mpcgpu_solve_sets(mpcgpu_engine* e, int n_sets, int planners, const double* 
     if (nidx > 0) scatter_params_kernel<<<592, 256, 0, st>>>(n, N, np, nidx, e->d_pidx, e->d_pvals, e->d_params);
     CK(cudaGetLastError());
     e->launches += (nidx > 0) ? 3 : 2;
+    if (ga) {      // guidance halfspaces built on the device from the obstacle predictions and the warm starts
+        const size_t ob_bytes = (size_t)n_sets * N * ga->n_obs * 2 * 8;
+        if (ob_bytes + (size_t)n > e->cap_obst) {
+            if (e->d_obst) cudaFree(e->d_obst);
+            e->d_obst = nullptr; e->cap_obst = 0;
+            CK(cudaMalloc((void**)&e->d_obst, ob_bytes + (size_t)n + 16));
+            e->cap_obst = ob_bytes + (size_t)n;
+        }
+        unsigned char* d_guided = (unsigned char*)e->d_obst + ob_bytes;
+        if (ob_bytes) CK(cudaMemcpyAsync(e->d_obst, ga->obst_pred, ob_bytes, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_guided, ga->guided, (size_t)n, cudaMemcpyHostToDevice, st));
+        int rc_ = mpcgpu_guidance_halfspaces_device(e, n_sets, planners, e->d_xs, e->d_x0, (const double*)e->d_obst, ga->n_obs, d_guided,
+                                                    ga->lin_base, ga->lin_count, ga->robot_radius, e->d_params, st);
+        if (rc_ != MPCGPU_OK) return rc_;
+    }
     e->chunks_timed = 0;
     int rc = launch_solve_on(e, st, e->d_counter, e->ev0, e->ev1, n, e->d_xinit, e->d_x0, e->d_params, num_iter ? e->d_num_iter : nullptr,
                              num_iter_all, nullptr, e->d_xtraj, e->d_utraj, e->d_pobj, e->d_exit, e->d_qps, e->d_res_eq, e->d_ipm);

@@ -15,7 +15,7 @@ _lib = None
 SYMBOLS = [
     "mpcgpu_num_configs", "mpcgpu_config_name", "mpcgpu_engine_create", "mpcgpu_engine_destroy", "mpcgpu_desc_query",
     "mpcgpu_mem_doubles", "mpcgpu_solve_batch", "mpcgpu_solve_batch_device", "mpcgpu_sync", "mpcgpu_solve_sets", "mpcgpu_select_best",
-    "mpcgpu_select_best_device", "mpcgpu_model_eval_doubles", "mpcgpu_model_eval", "mpcgpu_measure_fp64_peak", "mpcgpu_launch_count", "mpcgpu_last_kernel_ms", "mpcgpu_last_error", "mpcgpu_set_kernel_mode",
+    "mpcgpu_select_best_device", "mpcgpu_model_eval_doubles", "mpcgpu_model_eval", "mpcgpu_measure_fp64_peak", "mpcgpu_launch_count", "mpcgpu_last_kernel_ms", "mpcgpu_last_error", "mpcgpu_set_kernel_mode", "mpcgpu_guidance_halfspaces_device", "mpcgpu_solve_sets_guided",
 ]
 
 
@@ -179,6 +179,55 @@ class Engine:
                                         _ptr(out["qp_status"]), _ptr(out["res_eq"]), None, None, None, _ptr(out["best"]))
         self._check(rc, "mpcgpu_solve_sets")
         return out
+
+    def lin_constraint_block(self):
+        """(lin_base, lin_count): the guidance halfspace parameters lin_constraint_<j>_{a1,a2,b} must be 3 consecutive
+        slots per constraint (they are: the generator adds them in that order, guidance_constraints.py / linearized_constraints.py)"""
+        pm = self.parameter_map
+        cnt = sum(1 for k in pm if k.startswith("lin_constraint_") and k.endswith("_a1"))
+        if cnt == 0:
+            return 0, 0
+        base = pm["lin_constraint_0_a1"]
+        for j in range(cnt):
+            assert (pm["lin_constraint_%d_a1" % j], pm["lin_constraint_%d_a2" % j], pm["lin_constraint_%d_b" % j]) == (
+                base + 3 * j, base + 3 * j + 1, base + 3 * j + 2), "unexpected halfspace parameter layout"
+        return base, cnt
+
+    def solve_sets_guided(self, n_sets, planners, xinit_sets, shared_params, x0, obst_pred, guided, robot_radius, num_iter=10,
+                          param_idx=None, planner_params=None, out=None):
+        """mpcgpu_solve_sets_guided: halfspaces from obstacle predictions + warm starts, built on the device."""
+        n = n_sets * planners
+        if out is None:
+            out = self.alloc_outputs(n)
+            out["best"] = np.zeros(n_sets, np.int32)
+        lin_base, lin_count = self.lin_constraint_block()
+        obst_pred = np.ascontiguousarray(obst_pred, np.float64)
+        n_obs = obst_pred.shape[2] if obst_pred.ndim == 4 else 0
+        guided = np.ascontiguousarray(guided, np.uint8)
+        nidx = 0 if param_idx is None else int(np.asarray(param_idx).size)
+        pidx = None if nidx == 0 else np.ascontiguousarray(param_idx, np.int32)
+        pvals = None if nidx == 0 else np.ascontiguousarray(planner_params, np.float64)
+        vp = ctypes.c_void_p
+        self.lib.mpcgpu_solve_sets_guided.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, ctypes.c_int, vp, vp, ctypes.c_int,
+                                                      ctypes.c_int, ctypes.c_double, ctypes.c_int, vp, vp, vp, ctypes.c_int] + [vp] * 10
+        rc = self.lib.mpcgpu_solve_sets_guided(self.handle, n_sets, planners, _ptr(np.ascontiguousarray(xinit_sets, np.float64)),
+                                               _ptr(np.ascontiguousarray(shared_params, np.float64)), _ptr(np.ascontiguousarray(x0, np.float64)),
+                                               n_obs, _ptr(obst_pred), _ptr(guided), lin_base, lin_count, float(robot_radius), nidx,
+                                               _ptr(pidx), _ptr(pvals), None, int(num_iter), _ptr(out["xtraj"]), _ptr(out["utraj"]),
+                                               _ptr(out["pobj"]), _ptr(out["exit_code"]), _ptr(out["qp_status"]), _ptr(out["res_eq"]),
+                                               None, None, None, _ptr(out["best"]))
+        self._check(rc, "mpcgpu_solve_sets_guided")
+        return out
+
+    def guidance_halfspaces_device(self, n_sets, planners, xinit_sets, x0, obst_pred, n_obs, guided, robot_radius, params, stream=None):
+        """device pointers (ints); asynchronous"""
+        lin_base, lin_count = self.lin_constraint_block()
+        vp = ctypes.c_void_p
+        self.lib.mpcgpu_guidance_halfspaces_device.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, ctypes.c_int, vp, ctypes.c_int,
+                                                               ctypes.c_int, ctypes.c_double, vp, vp]
+        rc = self.lib.mpcgpu_guidance_halfspaces_device(self.handle, n_sets, planners, xinit_sets, x0, obst_pred, n_obs, guided, lin_base,
+                                                        lin_count, float(robot_radius), params, stream)
+        self._check(rc, "mpcgpu_guidance_halfspaces_device")
 
     def select_best(self, set_offsets, pobj, exit_code, obj_scale=None, obj_sub=None, disabled=None):
         set_offsets = np.ascontiguousarray(set_offsets, np.int32)

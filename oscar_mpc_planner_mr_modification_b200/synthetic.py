@@ -214,4 +214,10 @@ def make_batch(pmap, dims, n_sets, planners_per_set=1, seed=1234, guided=None, g
         params=np.ascontiguousarray(P.reshape(B, N * npar)),
         set_offsets=np.arange(0, B + 1, Pn, dtype=np.int32),
         n=B,
+        # inputs of the device-side halfspace construction (mpcgpu_solve_sets_guided): per-set obstacle predictions
+        # (prediction index i = stage k-1) and which planners follow a guidance trajectory
+        obst_pred=np.ascontiguousarray(opred[:, :, :M] if has_lin else opred[:, :, :0]),
+        guided=np.ascontiguousarray(np.tile(np.array([1 if (guided and not (Pn > 1 and h == Pn - 1)) else 0 for h in range(Pn)],
+                                                      np.uint8), S)),
+        robot_radius=ROBOT_RADIUS,
     )

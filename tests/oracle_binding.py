@@ -59,6 +59,18 @@ class Oracle:
                                     _ptr(out["res_eq"]), _ptr(out["ipm_iters"]), int(threads))
         return out
 
+    def guidance_halfspaces(self, n_sets, planners, xinit_sets, x0, obst_pred, guided, robot_radius, lin_base, lin_count, params):
+        """oracle_guidance_halfspaces: writes the halfspace slots of `params` [n, N*npar] in place"""
+        obst_pred = np.ascontiguousarray(obst_pred, np.float64)
+        n_obs = obst_pred.shape[2]
+        assert params.flags["C_CONTIGUOUS"] and params.dtype == np.float64
+        self.lib.oracle_guidance_halfspaces.argtypes = [ctypes.c_int] * 9 + [ctypes.c_void_p] * 4 + [ctypes.c_double, ctypes.c_void_p]
+        self.lib.oracle_guidance_halfspaces.restype = None
+        self.lib.oracle_guidance_halfspaces(n_sets, planners, self.N, self.nx, self.nu, self.npar, lin_base, lin_count, n_obs,
+                                            _ptr(np.ascontiguousarray(xinit_sets, np.float64)), _ptr(np.ascontiguousarray(x0, np.float64)),
+                                            _ptr(obst_pred), _ptr(np.ascontiguousarray(guided, np.uint8)), float(robot_radius), _ptr(params))
+        return params
+
     def select_best(self, set_offsets, pobj, exit_code, obj_scale=None, obj_sub=None, disabled=None):
         set_offsets = np.ascontiguousarray(set_offsets, np.int32)
         n_sets = set_offsets.size - 1

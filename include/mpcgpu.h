@@ -150,9 +150,9 @@ int mpcgpu_model_eval(mpcgpu_engine *e, int n, const double *z, const double *p,
 int mpcgpu_measure_fp64_peak(int device, double *tflops);
 
 /* Kernel choice (no reference counterpart).  Two kernels implement the same solve: the thread-per-stage kernel
- * (one warp per problem, 8 problems per SM: throughput) and the role-split kernel (one CTA of 4 warps per
- * problem: latency; compiled for configurations with enough general constraints).  AUTO takes the role-split
- * kernel for batches of at most 2 x SM-count problems.  Returns 1 if the configuration has a role-split kernel,
+ * (one warp per problem, 8 problems per SM: throughput) and the role-split kernel (one CTA of several warps
+ * per problem: latency; compiled for configurations with enough general constraints).  AUTO takes the role-split
+ * kernel for batches of at most SM-count problems (every problem has an SM to itself).  Returns 1 if the configuration has a role-split kernel,
  * 0 if not (SPLIT then falls back to the thread-per-stage kernel), negative on bad arguments. */
 #define MPCGPU_KERNEL_AUTO 0
 #define MPCGPU_KERNEL_STAGE 1

@@ -39,10 +39,12 @@ static cudaError_t launch_solve(int grid, int mode, cudaStream_t stream, int n, 
     if (err != cudaSuccess) return err;
     err = set_smem_attributes();
     if (err != cudaSuccess) return err;
-    // small batches (grid < 0) -> role-split kernel unless the caller pins a kernel
-    const bool split = USE_SPLIT && (mode == 2 || SPLIT_ALWAYS || (mode == 0 && grid < 0));
+    // small batches (grid < 0, at most one problem per SM) -> role-split kernel unless the caller pins a kernel
+    int sms = 148, dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const bool split = USE_SPLIT && (mode == 2 || SPLIT_ALWAYS || (mode == 0 && grid < 0 && -grid <= sms));
     if (split)
-        mpc_solve_split_kernel<<<grid < 0 ? -grid : (n < 148 * 8 ? n : 148 * 8), SPLIT_THREADS, SMEM_SPLIT, stream>>>(n, xinit, x0, params, num_iter, num_iter_all, mem,
+        mpc_solve_split_kernel<<<grid < 0 ? -grid : (n < sms * 4 ? n : sms * 4), SPLIT_THREADS, SMEM_SPLIT, stream>>>(n, xinit, x0, params, num_iter, num_iter_all, mem,
                                                                                           MEM_DOUBLES, xtraj, utraj, pobj, exit_code,
                                                                                           qp_status, res_eq, ipm_iters, work_counter);
     else if (grid < 0)      // latency mode: one problem per CTA, -grid CTAs

@@ -6,10 +6,11 @@
 //
 // Why: the thread-per-stage kernel keeps the WHOLE stage (iterate, Hessian, 14 box and NCG general inequality entries)
 // in one thread -- 255 registers plus ~2.7 KB of thread-local memory, 8 problems per SM, each advancing slowly on one
-// warp.  Here a problem owns 1 + NBR warps:
-//   role A (warp 0)      lane k = stage k: iterate, cost / dynamics linearisation, MIRROR, box entries, residuals,
-//                        the scalar decisions of the interior-point loop, and the cooperative Riccati recursion
-//   roles B (warps 1..)  lane k = stage k: a contiguous slice of the general inequality entries of that stage
+// warp.  Here a problem owns 2 + NBR warps:
+//   role A (warp 0)      lane k = stage k: iterate, cost / dynamics linearisation, MIRROR, residuals, the scalar
+//                        decisions of the interior-point loop, and the cooperative Riccati recursion
+//   role X (warp 1)      lane k = stage k: the 2 NZ box entries of that stage (multipliers, slacks in registers)
+//   roles B (warps 2..)  lane k = stage k: a contiguous slice of the general inequality entries of that stage
 //                        (constraint evaluation, multiplier-weighted constraint Hessian, the per-entry Newton algebra)
 // Roles meet at named-barrier points; B hands A its per-stage contributions (Hessian / gradient / residual terms,
 // step-length ratios, complementarity sums) through shared-memory slots that A adds in a fixed role order, so results
@@ -17,24 +18,26 @@
 // taken by A and published in shared memory.
 #pragma once
 
-#ifndef MPC_SPLIT_ROLES
-#define MPC_SPLIT_ROLES 3
+#ifndef MPC_SPLIT_ROLES          // roles B: slices of about 4 general entries (measured best for latency: 6 roles for 24 entries)
+#define MPC_SPLIT_ROLES (NCG >= 24 ? 6 : (NCG >= 12 ? 3 : 2))
 #endif
-#ifndef MPC_SPLIT_MIN_CTAS
-#define MPC_SPLIT_MIN_CTAS 3
+#ifndef MPC_SPLIT_MIN_CTAS       // 1: all 255 registers for role A (the kernel serves small batches: one CTA per SM)
+#define MPC_SPLIT_MIN_CTAS 1
 #endif
 constexpr int NBR = MPC_SPLIT_ROLES;
-constexpr int SPLIT_WARPS = 1 + NBR;
+constexpr int SPLIT_WARPS = 2 + NBR;             // role A, role X (box entries), NBR roles B
 constexpr int SPLIT_THREADS = SPLIT_WARPS * 32;
 constexpr int RPB = (NCG + NBR - 1) / NBR > 0 ? (NCG + NBR - 1) / NBR : 1;     // general entries per B role
 constexpr int NHP = NHS * (NHS + 1) / 2;                                       // packed block over the support of h
 constexpr int XS = NHP + 2 * NHS + 3;            // exchange slots per B role and stage: Hs | g | rg | nd nm sm
-constexpr bool SPLIT_OK = (NSTAGE + 1 <= 32) && NCG >= 2 * NBR;
+constexpr int XSX = 3 * NZ + 3;                  // exchange slots of role X per stage: diag Ht | g | rg | nd nm sm
+constexpr bool SPLIT_OK = (NSTAGE + 1 <= 32) && NCG >= 6 && NCG >= 2 * NBR;
 // shared memory of one problem (doubles)
 constexpr int SP_RS = 0;
 constexpr int SP_XCH = (RS_DOUBLES + 1) & ~1;    // [NBR][XS][32]
-constexpr int SP_PUB = SP_XCH + NBR * XS * 32;   // [2 NHS][32]: z and v on the support of h, published by role A
-constexpr int SP_DEC = SP_PUB + 2 * NHS * 32;    // decisions published by role A
+constexpr int SP_XCX = SP_XCH + NBR * XS * 32;   // [XSX][32] slots of role X
+constexpr int SP_PUB = SP_XCX + XSX * 32;        // [2 NZ][32]: z and v of every stage, published by role A (v: amended by role X)
+constexpr int SP_DEC = SP_PUB + 2 * NZ * 32;     // decisions published by role A
 constexpr int SP_DOUBLES = SP_DEC + 8;
 enum { DEC_CONT = 0, DEC_SIGMU = 1, DEC_STEP = 2, DEC_SQP = 3, DEC_STATUS = 4 };
 
@@ -87,7 +90,7 @@ __device__ __noinline__ void split_role_b(const int prob, const double* __restri
 #pragma unroll
             for (int i = 0; i < NZ; i++) zz[i] = 0.0;
 #pragma unroll
-            for (int a = 0; a < NHS; a++) zz[HSUP[a]] = pub[a * 32];
+            for (int a = 0; a < NHS; a++) zz[HSUP[a]] = pub[HSUP[a] * 32];
 #pragma unroll
             for (int i = 0; i < NPK; i++) Hh[i] = 0.0;
             if (ne > 0) {
@@ -105,8 +108,9 @@ __device__ __noinline__ void split_role_b(const int prob, const double* __restri
         }
         split_barrier();                                             // L2: constraint Hessian terms handed to A
         split_barrier();                                             // L3: A has initialised v
+        split_barrier();                                             // L4: role X has centred v inside the boxes
 #pragma unroll
-        for (int a = 0; a < NHS; a++) v3[a] = pub[(NHS + a) * 32];
+        for (int a = 0; a < NHS; a++) v3[a] = pub[(NZ + HSUP[a]) * 32];
         if (qp_warm) {
             for (int e = 0; e < ne; e++) { lamg[e] = clamp_lo(lamg[e], IPM_THR0); tg[e] = clamp_lo(tg[e], IPM_THR0); }
         } else {
@@ -240,6 +244,185 @@ __device__ __noinline__ void split_role_b(const int prob, const double* __restri
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// role X: the 2 NZ box entries of every stage (input box on path stages, state box on stages 1..N-1)
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __noinline__ void split_role_x(const int prob, const int num_iter, double* mem_g, const int mem_doubles, double* sm)
+{
+    const int k = threadIdx.x & 31;
+    const bool path = k < NSTAGE, xbox = path && k >= 1;
+    double* const rs = sm + SP_RS;
+    double* const xs = sm + SP_XCX + k;                                 // slot s of this stage: xs[s * 32]
+    double* const pub = sm + SP_PUB + k;
+    const double* const dec = sm + SP_DEC;
+    const double* const blk = rs + (path ? k : 0) * RSTRIDE;
+
+    double lamb[NCB], tb[NCB], itb[NCB], zl[NZ], zu[NZ], v[NZ], vo[NZ], dva[NZ], dv[NZ];
+#pragma unroll
+    for (int e = 0; e < NCB; e++) { lamb[e] = 0.0; tb[e] = 0.0; itb[e] = 0.0; }
+#pragma unroll
+    for (int i = 0; i < NZ; i++) { v[i] = 0.0; vo[i] = 0.0; dva[i] = 0.0; dv[i] = 0.0; zl[i] = 0.0; zu[i] = 0.0; }
+    int qp_warm = 0;
+    double* mem = mem_g ? mem_g + (size_t)prob * mem_doubles : nullptr;
+    if (mem && mem[0] != 0.0) {
+        const double* m = mem + 1 + (NSTAGE + 1) * NX;
+        if (path) for (int e = 0; e < NCB; e++) { lamb[e] = m[k * NC + e]; tb[e] = m[NSTAGE * NC + k * NC + e]; }
+        qp_warm = (mem[0] >= 2.0);
+    }
+
+    for (int it = 0; it < num_iter; it++) {
+        split_barrier();                                             // L1: z is published
+#pragma unroll
+        for (int i = 0; i < NZ; i++) { const double zi = pub[i * 32]; zl[i] = LBZ[i] - zi; zu[i] = UBZ[i] - zi; }
+        split_barrier();                                             // L2
+        split_barrier();                                             // L3: A has initialised v
+#pragma unroll
+        for (int i = 0; i < NZ; i++) v[i] = pub[(NZ + i) * 32];
+        if (qp_warm) {
+#pragma unroll
+            for (int i = 0; i < NZ; i++) {
+                const bool act = (i < NU) ? path : xbox;
+                if (act) {
+                    lamb[i] = clamp_lo(lamb[i], IPM_THR0); tb[i] = clamp_lo(tb[i], IPM_THR0);
+                    lamb[NZ + i] = clamp_lo(lamb[NZ + i], IPM_THR0); tb[NZ + i] = clamp_lo(tb[NZ + i], IPM_THR0);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NZ; i++) {
+                const bool act = (i < NU) ? path : xbox;
+                if (act) {
+                    const double dl = zl[i], du = zu[i];
+                    double tl = v[i] - dl, tu = du - v[i];
+                    if (tl < IPM_THR0) {
+                        if (tu < IPM_THR0) { v[i] = 0.5 * (dl + du); tl = IPM_THR0; tu = IPM_THR0; }
+                        else { tl = IPM_THR0; v[i] = dl + IPM_THR0; }
+                    } else if (tu < IPM_THR0) { tu = IPM_THR0; v[i] = du - IPM_THR0; }
+                    tb[i] = tl; tb[NZ + i] = tu;
+                    lamb[i] = IPM_MU0 / tl; lamb[NZ + i] = IPM_MU0 / tu;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < NZ; i++) pub[(NZ + i) * 32] = v[i];
+        }
+        split_barrier();                                             // L4: v is final for every role
+
+        double a_ = 0.0, sigmu = 0.0;
+        for (int kk = 0;; kk++) {
+            const bool upd = kk > 0;
+#pragma unroll
+            for (int i = 0; i < NZ; i++) { vo[i] = v[i]; if (upd) v[i] += a_ * dv[i]; }
+            double nd = 0.0, nm = 0.0, sm_ = 0.0;
+#pragma unroll
+            for (int i = 0; i < NZ; i++) {
+                const bool act = (i < NU) ? path : xbox;
+                double hd = 0.0, gg = 0.0, rr = 0.0;
+                if (act) {
+                    const double dl = zl[i], du = zu[i];
+                    {   // lower: chat = +e_i, d = dl
+                        double lam = lamb[i], t = tb[i];
+                        if (upd) {
+                            const IneqStep st = ineq_final(lam, itb[i], vo[i] - dl - t, dva[i], dv[i], sigmu);
+                            lam = clamp_lo(lam + a_ * st.dlam, IPM_LAM_MIN); t = clamp_lo(t + a_ * st.dt, IPM_T_MIN);
+                            lamb[i] = lam; tb[i] = t;
+                        }
+                        const double it_ = 1.0 / t;
+                        const double rd = v[i] - dl - t, G = lam * it_, m = lam * t;
+                        itb[i] = it_;
+                        hd += G; gg += G * rd; rr -= lam;
+                        nd = nanmax(nd, fabs(rd)); nm = nanmax(nm, fabs(m)); sm_ += m;
+                    }
+                    {   // upper: chat = -e_i, d = -du
+                        double lam = lamb[NZ + i], t = tb[NZ + i];
+                        if (upd) {
+                            const IneqStep st = ineq_final(lam, itb[NZ + i], du - vo[i] - t, -dva[i], -dv[i], sigmu);
+                            lam = clamp_lo(lam + a_ * st.dlam, IPM_LAM_MIN); t = clamp_lo(t + a_ * st.dt, IPM_T_MIN);
+                            lamb[NZ + i] = lam; tb[NZ + i] = t;
+                        }
+                        const double it_ = 1.0 / t;
+                        const double rd = du - v[i] - t, G = lam * it_, m = lam * t;
+                        itb[NZ + i] = it_;
+                        hd += G; gg -= G * rd; rr += lam;
+                        nd = nanmax(nd, fabs(rd)); nm = nanmax(nm, fabs(m)); sm_ += m;
+                    }
+                }
+                xs[i * 32] = hd; xs[(NZ + i) * 32] = gg; xs[(2 * NZ + i) * 32] = rr;
+            }
+            xs[(3 * NZ) * 32] = nd; xs[(3 * NZ + 1) * 32] = nm; xs[(3 * NZ + 2) * 32] = sm_;
+            split_barrier();                                         // 1
+            split_barrier();                                         // 2
+            if (dec[DEC_CONT] == 0.0) break;
+            split_barrier();                                         // 3
+#pragma unroll
+            for (int i = 0; i < NZ; i++) dva[i] = path ? blk[RO_DZ + i] : 0.0;
+
+            double abn = 1.0, abd = 1.0, S1 = 0.0, S2 = 0.0;
+#pragma unroll
+            for (int i = 0; i < NZ; i++) {
+                const bool act = (i < NU) ? path : xbox;
+                double V1 = 0.0, V2 = 0.0;
+                if (act) {
+                    const double dl = zl[i], du = zu[i];
+                    {
+                        const double lam = lamb[i], t = tb[i];
+                        const double it_ = itb[i];
+                        const IneqStep st = ineq_affine(lam, it_, v[i] - dl - t, dva[i]);
+                        step_limit(lam, st.dlam, abn, abd); step_limit(t, st.dt, abn, abd);
+                        S1 += lam * st.dt + t * st.dlam; S2 += st.dt * st.dlam;
+                        V1 += st.corr; V2 += it_;
+                    }
+                    {
+                        const double lam = lamb[NZ + i], t = tb[NZ + i];
+                        const double it_ = itb[NZ + i];
+                        const IneqStep st = ineq_affine(lam, it_, du - v[i] - t, -dva[i]);
+                        step_limit(lam, st.dlam, abn, abd); step_limit(t, st.dt, abn, abd);
+                        S1 += lam * st.dt + t * st.dlam; S2 += st.dt * st.dlam;
+                        V1 -= st.corr; V2 -= it_;
+                    }
+                }
+                xs[i * 32] = V1; xs[(NZ + i) * 32] = V2;
+            }
+            xs[(2 * NZ) * 32] = abn / abd; xs[(2 * NZ + 1) * 32] = S1; xs[(2 * NZ + 2) * 32] = S2;
+            split_barrier();                                         // 4
+            split_barrier();                                         // 5
+            sigmu = dec[DEC_SIGMU];
+            split_barrier();                                         // 6
+#pragma unroll
+            for (int i = 0; i < NZ; i++) dv[i] = path ? blk[RO_DZ + i] : 0.0;
+            double bn = 1.0, bd = 1.0;
+#pragma unroll
+            for (int i = 0; i < NZ; i++) {
+                const bool act = (i < NU) ? path : xbox;
+                if (act) {
+                    const double dl = zl[i], du = zu[i];
+                    {
+                        const double lam = lamb[i], t = tb[i];
+                        const IneqStep st = ineq_final(lam, itb[i], v[i] - dl - t, dva[i], dv[i], sigmu);
+                        step_limit(lam, st.dlam, bn, bd); step_limit(t, st.dt, bn, bd);
+                    }
+                    {
+                        const double lam = lamb[NZ + i], t = tb[NZ + i];
+                        const IneqStep st = ineq_final(lam, itb[NZ + i], du - v[i] - t, -dva[i], -dv[i], sigmu);
+                        step_limit(lam, st.dlam, bn, bd); step_limit(t, st.dt, bn, bd);
+                    }
+                }
+            }
+            xs[0] = bn / bd;
+            split_barrier();                                         // 7
+            split_barrier();                                         // 8
+            a_ = dec[DEC_STEP];
+        }
+        split_barrier();                                             // 9
+        qp_warm = 1;
+        if (dec[DEC_SQP] == 0.0) break;
+    }
+    split_barrier();                                                 // F
+    if (mem && dec[DEC_STATUS] == 0.0 && path) {
+        double* m = mem + 1 + (NSTAGE + 1) * NX;
+        for (int e = 0; e < NCB; e++) { m[k * NC + e] = lamb[e]; m[NSTAGE * NC + k * NC + e] = tb[e]; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // role A: everything else of Solver::solve()
 // ------------------------------------------------------------------------------------------------------------------
 __device__ __noinline__ void split_role_a(const int prob, const double* __restrict__ xinit_g, const double* __restrict__ x0_g,
@@ -252,6 +435,7 @@ __device__ __noinline__ void split_role_a(const int prob, const double* __restri
     const double* __restrict__ p = params_g + ((size_t)prob * NSTAGE + (path ? k : NSTAGE - 1)) * NP;
     double* const rs = sm + SP_RS;
     const double* const xch = sm + SP_XCH + k;                          // slot s of role r: xch[(r * XS + s) * 32]
+    const double* const xcx = sm + SP_XCX + k;                          // slot s of role X: xcx[s * 32]
     double* const pub = sm + SP_PUB + k;
     double* const dec = sm + SP_DEC;
     double* const blk = rs + (live ? k : 0) * RSTRIDE;
@@ -259,7 +443,7 @@ __device__ __noinline__ void split_role_a(const int prob, const double* __restri
     grp.xch = nullptr; grp.gid = 0; grp.wig = 0;
     static_assert(GW == 1 || !SPLIT_OK, "role-split kernel: one warp per role");
 
-    double z[NZ], pi[NX], v[NZ], qpi[NX], lamb[NCB], tb[NCB], xi[NX];
+    double z[NZ], pi[NX], v[NZ], qpi[NX], xi[NX];
 #pragma unroll
     for (int i = 0; i < NZ; i++) {
         z[i] = live ? x0_g[(size_t)prob * NZ * (NSTAGE + 1) + k * NZ + i] : 0.0;      // loadWarmstart (:274-284)
@@ -268,16 +452,13 @@ __device__ __noinline__ void split_role_a(const int prob, const double* __restri
     if (term) { z[0] = 0.0; z[1] = 0.0; }
 #pragma unroll
     for (int i = 0; i < NX; i++) { xi[i] = xinit_g[(size_t)prob * NX + i]; pi[i] = 0.0; qpi[i] = 0.0; }
-#pragma unroll
-    for (int e = 0; e < NCB; e++) { lamb[e] = 0.0; tb[e] = 0.0; }
     int qp_warm = 0;
     double* mem = mem_g ? mem_g + (size_t)prob * mem_doubles : nullptr;
     if (mem && mem[0] != 0.0) {                                         // persistent capsule memory: [flag][pi][lam][t][v]
         const double* m = mem + 1;
         if (live) for (int i = 0; i < NX; i++) pi[i] = m[k * NX + i];
         m += (NSTAGE + 1) * NX;
-        if (path) for (int e = 0; e < NCB; e++) { lamb[e] = m[k * NC + e]; tb[e] = m[NSTAGE * NC + k * NC + e]; }
-        m += 2 * NSTAGE * NC;
+        m += 2 * NSTAGE * NC;                                            // (box multipliers: role X, general: roles B)
         if (live) for (int i = 0; i < NZ; i++) v[i] = m[k * NZ + i];
         qp_warm = (mem[0] >= 2.0);
 #pragma unroll
@@ -296,7 +477,7 @@ __device__ __noinline__ void split_role_a(const int prob, const double* __restri
             grp.shift_down(pi, pin);
             grp.shift_down(zx_, xnx);
 #pragma unroll
-            for (int a = 0; a < NHS; a++) pub[a * 32] = z[HSUP[a]];
+            for (int i = 0; i < NZ; i++) pub[i * 32] = z[i];
             split_barrier();                                         // L1
 #pragma unroll
             for (int i = 0; i < NPK; i++) H[i] = 0.0;
@@ -347,44 +528,19 @@ __device__ __noinline__ void split_role_a(const int prob, const double* __restri
 #pragma unroll
             for (int i = 0; i < NX; i++) v[NU + i] = xi[i] - z[NU + i];
         }
-        if (qp_warm) {
 #pragma unroll
-            for (int i = 0; i < NZ; i++) {
-                const bool act = (i < NU) ? path : xbox;
-                if (act) {
-                    lamb[i] = clamp_lo(lamb[i], IPM_THR0); tb[i] = clamp_lo(tb[i], IPM_THR0);
-                    lamb[NZ + i] = clamp_lo(lamb[NZ + i], IPM_THR0); tb[NZ + i] = clamp_lo(tb[NZ + i], IPM_THR0);
-                }
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < NZ; i++) {
-                const bool act = (i < NU) ? path : xbox;
-                if (act) {
-                    const double dl = LBZ[i] - z[i], du = UBZ[i] - z[i];
-                    double tl = v[i] - dl, tu = du - v[i];
-                    if (tl < IPM_THR0) {
-                        if (tu < IPM_THR0) { v[i] = 0.5 * (dl + du); tl = IPM_THR0; tu = IPM_THR0; }
-                        else { tl = IPM_THR0; v[i] = dl + IPM_THR0; }
-                    } else if (tu < IPM_THR0) { tu = IPM_THR0; v[i] = du - IPM_THR0; }
-                    tb[i] = tl; tb[NZ + i] = tu;
-                    lamb[i] = IPM_MU0 / tl; lamb[NZ + i] = IPM_MU0 / tu;
-                }
-            }
-        }
-#pragma unroll
-        for (int a = 0; a < NHS; a++) pub[(NHS + a) * 32] = v[HSUP[a]];
+        for (int i = 0; i < NZ; i++) pub[(NZ + i) * 32] = v[i];
         PROF(2)
         split_barrier();                                             // L3
+        split_barrier();                                             // L4: role X has centred v inside the boxes (cold start)
+#pragma unroll
+        for (int i = 0; i < NZ; i++) v[i] = pub[(NZ + i) * 32];
         PROF(3)
 
         double alpha = 1.0, mu = 0.0;
         int kk = 0;
         bool isnan_ = false;
-        double itb[NCB];
         double dva[NZ], dv[NZ], dpi[NX], sigmu = 0.0, a_ = 0.0;
-#pragma unroll
-        for (int e = 0; e < NCB; e++) itb[e] = 0.0;
 #pragma unroll
         for (int i = 0; i < NZ; i++) { dva[i] = 0.0; dv[i] = 0.0; }
 #pragma unroll
@@ -430,43 +586,15 @@ __device__ __noinline__ void split_role_a(const int prob, const double* __restri
                 }
 #pragma unroll
                 for (int i = 0; i < NZ; i++) gt[i] = rg[i];
-#pragma unroll
-                for (int i = 0; i < NZ; i++) {
-                    const bool act = (i < NU) ? path : xbox;
-                    if (act) {
-                        const double dl = LBZ[i] - z[i], du = UBZ[i] - z[i];
-                        {   // lower: chat = +e_i, d = dl
-                            double lam = lamb[i], t = tb[i];
-                            if (upd) {
-                                const IneqStep st = ineq_final(lam, itb[i], vo[i] - dl - t, dva[i], dv[i], sigmu);
-                                lam = clamp_lo(lam + a_ * st.dlam, IPM_LAM_MIN); t = clamp_lo(t + a_ * st.dt, IPM_T_MIN);
-                                lamb[i] = lam; tb[i] = t;
-                            }
-                            const double it_ = 1.0 / t;
-                            const double rd = v[i] - dl - t, G = lam * it_, m = lam * t;
-                            itb[i] = it_;
-                            Ht[pk(i, i)] += G; gt[i] += G * rd; rg[i] -= lam;
-                            nd = nanmax(nd, fabs(rd)); nm = nanmax(nm, fabs(m)); sm_ += m;
-                        }
-                        {   // upper: chat = -e_i, d = -du
-                            double lam = lamb[NZ + i], t = tb[NZ + i];
-                            if (upd) {
-                                const IneqStep st = ineq_final(lam, itb[NZ + i], du - vo[i] - t, -dva[i], -dv[i], sigmu);
-                                lam = clamp_lo(lam + a_ * st.dlam, IPM_LAM_MIN); t = clamp_lo(t + a_ * st.dt, IPM_T_MIN);
-                                lamb[NZ + i] = lam; tb[NZ + i] = t;
-                            }
-                            const double it_ = 1.0 / t;
-                            const double rd = du - v[i] - t, G = lam * it_, m = lam * t;
-                            itb[NZ + i] = it_;
-                            Ht[pk(i, i)] += G; gt[i] -= G * rd; rg[i] += lam;
-                            nd = nanmax(nd, fabs(rd)); nm = nanmax(nm, fabs(m)); sm_ += m;
-                        }
-                    }
-                }
             }
             PROF(4)
             split_barrier();                                         // 1: the slices' DA terms are in the slots
             PROF(5)
+#pragma unroll
+            for (int i = 0; i < NZ; i++) {                           // box entries (role X)
+                Ht[pk(i, i)] += xcx[i * 32]; gt[i] += xcx[(NZ + i) * 32]; rg[i] += xcx[(2 * NZ + i) * 32];
+            }
+            nd = nanmax(nd, xcx[(3 * NZ) * 32]); nm = nanmax(nm, xcx[(3 * NZ + 1) * 32]); sm_ += xcx[(3 * NZ + 2) * 32];
             if (path) {
 #pragma unroll 1
                 for (int r = 0; r < NBR; r++) {
@@ -556,45 +684,23 @@ __device__ __noinline__ void split_role_a(const int prob, const double* __restri
                 dva[1] = path ? -r1 * iL1 : 0.0;
                 dva[0] = path ? -(r0 + L10 * dva[1]) * iL0 : 0.0;
             }
-            if (path) {                                              // the B roles read the step on the support of h
+            if (path) {                                              // roles X and B read the step from the blocks
 #pragma unroll
-                for (int a = 0; a < NHS; a++) if (HSUP[a] < NU) blk[RO_DZ + HSUP[a]] = dva[HSUP[a]];
+                for (int i = 0; i < NU; i++) blk[RO_DZ + i] = dva[i];
             }
             PROF(9)
             split_barrier();                                         // 3
             PROF(10)
 
             // ---- pass B (box entries): affine step length, mu_aff sums, corrector vectors
-            double abn = 1.0, abd = 1.0, S1 = 0.0, S2 = 0.0, V1[NZ], V2[NZ];
-#pragma unroll
-            for (int i = 0; i < NZ; i++) { V1[i] = 0.0; V2[i] = 0.0; }
-#pragma unroll
-            for (int i = 0; i < NZ; i++) {
-                const bool act = (i < NU) ? path : xbox;
-                if (act) {
-                    const double dl = LBZ[i] - z[i], du = UBZ[i] - z[i];
-                    {
-                        const double lam = lamb[i], t = tb[i];
-                        const double it_ = itb[i];
-                        const IneqStep st = ineq_affine(lam, it_, v[i] - dl - t, dva[i]);
-                        step_limit(lam, st.dlam, abn, abd); step_limit(t, st.dt, abn, abd);
-                        S1 += lam * st.dt + t * st.dlam; S2 += st.dt * st.dlam;
-                        V1[i] += st.corr; V2[i] += it_;
-                    }
-                    {
-                        const double lam = lamb[NZ + i], t = tb[NZ + i];
-                        const double it_ = itb[NZ + i];
-                        const IneqStep st = ineq_affine(lam, it_, du - v[i] - t, -dva[i]);
-                        step_limit(lam, st.dlam, abn, abd); step_limit(t, st.dt, abn, abd);
-                        S1 += lam * st.dt + t * st.dlam; S2 += st.dt * st.dlam;
-                        V1[i] -= st.corr; V2[i] -= it_;
-                    }
-                }
-            }
-            double ratio = abn / abd;
+            double S1 = 0.0, S2 = 0.0, V1[NZ], V2[NZ];
+            double ratio = 1.0;
             PROF(11)
             split_barrier();                                         // 4: the slices' pass-B terms are in the slots
             PROF(12)
+#pragma unroll
+            for (int i = 0; i < NZ; i++) { V1[i] = xcx[i * 32]; V2[i] = xcx[(NZ + i) * 32]; }      // box entries (role X)
+            ratio = fmin(ratio, xcx[(2 * NZ) * 32]); S1 += xcx[(2 * NZ + 1) * 32]; S2 += xcx[(2 * NZ + 2) * 32];
             if (path) {
 #pragma unroll 1
                 for (int r = 0; r < NBR; r++) {
@@ -666,7 +772,7 @@ __device__ __noinline__ void split_role_a(const int prob, const double* __restri
             }
             if (path) {
 #pragma unroll
-                for (int a = 0; a < NHS; a++) if (HSUP[a] < NU) blk[RO_DZ + HSUP[a]] = dv[HSUP[a]];
+                for (int i = 0; i < NU; i++) blk[RO_DZ + i] = dv[i];
             }
             PROF(16)
             split_barrier();                                         // 6
@@ -682,28 +788,11 @@ __device__ __noinline__ void split_role_a(const int prob, const double* __restri
             }
 
             // ---- pass C (box entries): step length of the corrected direction
-            double bn = 1.0, bd = 1.0;
-#pragma unroll
-            for (int i = 0; i < NZ; i++) {
-                const bool act = (i < NU) ? path : xbox;
-                if (act) {
-                    const double dl = LBZ[i] - z[i], du = UBZ[i] - z[i];
-                    {
-                        const double lam = lamb[i], t = tb[i];
-                        const IneqStep st = ineq_final(lam, itb[i], v[i] - dl - t, dva[i], dv[i], sigmu);
-                        step_limit(lam, st.dlam, bn, bd); step_limit(t, st.dt, bn, bd);
-                    }
-                    {
-                        const double lam = lamb[NZ + i], t = tb[NZ + i];
-                        const IneqStep st = ineq_final(lam, itb[NZ + i], du - v[i] - t, -dva[i], -dv[i], sigmu);
-                        step_limit(lam, st.dlam, bn, bd); step_limit(t, st.dt, bn, bd);
-                    }
-                }
-            }
-            double ratc = bn / bd;
+            double ratc = 1.0;
             PROF(18)
             split_barrier();                                         // 7: the slices' ratios are in slot 0
             PROF(19)
+            ratc = fmin(ratc, xcx[0]);                               // box entries (role X)
             if (path) {
 #pragma unroll 1
                 for (int r = 0; r < NBR; r++) ratc = fmin(ratc, xch[(size_t)r * XS * 32]);
@@ -783,7 +872,6 @@ __device__ __noinline__ void split_role_a(const int prob, const double* __restri
             if (k == 0) mem[0] = 2.0;
             if (live) for (int i = 0; i < NX; i++) m[k * NX + i] = pi[i];
             m += (NSTAGE + 1) * NX;
-            if (path) for (int e = 0; e < NCB; e++) { m[k * NC + e] = lamb[e]; m[NSTAGE * NC + k * NC + e] = tb[e]; }
             m += 2 * NSTAGE * NC;
             if (live) for (int i = 0; i < NZ; i++) m[k * NZ + i] = v[i];
         }
@@ -810,7 +898,9 @@ mpc_solve_split_kernel(int n, const double* __restrict__ xinit, const double* __
         if (role == 0)
             split_role_a(prob, xinit, x0, params, nit, mem, mem_doubles, xtraj, utraj, pobj, exit_code, qp_status, res_eq, ipm_iters,
                          s_split, n >> 31 /* 0, opaque to the compiler */);
+        else if (role == 1)
+            split_role_x(prob, nit, mem, mem_doubles, s_split);
         else
-            split_role_b(prob, params, nit, mem, mem_doubles, s_split, role - 1);
+            split_role_b(prob, params, nit, mem, mem_doubles, s_split, role - 2);
     }
 }

@@ -221,3 +221,58 @@ def make_batch(pmap, dims, n_sets, planners_per_set=1, seed=1234, guided=None, g
                                                       np.uint8), S)),
         robot_radius=ROBOT_RADIUS,
     )
+
+
+def make_multi_robot_batch(pmap, dims, n_scenarios, robots=3, planners_per_set=9, seed=1234, peer_spacing=1.7):
+    """BASELINE.json configs[3]: R robots x (8 guided + 1 non-guided) planners per scenario, one batch.
+
+    In the reference "inter-robot constraints" are the ordinary ellipsoid constraints with a peer's communicated
+    trajectory as the obstacle prediction (trajectoryCallback -> prepareObstacleData,
+    mpc_planner_jackalsimulator/src/jules_ros1_jackalplanner.cpp:521-678,800-834; data_preparation.cpp:202-237:
+    type ROBOT, radius = robot radius).  Here every robot of a scenario is one homotopy set of `make_batch`; the first
+    R-1 obstacle slots of robot r are overwritten with the peers' trajectories (their planner-0 warm starts, running
+    side by side `peer_spacing` apart), and the guidance halfspaces are rebuilt from the new predictions exactly as
+    linearized_constraints.cpp:49-189 does (numpy, no projection: see tests for the projected variant).
+    Problem index = (scenario * robots + robot) * planners + planner; `set_offsets` delimits one set per robot."""
+    N, nx, nu, npar, dt = dims["N"], dims["nx"], dims["nu"], dims["npar"], dims["dt"]
+    nz = nx + nu
+    S, Rn, Pn = n_scenarios, robots, planners_per_set
+    b = make_batch(pmap, dims, S * Rn, Pn, seed=seed)
+    M = b["obst_pred"].shape[2]
+    assert M >= Rn - 1, "configuration has too few obstacle slots for the peers"
+    x0 = b["x0"].reshape(S, Rn, Pn, N + 1, nz)
+    P = b["params"].reshape(S, Rn, Pn, N, npar)
+    ob = b["obst_pred"].reshape(S, Rn, N, M, 2)
+    for r in range(Rn):
+        slot = 0
+        for q in range(Rn):
+            if q == r:
+                continue
+            # peer q's communicated plan in robot r's frame: its planner-0 warm start, shifted sideways
+            traj = x0[:, q, 0, 1:, nu:nu + 2].copy()                       # (S, N, 2): positions of stages 1..N
+            traj = traj - x0[:, q, 0, :1, nu:nu + 2] + x0[:, r, 0, :1, nu:nu + 2]
+            traj[..., 1] += peer_spacing * (q - r)
+            ob[:, r, :, slot] = traj                                       # prediction index i = stage i+1
+            pre = "ellipsoid_obst_%d_" % slot
+            P[:, r, :, 1:, pmap[pre + "x"]] = traj[:, None, :N - 1, 0]
+            P[:, r, :, 1:, pmap[pre + "y"]] = traj[:, None, :N - 1, 1]
+            P[:, r, :, 1:, pmap[pre + "r"]] = ROBOT_RADIUS
+            slot += 1
+    # guidance halfspaces from the new predictions (linearized_constraints.cpp:84-105)
+    if "lin_constraint_0_a1" in pmap:
+        nlin = sum(1 for k in pmap if k.startswith("lin_constraint_") and k.endswith("_a1"))
+        for h in range(Pn - 1 if Pn > 1 else Pn):
+            pos = x0[:, :, h, 1:N, nu:nu + 2]                              # (S, R, N-1, 2)
+            for j in range(min(nlin, M)):
+                o = ob[:, :, :N - 1, j]
+                dvec = o - pos
+                dist = np.sqrt(dvec[..., 0] * dvec[..., 0] + dvec[..., 1] * dvec[..., 1])
+                a1, a2 = dvec[..., 0] / dist, dvec[..., 1] / dist
+                pre = "lin_constraint_%d_" % j
+                P[:, :, h, 1:, pmap[pre + "a1"]] = a1
+                P[:, :, h, 1:, pmap[pre + "a2"]] = a2
+                P[:, :, h, 1:, pmap[pre + "b"]] = a1 * o[..., 0] + a2 * o[..., 1] - (1e-3 + ROBOT_RADIUS)
+    b["params"] = np.ascontiguousarray(P.reshape(-1, N * npar))
+    b["obst_pred"] = np.ascontiguousarray(ob.reshape(S * Rn, N, M, 2))
+    b["robots"] = Rn
+    return b

@@ -328,7 +328,7 @@ __device__ __forceinline__ void dr_proj_dev(const double* p, const double* c, do
         out[0] = __dadd_rn(c[0], __dmul_rn(sx / n, r)); out[1] = __dadd_rn(c[1], __dmul_rn(sy / n, r));
     } else { out[0] = p[0]; out[1] = p[1]; }
 }
-__global__ void guidance_halfspaces_kernel(int n, int planners, int N, int nx, int nu, int npar, int lin_base, int lin_count, int n_obs,
+__global__ void guidance_halfspaces_kernel(int n, int planners, int N, int nx, int nu, int npar, int lin_base, int lin_count, int n_obs, int obs,
                                            const double* __restrict__ xinit_sets, const double* __restrict__ x0,
                                            const double* __restrict__ obst_pred, const unsigned char* __restrict__ guided,
                                            double robot_radius, double* __restrict__ params)
@@ -341,17 +341,17 @@ __global__ void guidance_halfspaces_kernel(int n, int planners, int N, int nx, i
         double* P = params + ((size_t)q * N + k) * npar + lin_base;
         const bool act = k > 0 && guided[q];
         double pos[2] = {0.0, 0.0};
-        const double* ob = obst_pred + ((size_t)s * N + (k > 0 ? k - 1 : 0)) * n_obs * 2;
+        const double* ob = obst_pred + ((size_t)s * N + (k > 0 ? k - 1 : 0)) * n_obs * obs;      // obs doubles per obstacle, (x, y) first
         if (act) {
             pos[0] = x0[((size_t)q * (N + 1) + k) * nz + nu]; pos[1] = x0[((size_t)q * (N + 1) + k) * nz + nu + 1];
             for (int it = 0; it < 3; it++)
                 for (int j = 0; j < n_obs; j++) {
-                    const double dx = pos[0] - ob[2 * j], dy = pos[1] - ob[2 * j + 1];
+                    const double dx = pos[0] - ob[obs * j], dy = pos[1] - ob[obs * j + 1];
                     if (norm2_dev(dx, dy) < r) {
                         double pa[2], ra[2], pb[2];
                         dr_proj_dev(pos, ob, r, pos, pa);
                         ra[0] = 2.0 * pa[0] - pos[0]; ra[1] = 2.0 * pa[1] - pos[1];
-                        dr_proj_dev(ra, ob + 2 * j, r, pos, pb);
+                        dr_proj_dev(ra, ob + obs * j, r, pos, pb);
                         pos[0] = 0.5 * (pos[0] + 2.0 * pb[0] - ra[0]); pos[1] = 0.5 * (pos[1] + 2.0 * pb[1] - ra[1]);
                     }
                 }
@@ -359,7 +359,7 @@ __global__ void guidance_halfspaces_kernel(int n, int planners, int N, int nx, i
         for (int j = 0; j < lin_count; j++) {
             double a1 = 1.0, a2 = 0.0, b = dummy_b;
             if (act && j < n_obs) {
-                const double ox = ob[2 * j], oy = ob[2 * j + 1];
+                const double ox = ob[obs * j], oy = ob[obs * j + 1];
                 const double dx = ox - pos[0], dy = oy - pos[1], dist = norm2_dev(dx, dy);
                 a1 = dx / dist; a2 = dy / dist;
                 b = __dsub_rn(__dadd_rn(__dmul_rn(a1, ox), __dmul_rn(a2, oy)), r);      // no FMA contraction: bit-identical to the host restatement
@@ -369,9 +369,21 @@ __global__ void guidance_halfspaces_kernel(int n, int planners, int N, int nx, i
     }
 }
 
+static int guidance_halfspaces_launch(mpcgpu_engine* e, int n_sets, int planners, const double* xinit_sets, const double* x0,
+                                      const double* obst_pred, int n_obs, int ob_stride, const unsigned char* guided, int lin_base,
+                                      int lin_count, double robot_radius, double* params, void* stream);
+
 int mpcgpu_guidance_halfspaces_device(mpcgpu_engine* e, int n_sets, int planners, const double* xinit_sets, const double* x0,
                                       const double* obst_pred, int n_obs, const unsigned char* guided, int lin_base, int lin_count,
                                       double robot_radius, double* params, void* stream)
+{
+    return guidance_halfspaces_launch(e, n_sets, planners, xinit_sets, x0, obst_pred, n_obs, 2, guided, lin_base, lin_count, robot_radius, params,
+                                      stream);
+}
+
+static int guidance_halfspaces_launch(mpcgpu_engine* e, int n_sets, int planners, const double* xinit_sets, const double* x0,
+                                      const double* obst_pred, int n_obs, int ob_stride, const unsigned char* guided, int lin_base,
+                                      int lin_count, double robot_radius, double* params, void* stream)
 {
     if (!e || n_sets < 0 || planners <= 0 || !xinit_sets || !x0 || (n_obs > 0 && !obst_pred) || n_obs < 0 || !guided || !params || lin_count < 0 ||
         lin_base < 0 || lin_base + 3 * lin_count > e->ops->np)
@@ -383,7 +395,7 @@ int mpcgpu_guidance_halfspaces_device(mpcgpu_engine* e, int n_sets, int planners
     const MpcConfigOps* o = e->ops;
     const long long total = n * o->N;
     const int blocks = (int)((total + 127) / 128 < 148 * 16 ? (total + 127) / 128 : 148 * 16);
-    guidance_halfspaces_kernel<<<blocks, 128, 0, st>>>((int)n, planners, o->N, o->nx, o->nu, o->np, lin_base, lin_count, n_obs, xinit_sets, x0,
+    guidance_halfspaces_kernel<<<blocks, 128, 0, st>>>((int)n, planners, o->N, o->nx, o->nu, o->np, lin_base, lin_count, n_obs, ob_stride, xinit_sets, x0,
                                                         obst_pred, guided, robot_radius, params);
     CK(cudaGetLastError());
     e->launches += 1;
@@ -392,15 +404,19 @@ int mpcgpu_guidance_halfspaces_device(mpcgpu_engine* e, int n_sets, int planners
 
 struct GuidedArgs {
     int n_obs, lin_base, lin_count;
-    const double* obst_pred;
+    const double* obst_pred;             // [n_sets][N][n_obs][ob_stride], (x, y) first
     const unsigned char* guided;
     double robot_radius;
+    int ob_stride = 2;                   // 4: obstacle tables (x, y, psi, r) of include/mpcgpu_wire.h
+    int ell_base = -1, ell_stride = 0, ell_off[7] = {0, 0, 0, 0, 0, 0, 0};      // >= 0: ellipsoid slots written from the table
 };
 static int solve_sets_impl(mpcgpu_engine* e, int n_sets, int planners, const double* xinit_sets, const double* shared_params,
                            const double* x0, int nidx, const int* param_idx, const double* planner_params, const GuidedArgs* ga,
                            const int* num_iter, int num_iter_all, double* xtraj, double* utraj, double* pobj, int* exit_code,
                            int* qp_status, double* res_eq, const double* obj_scale, const double* obj_sub, const unsigned char* disabled,
                            int* best_idx);
+extern "C" int mpcgpu_pack_obstacles_device(mpcgpu_engine* e, int n_sets, const double* xinit_sets, const double* table, int M, int ell_base,
+                                            int ell_stride, const int* ell_offsets, double* params, void* stream);
 
 int mpcgpu_solve_sets(mpcgpu_engine* e, int n_sets, int planners, const double* xinit_sets, const double* shared_params,
                       const double* x0, int nidx, const int* param_idx, const double* planner_params, const int* num_iter,
@@ -469,24 +485,32 @@ static int solve_sets_impl(mpcgpu_engine* e, int n_sets, int planners, const dou
         CK(cudaMemcpyAsync(e->d_pvals, planner_params, (size_t)n * N * nidx * 8, cudaMemcpyHostToDevice, st));
     }
     if (num_iter) CK(cudaMemcpyAsync(e->d_num_iter, num_iter, (size_t)n * 4, cudaMemcpyHostToDevice, st));
-    repeat_xinit_kernel<<<(n * nx + 255) / 256, 256, 0, st>>>(n, planners, nx, e->d_xs, e->d_xinit);
-    expand_params_kernel<<<1184, 256, 0, st>>>(n, planners, N, np, nidx, e->d_shared, e->d_pidx, e->d_pvals, e->d_params);
-    if (nidx > 0) scatter_params_kernel<<<592, 256, 0, st>>>(n, N, np, nidx, e->d_pidx, e->d_pvals, e->d_params);
-    CK(cudaGetLastError());
-    e->launches += (nidx > 0) ? 3 : 2;
-    if (ga) {      // guidance halfspaces built on the device from the obstacle predictions and the warm starts
-        const size_t ob_bytes = (size_t)n_sets * N * ga->n_obs * 2 * 8;
+    unsigned char* d_guided = nullptr;
+    if (ga) {      // obstacle predictions / tables + guided flags of the device-side constraint construction
+        const size_t ob_bytes = (size_t)n_sets * N * ga->n_obs * ga->ob_stride * 8;
         if (ob_bytes + (size_t)n > e->cap_obst) {
             if (e->d_obst) cudaFree(e->d_obst);
             e->d_obst = nullptr; e->cap_obst = 0;
             CK(cudaMalloc((void**)&e->d_obst, ob_bytes + (size_t)n + 16));
             e->cap_obst = ob_bytes + (size_t)n;
         }
-        unsigned char* d_guided = (unsigned char*)e->d_obst + ob_bytes;
+        d_guided = (unsigned char*)e->d_obst + ob_bytes;
         if (ob_bytes) CK(cudaMemcpyAsync(e->d_obst, ga->obst_pred, ob_bytes, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(d_guided, ga->guided, (size_t)n, cudaMemcpyHostToDevice, st));
-        int rc_ = mpcgpu_guidance_halfspaces_device(e, n_sets, planners, e->d_xs, e->d_x0, (const double*)e->d_obst, ga->n_obs, d_guided,
-                                                    ga->lin_base, ga->lin_count, ga->robot_radius, e->d_params, st);
+        if (ga->ell_base >= 0) {      // ellipsoid slots of the shared block from the tables, before it is expanded per planner
+            int rc_ = mpcgpu_pack_obstacles_device(e, n_sets, e->d_xs, (const double*)e->d_obst, ga->n_obs, ga->ell_base, ga->ell_stride, ga->ell_off,
+                                                   e->d_shared, st);
+            if (rc_ != MPCGPU_OK) return rc_;
+        }
+    }
+    repeat_xinit_kernel<<<(n * nx + 255) / 256, 256, 0, st>>>(n, planners, nx, e->d_xs, e->d_xinit);
+    expand_params_kernel<<<1184, 256, 0, st>>>(n, planners, N, np, nidx, e->d_shared, e->d_pidx, e->d_pvals, e->d_params);
+    if (nidx > 0) scatter_params_kernel<<<592, 256, 0, st>>>(n, N, np, nidx, e->d_pidx, e->d_pvals, e->d_params);
+    CK(cudaGetLastError());
+    e->launches += (nidx > 0) ? 3 : 2;
+    if (ga) {      // guidance halfspaces built on the device from the obstacle predictions and the warm starts
+        int rc_ = guidance_halfspaces_launch(e, n_sets, planners, e->d_xs, e->d_x0, (const double*)e->d_obst, ga->n_obs, ga->ob_stride, d_guided,
+                                             ga->lin_base, ga->lin_count, ga->robot_radius, e->d_params, st);
         if (rc_ != MPCGPU_OK) return rc_;
     }
     e->chunks_timed = 0;
@@ -622,3 +646,5 @@ float mpcgpu_last_kernel_ms(mpcgpu_engine* e)
 const char* mpcgpu_last_error(const mpcgpu_engine* e) { return e ? e->err.c_str() : "null engine"; }
 
 }  // extern "C"
+
+#include "mpcgpu_wire.inl"

@@ -12,9 +12,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def declared_symbols():
-    src = open(os.path.join(ROOT, "include", "mpcgpu.h")).read()
-    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(mpcgpu_[a-z0-9_]+)\s*\(", src)))
+    syms = set()
+    for h in sorted(os.listdir(os.path.join(ROOT, "include"))):      # every header of the C ABI (mpcgpu.h, mpcgpu_wire.h)
+        src = open(os.path.join(ROOT, "include", h)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        syms |= set(re.findall(r"\b(mpcgpu_[a-z0-9_]+)\s*\(", src))
+    return sorted(syms)
 
 
 def test_library_exports_every_declared_symbol():

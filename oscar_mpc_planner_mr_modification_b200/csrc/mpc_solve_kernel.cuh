@@ -80,6 +80,26 @@ __device__ __forceinline__ double nanmax(double a, double b)
     return __longlong_as_double((long long)(ua > ub ? ua : ub));
 }
 __device__ __forceinline__ double clamp_lo(double x, double lo) { return (x < lo) ? lo : x; }   // keeps NaN
+// Branch-free reciprocal square root: hardware approximation (rsqrt.approx.f64, ~2^-23) + one cubically convergent
+// correction y (1 + e/2 + 3 e^2/8), e = 1 - a y^2 (error below the rounding of a double).  Half the instructions of
+// rsqrt() and no slow-path branch, so two of them interleave in one in-order instruction stream (the two Cholesky
+// pivots of a Riccati stage); NaN for a < 0 or NaN input, which is what the failure detection relies on.
+#ifndef MPC_RSQRT_NB
+#define MPC_RSQRT_NB 1
+#endif
+__device__ __forceinline__ double rsqrt_nb(double a)
+{
+#if MPC_RSQRT_NB
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    const double m = a * y;
+    const double e = fma(-m, y, 1.0);
+    const double p = fma(0.375, e, 0.5);
+    return fma(y * e, p, y);
+#else
+    return rsqrt(a);
+#endif
+}
 __device__ __forceinline__ double warp_max(double v)
 {
 #pragma unroll
@@ -329,9 +349,7 @@ constexpr int RO_Q = RO_G + NPK;                 // row 7 of the packed augmente
 constexpr int RO_B = RO_Q + NZ;
 constexpr int RO_PRB = RO_B + NX * NB;
 constexpr int RO_DZ = RO_PRB + NX;
-constexpr int RO_ACL = RO_DZ + NZ;               // closed-loop matrix A + B K of the stage (role-split kernel: serial sweeps)
-constexpr int RO_BCL = RO_ACL + NX * NX;         // affine term of the sweep in progress
-constexpr int RO_END = RO_BCL + NX;
+constexpr int RO_END = RO_DZ + NZ;
 constexpr int RSTRIDE = RO_END | 1;              // odd stride: lane-parallel accesses (lane = stage) are conflict-free
 constexpr int RS_DOUBLES = (NSTAGE + 1) * RSTRIDE + NX * NB;   // per problem, incl. the T = P+ [W | rb] scratch
 static_assert(pk(NZ, 0) == NPK, "augmented row must follow the packed Hessian");
@@ -465,6 +483,7 @@ __device__ __forceinline__ double gate_tree(const double (&a)[n], int oz)
 // Lanes 0..27 own G(i,j); lanes 28..31 own q_j, two each (y = p+ + P+ rb); lane 28 also stores P+ rb.
 __device__ __noinline__ void riccati_factor_coop2(double* __restrict__ rs, const int oz)
 {
+    (void)oz;
     const int lane = threadIdx.x & 31;
     const bool ql = lane >= NPK;                        // q lanes
     int gi, gj;
@@ -497,7 +516,7 @@ __device__ __noinline__ void riccati_factor_coop2(double* __restrict__ rs, const
             }
             op[NPX + 4 * NX] = blk[o0];
             op[NPX + 4 * NX + 1] = blk[o1];
-            const double z0 = gate_tree(op, oz);
+            const double z0 = 0.0;      // (no gate here: the 25 independent FMAs of t = P+ c already overlap the load latency; gating cost 120 cycles per stage)
             double t[NX];
 #pragma unroll
             for (int l = 0; l < NX; l++) t[l] = z0;
@@ -527,9 +546,9 @@ __device__ __noinline__ void riccati_factor_coop2(double* __restrict__ rs, const
             op[5] = blk[RO_G + pk(NU + cj, 0)]; op[6] = blk[RO_G + pk(NU + cj, 1)];
             op[7] = blk[RO_G + pk(NU + ci, NU + cj)];
             op[8] = blk[RO_Q]; op[9] = blk[RO_Q + 1]; op[10] = blk[RO_Q + NU + ci];
-            const double g00 = op[0] + gate_tree(op, oz), g10 = op[1], g11 = op[2];
+            const double g00 = op[0], g10 = op[1], g11 = op[2];
             const double gi0 = op[3], gi1 = op[4], gj0 = op[5], gj1 = op[6], gxx = op[7], q0 = op[8], q1 = op[9], qi = op[10];
-            const double iL0 = rsqrt(g00), dd = rsqrt(g00 * g11 - g10 * g10);
+            const double iL0 = rsqrt_nb(g00), dd = rsqrt_nb(g00 * g11 - g10 * g10);
             const double L10 = g10 * iL0, iL1 = dd * (g00 * iL0);
             const double li0 = gi0 * iL0, li1 = (gi1 - li0 * L10) * iL1;
             const double lj0 = gj0 * iL0, lj1 = (gj1 - lj0 * L10) * iL1;
@@ -620,52 +639,169 @@ __device__ __noinline__ void riccati_backvec_coop(double* __restrict__ rs, const
     }
 }
 
-// ---- Substitution sweeps in closed-loop form (role-split kernel).  With Acl_k = A_k + B_k K_k parked per stage, both sweeps
-//      are x+ = Acl x + b (forward) / p = Acl' p+ + c (backward): lanes 0..4 own one component each, the five components are
-//      exchanged by shuffles (no shared-memory round trip on the dependency chain), the matrix row / column of the NEXT stage
-//      is loaded while the current one is combined.  The chain of a stage is one shuffle + a depth-3 FMA tree.
+// ---- Substitution sweeps in closed-loop form, blocked (role-split kernel).  With Acl_k = A_k + B_k K_k both sweeps are affine
+//      recurrences, x_{k+1} = Acl_k x_k + b_k (forward) and p_k = Acl_k' p_{k+1} + c_k (backward).  A dependent step costs
+//      ~170 cycles (exchange of the five components + a 5-term FMA tree), so the chain is shortened 4x: lane-parallel over
+//      the stages, M1_k = Acl_{k+1} Acl_k and M2_k = M1_{k+2} M1_k are formed once per factorisation (they serve all three
+//      sweeps; the backward sweep uses their transposes), every sweep condenses its vectors the same way (two lane-parallel
+//      levels), runs the serial recursion over every 4th stage only, and fills the stages in between lane-parallel again.
+//      Horizon padded to a multiple of 4 with identity stages.  Workspace: one block of SWS doubles per stage.
+constexpr int NPAD = ((NSTAGE + 3) / 4) * 4;
+constexpr int SW_A = 0, SW_M1 = NX * NX, SW_M2 = 2 * NX * NX, SW_B = 3 * NX * NX, SW_B1 = SW_B + NX, SW_B2 = SW_B1 + NX, SW_X = SW_B2 + NX;
+constexpr int SWS = (SW_X + NX) | 1;
+constexpr int SW_DOUBLES = (NPAD + 1) * SWS;
+
+// out = w + M v (TR: M' v); M row-major in shared memory
+template <bool TR>
+__device__ __forceinline__ void affine5(const double* __restrict__ M, const double* v, const double* w, double* out)
+{
+    double m[NX * NX];
+#pragma unroll
+    for (int i = 0; i < NX * NX; i++) m[i] = M[i];
+#pragma unroll
+    for (int i = 0; i < NX; i++) {
+        double acc = w[i];
+#pragma unroll
+        for (int j = 0; j < NX; j++) acc += (TR ? m[j * NX + i] : m[i * NX + j]) * v[j];
+        out[i] = acc;
+    }
+}
+// C = A B (row-major, registers in, shared memory out)
+__device__ __forceinline__ void matmul5(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C)
+{
+    double a[NX * NX], b[NX * NX];
+#pragma unroll
+    for (int i = 0; i < NX * NX; i++) { a[i] = A[i]; b[i] = B[i]; }
+#pragma unroll
+    for (int i = 0; i < NX; i++)
+#pragma unroll
+        for (int j = 0; j < NX; j++) {
+            double acc = 0.0;
+#pragma unroll
+            for (int l = 0; l < NX; l++) acc += a[i * NX + l] * b[l * NX + j];
+            C[i * NX + j] = acc;
+        }
+}
+// once per factorisation: SW_A of every stage (identity on the padding) -> SW_M1, SW_M2.  One full warp, lane = stage.
+__device__ __noinline__ void sweep_products(double* __restrict__ sw)
+{
+    // (one warp covers the padded horizon: callers require NPAD <= 32, SPLIT_OK)
+    const int k = threadIdx.x & 31;
+    const int k1 = k + 1 < NPAD ? k + 1 : NPAD - 1, k2 = k + 2 < NPAD ? k + 2 : NPAD - 1;      // (clamped lanes produce unused values)
+    double* __restrict__ me = sw + k * SWS;
+    if (k < NPAD) matmul5(sw + k1 * SWS + SW_A, me + SW_A, me + SW_M1);
+    __syncwarp();
+    if (k < NPAD) matmul5(sw + k2 * SWS + SW_M1, me + SW_M1, me + SW_M2);
+    __syncwarp();
+}
+// serial part over every 4th stage: lanes 0..4 own one component, exchange by shuffles
 template <bool FWD>
-__device__ __noinline__ void riccati_sweep_cl(double* __restrict__ rs, const int oz)
+__device__ __forceinline__ void sweep_serial4(double* __restrict__ sw)
 {
     const int lane = threadIdx.x & 31;
     const int i = lane < NX ? lane : NX - 1;
-    double x = 0.0;                                  // forward: dx_0 = 0
-    if (!FWD) x = rs[NSTAGE * RSTRIDE + RO_Q + NU + i];      // backward: p_N
-    else if (lane < NX) rs[RO_DZ + NU + i] = 0.0;
-    const int s0 = FWD ? 0 : NSTAGE - 1, ds = FWD ? 1 : -1;
-    double a[NX], c;
-    {
-        const double* __restrict__ blk = rs + s0 * RSTRIDE;
-#pragma unroll
-        for (int j = 0; j < NX; j++) a[j] = FWD ? blk[RO_ACL + i * NX + j] : blk[RO_ACL + j * NX + i];
-        c = blk[RO_BCL + i];
-    }
+    double x = FWD ? 0.0 : sw[NPAD * SWS + SW_X + i];
+    if (FWD && lane < NX) sw[SW_X + i] = 0.0;
 #pragma unroll 1
-    for (int n = 0, s = s0; n < NSTAGE; n++, s += ds) {
-        double an[NX], cn = 0.0;
-        if (n + 1 < NSTAGE) {                        // next stage's operands: independent of the recursion
-            const double* __restrict__ nb = rs + (s + ds) * RSTRIDE;
+    for (int q = 0; q < NPAD / 4; q++) {
+        const int k = FWD ? 4 * q : NPAD - 4 - 4 * q;
+        const double* __restrict__ blk = sw + k * SWS;
+        double a[NX], xs[NX];
 #pragma unroll
-            for (int j = 0; j < NX; j++) an[j] = FWD ? nb[RO_ACL + i * NX + j] : nb[RO_ACL + j * NX + i];
-            cn = nb[RO_BCL + i];
-        } else {
-#pragma unroll
-            for (int j = 0; j < NX; j++) an[j] = 0.0;
-        }
-        double xs[NX];
+        for (int j = 0; j < NX; j++) a[j] = FWD ? blk[SW_M2 + i * NX + j] : blk[SW_M2 + j * NX + i];
+        const double c = blk[SW_B2 + i];
 #pragma unroll
         for (int j = 0; j < NX; j++) xs[j] = __shfl_sync(FULL, x, j);
         static_assert(NX == 5, "FMA tree written for nx = 5");
-        (void)oz;                                        // (gating the shuffles like the loads of the factorisation measured slower)
         const double t0 = a[0] * xs[0] + c, t1 = a[1] * xs[1], t2 = a[4] * xs[4];
         x = ((a[2] * xs[2] + t0) + (a[3] * xs[3] + t1)) + t2;
-        if (lane < NX) {
-            if (FWD) rs[(s + 1) * RSTRIDE + RO_DZ + NU + i] = x;      // dx_{s+1}
-            else rs[s * RSTRIDE + RO_Q + NU + i] = x;                 // p_s
-        }
+        if (lane < NX) sw[(FWD ? k + 4 : k) * SWS + SW_X + i] = x;
+    }
+    __syncwarp();
+}
+// forward: in SW_B (b_k; 0 on the padding), out SW_X of stage k = x_k (x_0 = 0)
+__device__ __noinline__ void sweep_forward_blocked(double* __restrict__ sw)
+{
+    const int k = threadIdx.x & 31;
+    const int k1 = k + 1 < NPAD ? k + 1 : NPAD - 1, k2 = k + 2 < NPAD ? k + 2 : NPAD - 1;
+    double* __restrict__ me = sw + k * SWS;
+    double v[NX], w[NX], o[NX];
+    if (k < NPAD) {                                  // b1_k = A_{k+1} b_k + b_{k+1}
 #pragma unroll
-        for (int j = 0; j < NX; j++) a[j] = an[j];
-        c = cn;
+        for (int i = 0; i < NX; i++) { v[i] = me[SW_B + i]; w[i] = sw[k1 * SWS + SW_B + i]; }
+        affine5<false>(sw + k1 * SWS + SW_A, v, w, o);
+#pragma unroll
+        for (int i = 0; i < NX; i++) me[SW_B1 + i] = o[i];
+    }
+    __syncwarp();
+    if (k < NPAD) {                                  // b2_k = M1_{k+2} b1_k + b1_{k+2}
+#pragma unroll
+        for (int i = 0; i < NX; i++) { v[i] = o[i]; w[i] = sw[k2 * SWS + SW_B1 + i]; }
+        affine5<false>(sw + k2 * SWS + SW_M1, v, w, o);
+#pragma unroll
+        for (int i = 0; i < NX; i++) me[SW_B2 + i] = o[i];
+    }
+    __syncwarp();
+    sweep_serial4<true>(sw);                         // x_0, x_4, x_8, ...
+    if (k < NPAD && (k & 3) == 0) {                  // x_{k+2} = M1_k x_k + b1_k
+#pragma unroll
+        for (int i = 0; i < NX; i++) { v[i] = me[SW_X + i]; w[i] = me[SW_B1 + i]; }
+        affine5<false>(me + SW_M1, v, w, o);
+#pragma unroll
+        for (int i = 0; i < NX; i++) sw[(k + 2) * SWS + SW_X + i] = o[i];
+    }
+    __syncwarp();
+    if (k < NPAD && (k & 1) == 0) {                  // x_{k+1} = A_k x_k + b_k
+#pragma unroll
+        for (int i = 0; i < NX; i++) { v[i] = me[SW_X + i]; w[i] = me[SW_B + i]; }
+        affine5<false>(me + SW_A, v, w, o);
+#pragma unroll
+        for (int i = 0; i < NX; i++) sw[(k + 1) * SWS + SW_X + i] = o[i];
+    }
+    __syncwarp();
+}
+// backward: in SW_B (c_k; 0 on the padding) and p_NPAD in SW_X of block NPAD; out SW_X of stage k = p_k
+__device__ __noinline__ void sweep_backward_blocked(double* __restrict__ sw)
+{
+    const int k = threadIdx.x & 31;
+    const int k1 = k + 1 < NPAD ? k + 1 : NPAD - 1, k2 = k + 2 < NPAD ? k + 2 : NPAD - 1;
+    double* __restrict__ me = sw + k * SWS;
+    double v[NX], w[NX], o[NX];
+    if (k < NPAD) {                                  // c1_k = A_k' c_{k+1} + c_k
+#pragma unroll
+        for (int i = 0; i < NX; i++) { v[i] = sw[k1 * SWS + SW_B + i]; w[i] = me[SW_B + i]; }
+        if (k + 1 >= NPAD) {
+#pragma unroll
+            for (int i = 0; i < NX; i++) v[i] = 0.0;
+        }
+        affine5<true>(me + SW_A, v, w, o);
+#pragma unroll
+        for (int i = 0; i < NX; i++) me[SW_B1 + i] = o[i];
+    }
+    __syncwarp();
+    if (k < NPAD) {                                  // c2_k = M1_k' c1_{k+2} + c1_k
+#pragma unroll
+        for (int i = 0; i < NX; i++) { w[i] = o[i]; v[i] = (k + 2 < NPAD) ? sw[k2 * SWS + SW_B1 + i] : 0.0; }
+        affine5<true>(me + SW_M1, v, w, o);
+#pragma unroll
+        for (int i = 0; i < NX; i++) me[SW_B2 + i] = o[i];
+    }
+    __syncwarp();
+    sweep_serial4<false>(sw);                        // p_{NPAD-4}, ..., p_4, p_0
+    if (k < NPAD && (k & 3) == 2) {                  // p_k = M1_k' p_{k+2} + c1_k
+#pragma unroll
+        for (int i = 0; i < NX; i++) { v[i] = sw[(k + 2) * SWS + SW_X + i]; w[i] = me[SW_B1 + i]; }
+        affine5<true>(me + SW_M1, v, w, o);
+#pragma unroll
+        for (int i = 0; i < NX; i++) me[SW_X + i] = o[i];
+    }
+    __syncwarp();
+    if (k < NPAD && (k & 1) == 1) {                  // p_k = A_k' p_{k+1} + c_k
+#pragma unroll
+        for (int i = 0; i < NX; i++) { v[i] = sw[(k + 1) * SWS + SW_X + i]; w[i] = me[SW_B + i]; }
+        affine5<true>(me + SW_A, v, w, o);
+#pragma unroll
+        for (int i = 0; i < NX; i++) me[SW_X + i] = o[i];
     }
     __syncwarp();
 }
@@ -712,9 +848,9 @@ __device__ __noinline__ void mirror_generic(double* Hp)
                 const double apq = a[pk(q, p)], q2 = apq * apq;
                 if (q2 > 0.0) {
                     const double tau = a[pk(q, q)] - a[pk(p, p)];
-                    const double ir = rsqrt(tau * tau + 4.0 * q2);
+                    const double ir = rsqrt_nb(tau * tau + 4.0 * q2);
                     const double c2 = 0.5 + 0.5 * fabs(tau) * ir;
-                    const double ic = rsqrt(c2), c = c2 * ic;
+                    const double ic = rsqrt_nb(c2), c = c2 * ic;
                     const double sn = (tau >= 0.0 ? apq : -apq) * ir * ic, tt = sn * ic;
 #pragma unroll
                     for (int k = 0; k < JP; k++) {
@@ -806,9 +942,9 @@ __device__ __forceinline__ void mirror_block(double* Hp)
                 const double apq = a[q][p], q2 = apq * apq;
                 if (q2 > 0.0) {
                     const double tau = a[q][q] - a[p][p];
-                    const double ir = rsqrt(tau * tau + 4.0 * q2);
+                    const double ir = rsqrt_nb(tau * tau + 4.0 * q2);
                     const double c2 = 0.5 + 0.5 * fabs(tau) * ir;
-                    const double ic = rsqrt(c2), c = c2 * ic;
+                    const double ic = rsqrt_nb(c2), c = c2 * ic;
                     const double sn = (tau >= 0.0 ? apq : -apq) * ir * ic, tt = sn * ic;
 #pragma unroll
                     for (int k = 0; k < n; k++) {
@@ -1284,9 +1420,9 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
 #pragma unroll
                     for (int i = 0; i < NZ; i++) q[i] = gt[i];
                     wt_mul_add(Wv, y, q);
-                    iL0 = rsqrt(G[pk(0, 0)]);
+                    iL0 = rsqrt_nb(G[pk(0, 0)]);
                     L10 = G[pk(1, 0)] * iL0;
-                    iL1 = rsqrt(G[pk(1, 1)] - L10 * L10);
+                    iL1 = rsqrt_nb(G[pk(1, 1)] - L10 * L10);
 #pragma unroll
                     for (int i = 0; i < NX; i++) {
                         Lx0[i] = G[pk(NU + i, 0)] * iL0;

@@ -31,14 +31,15 @@ constexpr int RPB = (NCG + NBR - 1) / NBR > 0 ? (NCG + NBR - 1) / NBR : 1;     /
 constexpr int NHP = NHS * (NHS + 1) / 2;                                       // packed block over the support of h
 constexpr int XS = NHP + 2 * NHS + 3;            // exchange slots per B role and stage: Hs | g | rg | nd nm sm
 constexpr int XSX = 3 * NZ + 3;                  // exchange slots of role X per stage: diag Ht | g | rg | nd nm sm
-constexpr bool SPLIT_OK = (NSTAGE + 1 <= 32) && NCG >= 6 && NCG >= 2 * NBR;
+constexpr bool SPLIT_OK = (NSTAGE + 1 <= 32) && NPAD <= 32 && NCG >= 6 && NCG >= 2 * NBR;
 // shared memory of one problem (doubles)
 constexpr int SP_RS = 0;
 constexpr int SP_XCH = (RS_DOUBLES + 1) & ~1;    // [NBR][XS][32]
 constexpr int SP_XCX = SP_XCH + NBR * XS * 32;   // [XSX][32] slots of role X
 constexpr int SP_PUB = SP_XCX + XSX * 32;        // [2 NZ][32]: z and v of every stage, published by role A (v: amended by role X)
 constexpr int SP_DEC = SP_PUB + 2 * NZ * 32;     // decisions published by role A
-constexpr int SP_DOUBLES = SP_DEC + 8;
+constexpr int SP_SW = SP_DEC + 8;                // blocked-sweep workspace (SW_DOUBLES)
+constexpr int SP_DOUBLES = SP_SW + SW_DOUBLES;
 enum { DEC_CONT = 0, DEC_SIGMU = 1, DEC_STEP = 2, DEC_SQP = 3, DEC_STATUS = 4 };
 
 #ifdef MPC_PROF          // cycle accounting of role A (lane 0 of problem 0 prints it): a diagnostic build, never shipped
@@ -439,6 +440,8 @@ __device__ __noinline__ void split_role_a(const int prob, const double* __restri
     double* const pub = sm + SP_PUB + k;
     double* const dec = sm + SP_DEC;
     double* const blk = rs + (live ? k : 0) * RSTRIDE;
+    double* const sw = sm + SP_SW;                                      // blocked-sweep workspace
+    double* const swk = sw + k * SWS;                                   // (k < 32 <= NPAD + 1 blocks)
     Grp grp;                                                            // warp-level helpers (a role is one warp here)
     grp.xch = nullptr; grp.gid = 0; grp.wig = 0;
     static_assert(GW == 1 || !SPLIT_OK, "role-split kernel: one warp per role");
@@ -665,17 +668,23 @@ __device__ __noinline__ void split_role_a(const int prob, const double* __restri
                 closed_loop(Wv, Lx0, Lx1, L10, iL0, iL1, Acl, Bd);
                 const double k1 = -lv[1] * iL1, k0 = -(lv[0] + L10 * k1) * iL0;      // kff = -Luu^-T l
 #pragma unroll
-                for (int i = 0; i < NX * NX; i++) blk[RO_ACL + i] = Acl[i];
+                for (int i = 0; i < NX * NX; i++) swk[SW_A + i] = Acl[i];
 #pragma unroll
-                for (int i = 0; i < NX; i++) blk[RO_BCL + i] = rb[i] + Bd[i * NU] * k0 + Bd[i * NU + 1] * k1;
+                for (int i = 0; i < NX; i++) swk[SW_B + i] = rb[i] + Bd[i * NU] * k0 + Bd[i * NU + 1] * k1;
+            } else if (k < NPAD) {                                   // padding stages: identity
+#pragma unroll
+                for (int i = 0; i < NX * NX; i++) swk[SW_A + i] = (i / NX == i % NX) ? 1.0 : 0.0;
+#pragma unroll
+                for (int i = 0; i < NX; i++) swk[SW_B + i] = 0.0;
             }
             __syncwarp();
             PROF(22)
-            riccati_sweep_cl<true>(rs, oz);
+            sweep_products(sw);
+            sweep_forward_blocked(sw);
             PROF(23)
             if (live) {
 #pragma unroll
-                for (int i = 0; i < NX; i++) dva[NU + i] = blk[RO_DZ + NU + i];
+                for (int i = 0; i < NX; i++) dva[NU + i] = swk[SW_X + i];
             }
             {
                 double r0 = lv[0], r1 = lv[1];           // du = -Luu^-T (Lxu' dx + l)
@@ -686,7 +695,7 @@ __device__ __noinline__ void split_role_a(const int prob, const double* __restri
             }
             if (path) {                                              // roles X and B read the step from the blocks
 #pragma unroll
-                for (int i = 0; i < NU; i++) blk[RO_DZ + i] = dva[i];
+                for (int i = 0; i < NZ; i++) blk[RO_DZ + i] = dva[i];
             }
             PROF(9)
             split_barrier();                                         // 3
@@ -730,18 +739,22 @@ __device__ __noinline__ void split_role_a(const int prob, const double* __restri
                     for (int i = 0; i < NX; i++) {
                         double c_ = gt[NU + i] - Lx0[i] * lg0 - Lx1[i] * lg1;
 #pragma unroll
-                        for (int j = 0; j < NX; j++) c_ += blk[RO_ACL + j * NX + i] * Prb[j];
-                        blk[RO_BCL + i] = c_;
+                        for (int j = 0; j < NX; j++) c_ += swk[SW_A + j * NX + i] * Prb[j];
+                        swk[SW_B + i] = c_;
                     }
-                } else if (term) {
+                } else if (k < NPAD) {
 #pragma unroll
-                    for (int i = 0; i < NX; i++) blk[RO_Q + NU + i] = gt[NU + i];      // p_N
+                    for (int i = 0; i < NX; i++) swk[SW_B + i] = 0.0;
+                }
+                if (term) {
+#pragma unroll
+                    for (int i = 0; i < NX; i++) sw[NPAD * SWS + SW_X + i] = gt[NU + i];      // p_N (= p_NPAD: identity padding)
                 }
                 __syncwarp();
-                riccati_sweep_cl<false>(rs, oz);
+                sweep_backward_blocked(sw);
                 double pn[NX];
 #pragma unroll
-                for (int i = 0; i < NX; i++) { pv[i] = live ? blk[RO_Q + NU + i] : 0.0; pn[i] = path ? blk[RSTRIDE + RO_Q + NU + i] : 0.0; }
+                for (int i = 0; i < NX; i++) { pv[i] = live ? swk[SW_X + i] : 0.0; pn[i] = path ? swk[SWS + SW_X + i] : 0.0; }
                 if (path) {
                     double q0 = gt[0], q1 = gt[1];
 #pragma unroll
@@ -753,15 +766,15 @@ __device__ __noinline__ void split_role_a(const int prob, const double* __restri
                     lv[1] = (q1 - L10 * lv[0]) * iL1;
                     const double k1 = -lv[1] * iL1, k0 = -(lv[0] + L10 * k1) * iL0;
 #pragma unroll
-                    for (int i = 0; i < NX; i++) blk[RO_BCL + i] = rb[i] + Bd[i * NU] * k0 + Bd[i * NU + 1] * k1;
+                    for (int i = 0; i < NX; i++) swk[SW_B + i] = rb[i] + Bd[i * NU] * k0 + Bd[i * NU + 1] * k1;
                 }
                 __syncwarp();
             }
             PROF(15)
-            riccati_sweep_cl<true>(rs, oz);
+            sweep_forward_blocked(sw);
             if (live) {
 #pragma unroll
-                for (int i = 0; i < NX; i++) dv[NU + i] = blk[RO_DZ + NU + i];
+                for (int i = 0; i < NX; i++) dv[NU + i] = swk[SW_X + i];
             }
             {
                 double r0 = lv[0], r1 = lv[1];
@@ -772,7 +785,7 @@ __device__ __noinline__ void split_role_a(const int prob, const double* __restri
             }
             if (path) {
 #pragma unroll
-                for (int i = 0; i < NU; i++) blk[RO_DZ + i] = dv[i];
+                for (int i = 0; i < NZ; i++) blk[RO_DZ + i] = dv[i];
             }
             PROF(16)
             split_barrier();                                         // 6

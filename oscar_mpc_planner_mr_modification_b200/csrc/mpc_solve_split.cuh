@@ -157,7 +157,7 @@ __device__ __noinline__ void split_role_b(const int prob, const double* __restri
                 }
 #pragma unroll
                 for (int a = 0; a < NHS; a++) cv += C[r * NHS + a] * v3[a];
-                const double it_ = 1.0 / t;
+                const double it_ = rcp_nb(t);
                 const double rd = sg * cv - dg[e] - t, G = lam * it_, m = lam * t;
                 itg[e] = it_;
 #pragma unroll
@@ -326,7 +326,7 @@ __device__ __noinline__ void split_role_x(const int prob, const int num_iter, do
                             lam = clamp_lo(lam + a_ * st.dlam, IPM_LAM_MIN); t = clamp_lo(t + a_ * st.dt, IPM_T_MIN);
                             lamb[i] = lam; tb[i] = t;
                         }
-                        const double it_ = 1.0 / t;
+                        const double it_ = rcp_nb(t);
                         const double rd = v[i] - dl - t, G = lam * it_, m = lam * t;
                         itb[i] = it_;
                         hd += G; gg += G * rd; rr -= lam;
@@ -339,7 +339,7 @@ __device__ __noinline__ void split_role_x(const int prob, const int num_iter, do
                             lam = clamp_lo(lam + a_ * st.dlam, IPM_LAM_MIN); t = clamp_lo(t + a_ * st.dt, IPM_T_MIN);
                             lamb[NZ + i] = lam; tb[NZ + i] = t;
                         }
-                        const double it_ = 1.0 / t;
+                        const double it_ = rcp_nb(t);
                         const double rd = du - v[i] - t, G = lam * it_, m = lam * t;
                         itb[NZ + i] = it_;
                         hd += G; gg -= G * rd; rr += lam;

@@ -1147,8 +1147,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                     double mh[NH > 0 ? NH : 1], hv[NH > 0 ? NH : 1];
                     for (int r = 0; r < NH; r++) mh[r] = 0.0;
                     for (int e = 0; e < NCG; e++) mh[HROW[e]] -= HSGN[e] * lamg[e];   // lam_u - lam_l
-                    con_hess_add(z, p, mh, H);
-                    con_eval(z, p, hv, C);
+                    con_lin(z, p, mh, H, hv, C);      // Jacobian + multiplier-weighted Hessian in one traversal (shared subexpressions)
                     for (int e = 0; e < NCG; e++) dg[e] = HSGN[e] * (HBND[e] - hv[HROW[e]]);
                 }
                 mirror_packed(H);
@@ -1204,13 +1203,13 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                         else { tl = IPM_THR0; v[i] = dl + IPM_THR0; }
                     } else if (tu < IPM_THR0) { tu = IPM_THR0; v[i] = du - IPM_THR0; }
                     tb[i] = tl; tb[NZ + i] = tu;
-                    lamb[i] = IPM_MU0 / tl; lamb[NZ + i] = IPM_MU0 / tu;
+                    lamb[i] = IPM_MU0 * rcp_nb(tl); lamb[NZ + i] = IPM_MU0 * rcp_nb(tu);
                 }
             }
             if (path) for (int e = 0; e < NCG; e++) {
                 double tt = gen_dot(C, e, v) - dg[e];
                 if (tt < IPM_THR0) tt = IPM_THR0;
-                tg[e] = tt; lamg[e] = IPM_MU0 / tt;
+                tg[e] = tt; lamg[e] = IPM_MU0 * rcp_nb(tt);
             }
         }
 
@@ -1849,11 +1848,10 @@ __global__ void model_eval_kernel(int n, const double* __restrict__ z_g, const d
     cost_lin(z, p, g, H);
     for (int j = 0; j < NZ; j++) *o++ = g[j];
     for (int j = 0; j < NPK; j++) *o++ = H[j];
-    con_eval(z, p, hv, C);
+    for (int j = 0; j < NPK; j++) H[j] = 0.0;
+    con_lin(z, p, mh, H, hv, C);                 // the function the solve kernels use
     for (int j = 0; j < NH; j++) *o++ = hv[j];
     for (int j = 0; j < NH * NHS; j++) *o++ = C[j];
-    for (int j = 0; j < NPK; j++) H[j] = 0.0;
-    con_hess_add(z, p, mh, H);
     for (int j = 0; j < NPK; j++) *o++ = H[j];
 }
 

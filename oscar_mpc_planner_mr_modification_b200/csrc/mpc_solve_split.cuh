@@ -98,8 +98,7 @@ __device__ __noinline__ void split_role_b(const int prob, const double* __restri
                 double mh[RPB], hv[RPB];
                 for (int j = 0; j < RPB; j++) mh[j] = 0.0;
                 for (int e = 0; e < ne; e++) mh[HROW[e_lo + e] - r_lo] -= HSGN[e_lo + e] * lamg[e];      // lam_u - lam_l
-                con_hess_add_rows(zz, p, r_lo, r_hi, mh, Hh);
-                con_eval_rows(zz, p, r_lo, r_hi, hv, C);
+                con_lin_rows(zz, p, r_lo, r_hi, mh, Hh, hv, C);
                 for (int e = 0; e < ne; e++) dg[e] = HSGN[e_lo + e] * (HBND[e_lo + e] - hv[HROW[e_lo + e] - r_lo]);
             }
 #pragma unroll
@@ -122,7 +121,7 @@ __device__ __noinline__ void split_role_b(const int prob, const double* __restri
                 for (int a = 0; a < NHS; a++) s += C[r * NHS + a] * v3[a];
                 double tt = HSGN[e_lo + e] * s - dg[e];
                 if (tt < IPM_THR0) tt = IPM_THR0;
-                tg[e] = tt; lamg[e] = IPM_MU0 / tt;
+                tg[e] = tt; lamg[e] = IPM_MU0 * rcp_nb(tt);
             }
         }
 
@@ -299,7 +298,7 @@ __device__ __noinline__ void split_role_x(const int prob, const int num_iter, do
                         else { tl = IPM_THR0; v[i] = dl + IPM_THR0; }
                     } else if (tu < IPM_THR0) { tu = IPM_THR0; v[i] = du - IPM_THR0; }
                     tb[i] = tl; tb[NZ + i] = tu;
-                    lamb[i] = IPM_MU0 / tl; lamb[NZ + i] = IPM_MU0 / tu;
+                    lamb[i] = IPM_MU0 * rcp_nb(tl); lamb[NZ + i] = IPM_MU0 * rcp_nb(tu);
                 }
             }
 #pragma unroll

@@ -335,91 +335,61 @@ def emit_model_header(pb, name, sim_steps=3):
             mq[sym] = ("p[%d]" if i in fixed else "q[%d]") % i
         return mq
 
-    w("\n// hv[NH] = h(z,p);  C[r*NHS + s] = d h_r / d z_HSUP[s]")
-    w("__device__ __forceinline__ void con_eval(const double* z, const double* __restrict__ p, double* hv, double* C)\n{")
-    if flat:
-        w(emit_block([("hv[%d]" % i, h[i]) for i in flat] +
-                     [("C[%d]" % (i * nhs + s_), sp.diff(h[i], z[sup[s_]])) for i in flat for s_ in range(nhs)], m))
-    for gi, (r0, cnt, stride, fixed) in enumerate(groups):
-        w("#pragma unroll 1\n    for (int r = 0; r < %d; r++) {\n        const double* __restrict__ q = p + r * %d;" % (cnt, stride))
-        w(emit_block([("hv[%d + r]" % r0, h[r0])] +
-                     [("C[(%d + r) * %d + %d]" % (r0, nhs, s_), sp.diff(h[r0], z[sup[s_]])) for s_ in range(nhs)],
-                     qmap(r0, fixed), tmp_prefix="g%d_" % gi, indent="        "))
-        w("    }")
-    w("}")
-    w("\n// H(packed NZ) += sum_r mh[r] d2 h_r / dz2")
-    w("__device__ __forceinline__ void con_hess_add(const double* z, const double* __restrict__ p, const double* mh, double* H)\n{")
+    mhs = sp.symbols("mh0:%d" % max(nh, 1))
+
+    def hess_outputs(rows, msyms):
+        """packed-Hessian accumulations of sum_r msyms[r] h_r over the support of h"""
+        Lh = sum(msyms[i] * h[i] for i in rows)
+        gh = {s_: sp.diff(Lh, z[s_]) for s_ in sup}
+        outs = []
+        for a_ in sup:
+            for b_ in sup:
+                if b_ <= a_:
+                    e = sp.diff(gh[a_], z[b_])
+                    if e != 0:
+                        outs.append(("H[%d] +" % _idx(a_, b_), e))
+        return outs
+
+    # ---- both at once: one traversal of the rows with the common subexpressions (cos / sin / sqrt / reciprocals of the
+    #      obstacle parameters) shared between the Jacobian and the multiplier-weighted Hessian
+    w("\n// hv[NH] = h(z,p);  C[r*NHS + s] = d h_r / d z_HSUP[s];  H(packed NZ) += sum_r mh[r] d2 h_r / dz2")
+    w("__device__ __forceinline__ void con_lin(const double* z, const double* __restrict__ p, const double* mh, double* H, double* hv, double* C)\n{")
     if nh:
-        mhs = sp.symbols("mh0:%d" % nh)
-
-        def hess_outputs(rows, msyms):
-            Lh = sum(msyms[i] * h[i] for i in rows)
-            gh = {s_: sp.diff(Lh, z[s_]) for s_ in sup}
-            outs = []
-            for a_ in sup:
-                for b_ in sup:
-                    if b_ <= a_:
-                        e = sp.diff(gh[a_], z[b_])
-                        if e != 0:
-                            outs.append(("H[%d] +" % _idx(a_, b_), e))
-            return outs
-
         if flat:
-            outs = hess_outputs(flat, mhs)
             m3 = dict(m)
             m3.update({mhs[i]: "mh[%d]" % i for i in range(nh)})
-            if outs:
-                w(emit_block(outs, m3))
+            w(emit_block([("hv[%d]" % i, h[i]) for i in flat] +
+                         [("C[%d]" % (i * nhs + s_), sp.diff(h[i], z[sup[s_]])) for i in flat for s_ in range(nhs)] +
+                         hess_outputs(flat, mhs), m3))
         for gi, (r0, cnt, stride, fixed) in enumerate(groups):
-            outs = hess_outputs([r0], mhs)
-            if not outs:
-                continue
             mq = qmap(r0, fixed)
             mq[mhs[r0]] = "mh[%d + r]" % r0
             w("#pragma unroll 1\n    for (int r = 0; r < %d; r++) {\n        const double* __restrict__ q = p + r * %d;" % (cnt, stride))
-            w(emit_block(outs, mq, tmp_prefix="k%d_" % gi, indent="        "))
+            w(emit_block([("hv[%d + r]" % r0, h[r0])] +
+                         [("C[(%d + r) * %d + %d]" % (r0, nhs, s_), sp.diff(h[r0], z[sup[s_]])) for s_ in range(nhs)] +
+                         hess_outputs([r0], mhs), mq, tmp_prefix="l%d_" % gi, indent="        "))
+            w("    }")
+    w("}")
+    w("\n// the same restricted to the rows [r_lo, r_hi): hv, C, mh indexed by (row - r_lo)")
+    w("__device__ __forceinline__ void con_lin_rows(const double* z, const double* __restrict__ p, int r_lo, int r_hi, const double* mh, double* H, double* hv, double* C)\n{")
+    if nh:
+        for i in flat:
+            m3 = dict(m)
+            m3[mhs[i]] = "mh[o]"
+            w("    if (r_lo <= %d && %d < r_hi) {\n        const int o = %d - r_lo;" % (i, i, i))
+            w(emit_block([("hv[o]", h[i])] + [("C[o * %d + %d]" % (nhs, s_), sp.diff(h[i], z[sup[s_]])) for s_ in range(nhs)] +
+                         hess_outputs([i], mhs), m3, tmp_prefix="n%d_" % i, indent="        "))
+            w("    }")
+        for gi, (r0, cnt, stride, fixed) in enumerate(groups):
+            mq = qmap(r0, fixed)
+            mq[mhs[r0]] = "mh[o]"
+            w("#pragma unroll 1\n    for (int r = (r_lo > %d ? r_lo - %d : 0); r < (r_hi - %d < %d ? r_hi - %d : %d); r++) {" % (r0, r0, r0, cnt, r0, cnt))
+            w("        const double* __restrict__ q = p + r * %d;\n        const int o = %d + r - r_lo;" % (stride, r0))
+            w(emit_block([("hv[o]", h[r0])] + [("C[o * %d + %d]" % (nhs, s_), sp.diff(h[r0], z[sup[s_]])) for s_ in range(nhs)] +
+                         hess_outputs([r0], mhs), mq, tmp_prefix="m%d_" % gi, indent="        "))
             w("    }")
     w("}")
 
-    # ---- the same two functions restricted to the rows [r_lo, r_hi): outputs are indexed by (row - r_lo).  Used by the
-    #      role-split kernel, where the general constraints of a stage are shared out over several warps.
-    w("\n// rows [r_lo, r_hi) only: hv[r - r_lo], C[(r - r_lo)*NHS + s]")
-    w("__device__ __forceinline__ void con_eval_rows(const double* z, const double* __restrict__ p, int r_lo, int r_hi, double* hv, double* C)\n{")
-    for i in flat:
-        w("    if (r_lo <= %d && %d < r_hi) {\n        const int o = %d - r_lo;" % (i, i, i))
-        w(emit_block([("hv[o]", h[i])] + [("C[o * %d + %d]" % (nhs, s_), sp.diff(h[i], z[sup[s_]])) for s_ in range(nhs)],
-                     m, tmp_prefix="f%d_" % i, indent="        "))
-        w("    }")
-    for gi, (r0, cnt, stride, fixed) in enumerate(groups):
-        w("#pragma unroll 1\n    for (int r = (r_lo > %d ? r_lo - %d : 0); r < (r_hi - %d < %d ? r_hi - %d : %d); r++) {" % (r0, r0, r0, cnt, r0, cnt))
-        w("        const double* __restrict__ q = p + r * %d;\n        const int o = %d + r - r_lo;" % (stride, r0))
-        w(emit_block([("hv[o]", h[r0])] + [("C[o * %d + %d]" % (nhs, s_), sp.diff(h[r0], z[sup[s_]])) for s_ in range(nhs)],
-                     qmap(r0, fixed), tmp_prefix="g%d_" % gi, indent="        "))
-        w("    }")
-    w("}")
-    w("\n// rows [r_lo, r_hi) only: H(packed NZ) += sum_r mh[r - r_lo] d2 h_r / dz2")
-    w("__device__ __forceinline__ void con_hess_add_rows(const double* z, const double* __restrict__ p, int r_lo, int r_hi, const double* mh, double* H)\n{")
-    if nh:
-        for i in flat:
-            outs = hess_outputs([i], mhs)
-            if not outs:
-                continue
-            m3 = dict(m)
-            m3[mhs[i]] = "mh[%d - r_lo]" % i
-            w("    if (r_lo <= %d && %d < r_hi) {" % (i, i))
-            w(emit_block(outs, m3, tmp_prefix="e%d_" % i, indent="        "))
-            w("    }")
-        for gi, (r0, cnt, stride, fixed) in enumerate(groups):
-            outs = hess_outputs([r0], mhs)
-            if not outs:
-                continue
-            mq = qmap(r0, fixed)
-            mq[mhs[r0]] = "mh[%d + r - r_lo]" % r0
-            w("#pragma unroll 1\n    for (int r = (r_lo > %d ? r_lo - %d : 0); r < (r_hi - %d < %d ? r_hi - %d : %d); r++) {" % (r0, r0, r0, cnt, r0, cnt))
-            w("        const double* __restrict__ q = p + r * %d;" % stride)
-            w(emit_block(outs, mq, tmp_prefix="k%d_" % gi, indent="        "))
-            w("    }")
-    w("}")
     w("}  // namespace mpcgen")
     return "\n".join(out) + "\n"
 

@@ -1070,6 +1070,21 @@ __device__ __forceinline__ void step_limit(double val, double dval, double& bn, 
 {
     if (dval < 0.0 && val * bd < bn * (-dval)) { bn = val; bd = -dval; }
 }
+// The running minimum is a serial dependency across the entries (two multiplies + compare + selects per call): callers keep
+// TWO fractions -- one fed by the multipliers, one by the slacks -- and merge them at the end, which halves the chain.
+struct StepFrac {
+    double n0 = 1.0, d0 = 1.0, n1 = 1.0, d1 = 1.0;
+    __device__ __forceinline__ void add(double lam, double dlam, double t, double dt)
+    {
+        step_limit(lam, dlam, n0, d0);
+        step_limit(t, dt, n1, d1);
+    }
+    __device__ __forceinline__ double ratio() const
+    {
+        const bool second = n1 * d0 < n0 * d1;
+        return (second ? n1 : n0) / (second ? d1 : d0);
+    }
+};
 
 // ------------------------------------------------------------------------------------------------
 // One Solver::solve() on one warp
@@ -1494,7 +1509,8 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
             }   // !COOP
 
             // ---- pass B: affine step length, mu_aff sums, corrector vectors
-            double abn = 1.0, abd = 1.0, S1 = 0.0, S2 = 0.0, V1[NZ], V2[NZ];   // alpha_aff = abn/abd
+            StepFrac sfa;
+            double S1 = 0.0, S2 = 0.0, V1[NZ], V2[NZ];   // alpha_aff = sfa.ratio()
 #pragma unroll
             for (int i = 0; i < NZ; i++) { V1[i] = 0.0; V2[i] = 0.0; }
 #pragma unroll
@@ -1506,7 +1522,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                         const double lam = lamb[i], t = tb[i];
                         const double it_ = itb[i];
                         const IneqStep st = ineq_affine(lam, it_, v[i] - dl - t, dva[i]);
-                        step_limit(lam, st.dlam, abn, abd); step_limit(t, st.dt, abn, abd);
+                        sfa.add(lam, st.dlam, t, st.dt);
                         S1 += lam * st.dt + t * st.dlam; S2 += st.dt * st.dlam;
                         V1[i] += st.corr; V2[i] += it_;
                     }
@@ -1514,7 +1530,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                         const double lam = lamb[NZ + i], t = tb[NZ + i];
                         const double it_ = itb[NZ + i];
                         const IneqStep st = ineq_affine(lam, it_, du - v[i] - t, -dva[i]);
-                        step_limit(lam, st.dlam, abn, abd); step_limit(t, st.dt, abn, abd);
+                        sfa.add(lam, st.dlam, t, st.dt);
                         S1 += lam * st.dt + t * st.dlam; S2 += st.dt * st.dlam;
                         V1[i] -= st.corr; V2[i] -= it_;
                     }
@@ -1530,7 +1546,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                     for (int a = 0; a < NHS; a++) { cv += C[r * NHS + a] * v[HSUP[a]]; cd += C[r * NHS + a] * dva[HSUP[a]]; }
                     const double it_ = itg[e];
                     const IneqStep st = ineq_affine(lam, it_, sg * cv - dg[e] - t, sg * cd);
-                    step_limit(lam, st.dlam, abn, abd); step_limit(t, st.dt, abn, abd);
+                    sfa.add(lam, st.dlam, t, st.dt);
                     S1 += lam * st.dt + t * st.dlam; S2 += st.dt * st.dlam;
 #pragma unroll
                     for (int a = 0; a < NHS; a++) {
@@ -1539,7 +1555,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                     }
                 }
             }
-            const double alpha_aff = grp.min(abn / abd);
+            const double alpha_aff = grp.min(sfa.ratio());
             S1 = grp.sum(S1); S2 = grp.sum(S2);
             const double mu_aff = (mu * (double)IPM_COUNT + alpha_aff * S1 + alpha_aff * alpha_aff * S2) / (double)IPM_COUNT;
             const double rat = mu_aff / mu;
@@ -1680,7 +1696,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
             }   // !COOP
 
             // ---- pass C: step length of the corrected direction
-            double bn = 1.0, bd = 1.0;                  // alpha = bn/bd
+            StepFrac sfc;                  // alpha = sfc.ratio()
 #pragma unroll
             for (int i = 0; i < NZ; i++) {
                 const bool act = (i < NU) ? path : xbox;
@@ -1689,12 +1705,12 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                     {
                         const double lam = lamb[i], t = tb[i];
                         const IneqStep st = ineq_final(lam, itb[i], v[i] - dl - t, dva[i], dv[i], sigmu);
-                        step_limit(lam, st.dlam, bn, bd); step_limit(t, st.dt, bn, bd);
+                        sfc.add(lam, st.dlam, t, st.dt);
                     }
                     {
                         const double lam = lamb[NZ + i], t = tb[NZ + i];
                         const IneqStep st = ineq_final(lam, itb[NZ + i], du - v[i] - t, -dva[i], -dv[i], sigmu);
-                        step_limit(lam, st.dlam, bn, bd); step_limit(t, st.dt, bn, bd);
+                        sfc.add(lam, st.dlam, t, st.dt);
                     }
                 }
             }
@@ -1710,10 +1726,10 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                         cv += ca * v[HSUP[a]]; cda += ca * dva[HSUP[a]]; cd += ca * dv[HSUP[a]];
                     }
                     const IneqStep st = ineq_final(lam, itg[e], sg * cv - dg[e] - t, sg * cda, sg * cd, sigmu);
-                    step_limit(lam, st.dlam, bn, bd); step_limit(t, st.dt, bn, bd);
+                    sfc.add(lam, st.dlam, t, st.dt);
                 }
             }
-            alpha = grp.min(bn / bd);
+            alpha = grp.min(sfc.ratio());
             a_ = alpha < 1.0 ? alpha * IPM_STEP_SCALE : alpha;      // applied by the next pass DA
         }
         ipm_total += kk;

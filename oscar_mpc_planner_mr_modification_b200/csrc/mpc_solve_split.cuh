@@ -182,7 +182,8 @@ __device__ __noinline__ void split_role_b(const int prob, const double* __restri
             for (int a = 0; a < NHS; a++) dva3[a] = path ? blk[RO_DZ + HSUP[a]] : 0.0;
 
             // ---- pass B: affine step length, mu_aff sums, corrector vectors of this slice
-            double abn = 1.0, abd = 1.0, S1 = 0.0, S2 = 0.0, V1[NHS], V2[NHS];
+            StepFrac sfa;
+            double S1 = 0.0, S2 = 0.0, V1[NHS], V2[NHS];
 #pragma unroll
             for (int a = 0; a < NHS; a++) { V1[a] = 0.0; V2[a] = 0.0; }
 #pragma unroll GEN_UNROLL
@@ -194,7 +195,7 @@ __device__ __noinline__ void split_role_b(const int prob, const double* __restri
                 for (int a = 0; a < NHS; a++) { cv += C[r * NHS + a] * v3[a]; cd += C[r * NHS + a] * dva3[a]; }
                 const double it_ = itg[e];
                 const IneqStep st = ineq_affine(lam, it_, sg * cv - dg[e] - t, sg * cd);
-                step_limit(lam, st.dlam, abn, abd); step_limit(t, st.dt, abn, abd);
+                sfa.add(lam, st.dlam, t, st.dt);
                 S1 += lam * st.dt + t * st.dlam; S2 += st.dt * st.dlam;
 #pragma unroll
                 for (int a = 0; a < NHS; a++) {
@@ -204,7 +205,7 @@ __device__ __noinline__ void split_role_b(const int prob, const double* __restri
             }
 #pragma unroll
             for (int a = 0; a < NHS; a++) { xs[a * 32] = V1[a]; xs[(NHS + a) * 32] = V2[a]; }
-            xs[(2 * NHS) * 32] = abn / abd; xs[(2 * NHS + 1) * 32] = S1; xs[(2 * NHS + 2) * 32] = S2;
+            xs[(2 * NHS) * 32] = sfa.ratio(); xs[(2 * NHS + 1) * 32] = S1; xs[(2 * NHS + 2) * 32] = S2;
             split_barrier();                                         // 4: pass-B terms handed to A
             split_barrier();                                         // 5: sigma mu published
             sigmu = dec[DEC_SIGMU];
@@ -213,7 +214,7 @@ __device__ __noinline__ void split_role_b(const int prob, const double* __restri
             for (int a = 0; a < NHS; a++) dv3[a] = path ? blk[RO_DZ + HSUP[a]] : 0.0;
 
             // ---- pass C: step length of the corrected direction
-            double bn = 1.0, bd = 1.0;
+            StepFrac sfc;
 #pragma unroll GEN_UNROLL
             for (int e = 0; e < ne; e++) {
                 const int r = HROW[e_lo + e] - r_lo;
@@ -225,9 +226,9 @@ __device__ __noinline__ void split_role_b(const int prob, const double* __restri
                     cv += ca * v3[a]; cda += ca * dva3[a]; cd += ca * dv3[a];
                 }
                 const IneqStep st = ineq_final(lam, itg[e], sg * cv - dg[e] - t, sg * cda, sg * cd, sigmu);
-                step_limit(lam, st.dlam, bn, bd); step_limit(t, st.dt, bn, bd);
+                sfc.add(lam, st.dlam, t, st.dt);
             }
-            xs[0] = bn / bd;
+            xs[0] = sfc.ratio();
             split_barrier();                                         // 7: ratios handed to A
             split_barrier();                                         // 8: step length published
             a_ = dec[DEC_STEP];
@@ -355,7 +356,8 @@ __device__ __noinline__ void split_role_x(const int prob, const int num_iter, do
 #pragma unroll
             for (int i = 0; i < NZ; i++) dva[i] = path ? blk[RO_DZ + i] : 0.0;
 
-            double abn = 1.0, abd = 1.0, S1 = 0.0, S2 = 0.0;
+            StepFrac sfa;
+            double S1 = 0.0, S2 = 0.0;
 #pragma unroll
             for (int i = 0; i < NZ; i++) {
                 const bool act = (i < NU) ? path : xbox;
@@ -366,7 +368,7 @@ __device__ __noinline__ void split_role_x(const int prob, const int num_iter, do
                         const double lam = lamb[i], t = tb[i];
                         const double it_ = itb[i];
                         const IneqStep st = ineq_affine(lam, it_, v[i] - dl - t, dva[i]);
-                        step_limit(lam, st.dlam, abn, abd); step_limit(t, st.dt, abn, abd);
+                        sfa.add(lam, st.dlam, t, st.dt);
                         S1 += lam * st.dt + t * st.dlam; S2 += st.dt * st.dlam;
                         V1 += st.corr; V2 += it_;
                     }
@@ -374,21 +376,21 @@ __device__ __noinline__ void split_role_x(const int prob, const int num_iter, do
                         const double lam = lamb[NZ + i], t = tb[NZ + i];
                         const double it_ = itb[NZ + i];
                         const IneqStep st = ineq_affine(lam, it_, du - v[i] - t, -dva[i]);
-                        step_limit(lam, st.dlam, abn, abd); step_limit(t, st.dt, abn, abd);
+                        sfa.add(lam, st.dlam, t, st.dt);
                         S1 += lam * st.dt + t * st.dlam; S2 += st.dt * st.dlam;
                         V1 -= st.corr; V2 -= it_;
                     }
                 }
                 xs[i * 32] = V1; xs[(NZ + i) * 32] = V2;
             }
-            xs[(2 * NZ) * 32] = abn / abd; xs[(2 * NZ + 1) * 32] = S1; xs[(2 * NZ + 2) * 32] = S2;
+            xs[(2 * NZ) * 32] = sfa.ratio(); xs[(2 * NZ + 1) * 32] = S1; xs[(2 * NZ + 2) * 32] = S2;
             split_barrier();                                         // 4
             split_barrier();                                         // 5
             sigmu = dec[DEC_SIGMU];
             split_barrier();                                         // 6
 #pragma unroll
             for (int i = 0; i < NZ; i++) dv[i] = path ? blk[RO_DZ + i] : 0.0;
-            double bn = 1.0, bd = 1.0;
+            StepFrac sfc;
 #pragma unroll
             for (int i = 0; i < NZ; i++) {
                 const bool act = (i < NU) ? path : xbox;
@@ -397,16 +399,16 @@ __device__ __noinline__ void split_role_x(const int prob, const int num_iter, do
                     {
                         const double lam = lamb[i], t = tb[i];
                         const IneqStep st = ineq_final(lam, itb[i], v[i] - dl - t, dva[i], dv[i], sigmu);
-                        step_limit(lam, st.dlam, bn, bd); step_limit(t, st.dt, bn, bd);
+                        sfc.add(lam, st.dlam, t, st.dt);
                     }
                     {
                         const double lam = lamb[NZ + i], t = tb[NZ + i];
                         const IneqStep st = ineq_final(lam, itb[NZ + i], du - v[i] - t, -dva[i], -dv[i], sigmu);
-                        step_limit(lam, st.dlam, bn, bd); step_limit(t, st.dt, bn, bd);
+                        sfc.add(lam, st.dlam, t, st.dt);
                     }
                 }
             }
-            xs[0] = bn / bd;
+            xs[0] = sfc.ratio();
             split_barrier();                                         // 7
             split_barrier();                                         // 8
             a_ = dec[DEC_STEP];

@@ -1235,7 +1235,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
         int kk = 0;
         bool isnan_ = false;
         // state of the previous iteration's step, applied at the top of the next pass (fused update):
-        double itb[NCB], itg[NCG > 0 ? NCG : 1];     // 1/t of every entry, reused by passes B, C and the update
+        double itb[NCB];                             // 1/t of the box entries, reused by passes B, C and the update (general entries: recomputed)
         double dva[NZ], dv[NZ], dpi[NX], sigmu = 0.0, a_ = 0.0;
 #pragma unroll
         for (int e = 0; e < NCB; e++) itb[e] = 0.0;
@@ -1332,7 +1332,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                                 const double ca = C[r * NHS + a];
                                 cvo += ca * vo[HSUP[a]]; cda += ca * dva[HSUP[a]]; cd += ca * dv[HSUP[a]];
                             }
-                            const IneqStep st = ineq_final(lam, itg[e], sg * cvo - dg[e] - t, sg * cda, sg * cd, sigmu);
+                            const IneqStep st = ineq_final(lam, rcp_nb(t), sg * cvo - dg[e] - t, sg * cda, sg * cd, sigmu);      // 1/t recomputed: cheaper than a thread-local array
                             lam = clamp_lo(lam + a_ * st.dlam, IPM_LAM_MIN); t = clamp_lo(t + a_ * st.dt, IPM_T_MIN);
                             lamg[e] = lam; tg[e] = t;
                         }
@@ -1340,7 +1340,6 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                         for (int a = 0; a < NHS; a++) cv += C[r * NHS + a] * v[HSUP[a]];
                         const double it_ = rcp_nb(t);
                         const double rd = sg * cv - dg[e] - t, G = lam * it_, m = lam * t;
-                        itg[e] = it_;
 #pragma unroll
                         for (int a = 0; a < NHS; a++) {
                             const double ca = C[r * NHS + a];
@@ -1544,7 +1543,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                     double cv = 0.0, cd = 0.0;
 #pragma unroll
                     for (int a = 0; a < NHS; a++) { cv += C[r * NHS + a] * v[HSUP[a]]; cd += C[r * NHS + a] * dva[HSUP[a]]; }
-                    const double it_ = itg[e];
+                    const double it_ = rcp_nb(t);
                     const IneqStep st = ineq_affine(lam, it_, sg * cv - dg[e] - t, sg * cd);
                     sfa.add(lam, st.dlam, t, st.dt);
                     S1 += lam * st.dt + t * st.dlam; S2 += st.dt * st.dlam;
@@ -1725,7 +1724,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                         const double ca = C[r * NHS + a];
                         cv += ca * v[HSUP[a]]; cda += ca * dva[HSUP[a]]; cd += ca * dv[HSUP[a]];
                     }
-                    const IneqStep st = ineq_final(lam, itg[e], sg * cv - dg[e] - t, sg * cda, sg * cd, sigmu);
+                    const IneqStep st = ineq_final(lam, rcp_nb(t), sg * cv - dg[e] - t, sg * cda, sg * cd, sigmu);
                     sfc.add(lam, st.dlam, t, st.dt);
                 }
             }

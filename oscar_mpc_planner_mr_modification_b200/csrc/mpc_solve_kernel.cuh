@@ -34,6 +34,43 @@
 #define MPC_NS MPC_CAT(mpck_, MPC_CFG_TAG)   // one namespace per compiled configuration
 
 namespace MPC_NS {
+// Branch-free reciprocal square root: hardware approximation (rsqrt.approx.f64, ~2^-23) + one cubically convergent
+// correction y (1 + e/2 + 3 e^2/8), e = 1 - a y^2 (error below the rounding of a double).  Half the instructions of
+// rsqrt() and no slow-path branch, so two of them interleave in one in-order instruction stream (the two Cholesky
+// pivots of a Riccati stage); NaN for a < 0 or NaN input, which is what the failure detection relies on.
+#ifndef MPC_RSQRT_NB
+#define MPC_RSQRT_NB 1
+#endif
+__device__ __forceinline__ double rsqrt_nb(double a)
+{
+#if MPC_RSQRT_NB
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    const double m = a * y;
+    const double e = fma(-m, y, 1.0);
+    const double p = fma(0.375, e, 0.5);
+    return fma(y * e, p, y);
+#else
+    return rsqrt(a);
+#endif
+}
+// Branch-free reciprocal for the 1/t of every inequality entry (38 per stage and interior-point iteration): hardware
+// approximation (rcp.approx.f64, ~2^-23) + one cubically convergent correction y + y e (1 + e), e = 1 - t y.  The library
+// division is correctly rounded but costs ~3x the instructions plus a slow-path branch per call; this one is within one
+// ulp, which the parity tolerance (1e-6) does not see.  t > 0 here (slacks are clamped at 1e-16); NaN propagates.
+__device__ __forceinline__ double rcp_nb(double t)
+{
+#if MPC_RSQRT_NB
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(t));
+    const double e = fma(-t, y, 1.0);
+    return fma(y * e, 1.0 + e, y);
+#else
+    return 1.0 / t;
+#endif
+}
+// the emitted model code takes its reciprocals through this macro
+#define MPCGEN_RCP(x) rcp_nb(x)
 #include MPC_MODEL_HEADER
 using namespace mpcgen;
 
@@ -80,41 +117,6 @@ __device__ __forceinline__ double nanmax(double a, double b)
     return __longlong_as_double((long long)(ua > ub ? ua : ub));
 }
 __device__ __forceinline__ double clamp_lo(double x, double lo) { return (x < lo) ? lo : x; }   // keeps NaN
-// Branch-free reciprocal square root: hardware approximation (rsqrt.approx.f64, ~2^-23) + one cubically convergent
-// correction y (1 + e/2 + 3 e^2/8), e = 1 - a y^2 (error below the rounding of a double).  Half the instructions of
-// rsqrt() and no slow-path branch, so two of them interleave in one in-order instruction stream (the two Cholesky
-// pivots of a Riccati stage); NaN for a < 0 or NaN input, which is what the failure detection relies on.
-#ifndef MPC_RSQRT_NB
-#define MPC_RSQRT_NB 1
-#endif
-__device__ __forceinline__ double rsqrt_nb(double a)
-{
-#if MPC_RSQRT_NB
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
-    const double m = a * y;
-    const double e = fma(-m, y, 1.0);
-    const double p = fma(0.375, e, 0.5);
-    return fma(y * e, p, y);
-#else
-    return rsqrt(a);
-#endif
-}
-// Branch-free reciprocal for the 1/t of every inequality entry (38 per stage and interior-point iteration): hardware
-// approximation (rcp.approx.f64, ~2^-23) + one cubically convergent correction y + y e (1 + e), e = 1 - t y.  The library
-// division is correctly rounded but costs ~3x the instructions plus a slow-path branch per call; this one is within one
-// ulp, which the parity tolerance (1e-6) does not see.  t > 0 here (slacks are clamped at 1e-16); NaN propagates.
-__device__ __forceinline__ double rcp_nb(double t)
-{
-#if MPC_RSQRT_NB
-    double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(t));
-    const double e = fma(-t, y, 1.0);
-    return fma(y * e, 1.0 + e, y);
-#else
-    return 1.0 / t;
-#endif
-}
 __device__ __forceinline__ double warp_max(double v)
 {
 #pragma unroll

@@ -186,6 +186,9 @@ def emit_model_header(pb, name, sim_steps=3):
     w("// GENERATED by oscar_mpc_planner_mr_modification_b200/solver_generator/generate_cuda_solver.py -- do not edit.")
     w("// configuration: %s" % name)
     w("#pragma once")
+    w("#ifndef MPCGEN_RCP      // reciprocal used by the emitted expressions; the kernel header may map it to its branch-free version")
+    w("#define MPCGEN_RCP(x) (1.0/(x))")
+    w("#endif")
     w("namespace mpcgen {")
     w("constexpr int NX = %d, NU = %d, NZ = %d, NP = %d, NH = %d, NSTAGE = %d;" % (nx, nu, nz, npar, nh, pb["N"]))
     w("constexpr int NPK = %d;  // packed lower-triangular NZ x NZ" % npk)

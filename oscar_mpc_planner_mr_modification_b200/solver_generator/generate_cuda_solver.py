@@ -356,7 +356,8 @@ def emit_model_header(pb, name, sim_steps=3):
     # ---- both at once: one traversal of the rows with the common subexpressions (cos / sin / sqrt / reciprocals of the
     #      obstacle parameters) shared between the Jacobian and the multiplier-weighted Hessian
     w("\n// hv[NH] = h(z,p);  C[r*NHS + s] = d h_r / d z_HSUP[s];  H(packed NZ) += sum_r mh[r] d2 h_r / dz2")
-    w("__device__ __forceinline__ void con_lin(const double* z, const double* __restrict__ p, const double* mh, double* H, double* hv, double* C)\n{")
+    w("template <class CM>      // C: plain array or any type with operator[] (e.g. a shared-memory column accessor)")
+    w("__device__ __forceinline__ void con_lin(const double* z, const double* __restrict__ p, const double* mh, double* H, double* hv, CM&& C)\n{")
     if nh:
         if flat:
             m3 = dict(m)

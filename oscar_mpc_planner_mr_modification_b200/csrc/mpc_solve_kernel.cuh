@@ -20,6 +20,9 @@
 #ifndef MPC_GEN_UNROLL
 #define MPC_GEN_UNROLL 2   // general-constraint loops: entries in flight together (hides local-memory latency)
 #endif
+#ifndef MPC_SCAN_ALWAYS
+#define MPC_SCAN_ALWAYS 0   // 1: substitution sweeps as prefix scans in the throughput instantiation too
+#endif
 #ifndef MPC_WARPS_PER_CTA
 #define MPC_WARPS_PER_CTA 8
 #endif
@@ -1981,7 +1984,7 @@ mpc_solve_kernel(int n, const double* __restrict__ xinit, const double* __restri
         }
         if (prob >= n) return;
         const int nit = num_iter ? num_iter[prob] : num_iter_all;
-        solve_problem<(WPC != WARPS_PER_CTA)>(prob, xinit, x0, params, nit, mem, mem_doubles, xtraj, utraj, pobj, exit_code, qp_status, res_eq,
+        solve_problem<(WPC != WARPS_PER_CTA) || (MPC_SCAN_ALWAYS != 0)>(prob, xinit, x0, params, nit, mem, mem_doubles, xtraj, utraj, pobj, exit_code, qp_status, res_eq,
                       ipm_iters, s_hand[grp.gid], s_ric + (size_t)grp.gid * (COOP ? RS_DOUBLES : 0),
                       s_ric + (size_t)GROUPS * (COOP ? RS_DOUBLES : 0) + (size_t)grp.gid * LT_DOUBLES, n >> 31 /* 0, opaque to the compiler */, grp);
     }

@@ -93,6 +93,11 @@ constexpr int GEN_UNROLL = MPC_GEN_UNROLL;
 #define MPC_LT_SMEM 2
 #endif
 constexpr bool LT_SMEM = MPC_LT_SMEM != 0;
+#ifndef MPC_BOX_SMEM
+#define MPC_BOX_SMEM 0
+#endif
+constexpr int LT_ENTRY_DOUBLES = LT_SMEM ? ((MPC_LT_SMEM >= 2 ? 3 : 2) * NCG + (MPC_LT_SMEM >= 3 ? NH * NHS : 0)) : 0;
+constexpr int LT_DOUBLES = (LT_ENTRY_DOUBLES + (MPC_BOX_SMEM ? 2 * (NX + NU) : 0)) * GW * 32;      // per group: lam, t (d, C) of the general entries (+ 1/t of the boxes)
 struct SmemCol {
     double* p;
     __device__ __forceinline__ double& operator[](int e) const { return p[e * (((NSTAGE + 1 + 31) / 32) * 32)]; }
@@ -1384,7 +1389,12 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
         int kk = 0;
         bool isnan_ = false;
         // state of the previous iteration's step, applied at the top of the next pass (fused update):
+#if MPC_BOX_SMEM
+        // 1/t of the box entries (reused by passes B, C and the update) parked in shared memory: 28 registers less in the loop
+        const SmemCol itb{lt_sm + LT_ENTRY_DOUBLES * (GW * 32) + (grp.wig * 32 + (threadIdx.x & 31))};
+#else
         double itb[NCB];                             // 1/t of the box entries, reused by passes B, C and the update (general entries: recomputed)
+#endif
         double dva[NZ], dv[NZ], dpi[NX], sigmu = 0.0, a_ = 0.0;
 #pragma unroll
         for (int e = 0; e < NCB; e++) itb[e] = 0.0;
@@ -1946,7 +1956,6 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
 }
 
 constexpr int WARPS_PER_CTA = MPC_WARPS_PER_CTA;
-constexpr int LT_DOUBLES = LT_SMEM ? ((MPC_LT_SMEM >= 2 ? 3 : 2) * NCG + (MPC_LT_SMEM >= 3 ? NH * NHS : 0)) * GW * 32 : 0;      // per group: lam, t (d, C) of the general entries
 
 // Persistent grid: warp groups pull problem indices from a global counter (work per problem is data
 // dependent: 50-100 interior-point iterations), so late finishers do not idle a whole CTA.

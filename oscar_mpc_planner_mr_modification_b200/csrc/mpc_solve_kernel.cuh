@@ -92,12 +92,24 @@ constexpr int GEN_UNROLL = MPC_GEN_UNROLL;
 #ifndef MPC_LT_SMEM
 #define MPC_LT_SMEM 2
 #endif
-constexpr bool LT_SMEM = MPC_LT_SMEM != 0;
+#ifndef MPC_LT_MASK          // which arrays: bit 0 multipliers, 1 slacks, 2 right-hand sides d, 3 Jacobian rows C
+#define MPC_LT_MASK (MPC_LT_SMEM == 0 ? 0 : (MPC_LT_SMEM == 1 ? 3 : (MPC_LT_SMEM == 2 ? 7 : 15)))
+#endif
+constexpr bool LT_SMEM = MPC_LT_MASK != 0;
+constexpr bool LT_LAM = (MPC_LT_MASK & 1) != 0, LT_T = (MPC_LT_MASK & 2) != 0, LT_D = (MPC_LT_MASK & 4) != 0, LT_C = (MPC_LT_MASK & 8) != 0;
+constexpr int LT_OFF_LAM = 0, LT_OFF_T = LT_OFF_LAM + (LT_LAM ? NCG : 0), LT_OFF_D = LT_OFF_T + (LT_T ? NCG : 0),
+              LT_OFF_C = LT_OFF_D + (LT_D ? NCG : 0);
 #ifndef MPC_BOX_SMEM
 #define MPC_BOX_SMEM 0
 #endif
-constexpr int LT_ENTRY_DOUBLES = LT_SMEM ? ((MPC_LT_SMEM >= 2 ? 3 : 2) * NCG + (MPC_LT_SMEM >= 3 ? NH * NHS : 0)) : 0;
+constexpr int LT_ENTRY_DOUBLES = LT_OFF_C + (LT_C ? NH * NHS : 0);
 constexpr int LT_DOUBLES = (LT_ENTRY_DOUBLES + (MPC_BOX_SMEM ? 2 * (NX + NU) : 0)) * GW * 32;      // per group: lam, t (d, C) of the general entries (+ 1/t of the boxes)
+// column accessor: stride GW*32 doubles in shared memory ([entry][thread of the group]), stride 1 for a thread-local array
+template <bool SM>
+struct LtCol {
+    double* p;
+    __device__ __forceinline__ double& operator[](int e) const { return p[SM ? e * (((NSTAGE + 1 + 31) / 32) * 32) : e]; }
+};
 struct SmemCol {
     double* p;
     __device__ __forceinline__ double& operator[](int e) const { return p[e * (((NSTAGE + 1 + 31) / 32) * 32)]; }
@@ -1246,11 +1258,11 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
 
     double z[NZ], pi[NX], v[NZ], qpi[NX];
     double lamb[NCB], tb[NCB];
-#if MPC_LT_SMEM
-    const SmemCol lamg{lt_sm + (grp.wig * 32 + (threadIdx.x & 31))}, tg{lt_sm + NCG * (GW * 32) + (grp.wig * 32 + (threadIdx.x & 31))};
-#else
-    double lamg[NCG > 0 ? NCG : 1], tg[NCG > 0 ? NCG : 1];
-#endif
+    // general-entry state: shared-memory columns or thread-local arrays (MPC_LT_MASK); the unused alternative is optimised away
+    double* const lt_me = lt_sm + (grp.wig * 32 + (threadIdx.x & 31));
+    double lamg_loc[(!LT_LAM && NCG > 0) ? NCG : 1], tg_loc[(!LT_T && NCG > 0) ? NCG : 1];
+    const LtCol<LT_LAM> lamg{LT_LAM ? lt_me + LT_OFF_LAM * (GW * 32) : lamg_loc};
+    const LtCol<LT_T> tg{LT_T ? lt_me + LT_OFF_T * (GW * 32) : tg_loc};
 #pragma unroll
     for (int i = 0; i < NZ; i++) {
         z[i] = live ? x0_g[(size_t)prob * NZ * (NSTAGE + 1) + k * NZ + i] : 0.0;   // loadWarmstart (:274-284)
@@ -1284,16 +1296,9 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
     for (int it = 0; it < num_iter; it++) {
         // ======================= K1-K4: linearise at the current iterate ============================
         double H[NPK], g[NZ], Wv[NWV], b[NX];
-#if MPC_LT_SMEM >= 3
-        const SmemCol C{lt_sm + 3 * NCG * (GW * 32) + (grp.wig * 32 + (threadIdx.x & 31))};
-#else
-        double C[NH > 0 ? NH * NHS : 1];
-#endif
-#if MPC_LT_SMEM >= 2
-        const SmemCol dg{lt_sm + 2 * NCG * (GW * 32) + (grp.wig * 32 + (threadIdx.x & 31))};
-#else
-        double dg[NCG > 0 ? NCG : 1];
-#endif
+        double C_loc[(!LT_C && NH > 0) ? NH * NHS : 1], dg_loc[(!LT_D && NCG > 0) ? NCG : 1];
+        const LtCol<LT_C> C{LT_C ? lt_me + LT_OFF_C * (GW * 32) : C_loc};
+        const LtCol<LT_D> dg{LT_D ? lt_me + LT_OFF_D * (GW * 32) : dg_loc};
         {
             double pin[NX], xnx[NX], zx_[NX];
 #pragma unroll

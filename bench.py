@@ -128,14 +128,32 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": "solves/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit_json(line)
 
 
 def workload_name(cfg, planners, num_iter):
     return "%s: T-MPC++ homotopy sets, %d planners/set, N=30, dt=0.2, %d SQP-RTI iterations/solve" % (cfg, planners, num_iter)
 
 
+_REAL_STDOUT = None
+
+
+def emit_json(line):
+    """the ONE JSON line of the contract, on the process's original stdout"""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    # Libraries chat on stdout (NCCL prints its version banner there at NCCL_DEBUG=VERSION/WARN): everything written to fd 1
+    # during the run goes to stderr, the JSON line goes to the saved descriptor.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -166,8 +184,6 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"      # NCCL_DEBUG=VERSION prints a banner on stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
 
@@ -407,7 +423,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
                 "latency": latency, "e2e_sets": e2e_sets}
-        print(json.dumps(line))
+        emit_json(line)
 
 
 if __name__ == "__main__":

@@ -95,7 +95,8 @@ struct mpcgpu_engine {
     void* d_obst = nullptr; size_t cap_obst = 0;   // obstacle predictions + guided flags of mpcgpu_solve_sets_guided
     cudaStream_t stream = nullptr, stream2 = nullptr;   // stream2: second lane of the chunked host pipeline
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    cudaEvent_t cev0[4] = {nullptr, nullptr, nullptr, nullptr}, cev1[4] = {nullptr, nullptr, nullptr, nullptr};   // per chunk (host path)
+    static constexpr int MAX_CHUNKS = 6;
+    cudaEvent_t cev0[MAX_CHUNKS] = {}, cev1[MAX_CHUNKS] = {};   // per chunk (host path)
     int chunks_timed = 0;      // > 0: last_kernel_ms sums the chunk kernels of the last host call
     // device staging for the host-pointer entry points
     double *d_xinit = nullptr, *d_x0 = nullptr, *d_params = nullptr, *d_mem = nullptr, *d_xtraj = nullptr, *d_utraj = nullptr,
@@ -153,7 +154,7 @@ int mpcgpu_engine_create(const char* config_name, int device, int max_batch, mpc
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&e->ev0) != cudaSuccess || cudaEventCreate(&e->ev1) != cudaSuccess ||
-        [&] { for (int i = 0; i < 4; i++) if (cudaEventCreate(&e->cev0[i]) != cudaSuccess || cudaEventCreate(&e->cev1[i]) != cudaSuccess) return true; return false; }()) {
+        [&] { for (int i = 0; i < mpcgpu_engine::MAX_CHUNKS; i++) if (cudaEventCreate(&e->cev0[i]) != cudaSuccess || cudaEventCreate(&e->cev1[i]) != cudaSuccess) return true; return false; }()) {
         e->err = "stream/event creation failed";
         return fail(MPCGPU_ERR_CUDA);
     }
@@ -180,7 +181,7 @@ int mpcgpu_engine_destroy(mpcgpu_engine* e)
         if (p) cudaFree(p);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
-    for (int i = 0; i < 4; i++) { if (e->cev0[i]) cudaEventDestroy(e->cev0[i]); if (e->cev1[i]) cudaEventDestroy(e->cev1[i]); }
+    for (int i = 0; i < mpcgpu_engine::MAX_CHUNKS; i++) { if (e->cev0[i]) cudaEventDestroy(e->cev0[i]); if (e->cev1[i]) cudaEventDestroy(e->cev1[i]); }
     if (e->stream) cudaStreamDestroy(e->stream);
     if (e->stream2) cudaStreamDestroy(e->stream2);
     delete e;
@@ -263,16 +264,33 @@ int mpcgpu_solve_batch(mpcgpu_engine* e, int n, const double* xinit, const doubl
     // Chunked two-stream pipeline: the H2D copy of chunk c+1 and the D2H copy of chunk c-1 overlap the solve
     // kernel of chunk c (pinned host memory makes the copies truly asynchronous).  Chunks stay >= 8192
     // problems so that the persistent grid keeps several waves per launch.
-    int nchunk = n / 8192;
-    if (nchunk < 1) nchunk = 1;
-    if (nchunk > 4) nchunk = 4;
-    const int per = (n + nchunk - 1) / nchunk;
+    // A small first chunk (1/16 of the batch, at least 2048 problems) shortens the one copy nothing can overlap.
+    size_t bounds[mpcgpu_engine::MAX_CHUNKS + 1];
+    int nchunk = 0;
+    bounds[0] = 0;
+    if (B >= 4 * 8192) {
+        size_t first = B / 16;
+        if (first < 2048) first = 2048;
+        bounds[++nchunk] = first;
+    }
+    {
+        const size_t rest = B - bounds[nchunk];
+        int k = (int)(rest / 8192);
+        if (k < 1) k = 1;
+        if (k > 4) k = 4;
+        const size_t per_ = (rest + k - 1) / k;
+        for (int i = 0; i < k; i++) {
+            const size_t hi = bounds[nchunk] + per_;
+            bounds[nchunk + 1] = hi < B ? hi : B;
+            nchunk++;
+        }
+    }
     const size_t sx0 = (size_t)nz * (N + 1), spar = (size_t)N * o->np, sxt = (size_t)nx * (N + 1), sut = (size_t)nu * N,
                  smem_ = (size_t)o->mem_doubles;
     for (int c = 0; c < nchunk; c++) {
-        const size_t b0 = (size_t)c * per;
-        if (b0 >= B) break;
-        const size_t m = (b0 + per <= B) ? (size_t)per : B - b0;
+        const size_t b0 = bounds[c];
+        if (b0 >= B || bounds[c + 1] <= b0) { nchunk = c; break; }
+        const size_t m = bounds[c + 1] - b0;
         cudaStream_t st = (c & 1) ? e->stream2 : e->stream;
         int* counter = (c & 1) ? e->d_counter2 : e->d_counter;
         CK(cudaMemcpyAsync(e->d_xinit + b0 * nx, xinit + b0 * nx, m * nx * 8, cudaMemcpyHostToDevice, st));

@@ -494,18 +494,10 @@ static int solve_sets_impl(mpcgpu_engine* e, int n_sets, int planners, const dou
         e->cap_pvals = need_pv;
     }
     if (!e->d_pidx) CK(cudaMalloc((void**)&e->d_pidx, (size_t)np * 4));
-    CK(cudaMemcpyAsync(e->d_xs, xinit_sets, (size_t)n_sets * nx * 8, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(e->d_shared, shared_params, need_sh * 8, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(e->d_x0, x0, (size_t)n * nz * (N + 1) * 8, cudaMemcpyHostToDevice, st));
-    if (nidx > 0) {
-        if (nidx > np) return MPCGPU_ERR_ARG;
-        CK(cudaMemcpyAsync(e->d_pidx, param_idx, (size_t)nidx * 4, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(e->d_pvals, planner_params, (size_t)n * N * nidx * 8, cudaMemcpyHostToDevice, st));
-    }
-    if (num_iter) CK(cudaMemcpyAsync(e->d_num_iter, num_iter, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    const size_t ob_per_set = ga ? (size_t)N * ga->n_obs * ga->ob_stride : 0;       // doubles
     unsigned char* d_guided = nullptr;
     if (ga) {      // obstacle predictions / tables + guided flags of the device-side constraint construction
-        const size_t ob_bytes = (size_t)n_sets * N * ga->n_obs * ga->ob_stride * 8;
+        const size_t ob_bytes = (size_t)n_sets * ob_per_set * 8;
         if (ob_bytes + (size_t)n > e->cap_obst) {
             if (e->d_obst) cudaFree(e->d_obst);
             e->d_obst = nullptr; e->cap_obst = 0;
@@ -513,46 +505,98 @@ static int solve_sets_impl(mpcgpu_engine* e, int n_sets, int planners, const dou
             e->cap_obst = ob_bytes + (size_t)n;
         }
         d_guided = (unsigned char*)e->d_obst + ob_bytes;
-        if (ob_bytes) CK(cudaMemcpyAsync(e->d_obst, ga->obst_pred, ob_bytes, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(d_guided, ga->guided, (size_t)n, cudaMemcpyHostToDevice, st));
-        if (ga->ell_base >= 0) {      // ellipsoid slots of the shared block from the tables, before it is expanded per planner
-            int rc_ = mpcgpu_pack_obstacles_device(e, n_sets, e->d_xs, (const double*)e->d_obst, ga->n_obs, ga->ell_base, ga->ell_stride, ga->ell_off,
-                                                   e->d_shared, st);
-            if (rc_ != MPCGPU_OK) return rc_;
-        }
     }
-    repeat_xinit_kernel<<<(n * nx + 255) / 256, 256, 0, st>>>(n, planners, nx, e->d_xs, e->d_xinit);
-    expand_params_kernel<<<1184, 256, 0, st>>>(n, planners, N, np, nidx, e->d_shared, e->d_pidx, e->d_pvals, e->d_params);
-    if (nidx > 0) scatter_params_kernel<<<592, 256, 0, st>>>(n, N, np, nidx, e->d_pidx, e->d_pvals, e->d_params);
-    CK(cudaGetLastError());
-    e->launches += (nidx > 0) ? 3 : 2;
-    if (ga) {      // guidance halfspaces built on the device from the obstacle predictions and the warm starts
-        int rc_ = guidance_halfspaces_launch(e, n_sets, planners, e->d_xs, e->d_x0, (const double*)e->d_obst, ga->n_obs, ga->ob_stride, d_guided,
-                                             ga->lin_base, ga->lin_count, ga->robot_radius, e->d_params, st);
-        if (rc_ != MPCGPU_OK) return rc_;
+    // small data shared by every chunk
+    if (nidx > 0) {
+        if (nidx > np) return MPCGPU_ERR_ARG;
+        CK(cudaMemcpyAsync(e->d_pidx, param_idx, (size_t)nidx * 4, cudaMemcpyHostToDevice, st));
     }
-    e->chunks_timed = 0;
-    int rc = launch_solve_on(e, st, e->d_counter, e->ev0, e->ev1, n, e->d_xinit, e->d_x0, e->d_params, num_iter ? e->d_num_iter : nullptr,
-                             num_iter_all, nullptr, e->d_xtraj, e->d_utraj, e->d_pobj, e->d_exit, e->d_qps, e->d_res_eq, e->d_ipm);
-    if (rc != MPCGPU_OK) return rc;
-    // selection on the device, then everything back
     std::vector<int> off((size_t)n_sets + 1);
     for (int s_ = 0; s_ <= n_sets; s_++) off[s_] = s_ * planners;
     CK(cudaMemcpyAsync(e->d_offsets, off.data(), (size_t)(n_sets + 1) * 4, cudaMemcpyHostToDevice, st));
-    if (obj_scale) CK(cudaMemcpyAsync(e->d_scale, obj_scale, (size_t)n * 8, cudaMemcpyHostToDevice, st));
-    if (obj_sub) CK(cudaMemcpyAsync(e->d_sub, obj_sub, (size_t)n * 8, cudaMemcpyHostToDevice, st));
-    if (disabled) CK(cudaMemcpyAsync(e->d_disabled, disabled, (size_t)n, cudaMemcpyHostToDevice, st));
-    rc = mpcgpu_select_best_device(e, n_sets, e->d_offsets, e->d_pobj, e->d_exit, obj_scale ? e->d_scale : nullptr,
-                                   obj_sub ? e->d_sub : nullptr, disabled ? e->d_disabled : nullptr, e->d_best, st);
-    if (rc != MPCGPU_OK) return rc;
-    CK(cudaMemcpyAsync(xtraj, e->d_xtraj, (size_t)n * nx * (N + 1) * 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(utraj, e->d_utraj, (size_t)n * nu * N * 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(pobj, e->d_pobj, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(exit_code, e->d_exit, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(qp_status, e->d_qps, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(res_eq, e->d_res_eq, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(best_idx, e->d_best, (size_t)n_sets * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CK(cudaStreamSynchronize(st));      // d_pidx / d_offsets are read by both streams; `off` may go out of scope
+
+    // Chunks of whole homotopy sets on two streams: the copies of chunk c+1 overlap the kernels of chunk c (same scheme as
+    // mpcgpu_solve_batch: a small first chunk, then up to four more of >= ~8192 problems).
+    int bounds[mpcgpu_engine::MAX_CHUNKS + 1];
+    int nchunk = 0;
+    bounds[0] = 0;
+    const int sets8k = (8192 + planners - 1) / planners;
+    if (n_sets >= 4 * sets8k) {
+        int first = n_sets / 16;
+        if (first * planners < 2048) first = (2048 + planners - 1) / planners;
+        bounds[++nchunk] = first;
+    }
+    {
+        const int rest = n_sets - bounds[nchunk];
+        int k = rest / sets8k;
+        if (k < 1) k = 1;
+        if (k > 4) k = 4;
+        const int per_ = (rest + k - 1) / k;
+        for (int i = 0; i < k; i++) {
+            const int hi = bounds[nchunk] + per_;
+            bounds[nchunk + 1] = hi < n_sets ? hi : n_sets;
+            nchunk++;
+        }
+    }
+    for (int c = 0; c < nchunk; c++) {
+        const int s0 = bounds[c], ns = bounds[c + 1] - s0;
+        if (ns <= 0) { nchunk = c; break; }
+        const size_t p0 = (size_t)s0 * planners, m = (size_t)ns * planners;          // first problem, problems
+        cudaStream_t cs = (c & 1) ? e->stream2 : e->stream;
+        int* counter = (c & 1) ? e->d_counter2 : e->d_counter;
+        double* d_xs = e->d_xs + (size_t)s0 * nx;
+        double* d_sh = e->d_shared + (size_t)s0 * N * np;
+        CK(cudaMemcpyAsync(d_xs, xinit_sets + (size_t)s0 * nx, (size_t)ns * nx * 8, cudaMemcpyHostToDevice, cs));
+        CK(cudaMemcpyAsync(d_sh, shared_params + (size_t)s0 * N * np, (size_t)ns * N * np * 8, cudaMemcpyHostToDevice, cs));
+        CK(cudaMemcpyAsync(e->d_x0 + p0 * nz * (N + 1), x0 + p0 * nz * (N + 1), m * nz * (N + 1) * 8, cudaMemcpyHostToDevice, cs));
+        if (nidx > 0)
+            CK(cudaMemcpyAsync(e->d_pvals + p0 * N * nidx, planner_params + p0 * N * nidx, m * N * nidx * 8, cudaMemcpyHostToDevice, cs));
+        if (num_iter) CK(cudaMemcpyAsync(e->d_num_iter + p0, num_iter + p0, m * 4, cudaMemcpyHostToDevice, cs));
+        const double* d_ob = nullptr;
+        if (ga) {
+            d_ob = (const double*)e->d_obst + (size_t)s0 * ob_per_set;
+            if (ob_per_set) CK(cudaMemcpyAsync((void*)d_ob, ga->obst_pred + (size_t)s0 * ob_per_set, (size_t)ns * ob_per_set * 8, cudaMemcpyHostToDevice, cs));
+            CK(cudaMemcpyAsync(d_guided + p0, ga->guided + p0, m, cudaMemcpyHostToDevice, cs));
+            if (ga->ell_base >= 0) {      // ellipsoid slots of the shared block from the tables, before it is expanded per planner
+                int rc_ = mpcgpu_pack_obstacles_device(e, ns, d_xs, d_ob, ga->n_obs, ga->ell_base, ga->ell_stride, ga->ell_off, d_sh, cs);
+                if (rc_ != MPCGPU_OK) return rc_;
+            }
+        }
+        double* d_par = e->d_params + p0 * N * np;
+        repeat_xinit_kernel<<<(int)((m * nx + 255) / 256), 256, 0, cs>>>((int)m, planners, nx, d_xs, e->d_xinit + p0 * nx);
+        expand_params_kernel<<<1184, 256, 0, cs>>>((int)m, planners, N, np, nidx, d_sh, e->d_pidx, e->d_pvals + p0 * N * nidx, d_par);
+        if (nidx > 0) scatter_params_kernel<<<592, 256, 0, cs>>>((int)m, N, np, nidx, e->d_pidx, e->d_pvals + p0 * N * nidx, d_par);
+        CK(cudaGetLastError());
+        e->launches += (nidx > 0) ? 3 : 2;
+        if (ga) {      // guidance halfspaces built on the device from the obstacle predictions and the warm starts
+            int rc_ = guidance_halfspaces_launch(e, ns, planners, d_xs, e->d_x0 + p0 * nz * (N + 1), d_ob, ga->n_obs, ga->ob_stride, d_guided + p0,
+                                                 ga->lin_base, ga->lin_count, ga->robot_radius, d_par, cs);
+            if (rc_ != MPCGPU_OK) return rc_;
+        }
+        int rc = launch_solve_on(e, cs, counter, e->cev0[c], e->cev1[c], (int)m, e->d_xinit + p0 * nx, e->d_x0 + p0 * nz * (N + 1), d_par,
+                                 num_iter ? e->d_num_iter + p0 : nullptr, num_iter_all, nullptr, e->d_xtraj + p0 * nx * (N + 1),
+                                 e->d_utraj + p0 * nu * N, e->d_pobj + p0, e->d_exit + p0, e->d_qps + p0, e->d_res_eq + p0, e->d_ipm + p0);
+        if (rc != MPCGPU_OK) return rc;
+        // selection on the device, then everything back
+        if (obj_scale) CK(cudaMemcpyAsync(e->d_scale + p0, obj_scale + p0, m * 8, cudaMemcpyHostToDevice, cs));
+        if (obj_sub) CK(cudaMemcpyAsync(e->d_sub + p0, obj_sub + p0, m * 8, cudaMemcpyHostToDevice, cs));
+        if (disabled) CK(cudaMemcpyAsync(e->d_disabled + p0, disabled + p0, m, cudaMemcpyHostToDevice, cs));
+        // set offsets are absolute problem indices: the chunk passes the offset table from s0 on with the full arrays
+        rc = mpcgpu_select_best_device(e, ns, e->d_offsets + s0, e->d_pobj, e->d_exit, obj_scale ? e->d_scale : nullptr,
+                                       obj_sub ? e->d_sub : nullptr, disabled ? e->d_disabled : nullptr, e->d_best + s0, cs);
+        if (rc != MPCGPU_OK) return rc;
+        CK(cudaMemcpyAsync(xtraj + p0 * nx * (N + 1), e->d_xtraj + p0 * nx * (N + 1), m * nx * (N + 1) * 8, cudaMemcpyDeviceToHost, cs));
+        CK(cudaMemcpyAsync(utraj + p0 * nu * N, e->d_utraj + p0 * nu * N, m * nu * N * 8, cudaMemcpyDeviceToHost, cs));
+        CK(cudaMemcpyAsync(pobj + p0, e->d_pobj + p0, m * 8, cudaMemcpyDeviceToHost, cs));
+        CK(cudaMemcpyAsync(exit_code + p0, e->d_exit + p0, m * 4, cudaMemcpyDeviceToHost, cs));
+        CK(cudaMemcpyAsync(qp_status + p0, e->d_qps + p0, m * 4, cudaMemcpyDeviceToHost, cs));
+        CK(cudaMemcpyAsync(res_eq + p0, e->d_res_eq + p0, m * 8, cudaMemcpyDeviceToHost, cs));
+        CK(cudaMemcpyAsync(best_idx + s0, e->d_best + s0, (size_t)ns * 4, cudaMemcpyDeviceToHost, cs));
+    }
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaStreamSynchronize(e->stream2));
+    e->chunks_timed = nchunk;
     return MPCGPU_OK;
 }
 

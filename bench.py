@@ -51,11 +51,21 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "50"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
-    def stop(self):
+    def mark(self):
+        """number of samples written so far (call at the start of the timed region)"""
+        try:
+            with open(self.f.name) as fh:
+                return sum(1 for _ in fh)
+        except Exception:
+            return 0
+
+    def stop(self, first=0):
+        """statistics of the samples taken after `first` (the timed region); a region shorter than the sampling period
+        falls back to the samples just before it (same load: the warm-up steps)"""
         if self.p is None:
             return None
         self.p.terminate()
@@ -65,23 +75,25 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         for line in self.f.read().splitlines():
             c = [x.strip() for x in line.split(",")]
             if len(c) < 7:
                 continue
             try:
-                sm.append(float(c[0])); mx.append(float(c[1]))
+                rows.append((float(c[0]), float(c[1]), [nm for nm, v in zip(names, c[3:7]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for nm, v in zip(names, c[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
         os.unlink(self.f.name)
-        if not sm:
+        sel = rows[first:] if len(rows) > first else rows[-3:]
+        if not sel:
             return None
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        reasons = set()
+        for r in sel:
+            reasons.update(r[2])
+        return {"sm_mhz": float(np.median([r[0] for r in sel])), "sm_max_mhz": float(max(r[1] for r in sel)), "reasons": sorted(reasons),
+                "samples": len(sel), "in_timed_region": len(rows) > first}
 
 
 def bytes_per_solve(d):
@@ -235,10 +247,11 @@ def main():
     fp64_peak = engine.measure_fp64_peak(local_rank)
 
     # ---- value: device-resident, CUDA events on the launching stream, max over ranks
+    sampler = ClockSampler(local_rank)          # started before the warm-up so that a short timed region still has samples nearby
     for _ in range(args.warmup):
         step_device()
     barrier()
-    sampler = ClockSampler(local_rank)
+    clock_mark = sampler.mark()
     launches0 = eng.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kernel_ms = []
@@ -256,7 +269,7 @@ def main():
         torch.cuda.synchronize()
         kernel_ms.append(eng.last_kernel_ms())
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop(clock_mark)
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

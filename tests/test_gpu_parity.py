@@ -177,3 +177,21 @@ def test_multi_robot_sets_parity():
     og = eng.solve_sets_guided(scenarios * robots, planners, xs, shared, b["x0"], b["obst_pred"], b["guided"], b["robot_radius"], num_iter=10)
     check(dict(og, ipm_iters=ref_g["ipm_iters"]), ref_g)
     assert same_selection(og["best"], orc.select_best(b["set_offsets"], ref_g["pobj"], ref_g["exit_code"]), ref_g, b["set_offsets"])
+
+
+def test_kernel_dispatch_boundaries():
+    """AUTO mode switches kernels with the batch size (role-split up to one problem per SM, one-problem-per-CTA thread-per-
+    stage up to two per SM, persistent throughput grid above): the results must not depend on which side of a boundary a
+    batch falls."""
+    import torch
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    eng = engine.Engine("c2_tmpc12", device=0, max_batch=4 * sms)
+    orc = Oracle("c2_tmpc12")
+    b = synthetic.make_batch(eng.parameter_map, eng.dims, (2 * sms + 8) // 9 + 2, 9, seed=515)
+    ref = orc.solve_batch(b["xinit"], b["x0"], b["params"], num_iter=4)
+    for n in (sms - 1, sms, sms + 1, 2 * sms, 2 * sms + 1):
+        sl = slice(0, n)
+        out = eng.solve_batch(b["xinit"][sl], b["x0"][sl], b["params"][sl], num_iter=4)
+        np.testing.assert_array_equal(out["exit_code"], ref["exit_code"][sl])
+        ok = ref["exit_code"][sl] == 1
+        assert rel_err(out["xtraj"][ok], ref["xtraj"][sl][ok]).max() < REL_TOL, n

@@ -388,10 +388,6 @@ __device__ __noinline__ void forward_scan(const double* Wv, const double* Lx0, c
 //               After the factorisation of the stage, in place: iL0 @(0,0), L10 @(1,0), iL1 @(1,1), Lxu[i][0..1]
 //               @(2+i,0..1), P @(2+i,2+j), l = Luu^-1 q_u @(7,0..1), p @(7,2+i)
 //        RO_B   [W | rb], NX x (NZ+1) row-major      RO_PRB  P+ rb      RO_DZ  step of the stage [du; dx]
-#ifndef MPC_COOP
-#define MPC_COOP 0   // thread-per-stage kernel: 0 = lane-serial recursion in registers (best throughput), 1 = cooperative
-#endif
-constexpr bool COOP = MPC_COOP != 0;
 constexpr int NB = NZ + 1;
 constexpr int RO_G = 0;
 constexpr int RO_Q = RO_G + NPK;                 // row 7 of the packed augmented matrix: pk(NZ, j) == NPK + j
@@ -411,128 +407,13 @@ __device__ __forceinline__ void tri_unpack(int e, int& i, int& j)
     j = e - i * (i + 1) / 2;
 }
 
-// ptxas schedules a dot product over shared-memory operands as load, load, FMA, load, load, FMA, ... (it minimises
-// registers), which puts the shared-memory latency on the dependency chain once per TERM.  gate() returns +0.0 at run
-// time, but as a value that depends on every operand (oz is a zero the compiler cannot see through): using it as the
-// start of the accumulation forces all loads of a step to be issued before its first FMA.
-template <int n>
-__device__ __forceinline__ double gate(const double (&a)[n], int oz)
-{
-    int t = 0;
-#pragma unroll
-    for (int i = 0; i < n; i++) t |= __double2hiint(a[i]);
-    return __hiloint2double(t & oz, 0);
-}
-
-// backward recursion: factorisation + affine right-hand side.  In: blocks with Ht, gt, [W | rb]; block N holds
-// P_N = Ht_xx and p_N = gt_x in place.  Executed by one full warp.
-__device__ __noinline__ void riccati_factor_coop(double* __restrict__ rs, const int oz)
-{
-    const int lane = threadIdx.x & 31;
-    double* __restrict__ T = rs + (NSTAGE + 1) * RSTRIDE;
-    const int al = lane >> 3, aj = lane & 7;           // step A: T[al][aj] (round 1), T[4][aj] on lanes 0..7 (round 2)
-    int bi0, bj0, bi1, bj1;                             // step B: packed entries lane and 32 + lane (lanes 0..2)
-    tri_unpack(lane, bi0, bj0);
-    tri_unpack(lane < 3 ? 32 + lane : lane, bi1, bj1);
-    const int e1 = lane < 3 ? 32 + lane : lane;
-    int ci = 0, cj = 0;                                 // step C: lanes 0..14 own P(ci,cj); lanes 15..19 own row ci of Lxu and p
-    if (lane < NPX) tri_unpack(lane, ci, cj);
-    else if (lane < NPX + NX) ci = lane - NPX;
-#pragma unroll 1
-    for (int s = NSTAGE - 1; s >= 0; s--) {
-        double* __restrict__ blk = rs + s * RSTRIDE;
-        const double* __restrict__ nxt = blk + RSTRIDE;
-        // A: T = P+ [W | rb];  column 7: Prb = P+ rb, T = p+ + Prb
-        {
-            double op[3 * NX + 2];
-#pragma unroll
-            for (int m = 0; m < NX; m++) {
-                op[m] = nxt[RO_G + pk(NU + al, NU + m)];
-                op[NX + m] = blk[RO_B + m * NB + aj];
-                op[2 * NX + m] = nxt[RO_G + pk(NU + 4, NU + m)];
-            }
-            op[3 * NX] = nxt[RO_Q + NU + al];
-            op[3 * NX + 1] = nxt[RO_Q + NU + 4];
-            double acc = gate(op, oz), a2 = acc;
-#pragma unroll
-            for (int m = 0; m < NX; m++) { acc += op[m] * op[NX + m]; a2 += op[2 * NX + m] * op[NX + m]; }
-            if (aj == NZ) { blk[RO_PRB + al] = acc; acc += op[3 * NX]; }
-            T[al * NB + aj] = acc;
-            if (lane < NB) {
-                if (aj == NZ) { blk[RO_PRB + 4] = a2; a2 += op[3 * NX + 1]; }
-                T[4 * NB + aj] = a2;
-            }
-        }
-        __syncwarp();
-        // B: [[G, q], [q', -]] = [[Ht, gt], [gt', -]] + [W | rb]' T   (entry (i,j), i >= j: sum_l B[l][j] T[l][i])
-        {
-            double op[4 * NX + 2];
-#pragma unroll
-            for (int l = 0; l < NX; l++) {
-                op[l] = blk[RO_B + l * NB + bj0]; op[NX + l] = T[l * NB + bi0];
-                op[2 * NX + l] = blk[RO_B + l * NB + bj1]; op[3 * NX + l] = T[l * NB + bi1];
-            }
-            op[4 * NX] = blk[lane];
-            op[4 * NX + 1] = blk[e1];
-            const double z0 = gate(op, oz);
-            double acc = op[4 * NX] + z0, a2 = op[4 * NX + 1] + z0;
-#pragma unroll
-            for (int l = 0; l < NX; l++) { acc += op[l] * op[NX + l]; a2 += op[2 * NX + l] * op[3 * NX + l]; }
-            blk[lane] = acc;
-            if (lane < 3) blk[e1] = a2;
-        }
-        __syncwarp();
-        // C: two Cholesky pivots on the input block, P = Gxx - Lxu Lxu', l = Luu^-1 q_u, p = q_x - Lxu l
-        {
-            double op[11];
-            op[0] = blk[RO_G + pk(0, 0)]; op[1] = blk[RO_G + pk(1, 0)]; op[2] = blk[RO_G + pk(1, 1)];
-            op[3] = blk[RO_G + pk(NU + ci, 0)]; op[4] = blk[RO_G + pk(NU + ci, 1)];
-            op[5] = blk[RO_G + pk(NU + cj, 0)]; op[6] = blk[RO_G + pk(NU + cj, 1)];
-            op[7] = blk[RO_G + pk(NU + ci, NU + cj)];
-            op[8] = blk[RO_Q]; op[9] = blk[RO_Q + 1]; op[10] = blk[RO_Q + NU + ci];
-            const double g00 = op[0] + gate(op, oz), g10 = op[1], g11 = op[2];
-            const double gi0 = op[3], gi1 = op[4], gj0 = op[5], gj1 = op[6], gxx = op[7], q0 = op[8], q1 = op[9], qi = op[10];
-            const double iL0 = rsqrt(g00), L10 = g10 * iL0, iL1 = rsqrt(g11 - L10 * L10);
-            const double li0 = gi0 * iL0, li1 = (gi1 - li0 * L10) * iL1;
-            const double lj0 = gj0 * iL0, lj1 = (gj1 - lj0 * L10) * iL1;
-            const double pij = gxx - li0 * lj0 - li1 * lj1;
-            const double l0 = q0 * iL0, l1 = (q1 - L10 * l0) * iL1;
-            const double pvi = qi - li0 * l0 - li1 * l1;
-            __syncwarp();
-            if (lane < NPX) blk[RO_G + pk(NU + ci, NU + cj)] = pij;
-            else if (lane < NPX + NX) {
-                blk[RO_G + pk(NU + ci, 0)] = li0; blk[RO_G + pk(NU + ci, 1)] = li1; blk[RO_Q + NU + ci] = pvi;
-            } else if (lane == NPX + NX) {
-                blk[RO_G + pk(0, 0)] = iL0; blk[RO_G + pk(1, 0)] = L10; blk[RO_G + pk(1, 1)] = iL1;
-                blk[RO_Q] = l0; blk[RO_Q + 1] = l1;
-            }
-        }
-        __syncwarp();
-    }
-}
-
-// gate with a shallow dependency tree (groups of three OR-ed, the groups added: the mixed operators keep the
-// compiler from re-linearising the chain)
-template <int n>
-__device__ __forceinline__ double gate_tree(const double (&a)[n], int oz)
-{
-    int t = 0;
-#pragma unroll
-    for (int i = 0; i < n; i += 3) {
-        const int g = __double2hiint(a[i]) | __double2hiint(a[i + 1 < n ? i + 1 : i]) | __double2hiint(a[i + 2 < n ? i + 2 : i]);
-        t += g;
-    }
-    return __hiloint2double(t & oz, 0);
-}
-
 // Same recursion, shorter dependency chain per stage (the recursion is latency bound: 30 dependent stages):
 //  * one step for G = M + [W|rb]' P+ [W|rb]: every lane forms t = P+ c for its own column c of [W|rb] redundantly
 //    (25 independent-enough FMAs) and then its entry; no round trip through shared memory for T
 //  * the two Cholesky pivots run side by side: iL1 = rsqrt(g00 g11 - g10^2) * g00 * iL0
 // Lanes 0..27 own G(i,j); lanes 28..31 own q_j, two each (y = p+ + P+ rb); lane 28 also stores P+ rb.
-__device__ __noinline__ void riccati_factor_coop2(double* __restrict__ rs, const int oz)
+__device__ __noinline__ void riccati_factor_coop(double* __restrict__ rs)
 {
-    (void)oz;
     const int lane = threadIdx.x & 31;
     const bool ql = lane >= NPK;                        // q lanes
     int gi, gj;
@@ -565,10 +446,9 @@ __device__ __noinline__ void riccati_factor_coop2(double* __restrict__ rs, const
             }
             op[NPX + 4 * NX] = blk[o0];
             op[NPX + 4 * NX + 1] = blk[o1];
-            const double z0 = 0.0;      // (no gate here: the 25 independent FMAs of t = P+ c already overlap the load latency; gating cost 120 cycles per stage)
-            double t[NX];
-#pragma unroll
-            for (int l = 0; l < NX; l++) t[l] = z0;
+            double t[NX];                               // (loads and FMAs are left to the compiler's interleaving: the 25 independent
+#pragma unroll                                           //  FMAs overlap the load latency; forcing the loads first cost 120 cycles per stage)
+            for (int l = 0; l < NX; l++) t[l] = 0.0;
 #pragma unroll
             for (int m = 0; m < NX; m++)
 #pragma unroll
@@ -613,77 +493,6 @@ __device__ __noinline__ void riccati_factor_coop2(double* __restrict__ rs, const
                 blk[RO_Q] = l0; blk[RO_Q + 1] = l1;
             }
         }
-        __syncwarp();
-    }
-}
-
-// forward sweep: du_s = -Luu^-T (Lxu' dx_s + l_s), dx_{s+1} = rb_s + W_s [du_s; dx_s], dx_0 = 0  ->  RO_DZ of every block
-__device__ __noinline__ void riccati_forward_coop(double* __restrict__ rs, const int oz)
-{
-    const int lane = threadIdx.x & 31;
-    const int i = lane < NX ? lane : 0;
-    if (lane < NX) rs[RO_DZ + NU + lane] = 0.0;
-    __syncwarp();
-#pragma unroll 1
-    for (int s = 0; s < NSTAGE; s++) {
-        double* __restrict__ blk = rs + s * RSTRIDE;
-        double op[4 * NX + 8];       // dx | Lxu col 0 | Lxu col 1 | W[i][x] | l0 l1 | iL0 L10 iL1 | rb_i W[i][u0] W[i][u1]
-#pragma unroll
-        for (int j = 0; j < NX; j++) {
-            op[j] = blk[RO_DZ + NU + j];
-            op[NX + j] = blk[RO_G + pk(NU + j, 0)];
-            op[2 * NX + j] = blk[RO_G + pk(NU + j, 1)];
-            op[3 * NX + j] = blk[RO_B + i * NB + NU + j];
-        }
-        op[4 * NX] = blk[RO_Q]; op[4 * NX + 1] = blk[RO_Q + 1];
-        op[4 * NX + 2] = blk[RO_G + pk(0, 0)]; op[4 * NX + 3] = blk[RO_G + pk(1, 0)]; op[4 * NX + 4] = blk[RO_G + pk(1, 1)];
-        op[4 * NX + 5] = blk[RO_B + i * NB + NZ]; op[4 * NX + 6] = blk[RO_B + i * NB]; op[4 * NX + 7] = blk[RO_B + i * NB + 1];
-        const double z0 = gate(op, oz);
-        double r0 = op[4 * NX] + z0, r1 = op[4 * NX + 1] + z0, acc = op[4 * NX + 5] + z0;
-#pragma unroll
-        for (int j = 0; j < NX; j++) {
-            r0 += op[NX + j] * op[j];
-            r1 += op[2 * NX + j] * op[j];
-            acc += op[3 * NX + j] * op[j];
-        }
-        const double du1 = -r1 * op[4 * NX + 4];
-        const double du0 = -(r0 + op[4 * NX + 3] * du1) * op[4 * NX + 2];
-        acc += op[4 * NX + 6] * du0 + op[4 * NX + 7] * du1;
-        if (lane < NX) blk[RSTRIDE + RO_DZ + NU + i] = acc;
-        else if (lane == NX) { blk[RO_DZ] = du0; blk[RO_DZ + 1] = du1; }
-        __syncwarp();
-    }
-}
-
-// backward vector sweep of a new right-hand side (factorisation reused).  In: gt in row 7 of every block (block N:
-// p_N = gt_x).  q = gt + W' (p+ + P+ rb), l = Luu^-1 q_u, p = q_x - Lxu l  ->  row 7, in place
-__device__ __noinline__ void riccati_backvec_coop(double* __restrict__ rs, const int oz)
-{
-    const int lane = threadIdx.x & 31;
-    const int j = lane < NZ ? lane : 0;
-#pragma unroll 1
-    for (int s = NSTAGE - 1; s >= 0; s--) {
-        double* __restrict__ blk = rs + s * RSTRIDE;
-        const double* __restrict__ nxt = blk + RSTRIDE;
-        double op[3 * NX + 6];       // W[.][j] | p+ | Prb | gt_j | iL0 L10 iL1 | Lxu[j][0] Lxu[j][1]
-#pragma unroll
-        for (int l = 0; l < NX; l++) {
-            op[l] = blk[RO_B + l * NB + j];
-            op[NX + l] = nxt[RO_Q + NU + l];
-            op[2 * NX + l] = blk[RO_PRB + l];
-        }
-        op[3 * NX] = blk[RO_Q + j];
-        op[3 * NX + 1] = blk[RO_G + pk(0, 0)]; op[3 * NX + 2] = blk[RO_G + pk(1, 0)]; op[3 * NX + 3] = blk[RO_G + pk(1, 1)];
-        op[3 * NX + 4] = blk[RO_G + pk(j, 0)]; op[3 * NX + 5] = blk[RO_G + pk(j, 1)];
-        double acc = op[3 * NX] + gate(op, oz);
-#pragma unroll
-        for (int l = 0; l < NX; l++) acc += op[l] * (op[NX + l] + op[2 * NX + l]);
-        const double q0 = __shfl_sync(FULL, acc, 0), q1 = __shfl_sync(FULL, acc, 1);
-        const double l0 = q0 * op[3 * NX + 1];
-        const double l1 = (q1 - op[3 * NX + 2] * l0) * op[3 * NX + 3];
-        const double pvi = acc - op[3 * NX + 4] * l0 - op[3 * NX + 5] * l1;     // lanes 2..6: j = NU + i
-        if (lane < NU) blk[RO_Q + lane] = lane == 0 ? l0 : l1;
-        else if (lane < NZ) blk[RO_Q + lane] = pvi;
         __syncwarp();
     }
 }
@@ -1247,7 +1056,7 @@ template <bool SCAN>
 __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, const double* __restrict__ x0_g,
                               const double* __restrict__ params_g, int num_iter, double* mem_g, int mem_doubles,
                               double* xtraj_g, double* utraj_g, double* pobj_g, int* exit_g, int* qps_g,
-                              double* reseq_g, int* ipm_g, double* hb, double* rs, double* lt_sm, const int oz, const Grp grp)
+                              double* reseq_g, int* ipm_g, double* hb, double* lt_sm, const Grp grp)
 {
     const int k = grp.wig * 32 + (threadIdx.x & 31);   // stage owned by this thread
     const bool path = k < NSTAGE;             // has inputs, cost, constraints, dynamics
@@ -1328,18 +1137,6 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
             } else if (term) {
 #pragma unroll
                 for (int i = NU; i < NZ; i++) H[pk(i, i)] = REG_EPS;   // mirror(0) = eps I; no terminal cost
-            }
-        }
-
-        double* const blk = rs + (live ? k : 0) * RSTRIDE;      // this stage's block of the cooperative Riccati workspace
-        if constexpr (COOP) {
-            if (path) {
-                double Wd[NX * NZ];
-                w_to_dense(Wv, Wd);
-#pragma unroll
-                for (int l = 0; l < NX; l++)
-#pragma unroll
-                    for (int j = 0; j < NZ; j++) blk[RO_B + l * NB + j] = Wd[l * NZ + j];
             }
         }
 
@@ -1548,29 +1345,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
             //      input block: G = Ht + W'P+W, [Luu 0; Lxu I] from two Cholesky pivots, P = Gxx - Lxu Lxu'
             //      (the trailing update of the Cholesky factorisation: backward stable, no explicit
             //      inverse), l = Luu^-1 q_u, p = q_x - Lxu l.
-            if constexpr (COOP) {
-                // park Ht, gt, rb of every stage in shared memory; all lanes then run the recursion stage by stage
-                if (live) {
-#pragma unroll
-                    for (int i = 0; i < NPK; i++) blk[RO_G + i] = Ht[i];
-#pragma unroll
-                    for (int i = 0; i < NZ; i++) blk[RO_Q + i] = gt[i];
-                }
-                if (path) {
-#pragma unroll
-                    for (int i = 0; i < NX; i++) blk[RO_B + i * NB + NZ] = rb[i];
-                }
-                grp.sync();
-                if (grp.wig == 0) {
-                    riccati_factor_coop(rs, oz);
-                    riccati_forward_coop(rs, oz);
-                }
-                grp.sync();
-#pragma unroll
-                for (int i = 0; i < NZ; i++) dva[i] = (live && (path || i >= NU)) ? blk[RO_DZ + i] : 0.0;
-            }
             double P[NPX], pv[NX], Lx0[NX], Lx1[NX], Prb[NX], lv[NU], L10 = 0.0, iL0 = 0.0, iL1 = 0.0;
-            if constexpr (!COOP) {
 #pragma unroll
             for (int i = 0; i < NPX; i++) P[i] = 0.0;
 #pragma unroll
@@ -1669,7 +1444,6 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                 for (int i = 0; i < NX; i++) dva[NU + i] = hb[i];
             }
             }
-            }   // !COOP
 
             // ---- pass B: affine step length, mu_aff sums, corrector vectors
             StepFrac sfa;
@@ -1727,29 +1501,6 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
             for (int i = 0; i < NZ; i++) gt[i] += V1[i] - sigmu * V2[i];
 
             // ---- corrector solve (factorisation reused): backward vector sweep + forward sweep
-            if constexpr (COOP) {
-                if (live) {
-#pragma unroll
-                    for (int i = 0; i < NZ; i++) blk[RO_Q + i] = gt[i];
-                }
-                grp.sync();
-                if (grp.wig == 0) {
-                    riccati_backvec_coop(rs, oz);
-                    riccati_forward_coop(rs, oz);
-                }
-                grp.sync();
-#pragma unroll
-                for (int i = 0; i < NZ; i++) dv[i] = (live && (path || i >= NU)) ? blk[RO_DZ + i] : 0.0;
-                if (k >= 1 && live) {                   // dpi_k = P_k dx_k + p_k (lane-parallel)
-#pragma unroll
-                    for (int i = 0; i < NX; i++) {
-                        double a = blk[RO_Q + NU + i];
-#pragma unroll
-                        for (int j = 0; j < NX; j++) a += blk[RO_G + pk(NU + i, NU + j)] * dv[NU + j];
-                        dpi[i] = a;
-                    }
-                }
-            } else {
             if constexpr (SCAN) {
             {   // backward vector sweep as a scan: p_k = Acl_k' (p_{k+1} + P_{k+1} rb_k) + (gt_x - Lxu Luu^-1 gt_u)
                 Aff am;
@@ -1856,7 +1607,6 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                     dpi[i] = a;
                 }
             }
-            }   // !COOP
 
             // ---- pass C: step length of the corrected direction
             StepFrac sfc;                  // alpha = sfc.ratio()
@@ -1979,7 +1729,7 @@ mpc_solve_kernel(int n, const double* __restrict__ xinit, const double* __restri
     __shared__ double s_hand[GROUPS][NPX + NX + 4];
     __shared__ double s_xch[GROUPS][GW * XCH];
     __shared__ int s_prob[GROUPS];
-    extern __shared__ double s_ric[];           // [GROUPS][RS_DOUBLES] cooperative Riccati workspace
+    extern __shared__ double s_lt[];            // [GROUPS][LT_DOUBLES] per-entry state of the general inequality entries
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     Grp grp;
     grp.gid = warp / GW;
@@ -1999,8 +1749,7 @@ mpc_solve_kernel(int n, const double* __restrict__ xinit, const double* __restri
         if (prob >= n) return;
         const int nit = num_iter ? num_iter[prob] : num_iter_all;
         solve_problem<(WPC != WARPS_PER_CTA) || (MPC_SCAN_ALWAYS != 0)>(prob, xinit, x0, params, nit, mem, mem_doubles, xtraj, utraj, pobj, exit_code, qp_status, res_eq,
-                      ipm_iters, s_hand[grp.gid], s_ric + (size_t)grp.gid * (COOP ? RS_DOUBLES : 0),
-                      s_ric + (size_t)GROUPS * (COOP ? RS_DOUBLES : 0) + (size_t)grp.gid * LT_DOUBLES, n >> 31 /* 0, opaque to the compiler */, grp);
+                      ipm_iters, s_hand[grp.gid], s_lt + (size_t)grp.gid * LT_DOUBLES, grp);
     }
 }
 

@@ -430,7 +430,7 @@ __device__ __noinline__ void split_role_x(const int prob, const int num_iter, do
 __device__ __noinline__ void split_role_a(const int prob, const double* __restrict__ xinit_g, const double* __restrict__ x0_g,
                                           const double* __restrict__ params_g, const int num_iter, double* mem_g, const int mem_doubles,
                                           double* xtraj_g, double* utraj_g, double* pobj_g, int* exit_g, int* qps_g, double* reseq_g,
-                                          int* ipm_g, double* sm, const int oz)
+                                          int* ipm_g, double* sm)
 {
     const int k = threadIdx.x & 31;
     const bool path = k < NSTAGE, term = k == NSTAGE, live = k <= NSTAGE, xbox = path && k >= 1;
@@ -649,7 +649,7 @@ __device__ __noinline__ void split_role_a(const int prob, const double* __restri
             PROF(7)
             if (!cont) break;
             __syncwarp();
-            riccati_factor_coop2(rs, oz);
+            riccati_factor_coop(rs);
             PROF(8)
             // closed-loop matrices of every stage (lane-parallel), then the predictor sweep
             double Lx0[NX], Lx1[NX], Prb[NX], lv[NU], Bd[NX * NU], L10 = 0.0, iL0 = 0.0, iL1 = 0.0;
@@ -911,7 +911,7 @@ mpc_solve_split_kernel(int n, const double* __restrict__ xinit, const double* __
         const int nit = num_iter ? num_iter[prob] : num_iter_all;
         if (role == 0)
             split_role_a(prob, xinit, x0, params, nit, mem, mem_doubles, xtraj, utraj, pobj, exit_code, qp_status, res_eq, ipm_iters,
-                         s_split, n >> 31 /* 0, opaque to the compiler */);
+                         s_split);
         else if (role == 1)
             split_role_x(prob, nit, mem, mem_doubles, s_split);
         else

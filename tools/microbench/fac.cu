@@ -13,9 +13,9 @@ __global__ void kfac(const double* init, double* out, long long* cyc, int varian
     for (int i = threadIdx.x; i < RS_DOUBLES; i += 32) sm[i] = init[i];
     __syncwarp();
     const long long t0 = clock64();
-    if (variant == 0) riccati_factor_coop2(sm, oz);
-    else if (variant == 1) factor_v1(sm, oz);
-    else if (variant == 2) factor_v2(sm, oz);
+    if (variant == 0) riccati_factor_coop(sm);
+    else if (variant == 1) factor_v1(sm);
+    else if (variant == 2) factor_v2(sm);
     const long long t1 = clock64();
     __syncwarp();
     if (threadIdx.x == 0) cyc[variant] = t1 - t0;

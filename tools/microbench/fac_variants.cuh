@@ -2,6 +2,6 @@
 // (this round: branch-free rsqrt 872 -> 745 cycles per stage, no operand gate in the Cholesky step -> 690, none in the fused
 // G step -> 566, prefetch of the recursion-independent operands one stage ahead -> 660: rejected).
 namespace MPC_NS {
-__device__ __noinline__ void factor_v1(double* __restrict__ rs, const int oz) { riccati_factor_coop2(rs, oz); }
-__device__ __noinline__ void factor_v2(double* __restrict__ rs, const int oz) { riccati_factor_coop2(rs, oz); }
+__device__ __noinline__ void factor_v1(double* __restrict__ rs) { riccati_factor_coop(rs); }
+__device__ __noinline__ void factor_v2(double* __restrict__ rs) { riccati_factor_coop(rs); }
 }

@@ -175,7 +175,7 @@ def main():
     ap.add_argument("--sets", type=int, default=4096, help="homotopy sets per GPU per step")
     ap.add_argument("--num-iter", type=int, default=10, help="SQP-RTI iterations per solve (settings.yaml:18)")
     ap.add_argument("--ref-sets", type=int, default=128, help="homotopy sets per step of the CPU arm")
-    ap.add_argument("--cpu-sets", type=int, default=96, help="homotopy sets of the cpu_baseline sample")
+    ap.add_argument("--cpu-sets", type=int, default=384, help="homotopy sets of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--latency-reps", type=int, default=100, help="single-set latency repetitions (0 = skip)")
     args = ap.parse_args()

@@ -4,7 +4,7 @@ against the CPU oracle (exit codes bit-exact, worst relative trajectory error). 
 import os
 import sys, numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))      # (test infrastructure: the only place besides smoke / bench that may use oracle/)
 from oscar_mpc_planner_mr_modification_b200 import engine, synthetic
 from oracle_binding import Oracle
 tot = bad = 0

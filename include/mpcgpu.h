@@ -10,6 +10,7 @@
  */
 #ifndef MPCGPU_H
 #define MPCGPU_H
+#include <stddef.h>
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -52,7 +53,12 @@ int mpcgpu_mem_doubles(const mpcgpu_engine *e);
  *   params  [n * N * npar]           AcadosParameters::all_parameters   (:56), stage N reuses N-1 (:128-134)
  *   num_iter[n] or NULL              SQP-RTI iterations per problem; NULL => num_iter_all for all
  *                                    (Solver::_num_iterations; the wall-clock timeout rule of :108-116
- *                                    is evaluated by the host shim, which passes the resulting count)
+ *                                    is evaluated by the host shim, which passes the resulting count).
+ *                                    A NEGATIVE count -k runs k iterations with the completion step deferred: no
+ *                                    res_eq demotion and no reset of mem_inout on failure.  That is the stepwise
+ *                                    interface (solveOneIteration :145-160 keeps multipliers and QP memory between
+ *                                    iterations; the demotion :176-181 and the reset :187-191 happen once, in
+ *                                    completeOneIteration -- the host shim applies them there).
  *   mem_inout [n * mem_doubles] or NULL   persistent capsule memory (NLP multipliers + QP warm start):
  *                                    [flag][pi (N+1)*nx][lam N*nc][t N*nc][v (N+1)*(nu+nx)];
  *                                    flag 0 = fresh capsule, 1 = multipliers only (after
@@ -60,35 +66,76 @@ int mpcgpu_mem_doubles(const mpcgpu_engine *e);
  *                                    Zeroed on failure like Solver_acados_reset (:187-191).
  *   xtraj   [n * nx * (N+1)], utraj [n * nu * N]   AcadosOutput (:129-130)
  *   pobj[n] AcadosInfo::pobj; exit_code[n] return value of solve() (1 success, 0, 2, 3, 4: :197-203);
- *   qp_status[n] AcadosInfo::qp_status; res_eq[n] the value tested at :177;
+ *   qp_status[n] AcadosInfo::qp_status in the numbering Solver::explainExitFlag decodes (:409-420): 0 ok,
+ *                2 max iterations, 3 minimal step, 4 NaN; res_eq[n] the value tested at :177;
  *   ipm_iters[n] or NULL: total interior-point iterations (diagnostic). */
 int mpcgpu_solve_batch(mpcgpu_engine *e, int n, const double *xinit, const double *x0, const double *params,
                        const int *num_iter, int num_iter_all, double *mem_inout, double *xtraj, double *utraj,
                        double *pobj, int *exit_code, int *qp_status, double *res_eq, int *ipm_iters);
 
 /* Same contract with DEVICE pointers (inputs already resident in HBM); asynchronous on `stream`
- * (a cudaStream_t passed as void*, NULL = the engine's stream).  Use mpcgpu_sync() to wait. */
+ * (a cudaStream_t passed as void*, NULL = the engine's stream).  Every launch takes its own work counter from a ring
+ * of MPCGPU_MAX_INFLIGHT, so up to that many device calls of one engine may be in flight on different streams.
+ * mpcgpu_sync() waits for the engine's own streams AND for the most recent device call on a caller's stream. */
+#define MPCGPU_MAX_INFLIGHT 16
 int mpcgpu_solve_batch_device(mpcgpu_engine *e, int n, const double *xinit, const double *x0, const double *params,
                               const int *num_iter, int num_iter_all, double *mem_inout, double *xtraj, double *utraj,
                               double *pobj, int *exit_code, int *qp_status, double *res_eq, int *ipm_iters,
                               void *stream);
 int mpcgpu_sync(mpcgpu_engine *e);
 
+/* Optional arguments of the homotopy-set entries (NULL = none of them).  Plain pointers and sizes; HOST arrays.
+ *
+ * Consistency-cost post-processing.  Replaces: calculateConsistencyCostForSolver and its two call sites
+ *   (mpc_planner_modules/src/guidance_constraints.cpp:384-388,405-408,1025-1050): for a planner with
+ *   has_consistency_enabled the objective compared by FindBestPlanner is
+ *       pobj - consistency_weight * sum_{k=1}^{N-2} ((x_k - X_k)^2 + (y_k - Y_k)^2)
+ *   with (x_k, y_k) the SOLVED trajectory (getOutput(k, "x"/"y")), (X_k, Y_k) = _interpolated_prev_trajectory[k] (the
+ *   values setConsistencyParametersForPlanner loaded into prev_traj_x/y, :985-1023), NOT scaled by dt, accumulated in
+ *   stage order, multiplied by the weight once at the end, subtracted BEFORE the 0.75 selection weight (obj_scale).
+ *   It is evaluated on the device from the solver's output, state components ix / iy (model_map "x", "y").
+ * Persistent capsule memory.  Replaces: the per-planner local_solver capsules that live across control cycles
+ *   (guidance_constraints.cpp:17-25); `*solver = *_solver` (:323) resets only the QP memory
+ *   (acados_solver_interface.cpp:67-77), so the set entries downgrade flag 2 -> 1 (multipliers survive) before solving.
+ * Static halfspaces.  Replaces: module_data.static_obstacles in LinearizedConstraints::update
+ *   (linearized_constraints.cpp:107-127): n_static rows (a1, a2, b) per set and stage k >= 1, written behind the
+ *   obstacle rows of a guided planner (slot n_obs + h) and from slot h on for a non-guided planner (its obstacle list is
+ *   empty_data_, :326-329); only used by the entries that build the halfspaces on the device.
+ * Selected trajectory.  Replaces: the copy of the best planner's _output into the main solver
+ *   (guidance_constraints.cpp:520-522).  With best_xtraj / best_utraj the per-planner xtraj / utraj arguments of the set
+ *   entries may be NULL: only the decision record {best_idx, pobj, exit_code, qp_status, res_eq} per planner and ONE
+ *   trajectory per set travel back to the host (north_star: "only the per-problem cost and feasibility flags are gathered"). */
+typedef struct mpcgpu_set_options {
+    double consistency_weight;                 /* CONFIG["weights"]["consistency"] */
+    const double *prev_traj;                   /* [n_sets * N * 2] (X_k, Y_k), k = 0..N-1; NULL = no consistency term */
+    const unsigned char *consistency_enabled;  /* [n] planner.has_consistency_enabled; NULL = enabled for every planner */
+    int ix, iy;                                /* state indices of x and y inside xtraj (0, 1 for both unicycle models) */
+    double *mem_inout;                         /* [n * mem_doubles] persistent capsule memory, or NULL (fresh capsules) */
+    double *objective_out;                     /* [n] planner.result.objective after the post-processing, or NULL */
+    double *consistency_cost_out;              /* [n] the subtracted term (0 where not enabled), or NULL */
+    const double *static_halfspaces;           /* [n_sets * N * n_static * 3], or NULL */
+    int n_static;
+    double *best_xtraj;                        /* [n_sets * nx * (N+1)] trajectory of the selected planner (planner 0 of the */
+    double *best_utraj;                        /* [n_sets * nu * N]     set if none succeeded), or NULL; see below           */
+} mpcgpu_set_options;
+
 /* Homotopy-SET entry: what GuidanceConstraints::optimize does for one robot --
  * `*solver = *_solver` for every planner (guidance_constraints.cpp:323: all planners start from the main
  * solver's parameter block), planner-specific parameters on top (guidance halfspaces
- * linearized_constraints.cpp:150-189, consistency reference), one solve() each (:369) and FindBestPlanner
+ * linearized_constraints.cpp:150-189, consistency reference), one solve() each (:369), the objective post-processing
+ * (:373-420, incl. the consistency cost of the solved trajectory: `opt`) and FindBestPlanner
  * (:572-590) -- as ONE call for n_sets sets of `planners` planners.  The shared block travels once per
  * set: host->device bytes drop from P*N*npar to N*npar + P*N*nidx doubles per set.
  *   xinit_sets [n_sets*nx]; shared_params [n_sets*N*npar]; x0 [n*(nu+nx)*(N+1)], n = n_sets*planners,
  *   problem index = set*planners + planner; param_idx [nidx] flat parameter indices that differ per planner;
  *   planner_params [n*N*nidx] their values (stage-major); outputs as mpcgpu_solve_batch plus
- *   best_idx [n_sets] with the semantics of mpcgpu_select_best (obj_scale / obj_sub / disabled may be NULL). */
+ *   best_idx [n_sets] with the semantics of mpcgpu_select_best (obj_scale / obj_sub / disabled may be NULL);
+ *   obj_sub is a term known BEFORE the solve -- the consistency cost is not: it goes through `opt`. */
 int mpcgpu_solve_sets(mpcgpu_engine *e, int n_sets, int planners, const double *xinit_sets, const double *shared_params,
                       const double *x0, int nidx, const int *param_idx, const double *planner_params, const int *num_iter,
                       int num_iter_all, double *xtraj, double *utraj, double *pobj, int *exit_code, int *qp_status,
                       double *res_eq, const double *obj_scale, const double *obj_sub, const unsigned char *disabled,
-                      int *best_idx);
+                      int *best_idx, const mpcgpu_set_options *opt);
 
 /* Guidance halfspaces built ON THE DEVICE.
  * Replaces: LinearizedConstraints::update + projectToSafety + setParameters for the topology constraints of
@@ -97,7 +144,8 @@ int mpcgpu_solve_sets(mpcgpu_engine *e, int n_sets, int planners, const double *
  *           3 * (max_obstacles + add_halfspaces) parameters per planner and stage right before solve().
  * Writes the parameter slots lin_base + 3 j + {0,1,2} = (a1, a2, b) of constraint j < lin_count for every stage of every
  * problem (problem = set * planners + planner):
- *   stage 0 and non-guided planners (guided[q] == 0: update(state, empty_data_)): dummies (1, 0, xinit_x + 100);
+ *   stage 0 and non-guided planners (guided[q] == 0: update(state, empty_data_)): dummies (1, 0, xinit_x + 100)
+ *   (static halfspaces, if any: mpcgpu_set_options);
  *   guided planners, k >= 1: pos = warm start (x0) position of stage k, pushed out of the obstacles (3 sweeps of the
  *   Douglas-Rachford step, radius 1e-3 + robot_radius), a = (o - pos)/|o - pos|, b = a.o - (1e-3 + robot_radius) with
  *   o = obst_pred[set][k-1][j] (prediction.modes[0][k-1].position); slots j >= n_obs are dummies.
@@ -117,7 +165,7 @@ int mpcgpu_solve_sets_guided(mpcgpu_engine *e, int n_sets, int planners, const d
                              int lin_count, double robot_radius, int nidx, const int *param_idx, const double *planner_params,
                              const int *num_iter, int num_iter_all, double *xtraj, double *utraj, double *pobj, int *exit_code,
                              int *qp_status, double *res_eq, const double *obj_scale, const double *obj_sub,
-                             const unsigned char *disabled, int *best_idx);
+                             const unsigned char *disabled, int *best_idx, const mpcgpu_set_options *opt);
 
 /* Pick the best planner of each homotopy set.
  * Replaces: the objective post-processing of GuidanceConstraints::optimize and FindBestPlanner
@@ -148,6 +196,42 @@ int mpcgpu_model_eval(mpcgpu_engine *e, int n, const double *z, const double *p,
 /* Measurement helper (no reference counterpart): FP64 FMA peak of `device` in TFLOP/s from a register-
  * resident DFMA kernel (best of 5 after warm-up).  The FP64 roofline denominator of bench.py. */
 int mpcgpu_measure_fp64_peak(int device, double *tflops);
+
+/* Pinned (page-locked) host memory for the HOST-array entry points: copies from pinned buffers overlap the solve kernels
+ * of the chunked pipeline; pageable memory works but serialises.  No reference counterpart (plumbing). */
+int mpcgpu_alloc_pinned(size_t bytes, void **out);
+int mpcgpu_free_pinned(void *p);
+
+/* Several GPUs of one node behind ONE handle (north_star: "shards naturally across the 8 GPUs with one stream per
+ * GPU and no NCCL on the solve path; only the per-problem cost and feasibility flags are gathered").
+ * Replaces: the OpenMP team over planners (guidance_constraints.cpp:304) + one ROS node per robot, scaled out.
+ * Homotopy sets are partitioned BY SET into contiguous ranges, one per device, the remainder to the last device
+ * (mpcgpu_multi_shard_range; a set never straddles two devices because its argmin is taken on the device); every range is
+ * solved by that device's engine from its own host thread on its own streams; results land in the caller's arrays at the
+ * range's offsets -- the "gather" is the concatenation, no collective.  Arguments as the single-device entries. */
+typedef struct mpcgpu_multi mpcgpu_multi;
+int mpcgpu_multi_create(const char *config_name, const int *devices, int n_devices, int max_batch_per_device, mpcgpu_multi **out);
+int mpcgpu_multi_destroy(mpcgpu_multi *m);
+int mpcgpu_multi_num_devices(const mpcgpu_multi *m);
+mpcgpu_engine *mpcgpu_multi_engine(mpcgpu_multi *m, int i);
+int mpcgpu_multi_shard_range(int n_units, int n_devices, int i, int *begin, int *end);
+int mpcgpu_multi_solve_sets(mpcgpu_multi *m, int n_sets, int planners, const double *xinit_sets, const double *shared_params,
+                            const double *x0, int nidx, const int *param_idx, const double *planner_params, const int *num_iter,
+                            int num_iter_all, double *xtraj, double *utraj, double *pobj, int *exit_code, int *qp_status,
+                            double *res_eq, const double *obj_scale, const double *obj_sub, const unsigned char *disabled,
+                            int *best_idx, const mpcgpu_set_options *opt);
+int mpcgpu_multi_solve_sets_guided(mpcgpu_multi *m, int n_sets, int planners, const double *xinit_sets, const double *shared_params,
+                                   const double *x0, int n_obs, const double *obst_pred, const unsigned char *guided, int lin_base,
+                                   int lin_count, double robot_radius, int nidx, const int *param_idx, const double *planner_params,
+                                   const int *num_iter, int num_iter_all, double *xtraj, double *utraj, double *pobj,
+                                   int *exit_code, int *qp_status, double *res_eq, const double *obj_scale, const double *obj_sub,
+                                   const unsigned char *disabled, int *best_idx, const mpcgpu_set_options *opt);
+/* independent problems (no sets): contiguous ranges of problems */
+int mpcgpu_multi_solve_batch(mpcgpu_multi *m, int n, const double *xinit, const double *x0, const double *params,
+                             const int *num_iter, int num_iter_all, double *mem_inout, double *xtraj, double *utraj,
+                             double *pobj, int *exit_code, int *qp_status, double *res_eq, int *ipm_iters);
+/* max over the devices of the solve-kernel time of the last multi call (ms, CUDA events on each device) */
+float mpcgpu_multi_last_kernel_ms(mpcgpu_multi *m);
 
 /* Kernel choice (no reference counterpart).  Two kernels implement the same solve: the thread-per-stage kernel
  * (one warp per problem, 8 problems per SM: throughput) and the role-split kernel (one CTA of several warps

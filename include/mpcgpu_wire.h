@@ -64,7 +64,7 @@ int mpcgpu_solve_sets_tracks(mpcgpu_engine *e, int n_sets, int planners, const d
                              double robot_radius, int ell_base, int ell_stride, const int *ell_offsets, const int *num_iter,
                              int num_iter_all, double *xtraj, double *utraj, double *pobj, int *exit_code, int *qp_status,
                              double *res_eq, const double *obj_scale, const double *obj_sub, const unsigned char *disabled,
-                             int *best_idx);
+                             int *best_idx, const mpcgpu_set_options *opt);
 
 /* Solver section of mpc_planner_msgs/MPCMetrics from the engine's records of one homotopy set.
  * Replaces: the metrics fill of the planner node (jules_ros1_jackalplanner.cpp, _metrics_pub) for the fields the solve path

@@ -696,6 +696,10 @@ static int qp_solve(work_t *w, const REAL *dx0)
 static void solve_one(work_t *w, const REAL *xinit, const REAL *x0, const REAL *params, int num_iter, REAL *mem,
                       REAL *xtraj, REAL *utraj, REAL *pobj, int *exit_code, int *qp_status, REAL *res_eq, int *ipm_iters)
 {
+    /* num_iter < 0: |num_iter| iterations, completion deferred (stepwise interface, acados_solver_interface.cpp:145-160:
+     * no res_eq demotion, no reset on failure -- both belong to completeOneIteration, :176-191) */
+    const int defer = num_iter < 0;
+    if (defer) num_iter = -num_iter;
     /* persistent solver memory (multipliers survive between solve() calls on one capsule) */
     memset(w->pi, 0, sizeof(w->pi));
     memset(w->lam, 0, sizeof(w->lam));
@@ -748,13 +752,13 @@ static void solve_one(work_t *w, const REAL *xinit, const REAL *x0, const REAL *
         for (int i = 0; i < NX; i++) xtraj[k * NX + i] = w->x[k][i];
         if (k < NN) for (int i = 0; i < NU; i++) utraj[k * NU + i] = w->u[k][i];
     }
-    if (!(req <= RES_EQ_MAX) && status == 0) status = 4;
-    *pobj = cost; *res_eq = req; *qp_status = qps;
+    if (!(req <= RES_EQ_MAX) && status == 0 && !defer) status = 4;
+    *pobj = cost; *res_eq = req; *qp_status = (qps == 0) ? 0 : qps + 1;   /* acados numbering decoded at acados_solver_interface.cpp:409-420: 2 max-iter, 3 min-step, 4 NaN */
     *exit_code = (status == 0) ? 1 : (status == 1 ? 0 : status);
     if (ipm_iters) *ipm_iters = w->ipm_iters_total;
     if (mem) {
         if (status != 0) {
-            memset(mem, 0, sizeof(REAL) * oracle_mem_doubles()); /* Solver_acados_reset + reset_qp_memory (:187-191) */
+            if (!defer) memset(mem, 0, sizeof(REAL) * oracle_mem_doubles()); /* Solver_acados_reset + reset_qp_memory (:187-191) */
         } else {
             REAL *m = mem + 1;
             mem[0] = 2.0;
@@ -816,9 +820,23 @@ static void dr_proj(const double *p, const double *c, double r, const double *to
         out[0] = c[0] + sx / n * r; out[1] = c[1] + sy / n * r;
     } else { out[0] = p[0]; out[1] = p[1]; }
 }
+void oracle_guidance_halfspaces_static(int n_sets, int planners, int N, int nx, int nu, int npar, int lin_base, int lin_count,
+                                       int n_obs, const double *xinit_sets, const double *x0, const double *obst_pred,
+                                       const unsigned char *guided, double robot_radius, const double *stat, int n_static,
+                                       double *params);
 void oracle_guidance_halfspaces(int n_sets, int planners, int N, int nx, int nu, int npar, int lin_base, int lin_count,
                                 int n_obs, const double *xinit_sets, const double *x0, const double *obst_pred,
                                 const unsigned char *guided, double robot_radius, double *params)
+{
+    oracle_guidance_halfspaces_static(n_sets, planners, N, nx, nu, npar, lin_base, lin_count, n_obs, xinit_sets, x0, obst_pred, guided,
+                                      robot_radius, NULL, 0, params);
+}
+/* + module_data.static_obstacles (linearized_constraints.cpp:107-127): n_static rows (a1, a2, b) per set and stage k >= 1,
+ * behind the obstacle rows (guided) or from slot 0 (non-guided: empty obstacle list, guidance_constraints.cpp:326-329) */
+void oracle_guidance_halfspaces_static(int n_sets, int planners, int N, int nx, int nu, int npar, int lin_base, int lin_count,
+                                       int n_obs, const double *xinit_sets, const double *x0, const double *obst_pred,
+                                       const unsigned char *guided, double robot_radius, const double *stat, int n_static,
+                                       double *params)
 {
     const int nz = nx + nu;
     const double r = 1e-3 + robot_radius;
@@ -828,6 +846,13 @@ void oracle_guidance_halfspaces(int n_sets, int planners, int N, int nx, int nu,
         for (int k = 0; k < N; k++) {
             double *P = params + ((size_t)q * N + k) * npar + lin_base;
             for (int j = 0; j < lin_count; j++) { P[3 * j] = 1.0; P[3 * j + 1] = 0.0; P[3 * j + 2] = dummy_b; }
+            if (stat && k > 0) {
+                const int first = guided[q] ? n_obs : 0;
+                const double *sh = stat + ((size_t)s * N + k) * n_static * 3;
+                for (int h = 0; h < n_static && first + h < lin_count; h++) {
+                    P[3 * (first + h)] = sh[3 * h]; P[3 * (first + h) + 1] = sh[3 * h + 1]; P[3 * (first + h) + 2] = sh[3 * h + 2];
+                }
+            }
             if (k == 0 || !guided[q]) continue;
             const double *ob = obst_pred + ((size_t)s * N + (k - 1)) * n_obs * 2;
             double pos[2] = {x0[((size_t)q * (N + 1) + k) * nz + nu], x0[((size_t)q * (N + 1) + k) * nz + nu + 1]};
@@ -853,22 +878,50 @@ void oracle_guidance_halfspaces(int n_sets, int planners, int N, int nx, int nu,
     }
 }
 
-int oracle_select_best(int n_sets, const int *set_offsets, const double *pobj, const int *exit_code,
-                       const double *obj_scale, const double *obj_sub, const unsigned char *disabled, int *best_idx)
+/* calculateConsistencyCostForSolver (guidance_constraints.cpp:1025-1050): weight * sum_{k=1}^{N-2} (dx^2 + dy^2) between the
+ * SOLVED trajectory (getOutput(k, "x"/"y")) and _interpolated_prev_trajectory[k]; not scaled by dt.  Plain C++ semantics
+ * of the reference: no FMA contraction (oracle/Makefile compiles with -ffp-contract=off). */
+double oracle_consistency_cost(const double *xtraj, const double *prev, int N, int nx, int ix, int iy, double weight)
+{
+    double sum = 0.0;
+    for (int k = 1; k <= N - 2; k++) {
+        const double dx = xtraj[k * nx + ix] - prev[2 * k], dy = xtraj[k * nx + iy] - prev[2 * k + 1];
+        sum += dx * dx + dy * dy;
+    }
+    return weight * sum;
+}
+/* Objective post-processing + FindBestPlanner (guidance_constraints.cpp:373-420,572-590):
+ * objective = pobj [- consistency cost if has_consistency_enabled (:384-388,405-408)] [- obj_sub] [* obj_scale (:418-419)] */
+int oracle_select_best_cons(int n_sets, const int *set_offsets, const double *pobj, const int *exit_code,
+                            const double *obj_scale, const double *obj_sub, const unsigned char *disabled, int *best_idx,
+                            const double *xtraj, const double *prev_traj, const unsigned char *cons_enabled, double cons_weight,
+                            int N, int nx, int ix, int iy, double *objective_out, double *cons_out)
 {
     for (int s = 0; s < n_sets; s++) {
         double best = 1e10;
         int bi = -1;
         for (int i = set_offsets[s]; i < set_offsets[s + 1]; i++) {
-            if (disabled && disabled[i]) continue;
-            double obj = pobj[i];
+            double obj = pobj[i], cons = 0.0;
+            if (prev_traj && (!cons_enabled || cons_enabled[i])) {
+                cons = oracle_consistency_cost(xtraj + (size_t)i * (N + 1) * nx, prev_traj + (size_t)s * N * 2, N, nx, ix, iy, cons_weight);
+                obj -= cons;
+            }
             if (obj_sub) obj -= obj_sub[i];
             if (obj_scale) obj *= obj_scale[i];
+            if (objective_out) objective_out[i] = obj;
+            if (cons_out) cons_out[i] = cons;
+            if (disabled && disabled[i]) continue;
             if (exit_code[i] == 1 && obj < best) { best = obj; bi = i - set_offsets[s]; }
         }
         best_idx[s] = bi;
     }
     return 0;
+}
+int oracle_select_best(int n_sets, const int *set_offsets, const double *pobj, const int *exit_code,
+                       const double *obj_scale, const double *obj_sub, const unsigned char *disabled, int *best_idx)
+{
+    return oracle_select_best_cons(n_sets, set_offsets, pobj, exit_code, obj_scale, obj_sub, disabled, best_idx, NULL, NULL, NULL, 0.0, 0, 0,
+                                   0, 1, NULL, NULL);
 }
 
 /* ---- component entry points used by the unit tests ------------------------------------------ */

@@ -4,8 +4,8 @@
 
 namespace MPC_NS {
 
-constexpr size_t SMEM_THR = (size_t)(WARPS_PER_CTA / GW) * LT_DOUBLES * sizeof(double);   // per-entry state of the general inequality entries
-constexpr size_t SMEM_LAT = (size_t)LT_DOUBLES * sizeof(double);
+constexpr size_t SMEM_THR = (size_t)(WARPS_PER_CTA / GW) * (LT_DOUBLES + (COOP ? RS_DOUBLES : 0)) * sizeof(double);   // per-entry state of the general inequality entries
+constexpr size_t SMEM_LAT = (size_t)(LT_DOUBLES + (COOP ? RS_DOUBLES : 0)) * sizeof(double);
 #ifndef MPC_SPLIT
 #define MPC_SPLIT 1
 #endif

@@ -135,6 +135,11 @@ constexpr double JACOBI_TOL = 1e-24;   // stop when sum offdiag^2 <= tol * sum a
 // inequality entries over the whole horizon: u box + general on N stages, x box on stages 1..N-1
 constexpr int IPM_COUNT = NSTAGE * (2 * NU + NCG) + (NSTAGE - 1) * 2 * NX;
 
+// AcadosInfo::qp_status is read with ocp_nlp_get("qp_status") and decoded by Solver::explainExitFlag
+// (acados_solver_interface.cpp:409-420) in acados' return-value numbering: 2 max iterations, 3 minimal step, 4 NaN.
+// The interior-point loop keeps the HPIPM-raw code (0 ok, 1 max-iter, 2 min-step, 3 NaN); outputs carry the acados one.
+__host__ __device__ constexpr int qp_status_acados(int raw) { return raw == 0 ? 0 : raw + 1; }
+
 __host__ __device__ constexpr int pk(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
 
 __device__ __forceinline__ double shfl(double v, int src) { return __shfl_sync(FULL, v, src); }
@@ -388,6 +393,10 @@ __device__ __noinline__ void forward_scan(const double* Wv, const double* Lx0, c
 //               After the factorisation of the stage, in place: iL0 @(0,0), L10 @(1,0), iL1 @(1,1), Lxu[i][0..1]
 //               @(2+i,0..1), P @(2+i,2+j), l = Luu^-1 q_u @(7,0..1), p @(7,2+i)
 //        RO_B   [W | rb], NX x (NZ+1) row-major      RO_PRB  P+ rb      RO_DZ  step of the stage [du; dx]
+#ifndef MPC_COOP
+#define MPC_COOP 0   // thread-per-stage kernel: 1 = cooperative Riccati recursion (all lanes on one stage, shared-memory workspace)
+#endif
+constexpr bool COOP = (MPC_COOP != 0) && (((NSTAGE + 1 + 31) / 32) == 1);
 constexpr int NB = NZ + 1;
 constexpr int RO_G = 0;
 constexpr int RO_Q = RO_G + NPK;                 // row 7 of the packed augmented matrix: pk(NZ, j) == NPK + j
@@ -493,6 +502,76 @@ __device__ __noinline__ void riccati_factor_coop(double* __restrict__ rs)
                 blk[RO_Q] = l0; blk[RO_Q + 1] = l1;
             }
         }
+        __syncwarp();
+    }
+}
+
+// Cooperative substitution sweeps of the thread-per-stage kernel (MPC_COOP): all lanes on one stage, operands in the
+// shared-memory blocks, one __syncwarp per stage.  ~45 / ~35 warp-instructions per stage instead of ~60 single-lane ones
+// AND no register-resident factor (P, Lxu, p, P+ rb: 40 doubles per lane less).
+// forward: du_s = -Luu^-T (Lxu' dx_s + l_s), dx_{s+1} = rb_s + W_s [du_s; dx_s], dx_0 = 0  ->  RO_DZ of every block
+__device__ __noinline__ void riccati_forward_coop(double* __restrict__ rs)
+{
+    const int lane = threadIdx.x & 31;
+    const int i = lane < NX ? lane : 0;
+    if (lane < NX) rs[RO_DZ + NU + lane] = 0.0;
+    __syncwarp();
+#pragma unroll 1
+    for (int s = 0; s < NSTAGE; s++) {
+        double* __restrict__ blk = rs + s * RSTRIDE;
+        double dx[NX], l0c[NX], l1c[NX], wx[NX];
+#pragma unroll
+        for (int j = 0; j < NX; j++) {
+            dx[j] = blk[RO_DZ + NU + j];
+            l0c[j] = blk[RO_G + pk(NU + j, 0)];
+            l1c[j] = blk[RO_G + pk(NU + j, 1)];
+            wx[j] = blk[RO_B + i * NB + NU + j];
+        }
+        const double l0 = blk[RO_Q], l1 = blk[RO_Q + 1];
+        const double iL0 = blk[RO_G + pk(0, 0)], L10 = blk[RO_G + pk(1, 0)], iL1 = blk[RO_G + pk(1, 1)];
+        const double rbi = blk[RO_B + i * NB + NZ], wu0 = blk[RO_B + i * NB], wu1 = blk[RO_B + i * NB + 1];
+        double r0 = l0, r1 = l1, acc = rbi;
+#pragma unroll
+        for (int j = 0; j < NX; j++) {
+            r0 += l0c[j] * dx[j];
+            r1 += l1c[j] * dx[j];
+            acc += wx[j] * dx[j];
+        }
+        const double du1 = -r1 * iL1;
+        const double du0 = -(r0 + L10 * du1) * iL0;
+        acc += wu0 * du0 + wu1 * du1;
+        if (lane < NX) blk[RSTRIDE + RO_DZ + NU + i] = acc;
+        else if (lane == NX) { blk[RO_DZ] = du0; blk[RO_DZ + 1] = du1; }
+        __syncwarp();
+    }
+}
+// backward vector sweep of a new right-hand side (factorisation reused).  In: gt in row 7 of every block (block N:
+// p_N = gt_x).  q = gt + W' (p+ + P+ rb), l = Luu^-1 q_u, p = q_x - Lxu l  ->  row 7, in place
+__device__ __noinline__ void riccati_backvec_coop(double* __restrict__ rs)
+{
+    const int lane = threadIdx.x & 31;
+    const int j = lane < NZ ? lane : 0;
+#pragma unroll 1
+    for (int s = NSTAGE - 1; s >= 0; s--) {
+        double* __restrict__ blk = rs + s * RSTRIDE;
+        const double* __restrict__ nxt = blk + RSTRIDE;
+        double wc[NX], y[NX];
+#pragma unroll
+        for (int l = 0; l < NX; l++) {
+            wc[l] = blk[RO_B + l * NB + j];
+            y[l] = nxt[RO_Q + NU + l] + blk[RO_PRB + l];
+        }
+        const double iL0 = blk[RO_G + pk(0, 0)], L10 = blk[RO_G + pk(1, 0)], iL1 = blk[RO_G + pk(1, 1)];
+        const double lj0 = blk[RO_G + pk(j, 0)], lj1 = blk[RO_G + pk(j, 1)];      // lanes 2..6: row j - NU of Lxu
+        double acc = blk[RO_Q + j];
+#pragma unroll
+        for (int l = 0; l < NX; l++) acc += wc[l] * y[l];
+        const double q0 = __shfl_sync(FULL, acc, 0), q1 = __shfl_sync(FULL, acc, 1);
+        const double l0 = q0 * iL0;
+        const double l1 = (q1 - L10 * l0) * iL1;
+        const double pvi = acc - lj0 * l0 - lj1 * l1;
+        if (lane < NU) blk[RO_Q + lane] = lane == 0 ? l0 : l1;
+        else if (lane < NZ) blk[RO_Q + lane] = pvi;
         __syncwarp();
     }
 }
@@ -1056,8 +1135,13 @@ template <bool SCAN>
 __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, const double* __restrict__ x0_g,
                               const double* __restrict__ params_g, int num_iter, double* mem_g, int mem_doubles,
                               double* xtraj_g, double* utraj_g, double* pobj_g, int* exit_g, int* qps_g,
-                              double* reseq_g, int* ipm_g, double* hb, double* lt_sm, const Grp grp)
+                              double* reseq_g, int* ipm_g, double* hb, double* lt_sm, double* rs, const Grp grp)
 {
+    // num_iter < 0: |num_iter| iterations with the completion step DEFERRED -- the stepwise interface (solveOneIteration,
+    // acados_solver_interface.cpp:145-160) keeps multipliers and QP memory between iterations; the res_eq demotion and the
+    // reset on failure belong to completeOneIteration (:176-191) and are applied by the caller
+    const bool defer = num_iter < 0;
+    if (defer) num_iter = -num_iter;
     const int k = grp.wig * 32 + (threadIdx.x & 31);   // stage owned by this thread
     const bool path = k < NSTAGE;             // has inputs, cost, constraints, dynamics
     const bool term = k == NSTAGE;
@@ -1137,6 +1221,18 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
             } else if (term) {
 #pragma unroll
                 for (int i = NU; i < NZ; i++) H[pk(i, i)] = REG_EPS;   // mirror(0) = eps I; no terminal cost
+            }
+        }
+
+        double* const blk = rs + (live ? k : 0) * RSTRIDE;      // this stage's block of the cooperative Riccati workspace (MPC_COOP)
+        if constexpr (COOP) {
+            if (path) {
+                double Wd[NX * NZ];
+                w_to_dense(Wv, Wd);
+#pragma unroll
+                for (int l = 0; l < NX; l++)
+#pragma unroll
+                    for (int j = 0; j < NZ; j++) blk[RO_B + l * NB + j] = Wd[l * NZ + j];
             }
         }
 
@@ -1345,7 +1441,26 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
             //      input block: G = Ht + W'P+W, [Luu 0; Lxu I] from two Cholesky pivots, P = Gxx - Lxu Lxu'
             //      (the trailing update of the Cholesky factorisation: backward stable, no explicit
             //      inverse), l = Luu^-1 q_u, p = q_x - Lxu l.
+            if constexpr (COOP) {
+                // park Ht, gt, rb of every stage in shared memory; all lanes then run the recursion stage by stage
+                if (live) {
+#pragma unroll
+                    for (int i = 0; i < NPK; i++) blk[RO_G + i] = Ht[i];
+#pragma unroll
+                    for (int i = 0; i < NZ; i++) blk[RO_Q + i] = gt[i];
+                }
+                if (path) {
+#pragma unroll
+                    for (int i = 0; i < NX; i++) blk[RO_B + i * NB + NZ] = rb[i];
+                }
+                __syncwarp();
+                riccati_factor_coop(rs);
+                riccati_forward_coop(rs);
+#pragma unroll
+                for (int i = 0; i < NZ; i++) dva[i] = (live && (path || i >= NU)) ? blk[RO_DZ + i] : 0.0;
+            }
             double P[NPX], pv[NX], Lx0[NX], Lx1[NX], Prb[NX], lv[NU], L10 = 0.0, iL0 = 0.0, iL1 = 0.0;
+            if constexpr (!COOP) {
 #pragma unroll
             for (int i = 0; i < NPX; i++) P[i] = 0.0;
 #pragma unroll
@@ -1445,6 +1560,8 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
             }
             }
 
+            }   // !COOP
+
             // ---- pass B: affine step length, mu_aff sums, corrector vectors
             StepFrac sfa;
             double S1 = 0.0, S2 = 0.0, V1[NZ], V2[NZ];   // alpha_aff = sfa.ratio()
@@ -1501,6 +1618,26 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
             for (int i = 0; i < NZ; i++) gt[i] += V1[i] - sigmu * V2[i];
 
             // ---- corrector solve (factorisation reused): backward vector sweep + forward sweep
+            if constexpr (COOP) {
+                if (live) {
+#pragma unroll
+                    for (int i = 0; i < NZ; i++) blk[RO_Q + i] = gt[i];
+                }
+                __syncwarp();
+                riccati_backvec_coop(rs);
+                riccati_forward_coop(rs);
+#pragma unroll
+                for (int i = 0; i < NZ; i++) dv[i] = (live && (path || i >= NU)) ? blk[RO_DZ + i] : 0.0;
+                if (k >= 1 && live) {                   // dpi_k = P_k dx_k + p_k (lane-parallel)
+#pragma unroll
+                    for (int i = 0; i < NX; i++) {
+                        double a = blk[RO_Q + NU + i];
+#pragma unroll
+                        for (int j = 0; j < NX; j++) a += blk[RO_G + pk(NU + i, NU + j)] * dv[NU + j];
+                        dpi[i] = a;
+                    }
+                }
+            } else {
             if constexpr (SCAN) {
             {   // backward vector sweep as a scan: p_k = Acl_k' (p_{k+1} + P_{k+1} rb_k) + (gt_x - Lxu Luu^-1 gt_u)
                 Aff am;
@@ -1607,6 +1744,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                     dpi[i] = a;
                 }
             }
+            }   // !COOP
 
             // ---- pass C: step length of the corrected direction
             StepFrac sfc;                  // alpha = sfc.ratio()
@@ -1678,7 +1816,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
     // deterministic stage-order sum (matches the oracle's sequential accumulation)
     const double cost = grp.ordered_sum(cst);
     req = grp.max(req);
-    if (!(req <= RES_EQ_MAX) && status == 0) status = 4;
+    if (!(req <= RES_EQ_MAX) && status == 0 && !defer) status = 4;
     const int exit_code = (status == 0) ? 1 : (status == 1 ? 0 : status);
     if (live) {
 #pragma unroll
@@ -1689,12 +1827,13 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
         for (int i = 0; i < NU; i++) utraj_g[(size_t)prob * NU * NSTAGE + k * NU + i] = z[i];
     }
     if (k == 0) {
-        pobj_g[prob] = cost; exit_g[prob] = exit_code; qps_g[prob] = qps; reseq_g[prob] = req;
+        pobj_g[prob] = cost; exit_g[prob] = exit_code; qps_g[prob] = qp_status_acados(qps); reseq_g[prob] = req;
         if (ipm_g) ipm_g[prob] = ipm_total;
     }
     if (mem) {
         if (status != 0) {                                 // Solver_acados_reset + reset_qp_memory (:187-191)
-            for (int i = k; i < mem_doubles; i += 32 * GW) mem[i] = 0.0;
+            if (!defer)
+                for (int i = k; i < mem_doubles; i += 32 * GW) mem[i] = 0.0;
         } else {
             double* m = mem + 1;
             if (k == 0) mem[0] = 2.0;
@@ -1749,7 +1888,8 @@ mpc_solve_kernel(int n, const double* __restrict__ xinit, const double* __restri
         if (prob >= n) return;
         const int nit = num_iter ? num_iter[prob] : num_iter_all;
         solve_problem<(WPC != WARPS_PER_CTA) || (MPC_SCAN_ALWAYS != 0)>(prob, xinit, x0, params, nit, mem, mem_doubles, xtraj, utraj, pobj, exit_code, qp_status, res_eq,
-                      ipm_iters, s_hand[grp.gid], s_lt + (size_t)grp.gid * LT_DOUBLES, grp);
+                      ipm_iters, s_hand[grp.gid], s_lt + (size_t)grp.gid * LT_DOUBLES,
+                      s_lt + (size_t)GROUPS * LT_DOUBLES + (size_t)grp.gid * (COOP ? RS_DOUBLES : 0), grp);
     }
 }
 

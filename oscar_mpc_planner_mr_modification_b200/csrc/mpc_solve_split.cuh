@@ -430,7 +430,7 @@ __device__ __noinline__ void split_role_x(const int prob, const int num_iter, do
 __device__ __noinline__ void split_role_a(const int prob, const double* __restrict__ xinit_g, const double* __restrict__ x0_g,
                                           const double* __restrict__ params_g, const int num_iter, double* mem_g, const int mem_doubles,
                                           double* xtraj_g, double* utraj_g, double* pobj_g, int* exit_g, int* qps_g, double* reseq_g,
-                                          int* ipm_g, double* sm)
+                                          int* ipm_g, double* sm, const bool defer)
 {
     const int k = threadIdx.x & 31;
     const bool path = k < NSTAGE, term = k == NSTAGE, live = k <= NSTAGE, xbox = path && k >= 1;
@@ -855,7 +855,7 @@ __device__ __noinline__ void split_role_a(const int prob, const double* __restri
 #pragma unroll 1
     for (int l = 0; l < 32; l++) cost += __shfl_sync(FULL, cst, l);
     req = warp_max(req);
-    if (!(req <= RES_EQ_MAX) && status == 0) status = 4;
+    if (!(req <= RES_EQ_MAX) && status == 0 && !defer) status = 4;      // defer: completion belongs to the caller (stepwise interface)
     if (k == 0) dec[DEC_STATUS] = (double)status;
     split_barrier();                                                 // F
     const int exit_code = (status == 0) ? 1 : (status == 1 ? 0 : status);
@@ -875,12 +875,13 @@ __device__ __noinline__ void split_role_a(const int prob, const double* __restri
     }
 #endif
     if (k == 0) {
-        pobj_g[prob] = cost; exit_g[prob] = exit_code; qps_g[prob] = qps; reseq_g[prob] = req;
+        pobj_g[prob] = cost; exit_g[prob] = exit_code; qps_g[prob] = qp_status_acados(qps); reseq_g[prob] = req;
         if (ipm_g) ipm_g[prob] = ipm_total;
     }
     if (mem) {
         if (status != 0) {                                           // Solver_acados_reset + reset_qp_memory (:187-191)
-            for (int i = k; i < mem_doubles; i += 32) mem[i] = 0.0;
+            if (!defer)
+                for (int i = k; i < mem_doubles; i += 32) mem[i] = 0.0;
         } else {
             double* m = mem + 1;
             if (k == 0) mem[0] = 2.0;
@@ -908,10 +909,11 @@ mpc_solve_split_kernel(int n, const double* __restrict__ xinit, const double* __
         __syncthreads();
         const int prob = s_prob;
         if (prob >= n) return;
-        const int nit = num_iter ? num_iter[prob] : num_iter_all;
+        const int nit_raw = num_iter ? num_iter[prob] : num_iter_all;
+        const int nit = nit_raw < 0 ? -nit_raw : nit_raw;      // < 0: completion deferred (see solve_problem)
         if (role == 0)
             split_role_a(prob, xinit, x0, params, nit, mem, mem_doubles, xtraj, utraj, pobj, exit_code, qp_status, res_eq, ipm_iters,
-                         s_split);
+                         s_split, nit_raw < 0);
         else if (role == 1)
             split_role_x(prob, nit, mem, mem_doubles, s_split);
         else

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -19,23 +20,68 @@ std::vector<const MpcConfigOps*>& registry()
 
 // K7: one thread per homotopy set -- FindBestPlanner (guidance_constraints.cpp:572-590) with the
 // objective post-processing of :373-420.  Sequential, ascending, strict '<': bit-exact by construction.
+// Consistency term (calculateConsistencyCostForSolver, :1025-1050) from the SOLVED trajectory: squares and sums are kept
+// unfused (__dmul_rn / __dadd_rn) and accumulated in stage order so that the value is the one plain C++ computes.
+struct ConsArgs {
+    const double* xtraj = nullptr;         // [n][N+1][nx] solver output
+    const double* prev = nullptr;          // [n_sets][N][2], nullptr: no consistency term
+    const unsigned char* enabled = nullptr;
+    double weight = 0.0;
+    int N = 0, nx = 0, ix = 0, iy = 1;
+    double* obj_out = nullptr;
+    double* cons_out = nullptr;
+};
 __global__ void select_best_kernel(int n_sets, const int* __restrict__ set_offsets, const double* __restrict__ pobj,
                                    const int* __restrict__ exit_code, const double* __restrict__ obj_scale,
                                    const double* __restrict__ obj_sub, const unsigned char* __restrict__ disabled,
-                                   int* __restrict__ best_idx)
+                                   int* __restrict__ best_idx, const ConsArgs ca)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_sets) return;
     double best = 1e10;
     int bi = -1;
     for (int i = set_offsets[s]; i < set_offsets[s + 1]; i++) {
-        if (disabled && disabled[i]) continue;
-        double obj = pobj[i];
+        double obj = pobj[i], cons = 0.0;
+        if (ca.prev && (!ca.enabled || ca.enabled[i])) {
+            const double* x = ca.xtraj + (size_t)i * (ca.N + 1) * ca.nx;
+            const double* pr = ca.prev + (size_t)s * ca.N * 2;
+            double sum = 0.0;
+            for (int k = 1; k <= ca.N - 2; k++) {
+                const double dx = x[k * ca.nx + ca.ix] - pr[2 * k], dy = x[k * ca.nx + ca.iy] - pr[2 * k + 1];
+                sum = __dadd_rn(sum, __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+            }
+            cons = __dmul_rn(ca.weight, sum);
+            obj = obj - cons;
+        }
         if (obj_sub) obj = obj - obj_sub[i];
-        if (obj_scale) obj = obj * obj_scale[i];
+        if (obj_scale) obj = __dmul_rn(obj, obj_scale[i]);
+        if (ca.obj_out) ca.obj_out[i] = obj;
+        if (ca.cons_out) ca.cons_out[i] = cons;
+        if (disabled && disabled[i]) continue;
         if (exit_code[i] == 1 && obj < best) { best = obj; bi = i - set_offsets[s]; }
     }
     best_idx[s] = bi;
+}
+// `*solver = *_solver` resets the QP memory of the planner's capsule and keeps the NLP multipliers
+// (acados_solver_interface.cpp:67-77): flag 2 -> 1 in the persistent memory blob.
+__global__ void mem_flag_downgrade_kernel(int n, int mem_doubles, double* __restrict__ mem)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && mem[(size_t)i * mem_doubles] > 1.0) mem[(size_t)i * mem_doubles] = 1.0;
+}
+
+// The selected planner's trajectory of every set (guidance_constraints.cpp:520-522 copies best_solver->_output into the main
+// solver); planner 0 of the set when none succeeded.  One CTA per set, coalesced.
+__global__ void gather_best_kernel(int n_sets, const int* __restrict__ set_offsets, const int* __restrict__ best_idx, int sx, int su,
+                                   const double* __restrict__ xtraj, const double* __restrict__ utraj, double* __restrict__ bx,
+                                   double* __restrict__ bu)
+{
+    const int s = blockIdx.x;
+    if (s >= n_sets) return;
+    const int b = best_idx[s];
+    const size_t src = (size_t)set_offsets[s] + (b >= 0 ? b : 0);
+    for (int i = threadIdx.x; i < sx; i += blockDim.x) bx[(size_t)s * sx + i] = xtraj[src * sx + i];
+    for (int i = threadIdx.x; i < su; i += blockDim.x) bu[(size_t)s * su + i] = utraj[src * su + i];
 }
 
 // Compact parameter path: params[prob][k][:] <- shared[set][k][:], then the per-planner
@@ -101,8 +147,13 @@ struct mpcgpu_engine {
     // device staging for the host-pointer entry points
     double *d_xinit = nullptr, *d_x0 = nullptr, *d_params = nullptr, *d_mem = nullptr, *d_xtraj = nullptr, *d_utraj = nullptr,
            *d_pobj = nullptr, *d_res_eq = nullptr, *d_scale = nullptr, *d_sub = nullptr;
-    int *d_num_iter = nullptr, *d_exit = nullptr, *d_qps = nullptr, *d_ipm = nullptr, *d_counter = nullptr, *d_counter2 = nullptr, *d_offsets = nullptr,
+    int *d_num_iter = nullptr, *d_exit = nullptr, *d_qps = nullptr, *d_ipm = nullptr, *d_counters = nullptr, *d_offsets = nullptr,
         *d_best = nullptr;
+    unsigned long long launch_seq = 0;   // every solve launch takes its own work counter from the ring d_counters[MPCGPU_MAX_INFLIGHT]
+    int* next_counter() { return d_counters + (launch_seq++ % MPCGPU_MAX_INFLIGHT); }
+    double *d_prev = nullptr, *d_objout = nullptr, *d_consout = nullptr, *d_static = nullptr;   // set options, allocated on first use
+    unsigned char* d_consen = nullptr;
+    size_t cap_prev = 0, cap_static = 0;
     unsigned char* d_disabled = nullptr;
     double *d_shared = nullptr, *d_pvals = nullptr, *d_xs = nullptr;   // compact (per-set) inputs, allocated on first use
     int* d_pidx = nullptr;
@@ -148,7 +199,7 @@ int mpcgpu_engine_create(const char* config_name, int device, int max_batch, mpc
     AL(e->d_xinit, B * nx * 8); AL(e->d_x0, B * nz * (N + 1) * 8); AL(e->d_params, B * N * ops->np * 8);
     AL(e->d_mem, B * ops->mem_doubles * 8); AL(e->d_xtraj, B * nx * (N + 1) * 8); AL(e->d_utraj, B * nu * N * 8);
     AL(e->d_pobj, B * 8); AL(e->d_res_eq, B * 8); AL(e->d_scale, B * 8); AL(e->d_sub, B * 8);
-    AL(e->d_num_iter, B * 4); AL(e->d_exit, B * 4); AL(e->d_qps, B * 4); AL(e->d_ipm, B * 4); AL(e->d_counter, 4); AL(e->d_counter2, 4);
+    AL(e->d_num_iter, B * 4); AL(e->d_exit, B * 4); AL(e->d_qps, B * 4); AL(e->d_ipm, B * 4); AL(e->d_counters, 4 * MPCGPU_MAX_INFLIGHT);
     AL(e->d_offsets, (B + 1) * 4); AL(e->d_best, B * 4); AL(e->d_disabled, B);
 #undef AL
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -164,6 +215,10 @@ int mpcgpu_engine_create(const char* config_name, int device, int max_batch, mpc
         e->err = "occupancy query failed";
         return fail(MPCGPU_ERR_CUDA);
     }
+    if (const char* ov = std::getenv("MPCGPU_CTAS_PER_SM")) {      // tuning knob (tools/sweep experiments): cap the resident CTAs per SM
+        const int c = std::atoi(ov);
+        if (c > 0 && c < ctas) ctas = c;
+    }
     e->grid = sms * ctas;   // persistent grid: every SM holds its full complement of CTAs
     e->sms = sms;
     e->threads_per_cta = threads;
@@ -176,7 +231,8 @@ int mpcgpu_engine_destroy(mpcgpu_engine* e)
     if (!e) return MPCGPU_ERR_ARG;
     cudaSetDevice(e->device);
     void* ptrs[] = {e->d_obst, e->d_shared, e->d_pvals, e->d_xs, e->d_pidx, e->d_xinit, e->d_x0, e->d_params, e->d_mem, e->d_xtraj, e->d_utraj, e->d_pobj, e->d_res_eq, e->d_scale,
-                    e->d_sub, e->d_num_iter, e->d_exit, e->d_qps, e->d_ipm, e->d_counter, e->d_counter2, e->d_offsets, e->d_best, e->d_disabled};
+                    e->d_sub, e->d_num_iter, e->d_exit, e->d_qps, e->d_ipm, e->d_counters, e->d_offsets, e->d_best, e->d_disabled,
+                    e->d_prev, e->d_objout, e->d_consout, e->d_static, e->d_consen};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (e->ev0) cudaEventDestroy(e->ev0);
@@ -214,7 +270,7 @@ int mpcgpu_solve_batch_device(mpcgpu_engine* e, int n, const double* xinit, cons
     CK(cudaSetDevice(e->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
     e->chunks_timed = 0;
-    return launch_solve_on(e, st, e->d_counter, e->ev0, e->ev1, n, xinit, x0, params, num_iter, num_iter_all, mem_inout, xtraj, utraj,
+    return launch_solve_on(e, st, e->next_counter(), e->ev0, e->ev1, n, xinit, x0, params, num_iter, num_iter_all, mem_inout, xtraj, utraj,
                            pobj, exit_code, qp_status, res_eq, ipm_iters);
 }
 
@@ -246,10 +302,33 @@ int mpcgpu_sync(mpcgpu_engine* e)
     CK(cudaSetDevice(e->device));
     CK(cudaStreamSynchronize(e->stream));
     CK(cudaStreamSynchronize(e->stream2));
+    CK(cudaEventSynchronize(e->ev1));      // recorded behind the most recent device call, whatever stream it went to
     return MPCGPU_OK;
 }
 
+// drain both engine streams before an error return: earlier asynchronous copies may still touch the caller's host buffers
+static int drain(mpcgpu_engine* e, int rc)
+{
+    if (rc != MPCGPU_OK) { cudaStreamSynchronize(e->stream); cudaStreamSynchronize(e->stream2); }
+    return rc;
+}
+static int solve_batch_impl(mpcgpu_engine* e, int n, const double* xinit, const double* x0, const double* params,
+                            const int* num_iter, int num_iter_all, double* mem_inout, double* xtraj, double* utraj, double* pobj,
+                            int* exit_code, int* qp_status, double* res_eq, int* ipm_iters);
+
 int mpcgpu_solve_batch(mpcgpu_engine* e, int n, const double* xinit, const double* x0, const double* params,
+                       const int* num_iter, int num_iter_all, double* mem_inout, double* xtraj, double* utraj, double* pobj,
+                       int* exit_code, int* qp_status, double* res_eq, int* ipm_iters)
+{
+    if (!e || n < 0 || n > e->max_batch || !xinit || !x0 || !params || !xtraj || !utraj || !pobj || !exit_code ||
+        !qp_status || !res_eq)
+        return MPCGPU_ERR_ARG;
+    if (n == 0) return MPCGPU_OK;
+    return drain(e, solve_batch_impl(e, n, xinit, x0, params, num_iter, num_iter_all, mem_inout, xtraj, utraj, pobj, exit_code, qp_status,
+                                     res_eq, ipm_iters));
+}
+
+static int solve_batch_impl(mpcgpu_engine* e, int n, const double* xinit, const double* x0, const double* params,
                        const int* num_iter, int num_iter_all, double* mem_inout, double* xtraj, double* utraj, double* pobj,
                        int* exit_code, int* qp_status, double* res_eq, int* ipm_iters)
 {
@@ -292,7 +371,7 @@ int mpcgpu_solve_batch(mpcgpu_engine* e, int n, const double* xinit, const doubl
         if (b0 >= B || bounds[c + 1] <= b0) { nchunk = c; break; }
         const size_t m = bounds[c + 1] - b0;
         cudaStream_t st = (c & 1) ? e->stream2 : e->stream;
-        int* counter = (c & 1) ? e->d_counter2 : e->d_counter;
+        int* counter = e->next_counter();
         CK(cudaMemcpyAsync(e->d_xinit + b0 * nx, xinit + b0 * nx, m * nx * 8, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(e->d_x0 + b0 * sx0, x0 + b0 * sx0, m * sx0 * 8, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(e->d_params + b0 * spar, params + b0 * spar, m * spar * 8, cudaMemcpyHostToDevice, st));
@@ -327,7 +406,7 @@ int mpcgpu_select_best_device(mpcgpu_engine* e, int n_sets, const int* set_offse
     CK(cudaSetDevice(e->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
     select_best_kernel<<<(n_sets + 127) / 128, 128, 0, st>>>(n_sets, set_offsets, pobj, exit_code, obj_scale, obj_sub, disabled,
-                                                              best_idx);
+                                                              best_idx, ConsArgs());
     CK(cudaGetLastError());
     e->launches += 1;
     return MPCGPU_OK;
@@ -349,7 +428,7 @@ __device__ __forceinline__ void dr_proj_dev(const double* p, const double* c, do
 __global__ void guidance_halfspaces_kernel(int n, int planners, int N, int nx, int nu, int npar, int lin_base, int lin_count, int n_obs, int obs,
                                            const double* __restrict__ xinit_sets, const double* __restrict__ x0,
                                            const double* __restrict__ obst_pred, const unsigned char* __restrict__ guided,
-                                           double robot_radius, double* __restrict__ params)
+                                           double robot_radius, const double* __restrict__ stat, int n_static, double* __restrict__ params)
 {
     const long long total = (long long)n * N;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
@@ -384,24 +463,33 @@ __global__ void guidance_halfspaces_kernel(int n, int planners, int N, int nx, i
             }
             P[3 * j] = a1; P[3 * j + 1] = a2; P[3 * j + 2] = b;
         }
+        // module_data.static_obstacles (linearized_constraints.cpp:107-127): behind the obstacle rows; a non-guided planner's
+        // obstacle list is empty (update(state, empty_data_, ...), guidance_constraints.cpp:326-329), so its rows start at 0
+        if (stat && k > 0) {
+            const int first = guided[q] ? n_obs : 0;
+            const double* sh = stat + ((size_t)s * N + k) * n_static * 3;
+            for (int h = 0; h < n_static && first + h < lin_count; h++) {
+                P[3 * (first + h)] = sh[3 * h]; P[3 * (first + h) + 1] = sh[3 * h + 1]; P[3 * (first + h) + 2] = sh[3 * h + 2];
+            }
+        }
     }
 }
 
 static int guidance_halfspaces_launch(mpcgpu_engine* e, int n_sets, int planners, const double* xinit_sets, const double* x0,
                                       const double* obst_pred, int n_obs, int ob_stride, const unsigned char* guided, int lin_base,
-                                      int lin_count, double robot_radius, double* params, void* stream);
+                                      int lin_count, double robot_radius, const double* stat, int n_static, double* params, void* stream);
 
 int mpcgpu_guidance_halfspaces_device(mpcgpu_engine* e, int n_sets, int planners, const double* xinit_sets, const double* x0,
                                       const double* obst_pred, int n_obs, const unsigned char* guided, int lin_base, int lin_count,
                                       double robot_radius, double* params, void* stream)
 {
-    return guidance_halfspaces_launch(e, n_sets, planners, xinit_sets, x0, obst_pred, n_obs, 2, guided, lin_base, lin_count, robot_radius, params,
-                                      stream);
+    return guidance_halfspaces_launch(e, n_sets, planners, xinit_sets, x0, obst_pred, n_obs, 2, guided, lin_base, lin_count, robot_radius, nullptr, 0,
+                                      params, stream);
 }
 
 static int guidance_halfspaces_launch(mpcgpu_engine* e, int n_sets, int planners, const double* xinit_sets, const double* x0,
                                       const double* obst_pred, int n_obs, int ob_stride, const unsigned char* guided, int lin_base,
-                                      int lin_count, double robot_radius, double* params, void* stream)
+                                      int lin_count, double robot_radius, const double* stat, int n_static, double* params, void* stream)
 {
     if (!e || n_sets < 0 || planners <= 0 || !xinit_sets || !x0 || (n_obs > 0 && !obst_pred) || n_obs < 0 || !guided || !params || lin_count < 0 ||
         lin_base < 0 || lin_base + 3 * lin_count > e->ops->np)
@@ -414,7 +502,7 @@ static int guidance_halfspaces_launch(mpcgpu_engine* e, int n_sets, int planners
     const long long total = n * o->N;
     const int blocks = (int)((total + 127) / 128 < 148 * 16 ? (total + 127) / 128 : 148 * 16);
     guidance_halfspaces_kernel<<<blocks, 128, 0, st>>>((int)n, planners, o->N, o->nx, o->nu, o->np, lin_base, lin_count, n_obs, ob_stride, xinit_sets, x0,
-                                                        obst_pred, guided, robot_radius, params);
+                                                        obst_pred, guided, robot_radius, stat, n_static, params);
     CK(cudaGetLastError());
     e->launches += 1;
     return MPCGPU_OK;
@@ -432,17 +520,19 @@ static int solve_sets_impl(mpcgpu_engine* e, int n_sets, int planners, const dou
                            const double* x0, int nidx, const int* param_idx, const double* planner_params, const GuidedArgs* ga,
                            const int* num_iter, int num_iter_all, double* xtraj, double* utraj, double* pobj, int* exit_code,
                            int* qp_status, double* res_eq, const double* obj_scale, const double* obj_sub, const unsigned char* disabled,
-                           int* best_idx);
+                           int* best_idx, const mpcgpu_set_options* opt);
 extern "C" int mpcgpu_pack_obstacles_device(mpcgpu_engine* e, int n_sets, const double* xinit_sets, const double* table, int M, int ell_base,
                                             int ell_stride, const int* ell_offsets, double* params, void* stream);
 
 int mpcgpu_solve_sets(mpcgpu_engine* e, int n_sets, int planners, const double* xinit_sets, const double* shared_params,
                       const double* x0, int nidx, const int* param_idx, const double* planner_params, const int* num_iter,
                       int num_iter_all, double* xtraj, double* utraj, double* pobj, int* exit_code, int* qp_status, double* res_eq,
-                      const double* obj_scale, const double* obj_sub, const unsigned char* disabled, int* best_idx)
+                      const double* obj_scale, const double* obj_sub, const unsigned char* disabled, int* best_idx,
+                      const mpcgpu_set_options* opt)
 {
-    return solve_sets_impl(e, n_sets, planners, xinit_sets, shared_params, x0, nidx, param_idx, planner_params, nullptr, num_iter,
-                           num_iter_all, xtraj, utraj, pobj, exit_code, qp_status, res_eq, obj_scale, obj_sub, disabled, best_idx);
+    if (!e) return MPCGPU_ERR_ARG;
+    return drain(e, solve_sets_impl(e, n_sets, planners, xinit_sets, shared_params, x0, nidx, param_idx, planner_params, nullptr, num_iter,
+                                    num_iter_all, xtraj, utraj, pobj, exit_code, qp_status, res_eq, obj_scale, obj_sub, disabled, best_idx, opt));
 }
 
 int mpcgpu_solve_sets_guided(mpcgpu_engine* e, int n_sets, int planners, const double* xinit_sets, const double* shared_params,
@@ -450,24 +540,26 @@ int mpcgpu_solve_sets_guided(mpcgpu_engine* e, int n_sets, int planners, const d
                              int lin_count, double robot_radius, int nidx, const int* param_idx, const double* planner_params,
                              const int* num_iter, int num_iter_all, double* xtraj, double* utraj, double* pobj, int* exit_code,
                              int* qp_status, double* res_eq, const double* obj_scale, const double* obj_sub,
-                             const unsigned char* disabled, int* best_idx)
+                             const unsigned char* disabled, int* best_idx, const mpcgpu_set_options* opt)
 {
     if (!e || n_obs < 0 || (n_obs > 0 && !obst_pred) || !guided || lin_base < 0 || lin_count < 0 || lin_base + 3 * lin_count > e->ops->np)
         return MPCGPU_ERR_ARG;
     const GuidedArgs ga = {n_obs, lin_base, lin_count, obst_pred, guided, robot_radius};
-    return solve_sets_impl(e, n_sets, planners, xinit_sets, shared_params, x0, nidx, param_idx, planner_params, &ga, num_iter, num_iter_all,
-                           xtraj, utraj, pobj, exit_code, qp_status, res_eq, obj_scale, obj_sub, disabled, best_idx);
+    return drain(e, solve_sets_impl(e, n_sets, planners, xinit_sets, shared_params, x0, nidx, param_idx, planner_params, &ga, num_iter, num_iter_all,
+                                    xtraj, utraj, pobj, exit_code, qp_status, res_eq, obj_scale, obj_sub, disabled, best_idx, opt));
 }
 
 static int solve_sets_impl(mpcgpu_engine* e, int n_sets, int planners, const double* xinit_sets, const double* shared_params,
                            const double* x0, int nidx, const int* param_idx, const double* planner_params, const GuidedArgs* ga,
                            const int* num_iter, int num_iter_all, double* xtraj, double* utraj, double* pobj, int* exit_code,
                            int* qp_status, double* res_eq, const double* obj_scale, const double* obj_sub, const unsigned char* disabled,
-                           int* best_idx)
+                           int* best_idx, const mpcgpu_set_options* opt)
 {
     if (!e || n_sets < 0 || planners <= 0 || !xinit_sets || !shared_params || !x0 || nidx < 0 || (nidx > 0 && (!param_idx || !planner_params)) ||
-        !xtraj || !utraj || !pobj || !exit_code || !qp_status || !res_eq || !best_idx)
+        !pobj || !exit_code || !qp_status || !res_eq || !best_idx)
         return MPCGPU_ERR_ARG;
+    // per-planner trajectories are optional when the selected trajectory of every set is asked for instead
+    if ((!xtraj || !utraj) && !(opt && opt->best_xtraj && opt->best_utraj)) return MPCGPU_ERR_ARG;
     const long long nll = (long long)n_sets * planners;
     if (nll > e->max_batch) return MPCGPU_ERR_ARG;
     const int n = (int)nll;
@@ -494,6 +586,33 @@ static int solve_sets_impl(mpcgpu_engine* e, int n_sets, int planners, const dou
         e->cap_pvals = need_pv;
     }
     if (!e->d_pidx) CK(cudaMalloc((void**)&e->d_pidx, (size_t)np * 4));
+    // optional arguments (include/mpcgpu.h: mpcgpu_set_options)
+    const bool cons = opt && opt->prev_traj;
+    const bool want_obj = opt && (opt->objective_out || opt->consistency_cost_out);
+    double* mem_host = opt ? opt->mem_inout : nullptr;
+    const int n_static = (opt && opt->static_halfspaces && ga) ? opt->n_static : 0;
+    if (opt && (opt->n_static < 0 || (cons && (opt->ix < 0 || opt->ix >= nx || opt->iy < 0 || opt->iy >= nx)))) return MPCGPU_ERR_ARG;
+    if (cons || want_obj) {
+        if ((size_t)n_sets * N * 2 > e->cap_prev || !e->d_objout) {
+            for (void* q : {(void*)e->d_prev, (void*)e->d_objout, (void*)e->d_consout, (void*)e->d_consen})
+                if (q) cudaFree(q);
+            e->d_prev = e->d_objout = e->d_consout = nullptr; e->d_consen = nullptr; e->cap_prev = 0;
+            const size_t sets_cap = (size_t)(e->max_batch / planners + 1);
+            CK(cudaMalloc((void**)&e->d_prev, (sets_cap > (size_t)n_sets ? sets_cap : (size_t)n_sets) * N * 2 * 8));
+            CK(cudaMalloc((void**)&e->d_objout, (size_t)e->max_batch * 8));
+            CK(cudaMalloc((void**)&e->d_consout, (size_t)e->max_batch * 8));
+            CK(cudaMalloc((void**)&e->d_consen, (size_t)e->max_batch));
+            e->cap_prev = (sets_cap > (size_t)n_sets ? sets_cap : (size_t)n_sets) * N * 2;
+        }
+    }
+    const size_t st_per_set = (size_t)N * n_static * 3;
+    if (n_static > 0 && (size_t)n_sets * st_per_set > e->cap_static) {
+        if (e->d_static) cudaFree(e->d_static);
+        e->d_static = nullptr; e->cap_static = 0;
+        CK(cudaMalloc((void**)&e->d_static, (size_t)n_sets * st_per_set * 8));
+        e->cap_static = (size_t)n_sets * st_per_set;
+    }
+    const size_t smem_ = (size_t)o->mem_doubles;
     const size_t ob_per_set = ga ? (size_t)N * ga->n_obs * ga->ob_stride : 0;       // doubles
     unsigned char* d_guided = nullptr;
     if (ga) {      // obstacle predictions / tables + guided flags of the device-side constraint construction
@@ -544,7 +663,7 @@ static int solve_sets_impl(mpcgpu_engine* e, int n_sets, int planners, const dou
         if (ns <= 0) { nchunk = c; break; }
         const size_t p0 = (size_t)s0 * planners, m = (size_t)ns * planners;          // first problem, problems
         cudaStream_t cs = (c & 1) ? e->stream2 : e->stream;
-        int* counter = (c & 1) ? e->d_counter2 : e->d_counter;
+        int* counter = e->next_counter();
         double* d_xs = e->d_xs + (size_t)s0 * nx;
         double* d_sh = e->d_shared + (size_t)s0 * N * np;
         CK(cudaMemcpyAsync(d_xs, xinit_sets + (size_t)s0 * nx, (size_t)ns * nx * 8, cudaMemcpyHostToDevice, cs));
@@ -553,6 +672,18 @@ static int solve_sets_impl(mpcgpu_engine* e, int n_sets, int planners, const dou
         if (nidx > 0)
             CK(cudaMemcpyAsync(e->d_pvals + p0 * N * nidx, planner_params + p0 * N * nidx, m * N * nidx * 8, cudaMemcpyHostToDevice, cs));
         if (num_iter) CK(cudaMemcpyAsync(e->d_num_iter + p0, num_iter + p0, m * 4, cudaMemcpyHostToDevice, cs));
+        if (mem_host) {      // the planners' persistent capsules; `*solver = *_solver` keeps the multipliers, resets the QP memory
+            CK(cudaMemcpyAsync(e->d_mem + p0 * smem_, mem_host + p0 * smem_, m * smem_ * 8, cudaMemcpyHostToDevice, cs));
+            mem_flag_downgrade_kernel<<<(int)((m + 127) / 128), 128, 0, cs>>>((int)m, (int)smem_, e->d_mem + p0 * smem_);
+            e->launches += 1;
+        }
+        if (cons) {
+            CK(cudaMemcpyAsync(e->d_prev + (size_t)s0 * N * 2, opt->prev_traj + (size_t)s0 * N * 2, (size_t)ns * N * 2 * 8, cudaMemcpyHostToDevice, cs));
+            if (opt->consistency_enabled) CK(cudaMemcpyAsync(e->d_consen + p0, opt->consistency_enabled + p0, m, cudaMemcpyHostToDevice, cs));
+        }
+        if (n_static > 0)
+            CK(cudaMemcpyAsync(e->d_static + (size_t)s0 * st_per_set, opt->static_halfspaces + (size_t)s0 * st_per_set, (size_t)ns * st_per_set * 8,
+                               cudaMemcpyHostToDevice, cs));
         const double* d_ob = nullptr;
         if (ga) {
             d_ob = (const double*)e->d_obst + (size_t)s0 * ob_per_set;
@@ -571,11 +702,13 @@ static int solve_sets_impl(mpcgpu_engine* e, int n_sets, int planners, const dou
         e->launches += (nidx > 0) ? 3 : 2;
         if (ga) {      // guidance halfspaces built on the device from the obstacle predictions and the warm starts
             int rc_ = guidance_halfspaces_launch(e, ns, planners, d_xs, e->d_x0 + p0 * nz * (N + 1), d_ob, ga->n_obs, ga->ob_stride, d_guided + p0,
-                                                 ga->lin_base, ga->lin_count, ga->robot_radius, d_par, cs);
+                                                 ga->lin_base, ga->lin_count, ga->robot_radius,
+                                                 n_static > 0 ? e->d_static + (size_t)s0 * st_per_set : nullptr, n_static, d_par, cs);
             if (rc_ != MPCGPU_OK) return rc_;
         }
         int rc = launch_solve_on(e, cs, counter, e->cev0[c], e->cev1[c], (int)m, e->d_xinit + p0 * nx, e->d_x0 + p0 * nz * (N + 1), d_par,
-                                 num_iter ? e->d_num_iter + p0 : nullptr, num_iter_all, nullptr, e->d_xtraj + p0 * nx * (N + 1),
+                                 num_iter ? e->d_num_iter + p0 : nullptr, num_iter_all, mem_host ? e->d_mem + p0 * smem_ : nullptr,
+                                 e->d_xtraj + p0 * nx * (N + 1),
                                  e->d_utraj + p0 * nu * N, e->d_pobj + p0, e->d_exit + p0, e->d_qps + p0, e->d_res_eq + p0, e->d_ipm + p0);
         if (rc != MPCGPU_OK) return rc;
         // selection on the device, then everything back
@@ -583,11 +716,34 @@ static int solve_sets_impl(mpcgpu_engine* e, int n_sets, int planners, const dou
         if (obj_sub) CK(cudaMemcpyAsync(e->d_sub + p0, obj_sub + p0, m * 8, cudaMemcpyHostToDevice, cs));
         if (disabled) CK(cudaMemcpyAsync(e->d_disabled + p0, disabled + p0, m, cudaMemcpyHostToDevice, cs));
         // set offsets are absolute problem indices: the chunk passes the offset table from s0 on with the full arrays
-        rc = mpcgpu_select_best_device(e, ns, e->d_offsets + s0, e->d_pobj, e->d_exit, obj_scale ? e->d_scale : nullptr,
-                                       obj_sub ? e->d_sub : nullptr, disabled ? e->d_disabled : nullptr, e->d_best + s0, cs);
-        if (rc != MPCGPU_OK) return rc;
-        CK(cudaMemcpyAsync(xtraj + p0 * nx * (N + 1), e->d_xtraj + p0 * nx * (N + 1), m * nx * (N + 1) * 8, cudaMemcpyDeviceToHost, cs));
-        CK(cudaMemcpyAsync(utraj + p0 * nu * N, e->d_utraj + p0 * nu * N, m * nu * N * 8, cudaMemcpyDeviceToHost, cs));
+        {
+            ConsArgs ca;
+            ca.xtraj = e->d_xtraj; ca.N = N; ca.nx = nx;
+            if (cons) {
+                ca.prev = e->d_prev + (size_t)s0 * N * 2; ca.enabled = opt->consistency_enabled ? e->d_consen : nullptr;
+                ca.weight = opt->consistency_weight; ca.ix = opt->ix; ca.iy = opt->iy;
+            }
+            if (want_obj) { ca.obj_out = e->d_objout; ca.cons_out = e->d_consout; }
+            select_best_kernel<<<(ns + 127) / 128, 128, 0, cs>>>(ns, e->d_offsets + s0, e->d_pobj, e->d_exit, obj_scale ? e->d_scale : nullptr,
+                                                                  obj_sub ? e->d_sub : nullptr, disabled ? e->d_disabled : nullptr, e->d_best + s0, ca);
+            CK(cudaGetLastError());
+            e->launches += 1;
+        }
+        if (opt && opt->objective_out) CK(cudaMemcpyAsync(opt->objective_out + p0, e->d_objout + p0, m * 8, cudaMemcpyDeviceToHost, cs));
+        if (opt && opt->consistency_cost_out) CK(cudaMemcpyAsync(opt->consistency_cost_out + p0, e->d_consout + p0, m * 8, cudaMemcpyDeviceToHost, cs));
+        if (mem_host) CK(cudaMemcpyAsync(mem_host + p0 * smem_, e->d_mem + p0 * smem_, m * smem_ * 8, cudaMemcpyDeviceToHost, cs));
+        if (xtraj) CK(cudaMemcpyAsync(xtraj + p0 * nx * (N + 1), e->d_xtraj + p0 * nx * (N + 1), m * nx * (N + 1) * 8, cudaMemcpyDeviceToHost, cs));
+        if (utraj) CK(cudaMemcpyAsync(utraj + p0 * nu * N, e->d_utraj + p0 * nu * N, m * nu * N * 8, cudaMemcpyDeviceToHost, cs));
+        if (opt && opt->best_xtraj && opt->best_utraj) {
+            // the input staging of this chunk is free once its solve has run: the per-set trajectories are gathered into it
+            double* bx = e->d_x0 + p0 * nz * (N + 1);
+            double* bu = bx + (size_t)ns * nx * (N + 1);
+            gather_best_kernel<<<ns, 128, 0, cs>>>(ns, e->d_offsets + s0, e->d_best + s0, nx * (N + 1), nu * N, e->d_xtraj, e->d_utraj, bx, bu);
+            CK(cudaGetLastError());
+            e->launches += 1;
+            CK(cudaMemcpyAsync(opt->best_xtraj + (size_t)s0 * nx * (N + 1), bx, (size_t)ns * nx * (N + 1) * 8, cudaMemcpyDeviceToHost, cs));
+            CK(cudaMemcpyAsync(opt->best_utraj + (size_t)s0 * nu * N, bu, (size_t)ns * nu * N * 8, cudaMemcpyDeviceToHost, cs));
+        }
         CK(cudaMemcpyAsync(pobj + p0, e->d_pobj + p0, m * 8, cudaMemcpyDeviceToHost, cs));
         CK(cudaMemcpyAsync(exit_code + p0, e->d_exit + p0, m * 4, cudaMemcpyDeviceToHost, cs));
         CK(cudaMemcpyAsync(qp_status + p0, e->d_qps + p0, m * 4, cudaMemcpyDeviceToHost, cs));
@@ -678,6 +834,14 @@ int mpcgpu_measure_fp64_peak(int device, double* tflops)
     *tflops = best;
     return MPCGPU_OK;
 }
+
+int mpcgpu_alloc_pinned(size_t bytes, void** out)
+{
+    if (!out || bytes == 0) return MPCGPU_ERR_ARG;
+    *out = nullptr;
+    return cudaHostAlloc(out, bytes, cudaHostAllocPortable) == cudaSuccess ? MPCGPU_OK : MPCGPU_ERR_CUDA;
+}
+int mpcgpu_free_pinned(void* p) { return (!p || cudaFreeHost(p) == cudaSuccess) ? MPCGPU_OK : MPCGPU_ERR_CUDA; }
 
 int mpcgpu_set_kernel_mode(mpcgpu_engine* e, int mode)
 {

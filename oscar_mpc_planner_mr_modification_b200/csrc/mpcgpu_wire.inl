@@ -202,7 +202,8 @@ int mpcgpu_solve_sets_tracks(mpcgpu_engine* e, int n_sets, int planners, const d
                              const double* x0, int M, const double* table, const unsigned char* guided, int lin_base, int lin_count,
                              double robot_radius, int ell_base, int ell_stride, const int* ell_offsets, const int* num_iter,
                              int num_iter_all, double* xtraj, double* utraj, double* pobj, int* exit_code, int* qp_status, double* res_eq,
-                             const double* obj_scale, const double* obj_sub, const unsigned char* disabled, int* best_idx)
+                             const double* obj_scale, const double* obj_sub, const unsigned char* disabled, int* best_idx,
+                             const mpcgpu_set_options* opt)
 {
     if (!e || M < 0 || (M > 0 && !table) || !guided || !ell_offsets || lin_base < 0 || lin_count < 0 || lin_base + 3 * lin_count > e->ops->np ||
         ell_base < 0 || ell_stride <= 0 || (M > 0 && ell_base + M * ell_stride > e->ops->np))
@@ -213,8 +214,8 @@ int mpcgpu_solve_sets_tracks(mpcgpu_engine* e, int n_sets, int planners, const d
     ga.ob_stride = 4;
     ga.ell_base = ell_base; ga.ell_stride = ell_stride;
     for (int i = 0; i < 7; i++) ga.ell_off[i] = ell_offsets[i];
-    return solve_sets_impl(e, n_sets, planners, xinit_sets, shared_params, x0, 0, nullptr, nullptr, &ga, num_iter, num_iter_all, xtraj, utraj,
-                           pobj, exit_code, qp_status, res_eq, obj_scale, obj_sub, disabled, best_idx);
+    return drain(e, solve_sets_impl(e, n_sets, planners, xinit_sets, shared_params, x0, 0, nullptr, nullptr, &ga, num_iter, num_iter_all, xtraj, utraj,
+                                    pobj, exit_code, qp_status, res_eq, obj_scale, obj_sub, disabled, best_idx, opt));
 }
 
 long mpcgpu_wire_serialize_metrics(const mpcgpu_metrics* m, unsigned char* buf, size_t cap)

@@ -15,11 +15,21 @@ _lib = None
 SYMBOLS = [
     "mpcgpu_num_configs", "mpcgpu_config_name", "mpcgpu_engine_create", "mpcgpu_engine_destroy", "mpcgpu_desc_query",
     "mpcgpu_mem_doubles", "mpcgpu_solve_batch", "mpcgpu_solve_batch_device", "mpcgpu_sync", "mpcgpu_solve_sets", "mpcgpu_select_best",
+    "mpcgpu_alloc_pinned", "mpcgpu_free_pinned", "mpcgpu_multi_create", "mpcgpu_multi_destroy", "mpcgpu_multi_num_devices", "mpcgpu_multi_engine",
+    "mpcgpu_multi_shard_range", "mpcgpu_multi_solve_sets", "mpcgpu_multi_solve_sets_guided", "mpcgpu_multi_solve_batch", "mpcgpu_multi_last_kernel_ms",
     "mpcgpu_select_best_device", "mpcgpu_model_eval_doubles", "mpcgpu_model_eval", "mpcgpu_measure_fp64_peak", "mpcgpu_launch_count", "mpcgpu_last_kernel_ms", "mpcgpu_last_error", "mpcgpu_set_kernel_mode", "mpcgpu_guidance_halfspaces_device", "mpcgpu_solve_sets_guided",
 ]
 
 
 KERNEL_AUTO, KERNEL_STAGE, KERNEL_SPLIT = 0, 1, 2      # mpcgpu_set_kernel_mode (include/mpcgpu.h)
+
+
+class SetOptions(ctypes.Structure):
+    """struct mpcgpu_set_options (include/mpcgpu.h): optional arguments of the homotopy-set entries"""
+    _fields_ = [("consistency_weight", ctypes.c_double), ("prev_traj", ctypes.c_void_p), ("consistency_enabled", ctypes.c_void_p),
+                ("ix", ctypes.c_int), ("iy", ctypes.c_int), ("mem_inout", ctypes.c_void_p), ("objective_out", ctypes.c_void_p),
+                ("consistency_cost_out", ctypes.c_void_p), ("static_halfspaces", ctypes.c_void_p), ("n_static", ctypes.c_int),
+                ("best_xtraj", ctypes.c_void_p), ("best_utraj", ctypes.c_void_p)]
 
 
 def load_library():
@@ -162,21 +172,62 @@ class Engine:
                                                 _ptr(qp_status), _ptr(res_eq), _ptr(ipm_iters), _ptr(stream))
         self._check(rc, "mpcgpu_solve_batch_device")
 
-    def solve_sets(self, n_sets, planners, xinit_sets, shared_params, x0, param_idx, planner_params, num_iter=10, out=None):
+    def _set_options(self, out, n, prev_traj=None, cons_weight=0.0, cons_enabled=None, mem=None, static_halfspaces=None, n_sets=None,
+                     best_only=False):
+        """(ctypes pointer or None, keep-alive list) for struct mpcgpu_set_options; adds out["objective"], out["consistency_cost"]
+        and, with best_only, out["best_xtraj"] / out["best_utraj"] (the per-planner trajectories then stay on the device)"""
+        if prev_traj is None and mem is None and static_halfspaces is None and not best_only:
+            return None, []
+        keep = []
+        o = SetOptions()
+        o.consistency_weight = float(cons_weight)
+        o.ix, o.iy = self.model_map["x"][1] - self.nu, self.model_map["y"][1] - self.nu
+        if prev_traj is not None:
+            pv = np.ascontiguousarray(prev_traj, np.float64); keep.append(pv)
+            o.prev_traj = pv.ctypes.data
+            if cons_enabled is not None:
+                en = np.ascontiguousarray(cons_enabled, np.uint8); keep.append(en)
+                assert en.size == n
+                o.consistency_enabled = en.ctypes.data
+        out["objective"] = np.zeros(n); out["consistency_cost"] = np.zeros(n)
+        o.objective_out = out["objective"].ctypes.data
+        o.consistency_cost_out = out["consistency_cost"].ctypes.data
+        if mem is not None:
+            assert mem.dtype == np.float64 and mem.size == n * self.mem_doubles and mem.flags["C_CONTIGUOUS"]
+            o.mem_inout = mem.ctypes.data
+        if static_halfspaces is not None:
+            st = np.ascontiguousarray(static_halfspaces, np.float64); keep.append(st)
+            o.static_halfspaces = st.ctypes.data
+            o.n_static = int(st.shape[2])
+        if best_only:
+            out["best_xtraj"] = np.zeros((n_sets, self.nx * (self.N + 1))); out["best_utraj"] = np.zeros((n_sets, self.nu * self.N))
+            o.best_xtraj = out["best_xtraj"].ctypes.data
+            o.best_utraj = out["best_utraj"].ctypes.data
+        keep.append(o)
+        return ctypes.byref(o), keep
+
+    def solve_sets(self, n_sets, planners, xinit_sets, shared_params, x0, param_idx, planner_params, num_iter=10, out=None,
+                   obj_scale=None, disabled=None, **opts):
         """Compact homotopy-set entry: shared parameter block per set + per-planner overrides; returns the
-        per-problem outputs and `best` (selected planner per set)."""
+        per-problem outputs and `best` (selected planner per set).  opts: prev_traj, cons_weight, cons_enabled, mem
+        (struct mpcgpu_set_options)."""
         n = n_sets * planners
         if out is None:
             out = self.alloc_outputs(n)
             out["best"] = np.zeros(n_sets, np.int32)
+        opt, _keep = self._set_options(out, n, n_sets=n_sets, **opts)
+        best_only = bool(opts.get("best_only"))
+        sc = None if obj_scale is None else np.ascontiguousarray(obj_scale, np.float64)
+        ds = None if disabled is None else np.ascontiguousarray(disabled, np.uint8)
         idx = np.ascontiguousarray(param_idx, np.int32)
         vp = ctypes.c_void_p
-        self.lib.mpcgpu_solve_sets.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, ctypes.c_int, vp, vp, vp, ctypes.c_int] + [vp] * 10
+        self.lib.mpcgpu_solve_sets.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, ctypes.c_int, vp, vp, vp, ctypes.c_int] + [vp] * 11
         xs, sh, x0_, pv = (np.ascontiguousarray(a, np.float64) for a in (xinit_sets, shared_params, x0, planner_params))
         assert sh.size == n_sets * self.N * self.npar and x0_.size == n * self.nz * (self.N + 1) and pv.size == n * self.N * idx.size
         rc = self.lib.mpcgpu_solve_sets(self.handle, n_sets, planners, _ptr(xs), _ptr(sh), _ptr(x0_), int(idx.size), _ptr(idx), _ptr(pv), None,
-                                        int(num_iter), _ptr(out["xtraj"]), _ptr(out["utraj"]), _ptr(out["pobj"]), _ptr(out["exit_code"]),
-                                        _ptr(out["qp_status"]), _ptr(out["res_eq"]), None, None, None, _ptr(out["best"]))
+                                        int(num_iter), None if best_only else _ptr(out["xtraj"]), None if best_only else _ptr(out["utraj"]),
+                                        _ptr(out["pobj"]), _ptr(out["exit_code"]),
+                                        _ptr(out["qp_status"]), _ptr(out["res_eq"]), _ptr(sc), None, _ptr(ds), _ptr(out["best"]), opt)
         self._check(rc, "mpcgpu_solve_sets")
         return out
 
@@ -194,12 +245,17 @@ class Engine:
         return base, cnt
 
     def solve_sets_guided(self, n_sets, planners, xinit_sets, shared_params, x0, obst_pred, guided, robot_radius, num_iter=10,
-                          param_idx=None, planner_params=None, out=None):
-        """mpcgpu_solve_sets_guided: halfspaces from obstacle predictions + warm starts, built on the device."""
+                          param_idx=None, planner_params=None, out=None, obj_scale=None, disabled=None, **opts):
+        """mpcgpu_solve_sets_guided: halfspaces from obstacle predictions + warm starts, built on the device.
+        opts: prev_traj, cons_weight, cons_enabled, mem, static_halfspaces (struct mpcgpu_set_options)."""
         n = n_sets * planners
         if out is None:
             out = self.alloc_outputs(n)
             out["best"] = np.zeros(n_sets, np.int32)
+        opt, _keep = self._set_options(out, n, n_sets=n_sets, **opts)
+        best_only = bool(opts.get("best_only"))
+        sc = None if obj_scale is None else np.ascontiguousarray(obj_scale, np.float64)
+        ds = None if disabled is None else np.ascontiguousarray(disabled, np.uint8)
         lin_base, lin_count = self.lin_constraint_block()
         obst_pred = np.ascontiguousarray(obst_pred, np.float64)
         n_obs = obst_pred.shape[2] if obst_pred.ndim == 4 else 0
@@ -209,13 +265,13 @@ class Engine:
         pvals = None if nidx == 0 else np.ascontiguousarray(planner_params, np.float64)
         vp = ctypes.c_void_p
         self.lib.mpcgpu_solve_sets_guided.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, ctypes.c_int, vp, vp, ctypes.c_int,
-                                                      ctypes.c_int, ctypes.c_double, ctypes.c_int, vp, vp, vp, ctypes.c_int] + [vp] * 10
+                                                      ctypes.c_int, ctypes.c_double, ctypes.c_int, vp, vp, vp, ctypes.c_int] + [vp] * 11
         rc = self.lib.mpcgpu_solve_sets_guided(self.handle, n_sets, planners, _ptr(np.ascontiguousarray(xinit_sets, np.float64)),
                                                _ptr(np.ascontiguousarray(shared_params, np.float64)), _ptr(np.ascontiguousarray(x0, np.float64)),
                                                n_obs, _ptr(obst_pred), _ptr(guided), lin_base, lin_count, float(robot_radius), nidx,
-                                               _ptr(pidx), _ptr(pvals), None, int(num_iter), _ptr(out["xtraj"]), _ptr(out["utraj"]),
-                                               _ptr(out["pobj"]), _ptr(out["exit_code"]), _ptr(out["qp_status"]), _ptr(out["res_eq"]),
-                                               None, None, None, _ptr(out["best"]))
+                                               _ptr(pidx), _ptr(pvals), None, int(num_iter), None if best_only else _ptr(out["xtraj"]),
+                                               None if best_only else _ptr(out["utraj"]), _ptr(out["pobj"]), _ptr(out["exit_code"]), _ptr(out["qp_status"]), _ptr(out["res_eq"]),
+                                               _ptr(sc), None, _ptr(ds), _ptr(out["best"]), opt)
         self._check(rc, "mpcgpu_solve_sets_guided")
         return out
 
@@ -284,3 +340,107 @@ class Engine:
 
     def launch_count(self):
         return int(self.lib.mpcgpu_launch_count(self.handle))
+
+
+class MultiEngine:
+    """mpcgpu_multi_* (include/mpcgpu.h): several GPUs of one node behind one handle; homotopy sets partitioned by set into
+    contiguous ranges, one host thread + the engine's streams per device, no collective.  `devices` may repeat a device
+    (two engines on one GPU), which exercises the sharding on a single-GPU box."""
+
+    def __init__(self, config, devices, max_batch_per_device):
+        self.lib = load_library()
+        vp = ctypes.c_void_p
+        self.lib.mpcgpu_multi_create.argtypes = [ctypes.c_char_p, vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp)]
+        self.lib.mpcgpu_multi_destroy.argtypes = [vp]
+        self.lib.mpcgpu_multi_engine.argtypes = [vp, ctypes.c_int]
+        self.lib.mpcgpu_multi_engine.restype = vp
+        self.lib.mpcgpu_multi_last_kernel_ms.argtypes = [vp]
+        self.lib.mpcgpu_multi_last_kernel_ms.restype = ctypes.c_float
+        self.lib.mpcgpu_multi_num_devices.argtypes = [vp]
+        devs = np.ascontiguousarray(devices, np.int32)
+        h = vp()
+        rc = self.lib.mpcgpu_multi_create(config.encode(), _ptr(devs), int(devs.size), int(max_batch_per_device), ctypes.byref(h))
+        if rc != 0:
+            raise RuntimeError("mpcgpu_multi_create(%s, %s) failed with status %d (no CPU fallback)" % (config, list(devices), rc))
+        self.handle = h
+        self.devices = [int(d) for d in devs]
+        self.first = Engine.__new__(Engine)            # dimensions / maps / option packing of the first engine (not owned)
+        self.first.lib, self.first.handle, self.first.config = self.lib, None, config
+        self.first.parameter_map, self.first.model_map, st = load_maps(config)
+        N, nx, nu, npar, nh = (ctypes.c_int() for _ in range(5))
+        e0 = self.lib.mpcgpu_multi_engine(self.handle, 0)
+        self.lib.mpcgpu_desc_query(e0, ctypes.byref(N), ctypes.byref(nx), ctypes.byref(nu), ctypes.byref(npar), ctypes.byref(nh))
+        f = self.first
+        f.N, f.nx, f.nu, f.npar, f.nh = N.value, nx.value, nu.value, npar.value, nh.value
+        f.nz = f.nx + f.nu
+        f.mem_doubles = int(self.lib.mpcgpu_mem_doubles(e0))
+        self.N, self.nx, self.nu, self.npar, self.nz, self.mem_doubles = f.N, f.nx, f.nu, f.npar, f.nz, f.mem_doubles
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.mpcgpu_multi_destroy(self.handle)
+            self.handle = None
+
+    __del__ = close
+
+    def set_kernel_mode(self, mode):
+        self.lib.mpcgpu_set_kernel_mode.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        for i in range(len(self.devices)):
+            self.lib.mpcgpu_set_kernel_mode(self.lib.mpcgpu_multi_engine(self.handle, i), int(mode))
+
+    def shard_range(self, n_units, i):
+        b, e = ctypes.c_int(), ctypes.c_int()
+        self.lib.mpcgpu_multi_shard_range(int(n_units), len(self.devices), int(i), ctypes.byref(b), ctypes.byref(e))
+        return b.value, e.value
+
+    def last_kernel_ms(self):
+        return float(self.lib.mpcgpu_multi_last_kernel_ms(self.handle))
+
+    def alloc_outputs(self, n):
+        return dict(xtraj=np.zeros((n, (self.N + 1) * self.nx)), utraj=np.zeros((n, self.N * self.nu)), pobj=np.zeros(n),
+                    exit_code=np.zeros(n, np.int32), qp_status=np.zeros(n, np.int32), res_eq=np.zeros(n), ipm_iters=np.zeros(n, np.int32))
+
+    def solve_batch(self, xinit, x0, params, num_iter=10, mem=None, out=None):
+        n = xinit.shape[0]
+        out = out or self.alloc_outputs(n)
+        vp = ctypes.c_void_p
+        self.lib.mpcgpu_multi_solve_batch.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int] + [vp] * 8
+        a = [np.ascontiguousarray(v, np.float64) for v in (xinit, x0, params)]
+        rc = self.lib.mpcgpu_multi_solve_batch(self.handle, n, _ptr(a[0]), _ptr(a[1]), _ptr(a[2]), None, int(num_iter), _ptr(mem), _ptr(out["xtraj"]),
+                                               _ptr(out["utraj"]), _ptr(out["pobj"]), _ptr(out["exit_code"]), _ptr(out["qp_status"]),
+                                               _ptr(out["res_eq"]), _ptr(out["ipm_iters"]))
+        if rc != 0:
+            raise RuntimeError("mpcgpu_multi_solve_batch failed with status %d" % rc)
+        return out
+
+    def solve_sets(self, n_sets, planners, xinit_sets, shared_params, x0, param_idx, planner_params, num_iter=10, obj_scale=None,
+                   disabled=None, guided_args=None, **opts):
+        """mpcgpu_multi_solve_sets / _guided (guided_args = (obst_pred, guided, robot_radius, lin_base, lin_count))"""
+        n = n_sets * planners
+        out = self.alloc_outputs(n)
+        out["best"] = np.zeros(n_sets, np.int32)
+        opt, _keep = self.first._set_options(out, n, n_sets=n_sets, **opts)
+        best_only = bool(opts.get("best_only"))
+        sc = None if obj_scale is None else np.ascontiguousarray(obj_scale, np.float64)
+        ds = None if disabled is None else np.ascontiguousarray(disabled, np.uint8)
+        nidx = 0 if param_idx is None else int(np.asarray(param_idx).size)
+        idx = None if nidx == 0 else np.ascontiguousarray(param_idx, np.int32)
+        pv = None if nidx == 0 else np.ascontiguousarray(planner_params, np.float64)
+        xs, sh, x0_ = (np.ascontiguousarray(a, np.float64) for a in (xinit_sets, shared_params, x0))
+        vp = ctypes.c_void_p
+        xt, ut = (None, None) if best_only else (_ptr(out["xtraj"]), _ptr(out["utraj"]))
+        tail = [None, int(num_iter), xt, ut, _ptr(out["pobj"]), _ptr(out["exit_code"]), _ptr(out["qp_status"]), _ptr(out["res_eq"]), _ptr(sc), None,
+                _ptr(ds), _ptr(out["best"]), opt]
+        if guided_args is None:
+            self.lib.mpcgpu_multi_solve_sets.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, ctypes.c_int, vp, vp, vp, ctypes.c_int] + [vp] * 11
+            rc = self.lib.mpcgpu_multi_solve_sets(self.handle, n_sets, planners, _ptr(xs), _ptr(sh), _ptr(x0_), nidx, _ptr(idx), _ptr(pv), *tail)
+        else:
+            obst_pred, guided, robot_radius, lin_base, lin_count = guided_args
+            ob = np.ascontiguousarray(obst_pred, np.float64); g = np.ascontiguousarray(guided, np.uint8)
+            self.lib.mpcgpu_multi_solve_sets_guided.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, ctypes.c_int, vp, vp, ctypes.c_int,
+                                                                ctypes.c_int, ctypes.c_double, ctypes.c_int, vp, vp, vp, ctypes.c_int] + [vp] * 11
+            rc = self.lib.mpcgpu_multi_solve_sets_guided(self.handle, n_sets, planners, _ptr(xs), _ptr(sh), _ptr(x0_), int(ob.shape[2]), _ptr(ob), _ptr(g),
+                                                         int(lin_base), int(lin_count), float(robot_radius), nidx, _ptr(idx), _ptr(pv), *tail)
+        if rc != 0:
+            raise RuntimeError("mpcgpu_multi_solve_sets failed with status %d" % rc)
+        return out

@@ -11,6 +11,8 @@
 
 #include <iostream>
 #include <vector>
+#include <unordered_map>
+#include <utility>
 
 #include <mpc_planner_solver/state.h>
 
@@ -106,6 +108,18 @@ namespace MPCPlanner
         };
 
     private:
+        // name -> index tables built once in the constructor.  Replaces the per-call yaml-cpp lookups of
+        // acados_solver_interface.cpp:212-225,229-272,379-389 (`_parameter_map[parameter].as<int>()` in every
+        // setParameter / getOutput: the 3.3 ms "SetParameters" scope of the reference's traces)
+        struct VarInfo { bool is_state; int index; double lb, ub; };
+        std::unordered_map<std::string, int> _param_index;
+        std::unordered_map<std::string, VarInfo> _var_index;
+        std::vector<std::pair<std::string, VarInfo>> _vars;     // iteration order of _model_map
+        int paramIndex(const std::string &name) const;
+        const VarInfo &varInfo(const std::string &name) const;
+        double _last_res_eq{0.};
+        int _stepwise_status{0};
+
         mpcgpu_engine *_engine{nullptr};   // replaces the acados capsule + ocp_nlp_* handles
         std::vector<double> _mem;          // persistent capsule memory: NLP multipliers + QP warm start
         std::vector<double> _iterate;      // the solver's own (u,x) iterate (acados: nlp_out), x0 layout

@@ -25,10 +25,50 @@ namespace MPCPlanner
             const char *e = std::getenv("MPCGPU_DEVICE");
             return e ? std::atoi(e) : 0;
         }
-        // engine shared by Solver::solveBatch (all planners of a set / several robots in one launch)
+        // Engine(s) shared by Solver::solveBatch (all planners of a set / several robots in one launch).  MPCGPU_DEVICES=0,1,..
+        // lists several GPUs: the batch is then partitioned over them by mpcgpu_multi_solve_batch (contiguous ranges).
         std::mutex g_batch_mutex;
         mpcgpu_engine *g_batch_engine = nullptr;
+        mpcgpu_multi *g_batch_multi = nullptr;
         const int kBatchCapacity = 256;
+        std::vector<int> devicesFromEnv()
+        {
+            std::vector<int> d;
+            if (const char *e = std::getenv("MPCGPU_DEVICES"))
+                for (const char *p = e; *p;)
+                {
+                    char *end = nullptr;
+                    const long v = std::strtol(p, &end, 10);
+                    if (end == p)
+                        break;
+                    d.push_back((int)v);
+                    p = (*end == ',') ? end + 1 : end;
+                }
+            return d;
+        }
+        // pinned staging of solveBatch, grown on demand and reused: no allocation per control cycle
+        struct Staging
+        {
+            void *base = nullptr;
+            size_t bytes = 0;
+            void *get(size_t need)
+            {
+                if (need > bytes)
+                {
+                    if (base)
+                        mpcgpu_free_pinned(base);
+                    base = nullptr;
+                    bytes = 0;
+                    if (mpcgpu_alloc_pinned(need + need / 2, &base) != 0)
+                    {
+                        printf("mpcgpu_alloc_pinned(%zu) failed. Exiting.\n", need);
+                        exit(1);
+                    }
+                    bytes = need + need / 2;
+                }
+                return base;
+            }
+        } g_staging;
         double seconds(std::chrono::steady_clock::time_point t0)
         {
             return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -67,6 +107,16 @@ namespace MPCPlanner
         }
         _mem.assign(mpcgpu_mem_doubles(_engine), 0.0);
         _iterate.assign((size_t)nvar * (N + 1), 0.0);
+
+        // name -> index tables (one YAML traversal here instead of one lookup per setParameter / getOutput call)
+        for (YAML::const_iterator it = _parameter_map.begin(); it != _parameter_map.end(); ++it)
+            _param_index[it->first.as<std::string>()] = it->second.as<int>();
+        for (YAML::const_iterator it = _model_map.begin(); it != _model_map.end(); ++it)
+        {
+            VarInfo v{it->second[0].as<std::string>() == "x", it->second[1].as<int>(), it->second[2].as<double>(), it->second[3].as<double>()};
+            _var_index[it->first.as<std::string>()] = v;
+            _vars.emplace_back(it->first.as<std::string>(), v);
+        }
 
         reset();
     }
@@ -158,67 +208,99 @@ namespace MPCPlanner
         _iterations_requested = 0;
     }
 
-    // :145-160 -- one SQP-RTI iteration, continuing from the stored iterate and capsule memory
+    // :145-160 -- one SQP-RTI iteration, continuing from the stored iterate and capsule memory.  The engine runs it with the
+    // completion step deferred (num_iter = -1): multipliers and QP memory survive between iterations exactly as inside
+    // Solver_acados_solve; the res_eq demotion and the reset on failure happen once, in completeOneIteration().
     int Solver::solveOneIteration()
     {
         const auto t0 = std::chrono::steady_clock::now();
         double pobj = 0., res_eq = 0.;
         int exit_code = 0, qp_status = 0, ipm = 0;
-        int status = mpcgpu_solve_batch(_engine, 1, _params.xinit, _iterate.data(), _params.all_parameters, nullptr, 1, _mem.data(),
+        int status = mpcgpu_solve_batch(_engine, 1, _params.xinit, _iterate.data(), _params.all_parameters, nullptr, -1, _mem.data(),
                                         _output.xtraj, _output.utraj, &pobj, &exit_code, &qp_status, &res_eq, &ipm);
         if (status)
             return 1;
         _iterations_requested++;
         finish(pobj, exit_code, qp_status, res_eq, _iterations_requested, seconds(t0));
-        return exit_code == 1 ? 0 : (exit_code == 0 ? 1 : exit_code); // back to the acados convention
+        _last_res_eq = res_eq;
+        _stepwise_status = exit_code == 1 ? 0 : (exit_code == 0 ? 1 : exit_code); // back to the acados convention
+        return _stepwise_status;
     }
 
-    // :162-204
+    // :162-204 -- res_eq rule (:176-181), reset on failure (:187-191), exit-code map (:197-203)
     int Solver::completeOneIteration()
     {
+        int status = _stepwise_status;
+        if (!(_last_res_eq <= 1e-2) && status == 0)
+            status = 4; // ACADOS_QP_FAILURE
+        if (status != 0)
+            std::fill(_mem.begin(), _mem.end(), 0.0); // Solver_acados_reset + ocp_nlp_solver_reset_qp_memory
+        _exit_code_one_iter = (status == 0) ? 1 : (status == 1 ? 0 : status);
         return _exit_code_one_iter;
     }
 
+    int Solver::paramIndex(const std::string &name) const
+    {
+        auto it = _param_index.find(name);
+        if (it == _param_index.end())
+        {
+            LOG_ERROR("unknown solver parameter: " << name);
+            exit(1); // the reference throws from yaml-cpp's as<int>() on an undefined node
+        }
+        return it->second;
+    }
+
+    const Solver::VarInfo &Solver::varInfo(const std::string &name) const
+    {
+        auto it = _var_index.find(name);
+        if (it == _var_index.end())
+        {
+            LOG_ERROR("unknown model variable: " << name);
+            exit(1);
+        }
+        return it->second;
+    }
+
     // PARAMETERS // (:207-225)
-    bool Solver::hasParameter(std::string &&parameter) { return _parameter_map[parameter].IsDefined(); }
+    bool Solver::hasParameter(std::string &&parameter) { return _param_index.count(parameter) != 0; }
 
     void Solver::setParameter(int k, std::string &&parameter, double value)
     {
-        _params.all_parameters[k * npar + _parameter_map[parameter].as<int>()] = value;
+        _params.all_parameters[k * npar + paramIndex(parameter)] = value;
     }
 
     void Solver::setParameter(int k, std::string &parameter, double value)
     {
-        _params.all_parameters[k * npar + _parameter_map[parameter].as<int>()] = value;
+        _params.all_parameters[k * npar + paramIndex(parameter)] = value;
     }
 
     double Solver::getParameter(int k, std::string &&parameter)
     {
-        return _params.all_parameters[k * npar + _parameter_map[parameter].as<int>()];
+        return _params.all_parameters[k * npar + paramIndex(parameter)];
     }
 
     // XINIT // (:229-246)
     void Solver::setXinit(std::string &&state_name, double value)
     {
-        _params.xinit[_model_map[state_name][1].as<int>() - nu] = value;
+        _params.xinit[varInfo(state_name).index - nu] = value;
     }
 
     void Solver::setXinit(const State &state)
     {
-        for (YAML::const_iterator it = _model_map.begin(); it != _model_map.end(); ++it)
-            if (it->second[0].as<std::string>() == "x")
-                setXinit(it->first.as<std::string>(), state.get(it->first.as<std::string>()));
+        for (const auto &v : _vars)
+            if (v.second.is_state)
+                _params.xinit[v.second.index - nu] = state.get(std::string(v.first));
     }
 
     // WARMSTART // (:250-376)
     void Solver::setEgoPrediction(unsigned int k, std::string &&var_name, double value)
     {
-        _params.x0[k * nvar + _model_map[var_name][1].as<int>()] = value;
+        _params.x0[k * nvar + varInfo(var_name).index] = value;
     }
 
     double Solver::getEgoPrediction(unsigned int k, std::string &&var_name)
     {
-        return _params.x0[k * nvar + _model_map[var_name][1].as<int>()];
+        return _params.x0[k * nvar + varInfo(var_name).index];
     }
 
     void Solver::setEgoPredictionPosition(unsigned int k, const Eigen::Vector2d &value)
@@ -241,13 +323,8 @@ namespace MPCPlanner
     void Solver::initializeWithState(const State &initial_state)
     {
         for (int k = 0; k <= N; k++)
-            for (YAML::const_iterator it = _model_map.begin(); it != _model_map.end(); ++it)
-            {
-                if (it->second[0].as<std::string>() == "x")
-                    setEgoPrediction(k, it->first.as<std::string>(), initial_state.get(it->first.as<std::string>()));
-                else
-                    setEgoPrediction(k, it->first.as<std::string>(), 0.);
-            }
+            for (const auto &v : _vars)
+                _params.x0[k * nvar + v.second.index] = v.second.is_state ? initial_state.get(std::string(v.first)) : 0.;
     }
 
     void Solver::initializeWithBraking(const State &initial_state)
@@ -284,44 +361,41 @@ namespace MPCPlanner
         }
     }
 
+    // :344-376
     void Solver::initializeWarmstart(const State &initial_state, bool shift_previous_solution_forward)
     {
+        auto output = [&](int k, const VarInfo &v) { return v.is_state ? _output.xtraj[k * nx + v.index - nu] : _output.utraj[k * nu + v.index]; };
         if (shift_previous_solution_forward)
         {
             // [initial_state, x_2, x_3, ..., x_N-1, x_N-1]
             for (int k = 0; k <= N; k++)
-                for (YAML::const_iterator it = _model_map.begin(); it != _model_map.end(); ++it)
+                for (const auto &v : _vars)
                 {
-                    std::string name = it->first.as<std::string>();
-                    if (k == 0)
-                        setEgoPrediction(0, std::string(name), initial_state.get(std::string(name)));
-                    else if (k == N - 1)
-                        setEgoPrediction(N - 1, std::string(name), getOutput(N - 1, std::string(name)));
-                    else if (k == N)
-                        setEgoPrediction(N, std::string(name), getOutput(N - 1, std::string(name)));
+                    double value;
+                    if (k == 0) // the reference also calls initial_state.get() for the INPUT names here (:355), which indexes
+                                // State::_state at -nu (state.cpp:22: out of bounds); the shim loads 0 for inputs instead
+                        value = v.second.is_state ? initial_state.get(std::string(v.first)) : 0.;
+                    else if (k >= N - 1)
+                        value = output(N - 1, v.second);
                     else
-                        setEgoPrediction(k, std::string(name), getOutput(k + 1, std::string(name)));
+                        value = output(k + 1, v.second);
+                    _params.x0[k * nvar + v.second.index] = value;
                 }
         }
         else
         {
-            // [initial_state, x_1, x_2, ..., x_N-1, x_N]
+            // [initial_state, x_1, x_2, ..., x_N-1, x_N]  (the reference copies stages 0..N-1 of the previous output, :366-375)
             for (int k = 0; k < N; k++)
-                for (YAML::const_iterator it = _model_map.begin(); it != _model_map.end(); ++it)
-                {
-                    std::string name = it->first.as<std::string>();
-                    setEgoPrediction(k, std::string(name), getOutput(k, std::string(name)));
-                }
+                for (const auto &v : _vars)
+                    _params.x0[k * nvar + v.second.index] = output(k, v.second);
         }
     }
 
     // OUTPUT // (:379-389)
     double Solver::getOutput(int k, std::string &&state_name) const
     {
-        if (_model_map[state_name][0].as<std::string>() == "x")
-            return _output.xtraj[k * nx + _model_map[state_name][1].as<int>() - nu];
-        else
-            return _output.utraj[k * nu + _model_map[state_name][1].as<int>()];
+        const VarInfo &v = varInfo(state_name);
+        return v.is_state ? _output.xtraj[k * nx + v.index - nu] : _output.utraj[k * nu + v.index];
     }
 
     // :391-424
@@ -364,14 +438,15 @@ namespace MPCPlanner
     void Solver::printIfBoundLimited() const
     {
         for (int k = 0; k < N; k++)
-            for (YAML::const_iterator it = _model_map.begin(); it != _model_map.end(); ++it)
+            for (const auto &v : _vars)
             {
-                if (k == 0 && it->second[0].as<std::string>() == "x")
+                if (k == 0 && v.second.is_state)
                     continue;
-                if (std::abs(getOutput(k, it->first.as<std::string>()) - it->second[2].as<double>()) < 1e-2)
-                    LOG_WARN_THROTTLE(500, it->first.as<std::string>() + " limited by lower bound");
-                if (std::abs(getOutput(k, it->first.as<std::string>()) - it->second[3].as<double>()) < 1e-2)
-                    LOG_WARN_THROTTLE(500, it->first.as<std::string>() + " limited by upper bound");
+                const double value = v.second.is_state ? _output.xtraj[k * nx + v.second.index - nu] : _output.utraj[k * nu + v.second.index];
+                if (std::abs(value - v.second.lb) < 1e-2)
+                    LOG_WARN_THROTTLE(500, v.first + " limited by lower bound");
+                if (std::abs(value - v.second.ub) < 1e-2)
+                    LOG_WARN_THROTTLE(500, v.first + " limited by upper bound");
             }
     }
 
@@ -383,37 +458,50 @@ namespace MPCPlanner
         exit_codes.assign(n, 0);
         if (n == 0)
             return;
-        std::lock_guard<std::mutex> lock(g_batch_mutex);
-        if (!g_batch_engine && mpcgpu_engine_create(MPCGPU_CONFIG_NAME, deviceFromEnv(), kBatchCapacity, &g_batch_engine))
+        std::lock_guard<std::mutex> lock(g_batch_mutex);      // one shared engine: callers take turns (a call is one launch)
+        if (!g_batch_engine && !g_batch_multi)
         {
-            printf("mpcgpu_engine_create (batch) failed. Exiting.\n");
-            exit(1);
+            const std::vector<int> devs = devicesFromEnv();
+            int rc = devs.size() > 1 ? mpcgpu_multi_create(MPCGPU_CONFIG_NAME, devs.data(), (int)devs.size(), kBatchCapacity, &g_batch_multi)
+                                     : mpcgpu_engine_create(MPCGPU_CONFIG_NAME, devs.size() == 1 ? devs[0] : deviceFromEnv(), kBatchCapacity, &g_batch_engine);
+            if (rc)
+            {
+                printf("mpcgpu engine creation (batch) failed with status %d. Exiting.\n", rc);
+                exit(1);
+            }
         }
+        const int capacity = kBatchCapacity * (g_batch_multi ? mpcgpu_multi_num_devices(g_batch_multi) : 1);
         const Solver *s0 = solvers[0];
-        const int N = s0->N, nx = s0->nx, nu = s0->nu, nz = s0->nvar, np = s0->npar, md = (int)s0->_mem.size();
-        std::vector<double> xinit((size_t)n * nx), x0((size_t)n * nz * (N + 1)), par((size_t)n * N * np), mem((size_t)n * md),
-            xt((size_t)n * nx * (N + 1)), ut((size_t)n * nu * N), pobj(n), req(n);
-        std::vector<int> nit(n), ec(n), qs(n), ipm(n);
+        const size_t N = s0->N, nx = s0->nx, nu = s0->nu, nz = s0->nvar, np = s0->npar, md = s0->_mem.size(), B = (size_t)n;
+        // one pinned block, carved up: [xinit | x0 | par | mem | xt | ut | pobj | req | nit | ec | qs | ipm]
+        const size_t nd = B * (nx + nz * (N + 1) + N * np + md + nx * (N + 1) + nu * N + 2);
+        char *base = (char *)g_staging.get(nd * sizeof(double) + 4 * B * sizeof(int));
+        double *xinit = (double *)base, *x0 = xinit + B * nx, *par = x0 + B * nz * (N + 1), *mem = par + B * N * np, *xt = mem + B * md,
+               *ut = xt + B * nx * (N + 1), *pobj = ut + B * nu * N, *req = pobj + B;
+        int *nit = (int *)(req + B), *ec = nit + B, *qs = ec + B, *ipm = qs + B;
         for (int i = 0; i < n; i++)
         {
             Solver *s = solvers[i];
             s->initializeOneIteration();
             nit[i] = s->numIterationsForTimeout();
-            std::memcpy(&xinit[(size_t)i * nx], s->_params.xinit, sizeof(double) * nx);
-            std::memcpy(&x0[(size_t)i * nz * (N + 1)], s->_iterate.data(), sizeof(double) * nz * (N + 1));
-            std::memcpy(&par[(size_t)i * N * np], s->_params.all_parameters, sizeof(double) * N * np);
-            std::memcpy(&mem[(size_t)i * md], s->_mem.data(), sizeof(double) * md);
+            std::memcpy(xinit + i * nx, s->_params.xinit, sizeof(double) * nx);
+            std::memcpy(x0 + i * nz * (N + 1), s->_iterate.data(), sizeof(double) * nz * (N + 1));
+            std::memcpy(par + i * N * np, s->_params.all_parameters, sizeof(double) * N * np);
+            std::memcpy(mem + i * md, s->_mem.data(), sizeof(double) * md);
         }
         const auto t0 = std::chrono::steady_clock::now();
-        for (int b = 0; b < n; b += kBatchCapacity)
+        for (int b = 0; b < n; b += capacity)
         {
-            const int m = std::min(kBatchCapacity, n - b);
-            int status = mpcgpu_solve_batch(g_batch_engine, m, &xinit[(size_t)b * nx], &x0[(size_t)b * nz * (N + 1)],
-                                            &par[(size_t)b * N * np], &nit[b], 0, &mem[(size_t)b * md], &xt[(size_t)b * nx * (N + 1)],
-                                            &ut[(size_t)b * nu * N], &pobj[b], &ec[b], &qs[b], &req[b], &ipm[b]);
+            const int m = std::min(capacity, n - b);
+            const size_t o = (size_t)b;
+            int status = g_batch_multi
+                             ? mpcgpu_multi_solve_batch(g_batch_multi, m, xinit + o * nx, x0 + o * nz * (N + 1), par + o * N * np, nit + o, 0, mem + o * md,
+                                                        xt + o * nx * (N + 1), ut + o * nu * N, pobj + o, ec + o, qs + o, req + o, ipm + o)
+                             : mpcgpu_solve_batch(g_batch_engine, m, xinit + o * nx, x0 + o * nz * (N + 1), par + o * N * np, nit + o, 0, mem + o * md,
+                                                  xt + o * nx * (N + 1), ut + o * nu * N, pobj + o, ec + o, qs + o, req + o, ipm + o);
             if (status)
             {
-                LOG_ERROR("mpcgpu_solve_batch failed: " << mpcgpu_last_error(g_batch_engine));
+                LOG_ERROR("mpcgpu_solve_batch failed with status " << status);
                 return;
             }
         }
@@ -421,9 +509,9 @@ namespace MPCPlanner
         for (int i = 0; i < n; i++)
         {
             Solver *s = solvers[i];
-            std::memcpy(s->_output.xtraj, &xt[(size_t)i * nx * (N + 1)], sizeof(double) * nx * (N + 1));
-            std::memcpy(s->_output.utraj, &ut[(size_t)i * nu * N], sizeof(double) * nu * N);
-            std::memcpy(s->_mem.data(), &mem[(size_t)i * md], sizeof(double) * md);
+            std::memcpy(s->_output.xtraj, xt + i * nx * (N + 1), sizeof(double) * nx * (N + 1));
+            std::memcpy(s->_output.utraj, ut + i * nu * N, sizeof(double) * nu * N);
+            std::memcpy(s->_mem.data(), mem + i * md, sizeof(double) * md);
             exit_codes[i] = s->finish(pobj[i], ec[i], qs[i], req[i], nit[i], secs);
         }
     }

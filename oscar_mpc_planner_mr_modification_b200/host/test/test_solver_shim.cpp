@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstring>
 #include <memory>
+#include <thread>
 #include <vector>
 
 #include "mpc_planner_parameters.h"
@@ -121,7 +122,7 @@ int main(int argc, char **argv)
     solver.loadWarmstart();
     int exit_code = solver.solve();
     CHECK(exit_code == 1);
-    CHECK(solver._info.pobj > 0 && (solver._info.qp_status == 0 || solver._info.qp_status == 1) && solver._info.sqp_iter == 10);
+    CHECK(solver._info.pobj > 0 && (solver._info.qp_status == 0 || solver._info.qp_status == 2) && solver._info.sqp_iter == 10);
     CHECK_NEAR(solver.getOutput(0, "x"), 0.1, 1e-9);
     CHECK(solver.getOutput(5, "v") > 1.0 && solver.getOutput(solver.N, "x") > 5.0);
     mpcgpu_engine *eng = nullptr;
@@ -174,6 +175,111 @@ int main(int argc, char **argv)
         CHECK(e == codes[i]);
         CHECK(a[i]->_info.pobj == b[i]->_info.pobj);
         CHECK(std::memcmp(a[i]->_output.xtraj, b[i]->_output.xtraj, sizeof(a[i]->_output.xtraj)) == 0);
+    }
+
+    // ---- QP failure decoding (acados_solver_interface.cpp:391-424): the engine reports qp_status in the numbering the reference
+    //      decodes -- 2 max iterations, 3 minimal step, 4 NaN
+    {
+        Solver dec(30);
+        dec._info.qp_status = 2; CHECK(dec.explainExitFlag(4) == "QP Failure: Max Iterations");
+        dec._info.qp_status = 3; CHECK(dec.explainExitFlag(4) == "QP Failure: Minimal Step Reached");
+        dec._info.qp_status = 4; CHECK(dec.explainExitFlag(4) == "QP Failure: NAN in solution");
+        CHECK(dec.explainExitFlag(0) == "Failure (no more information)" && dec.explainExitFlag(3) == "Failure (minimum step size reached)");
+        // a NaN parameter: the interior-point loop stops with the NaN status, solve() returns ACADOS_QP_FAILURE (4)
+        Solver nan_case(31);
+        fillProblem(nan_case, st, 0.2);
+        nan_case._params.solver_timeout = 1.0;
+        nan_case.setParameter(3, "lag", std::nan(""));
+        nan_case.loadWarmstart();
+        int e = nan_case.solve();
+        CHECK(e == 4 && nan_case._info.qp_status == 4);
+        CHECK(nan_case.explainExitFlag(e) == "QP Failure: NAN in solution");
+        // an infeasible QP (two contradicting halfspaces x <= -100 and x >= 100 on every stage): the interior-point iteration
+        // diverges; it ends at the iteration limit or with a vanishing step, and the message must name that reason
+        if (nan_case.hasParameter("lin_constraint_1_a1"))
+        {
+            Solver inf_case(32);
+            fillProblem(inf_case, st, 0.2);
+            inf_case._params.solver_timeout = 1.0;
+            for (int k = 1; k < inf_case.N; k++)
+            {
+                setSolverParameterLinConstraintA1(k, inf_case._params, 1.0, 0); setSolverParameterLinConstraintA2(k, inf_case._params, 0.0, 0);
+                setSolverParameterLinConstraintB(k, inf_case._params, -100.0, 0);
+                setSolverParameterLinConstraintA1(k, inf_case._params, -1.0, 1); setSolverParameterLinConstraintA2(k, inf_case._params, 0.0, 1);
+                setSolverParameterLinConstraintB(k, inf_case._params, -100.0, 1);
+            }
+            inf_case.loadWarmstart();
+            e = inf_case.solve();
+            CHECK(e != 1);
+            const int q = inf_case._info.qp_status;
+            CHECK(q == 2 || q == 3 || q == 4);
+            if (e == 4)
+                CHECK(inf_case.explainExitFlag(e) == (q == 2 ? "QP Failure: Max Iterations" : (q == 3 ? "QP Failure: Minimal Step Reached" : "QP Failure: NAN in solution")));
+            std::printf("infeasible case: exit %d qp_status %d (%s)\n", e, q, inf_case.explainExitFlag(e).c_str());
+        }
+    }
+
+    // ---- warm starts (acados_solver_interface.cpp:286-376) against hand-computed values
+    {
+        Solver ws(40);
+        for (int k = 0; k <= ws.N; k++)
+            for (int i = 0; i < SOLVER_NX; i++) ws._output.xtraj[k * SOLVER_NX + i] = 100.0 * i + k;        // x_k[i] = 100 i + k
+        for (int k = 0; k < ws.N; k++)
+            for (int i = 0; i < SOLVER_NU; i++) ws._output.utraj[k * SOLVER_NU + i] = -(10.0 * i + k) - 1.0;  // u_k[i] = -(10 i + k) - 1
+        State now;
+        now.set("x", 7.0); now.set("y", 8.0); now.set("psi", 0.3); now.set("v", 1.1); now.set("spline", 2.2);
+        const int N = ws.N;
+        ws.initializeWarmstart(now, true);      // [initial_state, x_2, x_3, ..., x_N-1, x_N-1]
+        CHECK(ws.getEgoPrediction(0, "x") == 7.0 && ws.getEgoPrediction(0, "y") == 8.0 && ws.getEgoPrediction(0, "spline") == 2.2);
+        CHECK(ws.getEgoPrediction(1, "x") == 2.0 && ws.getEgoPrediction(1, "y") == 102.0 && ws.getEgoPrediction(1, "v") == 302.0);
+        CHECK(ws.getEgoPrediction(5, "psi") == 206.0 && ws.getEgoPrediction(5, "a") == -7.0 && ws.getEgoPrediction(5, "w") == -17.0);
+        CHECK(ws.getEgoPrediction(N - 2, "x") == N - 1.0 && ws.getEgoPrediction(N - 1, "x") == N - 1.0 && ws.getEgoPrediction(N, "x") == N - 1.0);
+        CHECK(ws.getEgoPrediction(N - 1, "a") == -(N - 1.0) - 1.0);
+        Solver keep(41);
+        std::memcpy(keep._output.xtraj, ws._output.xtraj, sizeof(ws._output.xtraj));
+        std::memcpy(keep._output.utraj, ws._output.utraj, sizeof(ws._output.utraj));
+        keep.setEgoPrediction(N, "x", -5.0);
+        keep.initializeWarmstart(now, false);   // previous output kept for stages 0..N-1; stage N is not touched (:366-375)
+        CHECK(keep.getEgoPrediction(0, "x") == 0.0 && keep.getEgoPrediction(3, "y") == 103.0 && keep.getEgoPrediction(N - 1, "v") == 300.0 + N - 1);
+        CHECK(keep.getEgoPrediction(4, "w") == -15.0 && keep.getEgoPrediction(N, "x") == -5.0);
+        Solver flat(42);
+        flat.initializeWithState(now);          // every stage = the state, inputs zero (:286-301)
+        for (int k = 0; k <= N; k += 7)
+            CHECK(flat.getEgoPrediction(k, "x") == 7.0 && flat.getEgoPrediction(k, "v") == 1.1 && flat.getEgoPrediction(k, "a") == 0.0 && flat.getEgoPrediction(k, "w") == 0.0);
+        Solver brk(43);
+        brk.initializeWithBraking(now);         // :303-342 with deceleration_at_infeasible
+        const double dec = std::abs(CONFIG["deceleration_at_infeasible"].as<double>());
+        double x = 7.0, y = 8.0, v = 1.1, sp = 2.2;
+        for (int k = 1; k <= 3; k++) { x += v * 0.2 * std::cos(0.3); y += v * 0.2 * std::sin(0.3); sp += v * 0.2; v = std::max(v - dec * 0.2, 0.0); }
+        CHECK(brk.getEgoPrediction(3, "x") == x && brk.getEgoPrediction(3, "y") == y && brk.getEgoPrediction(3, "v") == v && brk.getEgoPrediction(3, "spline") == sp);
+        CHECK(brk.getEgoPrediction(3, "a") == -dec && brk.getEgoPrediction(N, "v") == 0.0);
+        brk._output.xtraj[2 * SOLVER_NX + 3] = 3.0 - 0.005;      // v at its upper bound (3.0): printIfBoundLimited must not crash
+        brk.printIfBoundLimited();
+    }
+
+    // ---- threading contract: solve() from 8 threads on DISTINCT Solver objects, as the OpenMP team of
+    //      guidance_constraints.cpp:304,369 does -- bit-identical to the serial results
+    {
+        const int T = 8;
+        std::vector<std::unique_ptr<Solver>> par, ser;
+        for (int i = 0; i < T; i++)
+        {
+            par.emplace_back(new Solver(50 + i)); ser.emplace_back(new Solver(60 + i));
+            fillProblem(*par[i], st, 0.07 * i - 0.25); fillProblem(*ser[i], st, 0.07 * i - 0.25);
+            par[i]->_params.solver_timeout = 1.0; ser[i]->_params.solver_timeout = 1.0;
+        }
+        std::vector<int> ep(T), es(T);
+        std::vector<std::thread> th;
+        for (int i = 0; i < T; i++)
+            th.emplace_back([&, i] { for (int rep = 0; rep < 3; rep++) { par[i]->loadWarmstart(); ep[i] = par[i]->solve(); } });
+        for (auto &t : th) t.join();
+        for (int i = 0; i < T; i++)
+        {
+            for (int rep = 0; rep < 3; rep++) { ser[i]->loadWarmstart(); es[i] = ser[i]->solve(); }
+            CHECK(ep[i] == es[i] && par[i]->_info.pobj == ser[i]->_info.pobj && par[i]->_info.qp_status == ser[i]->_info.qp_status);
+            CHECK(std::memcmp(par[i]->_output.xtraj, ser[i]->_output.xtraj, sizeof(ser[i]->_output.xtraj)) == 0);
+            CHECK(std::memcmp(par[i]->_output.utraj, ser[i]->_output.utraj, sizeof(ser[i]->_output.utraj)) == 0);
+        }
     }
     std::printf("%s\n", g_fail ? "FAILED" : "OK");
     return g_fail ? 1 : 0;

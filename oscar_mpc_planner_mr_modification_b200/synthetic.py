@@ -276,3 +276,23 @@ def make_multi_robot_batch(pmap, dims, n_scenarios, robots=3, planners_per_set=9
     b["obst_pred"] = np.ascontiguousarray(ob.reshape(S * Rn, N, M, 2))
     b["robots"] = Rn
     return b
+
+
+def apply_consistency(batch, pmap, dims, planners, prev_traj, enabled, weight):
+    """Load the consistency parameters the way GuidanceConstraints::setConsistencyParametersForPlanner does
+    (mpc_planner_modules/src/guidance_constraints.cpp:985-1023): ONE interpolated previous trajectory per homotopy set
+    (prev_traj [n_sets, N, 2]); for a planner with has_consistency_enabled the stages 1..N-2 get (weight, X_k, Y_k), every
+    other stage and every other planner gets (0, 0, 0).  Modifies batch["params"] in place and returns the per-planner
+    flags as uint8 [n]."""
+    N, npar = dims["N"], dims["npar"]
+    n = batch["n"]
+    n_sets = n // planners
+    P = batch["params"].reshape(n_sets, planners, N, npar)
+    en = np.ascontiguousarray(enabled, np.uint8).reshape(n_sets, planners)
+    valid = np.zeros(N, bool)
+    valid[1:N - 1] = True
+    act = (en[:, :, None] != 0) & valid[None, None, :]
+    P[..., pmap["consistency_weight"]] = np.where(act, weight, 0.0)
+    P[..., pmap["prev_traj_x"]] = np.where(act, prev_traj[:, None, :, 0], 0.0)
+    P[..., pmap["prev_traj_y"]] = np.where(act, prev_traj[:, None, :, 1], 0.0)
+    return en.reshape(-1)

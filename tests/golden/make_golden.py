@@ -75,6 +75,7 @@ def solve_golden(cfg, n_sets, seed=2024):
 
 if __name__ == "__main__":
     for cfg in PLANNERS:
-        model_golden(cfg)
+        if "--solve-only" not in sys.argv:      # the model fixtures need /root/reference; the solve fixtures only the oracle
+            model_golden(cfg)
         solve_golden(cfg, 8 if PLANNERS[cfg] > 1 else 32)
         print("golden", cfg)

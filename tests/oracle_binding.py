@@ -59,17 +59,40 @@ class Oracle:
                                     _ptr(out["res_eq"]), _ptr(out["ipm_iters"]), int(threads))
         return out
 
-    def guidance_halfspaces(self, n_sets, planners, xinit_sets, x0, obst_pred, guided, robot_radius, lin_base, lin_count, params):
-        """oracle_guidance_halfspaces: writes the halfspace slots of `params` [n, N*npar] in place"""
+    def guidance_halfspaces(self, n_sets, planners, xinit_sets, x0, obst_pred, guided, robot_radius, lin_base, lin_count, params,
+                            static_halfspaces=None):
+        """oracle_guidance_halfspaces[_static]: writes the halfspace slots of `params` [n, N*npar] in place;
+        static_halfspaces [n_sets, N, n_static, 3] = module_data.static_obstacles rows (a1, a2, b)"""
         obst_pred = np.ascontiguousarray(obst_pred, np.float64)
         n_obs = obst_pred.shape[2]
         assert params.flags["C_CONTIGUOUS"] and params.dtype == np.float64
-        self.lib.oracle_guidance_halfspaces.argtypes = [ctypes.c_int] * 9 + [ctypes.c_void_p] * 4 + [ctypes.c_double, ctypes.c_void_p]
-        self.lib.oracle_guidance_halfspaces.restype = None
-        self.lib.oracle_guidance_halfspaces(n_sets, planners, self.N, self.nx, self.nu, self.npar, lin_base, lin_count, n_obs,
-                                            _ptr(np.ascontiguousarray(xinit_sets, np.float64)), _ptr(np.ascontiguousarray(x0, np.float64)),
-                                            _ptr(obst_pred), _ptr(np.ascontiguousarray(guided, np.uint8)), float(robot_radius), _ptr(params))
+        st = None if static_halfspaces is None else np.ascontiguousarray(static_halfspaces, np.float64)
+        fn = self.lib.oracle_guidance_halfspaces_static
+        fn.argtypes = [ctypes.c_int] * 9 + [ctypes.c_void_p] * 4 + [ctypes.c_double, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        fn.restype = None
+        fn(n_sets, planners, self.N, self.nx, self.nu, self.npar, lin_base, lin_count, n_obs,
+           _ptr(np.ascontiguousarray(xinit_sets, np.float64)), _ptr(np.ascontiguousarray(x0, np.float64)),
+           _ptr(obst_pred), _ptr(np.ascontiguousarray(guided, np.uint8)), float(robot_radius), _ptr(st),
+           0 if st is None else int(st.shape[2]), _ptr(params))
         return params
+
+    def select_best_cons(self, set_offsets, pobj, exit_code, xtraj, prev_traj, cons_weight, cons_enabled=None, obj_scale=None,
+                         obj_sub=None, disabled=None, ix=0, iy=1):
+        """objective post-processing with the consistency cost of the SOLVED trajectory + FindBestPlanner
+        (guidance_constraints.cpp:373-420,572-590,1025-1050); returns (best, objective, consistency_cost)"""
+        set_offsets = np.ascontiguousarray(set_offsets, np.int32)
+        n_sets, n = set_offsets.size - 1, int(set_offsets[-1])
+        best = np.zeros(n_sets, np.int32)
+        obj, cons = np.zeros(n), np.zeros(n)
+        f64 = lambda a: None if a is None else np.ascontiguousarray(a, np.float64)
+        u8 = lambda a: None if a is None else np.ascontiguousarray(a, np.uint8)
+        sc, sb, ds, en, xt, pv = f64(obj_scale), f64(obj_sub), u8(disabled), u8(cons_enabled), f64(xtraj), f64(prev_traj)
+        fn = self.lib.oracle_select_best_cons
+        vp = ctypes.c_void_p
+        fn.argtypes = [ctypes.c_int] + [vp] * 10 + [ctypes.c_double] + [ctypes.c_int] * 4 + [vp, vp]
+        fn(n_sets, _ptr(set_offsets), _ptr(f64(pobj)), _ptr(np.ascontiguousarray(exit_code, np.int32)), _ptr(sc), _ptr(sb), _ptr(ds),
+           _ptr(best), _ptr(xt), _ptr(pv), _ptr(en), float(cons_weight), self.N, self.nx, ix, iy, _ptr(obj), _ptr(cons))
+        return best, obj, cons
 
     def select_best(self, set_offsets, pobj, exit_code, obj_scale=None, obj_sub=None, disabled=None):
         set_offsets = np.ascontiguousarray(set_offsets, np.int32)

@@ -147,3 +147,48 @@ def test_solve_sets_guided_matches_host_built_parameters():
     ok = ref["exit_code"] == 1
     assert ok.sum() > 100
     assert np.abs(out["xtraj"][ok] - ref["xtraj"][ok]).max() < 1e-6
+
+
+def static_rows(n_sets, N, n_static, seed):
+    rng = np.random.default_rng(seed)
+    ang = rng.uniform(-np.pi, np.pi, (n_sets, N, n_static))
+    return np.ascontiguousarray(np.stack([np.cos(ang), np.sin(ang), rng.uniform(5.0, 9.0, ang.shape)], axis=-1))
+
+
+def test_oracle_static_halfspaces_follow_the_obstacle_rows():
+    """module_data.static_obstacles (linearized_constraints.cpp:107-127): behind the obstacle rows of a guided planner, from
+    slot 0 for the non-guided one (empty obstacle list), never at stage 0."""
+    orc, b = make(3, 7)
+    base, cnt = lin_block(orc.parameter_map)
+    b["obst_pred"] = np.ascontiguousarray(b["obst_pred"][:, :, :5])
+    st = static_rows(3, orc.N, 2, 1)
+    xs = np.ascontiguousarray(b["xinit"].reshape(3, PLANNERS, -1)[:, 0])
+    plain = orc.guidance_halfspaces(3, PLANNERS, xs, b["x0"], b["obst_pred"], b["guided"], b["robot_radius"], base, cnt, b["params"].copy())
+    P = orc.guidance_halfspaces(3, PLANNERS, xs, b["x0"], b["obst_pred"], b["guided"], b["robot_radius"], base, cnt, b["params"].copy(), st)
+    blk = lambda a: a.reshape(3, PLANNERS, orc.N, orc.npar)[..., base:base + 3 * cnt].reshape(3, PLANNERS, orc.N, cnt, 3)
+    P, plain = blk(P), blk(plain)
+    assert (P[:, :, 0] == plain[:, :, 0]).all()
+    assert (P[:, :PLANNERS - 1, 1:, 5:7] == st[:, None, 1:]).all() and (P[:, PLANNERS - 1, 1:, 0:2] == st[:, 1:]).all()
+    keep = np.ones(cnt, bool); keep[5:7] = False
+    assert (P[:, :PLANNERS - 1][:, :, :, keep] == plain[:, :PLANNERS - 1][:, :, :, keep]).all()
+    assert (P[:, PLANNERS - 1, :, 2:] == plain[:, PLANNERS - 1, :, 2:]).all()
+
+
+@pytest.mark.gpu
+def test_solve_sets_guided_with_static_halfspaces():
+    """static halfspaces through struct mpcgpu_set_options: the device-built parameter block equals the oracle's"""
+    eng = engine.Engine(CFG, 0, 256)
+    orc = Oracle(CFG)
+    n_sets = 6
+    b = synthetic.make_batch(eng.parameter_map, eng.dims, n_sets, PLANNERS, seed=33)
+    b["obst_pred"] = np.ascontiguousarray(b["obst_pred"][:, :, :8])      # 8 obstacles + 3 static rows + 1 dummy slot
+    st = static_rows(n_sets, eng.N, 3, 2)
+    base, cnt = eng.lin_constraint_block()
+    xs = np.ascontiguousarray(b["xinit"].reshape(n_sets, PLANNERS, eng.nx)[:, 0])
+    want = orc.guidance_halfspaces(n_sets, PLANNERS, xs, b["x0"], b["obst_pred"], b["guided"], b["robot_radius"], base, cnt, b["params"].copy(), st)
+    ref = eng.solve_batch(b["xinit"], b["x0"], want, num_iter=3)
+    shared = np.ascontiguousarray(b["params"].reshape(n_sets, PLANNERS, eng.N, eng.npar)[:, 0]).copy()
+    out = eng.solve_sets_guided(n_sets, PLANNERS, xs, shared, b["x0"], b["obst_pred"], b["guided"], b["robot_radius"], num_iter=3,
+                                static_halfspaces=st)
+    for k in ("xtraj", "utraj", "pobj", "exit_code"):
+        np.testing.assert_array_equal(out[k], ref[k])

@@ -229,11 +229,11 @@ def test_solve_sets_tracks_matches_host_built_parameters():
     best = np.zeros(n_sets, np.int32)
     vp = ctypes.c_void_p
     L.mpcgpu_solve_sets_tracks.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, ctypes.c_int, vp, vp, ctypes.c_int, ctypes.c_int,
-                                           ctypes.c_double, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_int] + [vp] * 10
+                                           ctypes.c_double, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_int] + [vp] * 11
     P = lambda a: a.ctypes.data
     rc = L.mpcgpu_solve_sets_tracks(eng.handle, n_sets, planners, P(xs), P(shared), P(b["x0"]), M, P(tables), P(b["guided"]), lin_base, lin_count,
                                     b["robot_radius"], base, stride, P(off), None, 5, P(out["xtraj"]), P(out["utraj"]), P(out["pobj"]),
-                                    P(out["exit_code"]), P(out["qp_status"]), P(out["res_eq"]), None, None, None, P(best))
+                                    P(out["exit_code"]), P(out["qp_status"]), P(out["res_eq"]), None, None, None, P(best), None)
     assert rc == 0, eng.last_error()
     np.testing.assert_array_equal(out["exit_code"], ref["exit_code"])
     np.testing.assert_array_equal(best, best_ref)

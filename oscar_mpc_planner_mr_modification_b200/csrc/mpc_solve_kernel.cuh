@@ -407,7 +407,9 @@ constexpr int RO_END = RO_DZ + NZ;
 constexpr int RSTRIDE = RO_END | 1;              // odd stride: lane-parallel accesses (lane = stage) are conflict-free
 constexpr int RS_DOUBLES = (NSTAGE + 1) * RSTRIDE + NX * NB;   // per problem, incl. the T = P+ [W | rb] scratch
 static_assert(pk(NZ, 0) == NPK, "augmented row must follow the packed Hessian");
-static_assert(NPK + NZ <= 35 && NX * NB <= 40 && NPX + NX < 32, "lane-role tables are written for nx = 5, nu = 2");
+// lane roles of the cooperative factor step (lanes 0..NPK-1 own G(i,j), the next ceil(NZ/2) lanes two entries of q each;
+// step C: NPX lanes own P(i,j), NX lanes a row of Lxu and p, one lane the pivots) for any nx, nu = 2 that fits a warp
+static_assert(NPK + (NZ + 1) / 2 <= 32 && NPX + NX < 32, "cooperative Riccati step: one warp must cover the lane roles");
 
 __device__ __forceinline__ void tri_unpack(int e, int& i, int& j)
 {
@@ -428,11 +430,13 @@ __device__ __noinline__ void riccati_factor_coop(double* __restrict__ rs)
     int gi, gj;
     tri_unpack(lane < NPK ? lane : 0, gi, gj);
     const int cc = ql ? NZ : gi;                        // column of [W|rb] that t is formed with
-    const int j0 = ql ? 2 * (lane - NPK) : gj;          // output columns
-    const int j1 = ql ? (j0 + 1 < NZ ? j0 + 1 : j0) : gj;
+    const int jq = 2 * (lane - NPK);
+    const bool qact = ql && jq < NZ;                    // (q lanes beyond ceil(NZ/2) idle: they recompute q_0 and store nothing)
+    const int j0 = ql ? (qact ? jq : 0) : gj;           // output columns
+    const int j1 = ql ? ((qact && jq + 1 < NZ) ? jq + 1 : j0) : gj;
     const int o0 = ql ? RO_Q + j0 : RO_G + lane;        // in/out offsets of the two entries
     const int o1 = ql ? RO_Q + j1 : o0;
-    const bool st1 = ql && (j0 + 1 < NZ);
+    const bool st0 = !ql || qact, st1 = qact && (jq + 1 < NZ);
     int ci = 0, cj = 0;                                 // step C: lanes 0..14 own P(ci,cj); lanes 15..19 own row ci of Lxu and p
     if (lane < NPX) tri_unpack(lane, ci, cj);
     else if (lane < NPX + NX) ci = lane - NPX;
@@ -473,7 +477,7 @@ __device__ __noinline__ void riccati_factor_coop(double* __restrict__ rs)
                 a0 += op[NPX + 2 * NX + l] * y;
                 a1 += op[NPX + 3 * NX + l] * y;
             }
-            blk[o0] = a0;
+            if (st0) blk[o0] = a0;
             if (st1) blk[o1] = a1;
         }
         __syncwarp();
@@ -649,9 +653,17 @@ __device__ __forceinline__ void sweep_serial4(double* __restrict__ sw)
         const double c = blk[SW_B2 + i];
 #pragma unroll
         for (int j = 0; j < NX; j++) xs[j] = __shfl_sync(FULL, x, j);
-        static_assert(NX == 5, "FMA tree written for nx = 5");
-        const double t0 = a[0] * xs[0] + c, t1 = a[1] * xs[1], t2 = a[4] * xs[4];
-        x = ((a[2] * xs[2] + t0) + (a[3] * xs[3] + t1)) + t2;
+        if constexpr (NX == 5) {                    // balanced FMA tree: the serial step is latency bound
+            const double t0 = a[0] * xs[0] + c, t1 = a[1] * xs[1], t2 = a[4] * xs[4];
+            x = ((a[2] * xs[2] + t0) + (a[3] * xs[3] + t1)) + t2;
+        } else {
+            double t0 = c, t1 = 0.0;
+#pragma unroll
+            for (int j = 0; j < NX; j += 2) t0 += a[j] * xs[j];
+#pragma unroll
+            for (int j = 1; j < NX; j += 2) t1 += a[j] * xs[j];
+            x = t0 + t1;
+        }
         if (lane < NX) sw[(FWD ? k + 4 : k) * SWS + SW_X + i] = x;
     }
     __syncwarp();
@@ -744,18 +756,17 @@ __device__ __noinline__ void sweep_backward_blocked(double* __restrict__ sw)
 }
 
 // ---- K4: MIRROR regularisation of one packed symmetric NZ x NZ block (cyclic Jacobi) -----------
-// Register-resident AND compact: the pair order is the round-robin tournament on NZ+1 = 8 positions
-// (position 7 is a decoupled dummy), i.e. every round rotates the FIXED position pairs (0,7)(1,6)(2,5)(3,4)
-// and then shifts positions 1..7 cyclically, so that one rolled loop body (4 rotations + a register
-// permutation) serves all 7 rounds of a sweep -- ~10 KB of code instead of >100 KB fully unrolled.
+// Register-resident AND compact: the pair order is the round-robin tournament on JP = NZ + (NZ odd) positions
+// (for 7 variables: 8 positions, position 7 is a decoupled dummy), i.e. every round rotates the FIXED position pairs
+// (0,JP-1)(1,JP-2)... and then shifts positions 1..JP-1 cyclically, so that one rolled loop body (JP/2 rotations + a register
+// permutation) serves all JP-1 rounds of a sweep -- ~10 KB of code instead of >100 KB fully unrolled.
 // Rotation without a division: ir = rsqrt(tau^2 + 4 a_pq^2), cos^2 = (1 + |tau| ir)/2, ic = rsqrt(cos^2),
 // c = cos^2 ic, s = sign(tau) a_pq ir ic, t = s ic   (tau = a_qq - a_pp).
-constexpr int JP = NZ + 1;                       // positions
+constexpr int JP = NZ + (NZ & 1);                // positions: an odd variable count gets a decoupled dummy position
 constexpr int JPK = JP * (JP + 1) / 2;
 __host__ __device__ constexpr int jsigma(int j) { return j == 0 ? 0 : (j == 1 ? JP - 1 : j - 1); }   // new position j <- old position
 __device__ __noinline__ void mirror_generic(double* Hp)
 {
-    static_assert(NZ == 7, "tournament table is written for 7 variables + 1 dummy");
     double a[JPK], V[NZ][JP];
 #pragma unroll
     for (int i = 0; i < JP; i++)

@@ -67,7 +67,10 @@ def make_batch(pmap, dims, n_sets, planners_per_set=1, seed=1234, guided=None, g
     M = sum(1 for k in pmap if k.startswith("ellipsoid_obst_") and k.endswith("_x"))
     Mg = sum(1 for k in pmap if k.startswith("gaussian_obst_") and k.endswith("_x"))
     Md = sum(1 for k in pmap if k.startswith("disc_0_decomp_") and k.endswith("_a1"))
-    Mall = max(M, Mg)
+    Ml = sum(1 for k in pmap if k.startswith("disc_0_lin_constraint_") and k.endswith("_a1"))      # LinearizedConstraintModule rows
+    Ml_dyn = max(Ml - 2, 0)                      # the last two rows play static halfspaces (road boundaries)
+    Mall = max(M, Mg, Ml_dyn)
+    has_spline = nx > 4                          # ContouringSecondOrderUnicycleModel; the plain unicycle has no path state
 
     # ---- per-set scenario ---------------------------------------------------------------------
     st = np.stack([rng.uniform(-0.5, 0.5, S), rng.uniform(-0.5, 0.5, S), rng.uniform(-0.3, 0.3, S),
@@ -112,15 +115,16 @@ def make_batch(pmap, dims, n_sets, planners_per_set=1, seed=1234, guided=None, g
             X[:, :, nu + 1] = pos[:, :, 1]
             X[:, :, nu + 2] = np.arctan2(vel[:, :, 1], vel[:, :, 0])
             X[:, :, nu + 3] = np.linalg.norm(vel, axis=2)
-            X[:, :, nu + 4] = np.concatenate([np.zeros((S, 1)), np.cumsum(X[:, :-1, nu + 3] * dt, axis=1)], axis=1)
-            X[:, 0, nu:] = st
+            if has_spline:
+                X[:, :, nu + 4] = np.concatenate([np.zeros((S, 1)), np.cumsum(X[:, :-1, nu + 3] * dt, axis=1)], axis=1)
+            X[:, 0, nu:] = st[:, :nx]
         else:
             # braking roll-out for the non-guided planner; constant-velocity cruise otherwise
             a = -DECELERATION if nonguided else 0.0
             x, y, psi, v, s = (st[:, i].copy() for i in range(5))
             for k in range(N + 1):
                 X[:, k, 0] = a
-                X[:, k, nu:] = np.stack([x, y, psi, v, s], axis=1)
+                X[:, k, nu:] = np.stack([x, y, psi, v, s], axis=1)[:, :nx]
                 x = x + v * dt * np.cos(psi)
                 y = y + v * dt * np.sin(psi)
                 s = s + v * dt
@@ -143,6 +147,10 @@ def make_batch(pmap, dims, n_sets, planners_per_set=1, seed=1234, guided=None, g
         setp("spline%d_start" % i, ts[:, i][:, None, None])
     setp("ego_disc_radius", ROBOT_RADIUS)
     setp("ego_disc_0_offset", 0.0)
+    if "goal_x" in pmap:        # GoalModule (goal_module.py:22-36): the third waypoint of the synthetic path; weights.goal of settings.yaml:79
+        setp("goal_weight", 1.0)
+        setp("goal_x", wx[:, 3][:, None, None])
+        setp("goal_y", wy[:, 3][:, None, None])
     if "prev_traj_x" in pmap:  # consistency reference: the planner's own warm start positions
         P[..., pmap["prev_traj_x"]] = x0[:, :, :N, nu + 0]
         P[..., pmap["prev_traj_y"]] = x0[:, :, :N, nu + 1]
@@ -207,7 +215,35 @@ def make_batch(pmap, dims, n_sets, planners_per_set=1, seed=1234, guided=None, g
                 P[:, h, 1:, pmap[pre + "a2"]] = a2
                 P[:, h, 1:, pmap[pre + "b"]] = b
 
-    xinit = np.repeat(st[:, None, :], Pn, axis=1)
+    if Ml:
+        # LinearizedConstraints::update / setParameters with _use_guidance = false (linearized_constraints.cpp:49-189): halfspaces
+        # from the warm-start DISC position towards obstacle j's prediction k-1, radius = obstacle + robot radius; stage 0 and
+        # unused slots: dummies (1, 0, x + 100).  The last two rows stand in for module_data.static_obstacles (:107-127):
+        # road boundaries |y - y0| <= 3.5.
+        dummy_b = st[:, 0] + 100.0
+        for j in range(Ml):
+            pre = "disc_0_lin_constraint_%d_" % j
+            P[..., pmap[pre + "a1"]] = 1.0
+            P[..., pmap[pre + "a2"]] = 0.0
+            P[..., pmap[pre + "b"]] = dummy_b[:, None, None]
+        for h in range(Pn):
+            pos = x0[:, h, 1:N, nu:nu + 2]
+            for j in range(Ml_dyn):
+                o = opred[:, :N - 1, j]
+                dvec = o - pos
+                dist = np.maximum(np.linalg.norm(dvec, axis=2), 1e-9)
+                a1, a2 = dvec[..., 0] / dist, dvec[..., 1] / dist
+                pre = "disc_0_lin_constraint_%d_" % j
+                P[:, h, 1:, pmap[pre + "a1"]] = a1
+                P[:, h, 1:, pmap[pre + "a2"]] = a2
+                P[:, h, 1:, pmap[pre + "b"]] = a1 * o[..., 0] + a2 * o[..., 1] - (OBSTACLE_RADIUS + ROBOT_RADIUS)
+            for j, sgn in zip(range(Ml_dyn, Ml), (1.0, -1.0)):
+                pre = "disc_0_lin_constraint_%d_" % j
+                P[:, h, 1:, pmap[pre + "a1"]] = 0.0
+                P[:, h, 1:, pmap[pre + "a2"]] = sgn
+                P[:, h, 1:, pmap[pre + "b"]] = (sgn * st[:, 1] + 3.5)[:, None]
+
+    xinit = np.repeat(st[:, None, :nx], Pn, axis=1)
     return dict(
         xinit=np.ascontiguousarray(xinit.reshape(B, nx)),
         x0=np.ascontiguousarray(x0.reshape(B, (N + 1) * nz)),

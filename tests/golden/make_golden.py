@@ -23,7 +23,7 @@ import reference_problem as rp  # noqa: E402
 from oracle_binding import Oracle  # noqa: E402
 from oscar_mpc_planner_mr_modification_b200 import synthetic  # noqa: E402
 
-PLANNERS = {"c1_basic": 1, "tmpc_shipped": 5, "c2_tmpc12": 9, "c5_ccmpc": 1}
+PLANNERS = {"c1_basic": 1, "tmpc_shipped": 5, "c2_tmpc12": 9, "c5_ccmpc": 1, "c6_goal_unicycle": 1, "c7_linearized": 1}
 
 
 def model_golden(cfg, npts=12, seed=11):

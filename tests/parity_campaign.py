@@ -9,7 +9,7 @@ from oscar_mpc_planner_mr_modification_b200 import engine, synthetic
 from oracle_binding import Oracle
 tot = bad = 0
 worst = 0.0
-for cfg, pl, sets in (("c2_tmpc12", 9, 64), ("tmpc_shipped", 5, 96), ("c1_basic", 1, 400), ("c5_ccmpc", 1, 200)):
+for cfg, pl, sets in (("c2_tmpc12", 9, 64), ("tmpc_shipped", 5, 96), ("c1_basic", 1, 400), ("c5_ccmpc", 1, 200), ("c6_goal_unicycle", 1, 400), ("c7_linearized", 1, 400)):
     eng = engine.Engine(cfg, 0, 4096); orc = Oracle(cfg)
     has_split = eng.set_kernel_mode(0)
     for seed in (101, 202, 303, 404):

@@ -32,13 +32,19 @@ def test_library_exports_every_declared_symbol():
 def test_registered_configurations_and_maps():
     lib = engine.load_library()
     names = [lib.mpcgpu_config_name(i).decode() for i in range(lib.mpcgpu_num_configs())]
-    assert set(names) == {"c1_basic", "tmpc_shipped", "c2_tmpc12", "c5_ccmpc"}
-    expect = {"c1_basic": (83, 4, 30), "tmpc_shipped": (98, 8, 30), "c2_tmpc12": (175, 24, 30), "c5_ccmpc": (115, 16, 50)}
+    assert set(names) == {"c1_basic", "tmpc_shipped", "c2_tmpc12", "c5_ccmpc", "c6_goal_unicycle", "c7_linearized"}
+    expect = {"c1_basic": (83, 4, 30), "tmpc_shipped": (98, 8, 30), "c2_tmpc12": (175, 24, 30), "c5_ccmpc": (115, 16, 50),
+              "c6_goal_unicycle": (35, 4, 30),      # base 2 + goal 3 + ellipsoid 2 + 4 x 7 (goal_module.py:22-26, ellipsoid_constraints.py:41-49)
+              "c7_linearized": (72, 6, 30)}         # 53 + disc offset 1 + 6 x 3 (linearized_constraints.py:41-49)
     for n in names:
         pmap, mmap, st = engine.load_maps(n)
-        assert st == dict(N=expect[n][2], nx=5, nu=2, nvar=7, npar=expect[n][0])
+        nx = 4 if n == "c6_goal_unicycle" else 5
+        assert st == dict(N=expect[n][2], nx=nx, nu=2, nvar=nx + 2, npar=expect[n][0])
         assert len(pmap) == expect[n][0] and sorted(pmap.values()) == list(range(expect[n][0]))
-        assert mmap["a"][:2] == ["u", 0] and mmap["spline"][:2] == ["x", 6] and mmap["v"][2:] == [-0.01, 3.0]
+        if nx == 5:      # ContouringSecondOrderUnicycleModel (solver_model.py:193-205)
+            assert mmap["a"][:2] == ["u", 0] and mmap["spline"][:2] == ["x", 6] and mmap["v"][2:] == [-0.01, 3.0]
+        else:            # SecondOrderUnicycleModel (solver_model.py:170-181): no spline state, its own bounds
+            assert "spline" not in mmap and mmap["w"][2:] == [-2.0, 2.0] and mmap["v"] == ["x", 5, -2.0, 3.0] and mmap["x"][2:] == [-200.0, 200.0]
     pm = engine.load_maps("c2_tmpc12")[0]
     assert pm["acceleration"] == 0 and pm["spline_x0_a"] == 8 and pm["lin_constraint_0_a1"] == 53
     assert pm["ego_disc_radius"] == 89 and pm["ellipsoid_obst_0_x"] == 91 and pm["ellipsoid_obst_11_r"] == 174

@@ -20,7 +20,7 @@ needs_ref = pytest.mark.skipif(not rp.reference_available(), reason="/root/refer
 COMPAT = os.path.join(ROOT, "oscar_mpc_planner_mr_modification_b200", "solver_generator", "casadi_compat")
 
 
-@pytest.mark.parametrize("cfg", ["c1_basic", "tmpc_shipped", "c2_tmpc12", "c5_ccmpc"])
+@pytest.mark.parametrize("cfg", ["c1_basic", "tmpc_shipped", "c2_tmpc12", "c5_ccmpc", "c6_goal_unicycle", "c7_linearized"])
 def test_maps_agree_with_oracle_model(cfg):
     """Two independent extraction paths (reference solver_definition.py for the oracle, the emitter's own
     loops for the product) give the same parameter order and dimensions."""
@@ -32,7 +32,10 @@ def test_maps_agree_with_oracle_model(cfg):
     hdr = open(os.path.join(engine.config_dir(cfg), "model.cuh")).read()
     assert "NH = %d" % orc.nh in hdr and "NCG = %d" % (orc.nc - 2 * orc.nz) in hdr
     par = open(os.path.join(engine.config_dir(cfg), "mpc_planner_parameters.h")).read()
-    for fn in ("setSolverParameterAcceleration", "setSolverParameterSplineXA", "setSolverParameterEgoDiscRadius"):
+    fns = ["setSolverParameterAcceleration"]
+    fns += ["setSolverParameterSplineXA"] if "spline_x0_a" in pmap else ["setSolverParameterGoalX", "setSolverParameterGoalWeight"]
+    fns += ["setSolverParameterEgoDiscRadius"] if "ego_disc_radius" in pmap else ["setSolverParameterEgoDiscOffset", "setSolverParameterLinConstraintA1"]
+    for fn in fns:
         assert fn in par        # generate_cpp_files.py:235-254 naming rule
 
 

@@ -9,7 +9,7 @@ from oscar_mpc_planner_mr_modification_b200 import engine, synthetic
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-PLANNERS = {"c1_basic": 1, "tmpc_shipped": 5, "c2_tmpc12": 9, "c5_ccmpc": 1}
+PLANNERS = {"c1_basic": 1, "tmpc_shipped": 5, "c2_tmpc12": 9, "c5_ccmpc": 1, "c6_goal_unicycle": 1, "c7_linearized": 1}
 REL_TOL = 1e-6
 
 
@@ -49,10 +49,10 @@ def test_emitted_device_functions_match_reference_expressions(cfg):
         orc.lib.oracle_integrate(P(z[eng.nu:].copy()), P(z[:eng.nu].copy()), P(p), P(pi[i].copy()), P(xn), P(W), P(Hd))
         np.testing.assert_allclose(r["xn"][i], xn, rtol=1e-12, atol=1e-13)
         np.testing.assert_allclose(r["W"][i].reshape(eng.nx, eng.nz), W, rtol=1e-10, atol=1e-12)
-        np.testing.assert_allclose(unpack(r["Hdyn"][i]), Hd, rtol=1e-9, atol=1e-11)
+        np.testing.assert_allclose(unpack(r["Hdyn"][i], eng.nz), Hd, rtol=1e-9, atol=1e-11)
         o = model_eval(orc, z, p, np.zeros(eng.nx), mh[i].copy())
-        np.testing.assert_allclose(unpack(r["Hcost"][i]), dt * o["Hc"], rtol=1e-9, atol=1e-11)
-        np.testing.assert_allclose(unpack(r["Hcon"][i]), o["Hh"], rtol=1e-9, atol=1e-10)
+        np.testing.assert_allclose(unpack(r["Hcost"][i], eng.nz), dt * o["Hc"], rtol=1e-9, atol=1e-11)
+        np.testing.assert_allclose(unpack(r["Hcon"][i], eng.nz), o["Hh"], rtol=1e-9, atol=1e-10)
 
 
 @pytest.mark.parametrize("cfg", sorted(PLANNERS))

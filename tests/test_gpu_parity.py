@@ -66,7 +66,7 @@ def same_selection(best, ref_best, ref, set_offsets, tie=1e-9):
     return True
 
 
-@pytest.mark.parametrize("cfg,planners", [("c1_basic", 1), ("tmpc_shipped", 5), ("c2_tmpc12", 9), ("c5_ccmpc", 1)])
+@pytest.mark.parametrize("cfg,planners", [("c1_basic", 1), ("tmpc_shipped", 5), ("c2_tmpc12", 9), ("c5_ccmpc", 1), ("c6_goal_unicycle", 1), ("c7_linearized", 1)])
 @pytest.mark.parametrize("num_iter", [1, 10])
 def test_solve_parity(cfg, planners, num_iter):
     n_sets = 16 if planners > 1 else 64

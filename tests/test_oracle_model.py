@@ -10,7 +10,7 @@ import pytest
 from oracle_binding import Oracle
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CONFIGS = ["c1_basic", "tmpc_shipped", "c2_tmpc12", "c5_ccmpc"]
+CONFIGS = ["c1_basic", "tmpc_shipped", "c2_tmpc12", "c5_ccmpc", "c6_goal_unicycle", "c7_linearized"]
 P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
 
 

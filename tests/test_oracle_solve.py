@@ -12,7 +12,7 @@ from oscar_mpc_planner_mr_modification_b200 import synthetic
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
-PLANNERS = {"c1_basic": 1, "tmpc_shipped": 5, "c2_tmpc12": 9, "c5_ccmpc": 1}
+PLANNERS = {"c1_basic": 1, "tmpc_shipped": 5, "c2_tmpc12": 9, "c5_ccmpc": 1, "c6_goal_unicycle": 1, "c7_linearized": 1}
 
 
 def qp_debug(orc, xinit, x0, params):

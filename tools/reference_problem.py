@@ -41,6 +41,13 @@ CONFIGS = {
     "tmpc_shipped": dict(kind="tmpc_consistency", max_obstacles=4, N=30),
     "c2_tmpc12": dict(kind="tmpc", max_obstacles=12, N=30),
     "c5_ccmpc": dict(kind="ccmpc_decomp", max_obstacles=4, N=50),
+    # north_star's second dynamics model and the goal module: SecondOrderUnicycleModel (nx = 4, solver_model.py:170-190) with
+    # base weights + GoalModule (goal_module.py:22-36) + ellipsoid obstacles -- configuration_lmpcc
+    # (generate_jackalsimulator_solver.py:118-134) without the path-velocity module, which needs the spline state
+    "c6_goal_unicycle": dict(kind="goal_unicycle", max_obstacles=4, N=30),
+    # LinearizedConstraintModule (linearized_constraints.py:17-95; an option of generate_rosnavigation_solver.py:57):
+    # MPCC + 6 halfspaces a1 x_disc + a2 y_disc <= b per stage on the disc position
+    "c7_linearized": dict(kind="linearized", max_obstacles=6, N=30),
 }
 
 
@@ -72,10 +79,22 @@ def build_modules(config_name):
         from gaussian_constraints import GaussianConstraintModule
         from guidance_constraints import GuidanceConstraintModule
         from decomp_constraints import DecompConstraintModule
-        from solver_model import ContouringSecondOrderUnicycleModel
+        from goal_module import GoalModule
+        from linearized_constraints import LinearizedConstraintModule
+        from solver_model import ContouringSecondOrderUnicycleModel, SecondOrderUnicycleModel
+
+    kind = cfg["kind"]
+    modules = ModuleManager()
+    if kind == "goal_unicycle":  # generate_jackalsimulator_solver.py:118-134 on the plain unicycle (solver_model.py:170-190)
+        model = SecondOrderUnicycleModel()
+        base = modules.add_module(MPCBaseModule(settings))
+        base.weigh_variable(var_name="a", weight_names="acceleration")
+        base.weigh_variable(var_name="w", weight_names="angular_velocity")
+        modules.add_module(GoalModule(settings))
+        modules.add_module(EllipsoidConstraintModule(settings))
+        return modules, model, settings
 
     # generate_jackalsimulator_solver.py:37-58 (configuration_no_obstacles)
-    modules = ModuleManager()
     model = ContouringSecondOrderUnicycleModel()
     base = modules.add_module(MPCBaseModule(settings))
     base.weigh_variable(var_name="a", weight_names="acceleration")
@@ -84,8 +103,9 @@ def build_modules(config_name):
                         cost_function=lambda x, w: w[0] * (x - w[1]) ** 2)
     modules.add_module(ContouringModule(settings))
 
-    kind = cfg["kind"]
-    if kind == "basic":  # :61-67
+    if kind == "linearized":  # generate_rosnavigation_solver.py:57 (commented alternative): LinearizedConstraintModule
+        modules.add_module(LinearizedConstraintModule(settings))
+    elif kind == "basic":  # :61-67
         modules.add_module(EllipsoidConstraintModule(settings))
     elif kind == "tmpc":  # :95-105
         modules.add_module(GuidanceConstraintModule(settings, constraint_submodule=EllipsoidConstraintModule))

@@ -31,7 +31,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "MPC solves/sec (N=30 SQP-RTI batch)"
-PLANNERS = {"c1_basic": 1, "tmpc_shipped": 5, "c2_tmpc12": 9}
+PLANNERS = {"c1_basic": 1, "tmpc_shipped": 5, "c2_tmpc12": 9, "c5_ccmpc": 1, "c6_goal_unicycle": 1, "c7_linearized": 1}
 
 
 def load_json(path, default=None):
@@ -137,14 +137,15 @@ def run_reference(args):
             "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(cfg, planners, args.num_iter), "sample": sample},
-            "cpu_baseline": {"value": value, "unit": "solves/s", "cores": threads, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "solves/s", "cores": threads, "kind": "port", "sample": sample,
+                             "cores_policy": "all host cores (os.cpu_count()), OpenMP over problems -- the same policy as cpu_baseline of the GPU arm"},
             "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit_json(line)
 
 
 def workload_name(cfg, planners, num_iter):
-    return "%s: T-MPC++ homotopy sets, %d planners/set, N=30, dt=0.2, %d SQP-RTI iterations/solve" % (cfg, planners, num_iter)
+    return "%s: T-MPC++ homotopy sets, %d planners/set, N=%d, dt=0.2, %d SQP-RTI iterations/solve" % (cfg, planners, 50 if cfg == "c5_ccmpc" else 30, num_iter)
 
 
 _REAL_STDOUT = None
@@ -175,7 +176,8 @@ def main():
     ap.add_argument("--sets", type=int, default=4096, help="homotopy sets per GPU per step")
     ap.add_argument("--num-iter", type=int, default=10, help="SQP-RTI iterations per solve (settings.yaml:18)")
     ap.add_argument("--ref-sets", type=int, default=128, help="homotopy sets per step of the CPU arm")
-    ap.add_argument("--cpu-sets", type=int, default=384, help="homotopy sets of the cpu_baseline sample")
+    ap.add_argument("--cpu-sets", type=int, default=0, help="homotopy sets of the cpu_baseline sample (0: ~20 s of CPU work on all cores)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra measurements (other iteration counts / configurations)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--latency-reps", type=int, default=100, help="single-set latency repetitions (0 = skip)")
     args = ap.parse_args()
@@ -207,19 +209,22 @@ def main():
     N, nx, nu, npar = d["N"], d["nx"], d["nu"], d["npar"]
     nz = nx + nu
 
-    # ---- synthetic batch of this rank's shard (independent homotopy sets; no data-path collective)
+    # ---- synthetic batches of this rank's shard (independent homotopy sets; no data-path collective).  TWO resident batches are
+    #      rotated between steps so that no step re-solves what the previous one left in L2 (each is larger than L2 anyway).
     t_gen = time.perf_counter()
-    batch = synthetic.make_batch(eng.parameter_map, d, n_sets, planners, seed=1234 + 7919 * rank)
-    t_gen = time.perf_counter() - t_gen
+    batches = [synthetic.make_batch(eng.parameter_map, d, n_sets, planners, seed=1234 + 7919 * rank + 104729 * i) for i in range(2)]
+    batch = batches[0]
+    t_gen = (time.perf_counter() - t_gen) / len(batches)
 
     def pinned(a):
         t = torch.empty(a.shape, dtype=torch.float64 if a.dtype == np.float64 else torch.int32, pin_memory=True)
         t.numpy()[...] = a
         return t
 
-    h_xinit, h_x0, h_params = pinned(batch["xinit"]), pinned(batch["x0"]), pinned(batch["params"])
+    h_in = [(pinned(b["xinit"]), pinned(b["x0"]), pinned(b["params"])) for b in batches]
+    h_xinit, h_x0, h_params = h_in[0]
     h_offsets = pinned(batch["set_offsets"])
-    d_xinit, d_x0, d_params = h_xinit.to(dev), h_x0.to(dev), h_params.to(dev)
+    d_in = [tuple(t.to(dev) for t in h) for h in h_in]
     d_offsets = h_offsets.to(dev)
     d_xtraj = torch.empty((n, (N + 1) * nx), dtype=torch.float64, device=dev)
     d_utraj = torch.empty((n, N * nu), dtype=torch.float64, device=dev)
@@ -231,10 +236,14 @@ def main():
     d_best = torch.empty(n_sets, dtype=torch.int32, device=dev)
     stream = torch.cuda.Stream(device=dev)      # a real (non-default) stream: the engine launches on it, events record on it
     torch.cuda.synchronize()
+    step_no = [0]
 
-    def step_device():
-        eng.solve_batch_device(n, d_xinit.data_ptr(), d_x0.data_ptr(), d_params.data_ptr(), args.num_iter, d_xtraj.data_ptr(),
-                               d_utraj.data_ptr(), d_pobj.data_ptr(), d_exit.data_ptr(), d_qps.data_ptr(), d_res.data_ptr(),
+    def step_device(which=None, num_iter=None):
+        i = step_no[0] % len(d_in) if which is None else which
+        step_no[0] += 1
+        xi_, x0_, pr_ = d_in[i]
+        eng.solve_batch_device(n, xi_.data_ptr(), x0_.data_ptr(), pr_.data_ptr(), args.num_iter if num_iter is None else num_iter,
+                               d_xtraj.data_ptr(), d_utraj.data_ptr(), d_pobj.data_ptr(), d_exit.data_ptr(), d_qps.data_ptr(), d_res.data_ptr(),
                                ipm_iters=d_ipm.data_ptr(), stream=stream.cuda_stream)
         eng.select_best_device(n_sets, d_offsets.data_ptr(), d_pobj.data_ptr(), d_exit.data_ptr(), d_best.data_ptr(),
                                stream=stream.cuda_stream)
@@ -264,10 +273,12 @@ def main():
     total_ms = ev0.elapsed_time(ev1)
     launches = eng.launch_count() - launches0
     # solve-kernel duration (events recorded by the engine around the kernel, same stream): one more pass
-    for _ in range(3):
-        step_device()
+    ipm_means = []
+    for i in (1, 0, 1, 0):
+        step_device(which=i)
         torch.cuda.synchronize()
         kernel_ms.append(eng.last_kernel_ms())
+        ipm_means.append(float(d_ipm.float().mean().item()))
     barrier()
     clocks = sampler.stop(clock_mark)
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
@@ -276,8 +287,8 @@ def main():
     total_ms_max = float(t.item())
     value = world * n * args.steps / (total_ms_max * 1e-3)
 
-    exit_codes = d_exit.cpu().numpy()
-    ipm_mean = float(d_ipm.cpu().numpy().mean())
+    exit_codes = d_exit.cpu().numpy()           # (batch 0: the last pass above)
+    ipm_mean = float(np.mean(ipm_means))        # over both resident batches, like the kernel time
     best = d_best.cpu().numpy()
 
     # ---- e2e: the C-ABI call a user makes, pinned host buffers, H2D + kernel + D2H + select inside
@@ -287,17 +298,21 @@ def main():
     xi_np, x0_np, p_np = h_xinit.numpy(), h_x0.numpy(), h_params.numpy()
     off_np = h_offsets.numpy()
 
-    def step_e2e():
-        eng.solve_batch(xi_np, x0_np, p_np, num_iter=args.num_iter, out=np_out)
+    h_np = [tuple(t.numpy() for t in h) for h in h_in]
+
+    def step_e2e(which):
+        a, b_, c = h_np[which]
+        eng.solve_batch(a, b_, c, num_iter=args.num_iter, out=np_out)
         return eng.select_best(off_np, np_out["pobj"], np_out["exit_code"])
 
-    step_e2e()
+    step_e2e(1)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        best_e2e = step_e2e()
+    for i in range(args.steps):
+        step_e2e((i + 1) % 2)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    best_e2e = step_e2e(0)
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -371,8 +386,91 @@ def main():
                    "p50": float(np.percentile(lat, 50)), "p95": float(np.percentile(lat, 95)), "reps": int(args.latency_reps)}
         eng1.close()
 
-    # ---- roofline of the dominant kernel (mpc_solve_kernel)
+    # ---- SURVEY 8(d) beside the headline: the same workload at ONE iteration (the fork's effective behaviour) and the
+    #      other configurations (throughput + FP64 fraction each), device-resident, kernel timed by the engine's CUDA events
     flops = load_json(os.path.join(ROOT, "oracle", "flops.json"), {})
+    extra = None
+    if not args.no_extra:
+        extra = {}
+
+        def frac_of(cfgname, nit, rate, ipm):
+            fl = flops.get("%s/iter%d" % (cfgname, nit))
+            if not fl:
+                return None, None
+            fps = fl["flops_fixed_part"] + fl["flops_per_ipm_iter"] * ipm
+            return fps, fps * rate / 1e12 / fp64_peak
+
+        kms1 = []
+        for i in (0, 1, 0, 1):
+            step_device(which=i, num_iter=1)
+            torch.cuda.synchronize()
+            kms1.append(eng.last_kernel_ms())
+        ipm1 = float(d_ipm.float().mean().item())
+        r1 = n / (float(np.mean(kms1[1:])) * 1e-3)
+        fps1, fr1 = frac_of(cfg, 1, r1, ipm1)
+        extra["%s/iter1" % cfg] = {"solves_per_s_per_gpu": r1, "kernel_ms": float(np.mean(kms1[1:])), "ipm_iters_mean": ipm1,
+                                   "success_frac": float((d_exit == 1).float().mean().item()), "flops_per_solve": fps1, "fp64_frac": fr1, "n": n}
+        step_device(which=0)                      # leave the buffers as the e2e comparison expects them
+        torch.cuda.synchronize()
+        for ocfg in [c for c in sorted(PLANNERS) if c != cfg]:
+            opl = PLANNERS[ocfg]
+            osets = max(148 * 8 * 4 // opl, 1)     # >= 4 waves of the persistent grid
+            oeng = engine.Engine(ocfg, device=local_rank, max_batch=osets * opl)
+            ob = synthetic.make_batch(oeng.parameter_map, oeng.dims, osets, opl, seed=99 + rank)
+            o_d = [torch.from_numpy(ob[k]).to(dev) for k in ("xinit", "x0", "params")]
+            on = ob["n"]
+            o_out = [torch.empty((on, (oeng.N + 1) * oeng.nx), dtype=torch.float64, device=dev), torch.empty((on, oeng.N * oeng.nu), dtype=torch.float64, device=dev),
+                     torch.empty(on, dtype=torch.float64, device=dev), torch.empty(on, dtype=torch.int32, device=dev),
+                     torch.empty(on, dtype=torch.int32, device=dev), torch.empty(on, dtype=torch.float64, device=dev), torch.empty(on, dtype=torch.int32, device=dev)]
+            torch.cuda.synchronize()
+            for nit in (10, 1):
+                ms_ = []
+                for _ in range(3):
+                    oeng.solve_batch_device(on, o_d[0].data_ptr(), o_d[1].data_ptr(), o_d[2].data_ptr(), nit, o_out[0].data_ptr(), o_out[1].data_ptr(),
+                                            o_out[2].data_ptr(), o_out[3].data_ptr(), o_out[4].data_ptr(), o_out[5].data_ptr(), ipm_iters=o_out[6].data_ptr(),
+                                            stream=stream.cuda_stream)
+                    torch.cuda.synchronize()
+                    ms_.append(oeng.last_kernel_ms())
+                rate_ = on / (float(np.mean(ms_[1:])) * 1e-3)
+                ipm_ = float(o_out[6].float().mean().item())
+                fps_, fr_ = frac_of(ocfg, nit, rate_, ipm_)
+                extra["%s/iter%d" % (ocfg, nit)] = {"solves_per_s_per_gpu": rate_, "kernel_ms": float(np.mean(ms_[1:])), "ipm_iters_mean": ipm_,
+                                                    "success_frac": float((o_out[3] == 1).float().mean().item()), "flops_per_solve": fps_, "fp64_frac": fr_,
+                                                    "n": on, "N": oeng.N, "nx": oeng.nx, "npar": oeng.npar, "nh": oeng.nh}
+            del o_d, o_out
+            oeng.close()
+        torch.cuda.empty_cache()
+
+    # ---- several GPUs from ONE process (mpcgpu_multi_*: one host thread + streams per device, by-set partition, only the decision
+    #      records and the selected trajectory of every set come back): rank 0 drives all GPUs of the job while the other ranks wait
+    e2e_multi = None
+    if world > 1:
+        barrier()
+        if rank == 0:
+            multi = engine.MultiEngine(cfg, list(range(world)), n)
+            Pv = h_np[0][2].reshape(n_sets, planners, N, npar)
+            differs_m = np.nonzero((Pv[:64] != Pv[:64, :1]).any(axis=(0, 1, 2)))[0].astype(np.int32)
+            tot_sets = n_sets * world
+            m_xs = pinned(np.tile(np.ascontiguousarray(h_np[0][0].reshape(n_sets, planners, nx)[:, 0]), (world, 1))).numpy()
+            m_sh = pinned(np.tile(np.ascontiguousarray(Pv[:, 0]), (world, 1, 1))).numpy()
+            m_x0 = pinned(np.tile(h_np[0][1], (world, 1))).numpy()
+            m_pv = pinned(np.tile(np.ascontiguousarray(Pv[..., differs_m]), (world, 1, 1, 1))).numpy()
+            run_m = lambda: multi.solve_sets(tot_sets, planners, m_xs, m_sh, m_x0, differs_m, m_pv, num_iter=args.num_iter, best_only=True)
+            om = run_m()
+            t0 = time.perf_counter()
+            for _ in range(max(2, args.steps // 2)):
+                om = run_m()
+            dtm = (time.perf_counter() - t0) / max(2, args.steps // 2)
+            assert (om["best"][:n_sets] == best).all() and (om["best"].reshape(world, n_sets) == best[None]).all()
+            e2e_multi = {"value": tot_sets * planners / dtm, "unit": "solves/s", "devices": world, "process": "one (rank 0), a host thread per GPU",
+                         "h2d_bytes_per_step": int((m_xs.size + m_sh.size + m_x0.size + m_pv.size) * 8),
+                         "d2h_bytes_per_step": int(tot_sets * planners * 28 + tot_sets * (4 + ((N + 1) * nx + N * nu) * 8)),
+                         "kernel_ms_max_over_devices": multi.last_kernel_ms(),
+                         "what": "mpcgpu_multi_solve_sets: contiguous ranges of whole sets per GPU, device-side selection, decision records + the selected trajectory gathered"}
+            multi.close()
+        barrier()
+
+    # ---- roofline of the dominant kernel (mpc_solve_kernel)
     fkey = "%s/iter%d" % (cfg, args.num_iter)
     kms = float(np.mean(kernel_ms))
     roofline = None
@@ -386,11 +484,18 @@ def main():
         hbm_ach = bytes_per_solve(d) * n / (kms * 1e-3) / 1e9
         tr = load_json(os.path.join(ROOT, "profiles", "traffic.json"), {}).get(fkey)
         traffic = tr["dram_bytes_per_solve"] * n if tr else None     # per launch, from the committed ncu --set full capture
+        ex = load_json(os.path.join(ROOT, "profiles", "executed_flops.json"), {}).get(fkey)
+        executed = None
+        if ex:      # FP64 operations the kernel actually EXECUTES (ncu thread-instruction counts; the sparsity of W is exploited,
+                    # so it is about half the dense algorithmic count the fraction above is quoted on)
+            exf = ex["executed_flops_per_ipm_iter"] * ipm_mean
+            executed = {"flops_per_solve": exf, "achieved": exf * n / (kms * 1e-3) / 1e12, "unit": "TFLOP/s",
+                        "frac": exf * n / (kms * 1e-3) / 1e12 / fp64_peak, "source": ex["source"]}
         roofline = {"bound": "fp64", "kernel": "mpc_solve_kernel", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                     "frac": achieved / fp64_peak, "traffic": traffic,
                     "traffic_note": "DRAM bytes per launch (ncu) vs %d algorithmic: thread-local arrays / spills written back through L2" % (bytes_per_solve(d) * n),
                     "peak_source": "DFMA micro-kernel measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
-                    "flops_per_solve": fps, "kernel_ms": kms,
+                    "flops_per_solve": fps, "kernel_ms": kms, "executed": executed,
                     "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
                             "bytes_per_solve": bytes_per_solve(d),
                             "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"}}
@@ -398,24 +503,30 @@ def main():
     # ---- CPU baseline beside it (rank 0, N=1 only): the oracle port on the box's host cores
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        threads = min(8, os.cpu_count() or 1)       # mirrors `omp parallel for num_threads(8)` (guidance_constraints.cpp:304)
-        rate, dt, cnt = cpu_oracle_rate(cfg, planners, args.num_iter, args.cpu_sets, threads)
+        # ONE core-count policy for every CPU throughput figure of this file (cpu_baseline here and the --impl reference arm):
+        # all host cores, OpenMP over problems.  The single-set LATENCY uses the reference's own team size instead
+        # (`omp parallel for num_threads(8)` over the planners of one set, guidance_constraints.cpp:304).
+        threads = os.cpu_count() or 1
+        cpu_sets = args.cpu_sets if args.cpu_sets > 0 else max(32, int(20.0 * 140.0 * threads / planners))      # ~20 s of CPU work
+        rate, dt, cnt = cpu_oracle_rate(cfg, planners, args.num_iter, cpu_sets, threads)
         if latency is not None:      # the same single-set latency on the host cores (OpenMP over the planners)
             from oracle_binding import Oracle
             orc = Oracle(cfg)
             cl = []
+            lat_threads = min(8, threads)
             for rep in range(12):
                 sl = slice(rep * planners, (rep + 1) * planners)
                 t0 = time.perf_counter()
-                r = orc.solve_batch(xi_np[sl], x0_np[sl], p_np[sl], num_iter=args.num_iter, threads=threads)
+                r = orc.solve_batch(xi_np[sl], x0_np[sl], p_np[sl], num_iter=args.num_iter, threads=lat_threads)
                 orc.select_best(np.array([0, planners], np.int32), r["pobj"], r["exit_code"])
                 cl.append((time.perf_counter() - t0) * 1e3)
             latency["cpu_port_p50"] = float(np.percentile(cl[2:], 50))
-            latency["cpu_cores"] = threads
+            latency["cpu_cores"] = lat_threads
             latency["reference_measured_ms"] = "35.3 mean / 34.6 p50 ('Optimization' scope, 5 planners, reference traces, BASELINE.md)"
         cpu_baseline = {"value": rate, "unit": "solves/s", "cores": threads, "kind": "port",
+                        "cores_policy": "all host cores (os.cpu_count()), OpenMP over problems -- the same policy as the --impl reference arm",
                         "sample": "%d homotopy sets x %d planners (%d solves, %.1f s wall) of the same workload" % (
-                            args.cpu_sets, planners, cnt, dt),
+                            cpu_sets, planners, cnt, dt),
                         "reference_measured": "20-25 ms per planner solve on the reference's own traces (BASELINE.md), i.e. 40-50 solves/s/core"}
 
     if dist is not None:
@@ -432,10 +543,11 @@ def main():
                            "solves_per_gpu_per_step": n, "l2": "inputs (%.2f GB/GPU) larger than L2" % (h2d / 1e9),
                            "parallelism": "sets sharded over %d GPU(s), no collective on the solve path" % world,
                            "success_frac": float((exit_codes == 1).mean()), "ipm_iters_mean": ipm_mean,
-                           "host_generation_s": t_gen},
+                           "host_generation_s": t_gen, "resident_batches": len(batches),
+                           "inputs": "two resident batches rotated between steps: no step re-solves the inputs of the previous one"},
                 "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
-                "latency": latency, "e2e_sets": e2e_sets}
+                "latency": latency, "e2e_sets": e2e_sets, "e2e_multi": e2e_multi, "extra": extra}
         emit_json(line)
 
 

@@ -15,7 +15,7 @@ sys.path.insert(0, os.path.join(HERE, "..", "tests"))
 from oracle_binding import Oracle  # noqa: E402
 from oscar_mpc_planner_mr_modification_b200 import synthetic  # noqa: E402
 
-WORKLOADS = {"c1_basic": 1, "tmpc_shipped": 5, "c2_tmpc12": 9}
+WORKLOADS = {"c1_basic": 1, "tmpc_shipped": 5, "c2_tmpc12": 9, "c5_ccmpc": 1, "c6_goal_unicycle": 1, "c7_linearized": 1}
 
 
 def count(cfg, planners, num_iter, n_sets=16, seed=1234):

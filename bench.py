@@ -363,6 +363,32 @@ def main():
             if dist is not None:
                 dist.all_reduce(tg_, op=dist.ReduceOp.MAX)
             assert (go["best"] == best).all()
+            # ---- struct-of-tables (mpcgpu_solve_sets_tables): stage-invariant parameters once per set, obstacle table,
+            #      warm starts; the parameter block is built on the device
+            lay = eng.table_layout()
+            inv_idx = lay["invariant_idx"]
+            if lay.get("ellipsoid") and set(range(npar)) - set(inv_idx.tolist()) <= (set(range(lin_base, lin_base + 3 * lin_count)) |
+                                                                                    set(range(lay["ellipsoid"]["base"], lay["ellipsoid"]["base"] + lay["ellipsoid"]["count"] * lay["ellipsoid"]["stride"]))):
+                h_inv = pinned(np.ascontiguousarray(Pv[:, 0, 0][:, inv_idx]))
+                h_rad = pinned(np.full((n_sets, batch["obst_pred"].shape[2]), synthetic.OBSTACLE_RADIUS))
+                to = dict(np_out)
+                to["best"] = pinned(np.zeros(n_sets, np.int32)).numpy()
+                run_t = lambda: eng.solve_sets_tables(n_sets, planners, h_xs.numpy(), h_inv.numpy(), h_ob.numpy(), x0_np, guided=h_g.numpy(),
+                                                      robot_radius=batch["robot_radius"], obstacle_radius=h_rad.numpy(), num_iter=args.num_iter, out=to)
+                ot = run_t()
+                barrier()
+                t0 = time.perf_counter()
+                for _ in range(args.steps):
+                    run_t()
+                torch.cuda.synchronize()
+                tt_ = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+                if dist is not None:
+                    dist.all_reduce(tt_, op=dist.ReduceOp.MAX)
+                assert (to["best"] == best).all()
+                e2e_sets["tables"] = {"value": world * n * args.steps / float(tt_.item()), "unit": "solves/s", "h2d_bytes_per_step": int(ot["h2d_bytes"]),
+                                      "h2d_bytes_per_solve": ot["h2d_bytes"] / n,
+                                      "what": "mpcgpu_solve_sets_tables: %d stage-invariant parameters once per set + obstacle table + warm starts; the [N][npar] "
+                                              "block is built on the device (ellipsoid slots, guidance halfspaces)" % inv_idx.size}
             e2e_sets["guided"] = {"value": world * n * args.steps / float(tg_.item()), "unit": "solves/s",
                                   "h2d_bytes_per_step": int((h_shared.numel() + h_xs.numel() + h_x0.numel() + h_ob.numel()) * 8 + h_g.numel()),
                                   "what": "mpcgpu_solve_sets_guided: halfspaces built on the device from %d obstacle predictions per set "

@@ -167,6 +167,45 @@ int mpcgpu_solve_sets_guided(mpcgpu_engine *e, int n_sets, int planners, const d
                              int *qp_status, double *res_eq, const double *obj_scale, const double *obj_sub,
                              const unsigned char *disabled, int *best_idx, const mpcgpu_set_options *opt);
 
+/* Struct-of-tables parameter path: what the caller knows once per control cycle, in the shape it knows it.
+ * Replaces: the k-loop `for k < N: for module: setParameters(data, module_data, k)` (mpc_planner/src/planner.cpp:153-159) and
+ *           the string-keyed / if-chain setters underneath it (acados_solver_interface.cpp:212-225,
+ *           solver_generator/generate_cpp_files.py:235-254): N * npar doubles per planner written on the host and copied.
+ * Here the per-set parameter block [N][npar] is BUILT ON THE DEVICE from
+ *   invariant  [n_sets][n_invariant]     parameters with the same value at every stage (weights, the 5 spline segments
+ *                                        contouring.cpp:96-126, disc radius / offsets), flat indices invariant_idx[n_invariant];
+ *   stage      [n_sets][N][n_stage]      parameters that change per stage and are shared by the planners of a set (e.g. decomp
+ *                                        halfspaces), flat indices stage_idx[n_stage]; may be empty;
+ *   obstacles  [n_sets][N][M][ob_stride] prediction step i of obstacle j: (x, y) for ob_stride 2 (psi = 0, radius from
+ *                                        obstacle_radius[n_sets][M]) or (x, y, psi, r) for ob_stride 4 -> ellipsoid slots
+ *                                        (EllipsoidConstraints::setParameters, ellipsoid_constraints.cpp:34-90: stage k <- step k-1,
+ *                                        dummies at k = 0; ell_base < 0: none) and, with guided != NULL, the guidance halfspaces
+ *                                        (see mpcgpu_guidance_halfspaces_device);
+ * every other parameter is zero unless a per-planner override (param_idx / planner_params) writes it.  The generated
+ * mpc_planner_tables.h / tables.yaml of a configuration list the invariant indices and the slot layout.
+ * For the benchmark configuration this is 2.4 KB host->device per solve instead of 15 KB (mpcgpu_solve_sets) or 44 KB (flat). */
+typedef struct mpcgpu_param_tables {
+    int n_invariant;
+    const int *invariant_idx;
+    const double *invariant;
+    int n_stage;
+    const int *stage_idx;
+    const double *stage;
+    int M, ob_stride;
+    const double *obstacles;
+    const double *obstacle_radius;
+    int ell_base, ell_stride;
+    const int *ell_offsets;                    /* [7]: x, y, psi, major, minor, chi, r inside an obstacle's block */
+    const unsigned char *guided;               /* [n] or NULL: no halfspaces built on the device */
+    int lin_base, lin_count;
+    double robot_radius;
+} mpcgpu_param_tables;
+int mpcgpu_solve_sets_tables(mpcgpu_engine *e, int n_sets, int planners, const double *xinit_sets, const mpcgpu_param_tables *tables,
+                             const double *x0, int nidx, const int *param_idx, const double *planner_params, const int *num_iter,
+                             int num_iter_all, double *xtraj, double *utraj, double *pobj, int *exit_code, int *qp_status,
+                             double *res_eq, const double *obj_scale, const double *obj_sub, const unsigned char *disabled,
+                             int *best_idx, const mpcgpu_set_options *opt);
+
 /* Pick the best planner of each homotopy set.
  * Replaces: the objective post-processing of GuidanceConstraints::optimize and FindBestPlanner
  *           (mpc_planner_modules/src/guidance_constraints.cpp:373-420,572-590):

@@ -109,6 +109,25 @@ __global__ void scatter_params_kernel(int n, int N, int npar, int nidx, const in
         params[pk_ * npar + idx[j]] = vals[t];
     }
 }
+// struct-of-tables path: the per-set block [N][npar] from the stage-invariant values (broadcast over the stages)
+// and the per-stage shared values; every other slot has been zeroed
+__global__ void scatter_invariant_kernel(int n_sets, int N, int npar, int n_inv, const int* __restrict__ idx, const double* __restrict__ vals,
+                                         double* __restrict__ shared)
+{
+    const size_t total = (size_t)n_sets * N * n_inv;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(t % n_inv);
+        const size_t sk = t / n_inv;               // set * N + k
+        shared[sk * npar + idx[i]] = vals[(sk / N) * n_inv + i];
+    }
+}
+__global__ void scatter_stage_kernel(int n_sets, int N, int npar, int n_stg, const int* __restrict__ idx, const double* __restrict__ vals,
+                                     double* __restrict__ shared)
+{
+    const size_t total = (size_t)n_sets * N * n_stg;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x)
+        shared[(t / n_stg) * npar + idx[t % n_stg]] = vals[t];
+}
 __global__ void repeat_xinit_kernel(int n, int planners, int nx, const double* __restrict__ xs, double* __restrict__ xinit)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -152,6 +171,8 @@ struct mpcgpu_engine {
     unsigned long long launch_seq = 0;   // every solve launch takes its own work counter from the ring d_counters[MPCGPU_MAX_INFLIGHT]
     int* next_counter() { return d_counters + (launch_seq++ % MPCGPU_MAX_INFLIGHT); }
     double *d_prev = nullptr, *d_objout = nullptr, *d_consout = nullptr, *d_static = nullptr;   // set options, allocated on first use
+    double* d_tab = nullptr; size_t cap_tab = 0;      // struct-of-tables inputs: [invariant | stage | obstacle radius] doubles, then the index arrays
+    int* d_tabidx = nullptr; size_t cap_tabidx = 0;
     unsigned char* d_consen = nullptr;
     size_t cap_prev = 0, cap_static = 0;
     unsigned char* d_disabled = nullptr;
@@ -232,7 +253,7 @@ int mpcgpu_engine_destroy(mpcgpu_engine* e)
     cudaSetDevice(e->device);
     void* ptrs[] = {e->d_obst, e->d_shared, e->d_pvals, e->d_xs, e->d_pidx, e->d_xinit, e->d_x0, e->d_params, e->d_mem, e->d_xtraj, e->d_utraj, e->d_pobj, e->d_res_eq, e->d_scale,
                     e->d_sub, e->d_num_iter, e->d_exit, e->d_qps, e->d_ipm, e->d_counters, e->d_offsets, e->d_best, e->d_disabled,
-                    e->d_prev, e->d_objout, e->d_consout, e->d_static, e->d_consen};
+                    e->d_prev, e->d_objout, e->d_consout, e->d_static, e->d_consen, e->d_tab, e->d_tabidx};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (e->ev0) cudaEventDestroy(e->ev0);
@@ -515,7 +536,10 @@ struct GuidedArgs {
     double robot_radius;
     int ob_stride = 2;                   // 4: obstacle tables (x, y, psi, r) of include/mpcgpu_wire.h
     int ell_base = -1, ell_stride = 0, ell_off[7] = {0, 0, 0, 0, 0, 0, 0};      // >= 0: ellipsoid slots written from the table
+    const mpcgpu_param_tables* tab = nullptr;      // struct-of-tables path: the shared block is BUILT on the device (no shared_params)
 };
+static int pack_obstacles_launch(mpcgpu_engine* e, int n_sets, const double* xinit_sets, const double* table, int obs, const double* radius, int M,
+                                 int ell_base, int ell_stride, const int* off, double* params, void* stream);
 static int solve_sets_impl(mpcgpu_engine* e, int n_sets, int planners, const double* xinit_sets, const double* shared_params,
                            const double* x0, int nidx, const int* param_idx, const double* planner_params, const GuidedArgs* ga,
                            const int* num_iter, int num_iter_all, double* xtraj, double* utraj, double* pobj, int* exit_code,
@@ -555,7 +579,8 @@ static int solve_sets_impl(mpcgpu_engine* e, int n_sets, int planners, const dou
                            int* qp_status, double* res_eq, const double* obj_scale, const double* obj_sub, const unsigned char* disabled,
                            int* best_idx, const mpcgpu_set_options* opt)
 {
-    if (!e || n_sets < 0 || planners <= 0 || !xinit_sets || !shared_params || !x0 || nidx < 0 || (nidx > 0 && (!param_idx || !planner_params)) ||
+    const mpcgpu_param_tables* tab = ga ? ga->tab : nullptr;
+    if (!e || n_sets < 0 || planners <= 0 || !xinit_sets || (!shared_params && !tab) || !x0 || nidx < 0 || (nidx > 0 && (!param_idx || !planner_params)) ||
         !pobj || !exit_code || !qp_status || !res_eq || !best_idx)
         return MPCGPU_ERR_ARG;
     // per-planner trajectories are optional when the selected trajectory of every set is asked for instead
@@ -615,7 +640,32 @@ static int solve_sets_impl(mpcgpu_engine* e, int n_sets, int planners, const dou
     const size_t smem_ = (size_t)o->mem_doubles;
     const size_t ob_per_set = ga ? (size_t)N * ga->n_obs * ga->ob_stride : 0;       // doubles
     unsigned char* d_guided = nullptr;
-    if (ga) {      // obstacle predictions / tables + guided flags of the device-side constraint construction
+    size_t tab_inv = 0, tab_stg = 0, tab_rad = 0;      // offsets (doubles) inside d_tab
+    if (tab) {
+        if (tab->n_invariant < 0 || tab->n_stage < 0 || (tab->n_invariant > 0 && (!tab->invariant_idx || !tab->invariant)) ||
+            (tab->n_stage > 0 && (!tab->stage_idx || !tab->stage)) || tab->n_invariant > np || tab->n_stage > np)
+            return MPCGPU_ERR_ARG;
+        for (int i = 0; i < tab->n_invariant; i++) if (tab->invariant_idx[i] < 0 || tab->invariant_idx[i] >= np) return MPCGPU_ERR_ARG;
+        for (int i = 0; i < tab->n_stage; i++) if (tab->stage_idx[i] < 0 || tab->stage_idx[i] >= np) return MPCGPU_ERR_ARG;
+        tab_stg = (size_t)n_sets * tab->n_invariant;
+        tab_rad = tab_stg + (size_t)n_sets * N * tab->n_stage;
+        const size_t need = tab_rad + (size_t)n_sets * (tab->obstacle_radius ? tab->M : 0) + 1;
+        if (need > e->cap_tab) {
+            if (e->d_tab) cudaFree(e->d_tab);
+            e->d_tab = nullptr; e->cap_tab = 0;
+            CK(cudaMalloc((void**)&e->d_tab, need * 8));
+            e->cap_tab = need;
+        }
+        if ((size_t)(tab->n_invariant + tab->n_stage + 1) > e->cap_tabidx) {
+            if (e->d_tabidx) cudaFree(e->d_tabidx);
+            e->d_tabidx = nullptr; e->cap_tabidx = 0;
+            CK(cudaMalloc((void**)&e->d_tabidx, (size_t)(2 * np + 1) * 4));
+            e->cap_tabidx = (size_t)(2 * np + 1);
+        }
+        if (tab->n_invariant) CK(cudaMemcpyAsync(e->d_tabidx, tab->invariant_idx, (size_t)tab->n_invariant * 4, cudaMemcpyHostToDevice, st));
+        if (tab->n_stage) CK(cudaMemcpyAsync(e->d_tabidx + tab->n_invariant, tab->stage_idx, (size_t)tab->n_stage * 4, cudaMemcpyHostToDevice, st));
+    }
+    if (ga && (ga->guided || ob_per_set)) {      // obstacle predictions / tables + guided flags of the device-side constraint construction
         const size_t ob_bytes = (size_t)n_sets * ob_per_set * 8;
         if (ob_bytes + (size_t)n > e->cap_obst) {
             if (e->d_obst) cudaFree(e->d_obst);
@@ -667,7 +717,26 @@ static int solve_sets_impl(mpcgpu_engine* e, int n_sets, int planners, const dou
         double* d_xs = e->d_xs + (size_t)s0 * nx;
         double* d_sh = e->d_shared + (size_t)s0 * N * np;
         CK(cudaMemcpyAsync(d_xs, xinit_sets + (size_t)s0 * nx, (size_t)ns * nx * 8, cudaMemcpyHostToDevice, cs));
-        CK(cudaMemcpyAsync(d_sh, shared_params + (size_t)s0 * N * np, (size_t)ns * N * np * 8, cudaMemcpyHostToDevice, cs));
+        if (tab) {      // build the per-set block on the device: zero, invariant values broadcast over the stages, per-stage values
+            CK(cudaMemsetAsync(d_sh, 0, (size_t)ns * N * np * 8, cs));
+            if (tab->n_invariant) {
+                double* dv = e->d_tab + tab_inv + (size_t)s0 * tab->n_invariant;
+                CK(cudaMemcpyAsync(dv, tab->invariant + (size_t)s0 * tab->n_invariant, (size_t)ns * tab->n_invariant * 8, cudaMemcpyHostToDevice, cs));
+                scatter_invariant_kernel<<<296, 256, 0, cs>>>(ns, N, np, tab->n_invariant, e->d_tabidx, dv, d_sh);
+                e->launches += 1;
+            }
+            if (tab->n_stage) {
+                double* dv = e->d_tab + tab_stg + (size_t)s0 * N * tab->n_stage;
+                CK(cudaMemcpyAsync(dv, tab->stage + (size_t)s0 * N * tab->n_stage, (size_t)ns * N * tab->n_stage * 8, cudaMemcpyHostToDevice, cs));
+                scatter_stage_kernel<<<296, 256, 0, cs>>>(ns, N, np, tab->n_stage, e->d_tabidx + tab->n_invariant, dv, d_sh);
+                e->launches += 1;
+            }
+            if (tab->obstacle_radius)
+                CK(cudaMemcpyAsync(e->d_tab + tab_rad + (size_t)s0 * tab->M, tab->obstacle_radius + (size_t)s0 * tab->M, (size_t)ns * tab->M * 8,
+                                   cudaMemcpyHostToDevice, cs));
+            CK(cudaGetLastError());
+        } else
+            CK(cudaMemcpyAsync(d_sh, shared_params + (size_t)s0 * N * np, (size_t)ns * N * np * 8, cudaMemcpyHostToDevice, cs));
         CK(cudaMemcpyAsync(e->d_x0 + p0 * nz * (N + 1), x0 + p0 * nz * (N + 1), m * nz * (N + 1) * 8, cudaMemcpyHostToDevice, cs));
         if (nidx > 0)
             CK(cudaMemcpyAsync(e->d_pvals + p0 * N * nidx, planner_params + p0 * N * nidx, m * N * nidx * 8, cudaMemcpyHostToDevice, cs));
@@ -688,9 +757,10 @@ static int solve_sets_impl(mpcgpu_engine* e, int n_sets, int planners, const dou
         if (ga) {
             d_ob = (const double*)e->d_obst + (size_t)s0 * ob_per_set;
             if (ob_per_set) CK(cudaMemcpyAsync((void*)d_ob, ga->obst_pred + (size_t)s0 * ob_per_set, (size_t)ns * ob_per_set * 8, cudaMemcpyHostToDevice, cs));
-            CK(cudaMemcpyAsync(d_guided + p0, ga->guided + p0, m, cudaMemcpyHostToDevice, cs));
+            if (ga->guided) CK(cudaMemcpyAsync(d_guided + p0, ga->guided + p0, m, cudaMemcpyHostToDevice, cs));
             if (ga->ell_base >= 0) {      // ellipsoid slots of the shared block from the tables, before it is expanded per planner
-                int rc_ = mpcgpu_pack_obstacles_device(e, ns, d_xs, d_ob, ga->n_obs, ga->ell_base, ga->ell_stride, ga->ell_off, d_sh, cs);
+                int rc_ = pack_obstacles_launch(e, ns, d_xs, d_ob, ga->ob_stride, (tab && tab->obstacle_radius) ? e->d_tab + tab_rad + (size_t)s0 * tab->M : nullptr,
+                                                ga->n_obs, ga->ell_base, ga->ell_stride, ga->ell_off, d_sh, cs);
                 if (rc_ != MPCGPU_OK) return rc_;
             }
         }
@@ -700,7 +770,7 @@ static int solve_sets_impl(mpcgpu_engine* e, int n_sets, int planners, const dou
         if (nidx > 0) scatter_params_kernel<<<592, 256, 0, cs>>>((int)m, N, np, nidx, e->d_pidx, e->d_pvals + p0 * N * nidx, d_par);
         CK(cudaGetLastError());
         e->launches += (nidx > 0) ? 3 : 2;
-        if (ga) {      // guidance halfspaces built on the device from the obstacle predictions and the warm starts
+        if (ga && ga->guided) {      // guidance halfspaces built on the device from the obstacle predictions and the warm starts
             int rc_ = guidance_halfspaces_launch(e, ns, planners, d_xs, e->d_x0 + p0 * nz * (N + 1), d_ob, ga->n_obs, ga->ob_stride, d_guided + p0,
                                                  ga->lin_base, ga->lin_count, ga->robot_radius,
                                                  n_static > 0 ? e->d_static + (size_t)s0 * st_per_set : nullptr, n_static, d_par, cs);
@@ -754,6 +824,32 @@ static int solve_sets_impl(mpcgpu_engine* e, int n_sets, int planners, const dou
     CK(cudaStreamSynchronize(e->stream2));
     e->chunks_timed = nchunk;
     return MPCGPU_OK;
+}
+
+int mpcgpu_solve_sets_tables(mpcgpu_engine* e, int n_sets, int planners, const double* xinit_sets, const mpcgpu_param_tables* tab,
+                             const double* x0, int nidx, const int* param_idx, const double* planner_params, const int* num_iter,
+                             int num_iter_all, double* xtraj, double* utraj, double* pobj, int* exit_code, int* qp_status, double* res_eq,
+                             const double* obj_scale, const double* obj_sub, const unsigned char* disabled, int* best_idx,
+                             const mpcgpu_set_options* opt)
+{
+    if (!e || !tab || tab->M < 0 || (tab->M > 0 && (!tab->obstacles || (tab->ob_stride != 2 && tab->ob_stride != 4))) ||
+        (tab->M > 0 && tab->ob_stride == 2 && tab->ell_base >= 0 && !tab->obstacle_radius))
+        return MPCGPU_ERR_ARG;
+    const int np = e->ops->np;
+    if (tab->ell_base >= 0) {
+        if (!tab->ell_offsets || tab->ell_stride <= 0 || tab->ell_base + tab->M * tab->ell_stride > np) return MPCGPU_ERR_ARG;
+        for (int i = 0; i < 7; i++)
+            if (tab->ell_offsets[i] < 0 || tab->ell_offsets[i] >= tab->ell_stride) return MPCGPU_ERR_ARG;
+    }
+    if (tab->guided && (tab->lin_base < 0 || tab->lin_count < 0 || tab->lin_base + 3 * tab->lin_count > np)) return MPCGPU_ERR_ARG;
+    GuidedArgs ga = {tab->M, tab->lin_base, tab->lin_count, tab->obstacles, tab->guided, tab->robot_radius};
+    ga.ob_stride = tab->M > 0 ? tab->ob_stride : 2;
+    ga.ell_base = tab->M > 0 ? tab->ell_base : -1; ga.ell_stride = tab->ell_stride;
+    if (ga.ell_base >= 0)
+        for (int i = 0; i < 7; i++) ga.ell_off[i] = tab->ell_offsets[i];
+    ga.tab = tab;
+    return drain(e, solve_sets_impl(e, n_sets, planners, xinit_sets, nullptr, x0, nidx, param_idx, planner_params, &ga, num_iter, num_iter_all, xtraj,
+                                    utraj, pobj, exit_code, qp_status, res_eq, obj_scale, obj_sub, disabled, best_idx, opt));
 }
 
 int mpcgpu_select_best(mpcgpu_engine* e, int n_sets, const int* set_offsets, const double* pobj, const int* exit_code,

@@ -90,7 +90,7 @@ struct Writer {
 
 __global__ void pack_obstacles_kernel(int n_sets, int N, int nx, int npar, int M, int ell_base, int ell_stride, int o_x, int o_y, int o_psi,
                                       int o_major, int o_minor, int o_chi, int o_r, const double* __restrict__ xinit_sets,
-                                      const double* __restrict__ table, double* __restrict__ params)
+                                      const double* __restrict__ table, int obs, const double* __restrict__ radius, double* __restrict__ params)
 {
     const long long total = (long long)n_sets * N * M;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
@@ -100,8 +100,10 @@ __global__ void pack_obstacles_kernel(int n_sets, int N, int nx, int npar, int M
         if (k == 0) {                                                     // ellipsoid_constraints.cpp:30-31,42-56
             x = xinit_sets[(size_t)s * nx] + 50.0; y = xinit_sets[(size_t)s * nx + 1] + 50.0; psi = 0.0; r = 0.1;
         } else {                                                          // :66-77 (prediction step k-1)
-            const double* T = table + (((size_t)s * N + (k - 1)) * M + j) * 4;
-            x = T[0]; y = T[1]; psi = T[2]; r = T[3];
+            const double* T = table + (((size_t)s * N + (k - 1)) * M + j) * obs;      // obs = 4: (x, y, psi, r); 2: (x, y) + radius table
+            x = T[0]; y = T[1];
+            psi = obs >= 4 ? T[2] : 0.0;
+            r = obs >= 4 ? T[3] : radius[(size_t)s * M + j];
         }
         P[o_x] = x; P[o_y] = y; P[o_psi] = psi; P[o_r] = r; P[o_major] = 0.0; P[o_minor] = 0.0; P[o_chi] = 1.0;
     }
@@ -179,9 +181,17 @@ int mpcgpu_obstacle_table(const mpcgpu_track* tracks, const double* steps, int n
     return kept;
 }
 
+static int pack_obstacles_launch(mpcgpu_engine* e, int n_sets, const double* xinit_sets, const double* table, int obs, const double* radius, int M,
+                                 int ell_base, int ell_stride, const int* off, double* params, void* stream);
 int mpcgpu_pack_obstacles_device(mpcgpu_engine* e, int n_sets, const double* xinit_sets, const double* table, int M, int ell_base,
                                  int ell_stride, const int* off, double* params, void* stream)
 {
+    return pack_obstacles_launch(e, n_sets, xinit_sets, table, 4, nullptr, M, ell_base, ell_stride, off, params, stream);
+}
+static int pack_obstacles_launch(mpcgpu_engine* e, int n_sets, const double* xinit_sets, const double* table, int obs, const double* radius, int M,
+                                 int ell_base, int ell_stride, const int* off, double* params, void* stream)
+{
+    if (obs != 4 && !(obs == 2 && radius)) return MPCGPU_ERR_ARG;
     if (!e || n_sets < 0 || M < 0 || !xinit_sets || (M > 0 && !table) || !off || !params || ell_base < 0 || ell_stride <= 0) return MPCGPU_ERR_ARG;
     for (int i = 0; i < 7; i++)
         if (off[i] < 0 || off[i] >= ell_stride) return MPCGPU_ERR_ARG;
@@ -192,7 +202,7 @@ int mpcgpu_pack_obstacles_device(mpcgpu_engine* e, int n_sets, const double* xin
     const long long total = (long long)n_sets * e->ops->N * M;
     const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
     pack_obstacles_kernel<<<blocks, 256, 0, st>>>(n_sets, e->ops->N, e->ops->nx, e->ops->np, M, ell_base, ell_stride, off[0], off[1], off[2], off[3],
-                                                   off[4], off[5], off[6], xinit_sets, table, params);
+                                                   off[4], off[5], off[6], xinit_sets, table, obs, radius, params);
     CK(cudaGetLastError());
     e->launches += 1;
     return MPCGPU_OK;

@@ -15,7 +15,7 @@ _lib = None
 SYMBOLS = [
     "mpcgpu_num_configs", "mpcgpu_config_name", "mpcgpu_engine_create", "mpcgpu_engine_destroy", "mpcgpu_desc_query",
     "mpcgpu_mem_doubles", "mpcgpu_solve_batch", "mpcgpu_solve_batch_device", "mpcgpu_sync", "mpcgpu_solve_sets", "mpcgpu_select_best",
-    "mpcgpu_alloc_pinned", "mpcgpu_free_pinned", "mpcgpu_multi_create", "mpcgpu_multi_destroy", "mpcgpu_multi_num_devices", "mpcgpu_multi_engine",
+    "mpcgpu_alloc_pinned", "mpcgpu_free_pinned", "mpcgpu_solve_sets_tables", "mpcgpu_multi_create", "mpcgpu_multi_destroy", "mpcgpu_multi_num_devices", "mpcgpu_multi_engine",
     "mpcgpu_multi_shard_range", "mpcgpu_multi_solve_sets", "mpcgpu_multi_solve_sets_guided", "mpcgpu_multi_solve_batch", "mpcgpu_multi_last_kernel_ms",
     "mpcgpu_select_best_device", "mpcgpu_model_eval_doubles", "mpcgpu_model_eval", "mpcgpu_measure_fp64_peak", "mpcgpu_launch_count", "mpcgpu_last_kernel_ms", "mpcgpu_last_error", "mpcgpu_set_kernel_mode", "mpcgpu_guidance_halfspaces_device", "mpcgpu_solve_sets_guided",
 ]
@@ -91,6 +91,15 @@ def measure_fp64_peak(device=0):
     if rc != 0:
         raise RuntimeError("mpcgpu_measure_fp64_peak failed: %d" % rc)
     return v.value
+
+
+class ParamTables(ctypes.Structure):
+    """struct mpcgpu_param_tables (include/mpcgpu.h): the struct-of-tables parameter path"""
+    _fields_ = [("n_invariant", ctypes.c_int), ("invariant_idx", ctypes.c_void_p), ("invariant", ctypes.c_void_p),
+                ("n_stage", ctypes.c_int), ("stage_idx", ctypes.c_void_p), ("stage", ctypes.c_void_p),
+                ("M", ctypes.c_int), ("ob_stride", ctypes.c_int), ("obstacles", ctypes.c_void_p), ("obstacle_radius", ctypes.c_void_p),
+                ("ell_base", ctypes.c_int), ("ell_stride", ctypes.c_int), ("ell_offsets", ctypes.c_void_p),
+                ("guided", ctypes.c_void_p), ("lin_base", ctypes.c_int), ("lin_count", ctypes.c_int), ("robot_radius", ctypes.c_double)]
 
 
 class MpcGpuError(RuntimeError):
@@ -273,6 +282,64 @@ class Engine:
                                                None if best_only else _ptr(out["utraj"]), _ptr(out["pobj"]), _ptr(out["exit_code"]), _ptr(out["qp_status"]), _ptr(out["res_eq"]),
                                                _ptr(sc), None, _ptr(ds), _ptr(out["best"]), opt)
         self._check(rc, "mpcgpu_solve_sets_guided")
+        return out
+
+    def table_layout(self):
+        """generated/<config>/tables.yaml: invariant parameter indices and the obstacle / halfspace slot layout"""
+        with open(os.path.join(config_dir(self.config), "tables.yaml")) as f:
+            t = yaml.safe_load(f)
+        t["invariant_idx"] = np.array([self.parameter_map[n] for n in t["invariant"]], np.int32)
+        return t
+
+    def solve_sets_tables(self, n_sets, planners, xinit_sets, invariant, obstacles, x0, guided=None, robot_radius=0.0, obstacle_radius=None,
+                          stage_idx=None, stage=None, param_idx=None, planner_params=None, num_iter=10, out=None, obj_scale=None, disabled=None,
+                          **opts):
+        """mpcgpu_solve_sets_tables: stage-invariant parameters [n_sets, n_invariant] (order of table_layout()["invariant"]), obstacle
+        table [n_sets, N, M, 2|4], warm starts; the parameter block is built on the device."""
+        n = n_sets * planners
+        if out is None:
+            out = self.alloc_outputs(n)
+            out["best"] = np.zeros(n_sets, np.int32)
+        opt, _keep = self._set_options(out, n, n_sets=n_sets, **opts)
+        best_only = bool(opts.get("best_only"))
+        lay = self.table_layout()
+        f64 = lambda a: None if a is None else np.ascontiguousarray(a, np.float64)
+        inv, ob, rad, stg = f64(invariant), f64(obstacles), f64(obstacle_radius), f64(stage)
+        sidx = None if stage_idx is None else np.ascontiguousarray(stage_idx, np.int32)
+        g = None if guided is None else np.ascontiguousarray(guided, np.uint8)
+        t = ParamTables()
+        t.n_invariant = int(lay["invariant_idx"].size); t.invariant_idx = lay["invariant_idx"].ctypes.data; t.invariant = inv.ctypes.data
+        assert inv.size == n_sets * t.n_invariant
+        if sidx is not None:
+            t.n_stage = int(sidx.size); t.stage_idx = sidx.ctypes.data; t.stage = stg.ctypes.data
+        t.M = 0 if ob is None else int(ob.shape[2]); t.ob_stride = 2 if ob is None else int(ob.shape[3])
+        if ob is not None:
+            t.obstacles = ob.ctypes.data
+        if rad is not None:
+            t.obstacle_radius = rad.ctypes.data
+        ell = lay.get("ellipsoid")
+        off = np.array(ell["offsets"], np.int32) if ell else None
+        t.ell_base = ell["base"] if ell else -1
+        t.ell_stride = ell["stride"] if ell else 0
+        if ell:
+            t.ell_offsets = off.ctypes.data
+        lin = lay.get("guidance_halfspaces")
+        if g is not None and lin:
+            t.guided = g.ctypes.data; t.lin_base = lin["base"]; t.lin_count = lin["count"]; t.robot_radius = float(robot_radius)
+        sc = None if obj_scale is None else np.ascontiguousarray(obj_scale, np.float64)
+        ds = None if disabled is None else np.ascontiguousarray(disabled, np.uint8)
+        nidx = 0 if param_idx is None else int(np.asarray(param_idx).size)
+        pidx = None if nidx == 0 else np.ascontiguousarray(param_idx, np.int32)
+        pvals = None if nidx == 0 else np.ascontiguousarray(planner_params, np.float64)
+        vp = ctypes.c_void_p
+        self.lib.mpcgpu_solve_sets_tables.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, ctypes.c_int, vp, vp, vp, ctypes.c_int] + [vp] * 11
+        rc = self.lib.mpcgpu_solve_sets_tables(self.handle, n_sets, planners, _ptr(f64(xinit_sets)), ctypes.byref(t), _ptr(f64(x0)), nidx, _ptr(pidx),
+                                               _ptr(pvals), None, int(num_iter), None if best_only else _ptr(out["xtraj"]),
+                                               None if best_only else _ptr(out["utraj"]), _ptr(out["pobj"]), _ptr(out["exit_code"]),
+                                               _ptr(out["qp_status"]), _ptr(out["res_eq"]), _ptr(sc), None, _ptr(ds), _ptr(out["best"]), opt)
+        self._check(rc, "mpcgpu_solve_sets_tables")
+        out["h2d_bytes"] = int(8 * (inv.size + (0 if ob is None else ob.size) + (0 if rad is None else rad.size) + (0 if stg is None else stg.size)
+                                    + np.asarray(x0).size + np.asarray(xinit_sets).size + (0 if pvals is None else pvals.size)) + (0 if g is None else g.size))
         return out
 
     def guidance_halfspaces_device(self, n_sets, planners, xinit_sets, x0, obst_pred, n_obs, guided, robot_radius, params, stream=None):

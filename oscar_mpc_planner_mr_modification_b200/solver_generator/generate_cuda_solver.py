@@ -418,6 +418,56 @@ def emit_parameter_header(pb):
     return "\n".join(out) + "\n"
 
 
+# ---- struct-of-tables parameter path --------------------------------------------------------------------
+# Which parameters the reference's C++ modules write with the SAME value at every stage (weights from CONFIG:
+# mpc_base / contouring / goal setParameters; the spline segments: contouring.cpp:96-126; disc radius / offsets) and which are
+# per-stage tables (obstacle slots: ellipsoid_constraints.cpp:34-90, gaussian_constraints.cpp:31-79; halfspaces:
+# linearized_constraints.cpp:150-189, decomp_constraints.cpp:150-189; the consistency reference: guidance_constraints.cpp:985-1023).
+_STAGE_PREFIXES = ("ellipsoid_obst_", "gaussian_obst_", "lin_constraint_", "disc_", "consistency_weight", "prev_traj_")
+
+
+def classify_parameters(pb):
+    names = pb["param_names"]
+    per_stage = [i for i, n in enumerate(names) if n.startswith(_STAGE_PREFIXES)]
+    invariant = [i for i in range(len(names)) if i not in set(per_stage)]
+    pm = {n: i for i, n in enumerate(names)}
+    M = sum(1 for n in names if n.startswith("ellipsoid_obst_") and n.endswith("_x"))
+    ell = None
+    if M:
+        base = pm["ellipsoid_obst_0_x"]
+        stride = (pm["ellipsoid_obst_1_x"] - base) if M > 1 else 7
+        base = min(pm["ellipsoid_obst_0_" + f] for f in ("x", "y", "psi", "major", "minor", "chi", "r"))
+        ell = dict(count=M, base=base, stride=stride, offsets=[pm["ellipsoid_obst_0_" + f] - base for f in ("x", "y", "psi", "major", "minor", "chi", "r")])
+    nlin = sum(1 for n in names if n.startswith("lin_constraint_") and n.endswith("_a1"))
+    lin = dict(count=nlin, base=pm["lin_constraint_0_a1"]) if nlin else None
+    return dict(invariant=invariant, per_stage=per_stage, ellipsoid=ell, guidance_halfspaces=lin)
+
+
+def emit_tables_header(pb, name):
+    """mpc_planner_tables.h: the struct-of-tables a caller fills ONCE per control cycle instead of N x npar setParameter calls"""
+    c = classify_parameters(pb)
+    names = pb["param_names"]
+    out = ["// GENERATED -- struct-of-tables parameter path of configuration %s (SURVEY 8 f2): stage-invariant parameters travel" % name,
+           "// once per homotopy set, obstacle predictions as a table; the engine expands them to all_parameters on the device",
+           "// (mpcgpu_solve_sets_tables, include/mpcgpu.h).  Replaces: the k-loop over modules->setParameters (mpc_planner/src/planner.cpp:153-159)",
+           "// through the generated setSolverParameter<Bundle> if-chains (solver_generator/generate_cpp_files.py:235-254).",
+           "#pragma once", "namespace MPCPlanner {", "struct SolverTables {",
+           "    static constexpr int n_invariant = %d;" % len(c["invariant"]),
+           "    // flat parameter indices, in the order of `invariant` below",
+           "    static constexpr int invariant_idx[%d] = {%s};" % (max(len(c["invariant"]), 1), ", ".join(str(i) for i in c["invariant"]) or "0"),
+           "    double invariant[%d] = {};   // %s" % (max(len(c["invariant"]), 1), ", ".join(names[i] for i in c["invariant"][:8]) + (", ..." if len(c["invariant"]) > 8 else ""))]
+    for pos, i in enumerate(c["invariant"]):
+        out.append("    static constexpr int inv_%s = %d;" % (names[i], pos))
+    if c["ellipsoid"]:
+        e = c["ellipsoid"]
+        out += ["    static constexpr int max_obstacles = %d, ell_base = %d, ell_stride = %d;" % (e["count"], e["base"], e["stride"]),
+                "    static constexpr int ell_offsets[7] = {%s};   // x, y, psi, major, minor, chi, r inside an obstacle's block" % ", ".join(str(v) for v in e["offsets"])]
+    if c["guidance_halfspaces"]:
+        out.append("    static constexpr int lin_base = %d, lin_count = %d;" % (c["guidance_halfspaces"]["base"], c["guidance_halfspaces"]["count"]))
+    out += ["};", "}  // namespace MPCPlanner"]
+    return "\n".join(out) + "\n"
+
+
 def generate_cuda_solver(modules, settings, model, name, out_dir):
     pb = extract_problem(modules, settings, model)
     os.makedirs(out_dir, exist_ok=True)
@@ -441,6 +491,12 @@ def generate_cuda_solver(modules, settings, model, name, out_dir):
         mmap[s] = ["u", i, pb["lb"][i], pb["ub"][i]]
     with open(os.path.join(out_dir, "model_map.yaml"), "w") as f:
         yaml.dump(mmap, f, default_flow_style=False)
+    with open(os.path.join(out_dir, "mpc_planner_tables.h"), "w") as f:
+        f.write(emit_tables_header(pb, name))
+    cls = classify_parameters(pb)
+    with open(os.path.join(out_dir, "tables.yaml"), "w") as f:
+        yaml.dump(dict(invariant=[pb["param_names"][i] for i in cls["invariant"]], per_stage=[pb["param_names"][i] for i in cls["per_stage"]],
+                       ellipsoid=cls["ellipsoid"], guidance_halfspaces=cls["guidance_halfspaces"]), f, default_flow_style=None)
     with open(os.path.join(out_dir, "solver_settings.yaml"), "w") as f:
         yaml.dump(dict(N=pb["N"], nx=pb["nx"], nu=pb["nu"], nvar=pb["nx"] + pb["nu"], npar=len(pb["p"])), f,
                   default_flow_style=False)

@@ -107,3 +107,51 @@ def test_set_entry_carries_the_planner_capsules_across_cycles():
     fresh = eng.solve_batch(b["xinit"], b["x0"], b["params"], num_iter=2)
     okk = (flat["exit_code"] == 1) & (fresh["exit_code"] == 1)
     assert np.abs(flat["xtraj"][okk] - fresh["xtraj"][okk]).max() > 1e-9      # the surviving multipliers do change the second cycle
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg,planners", [("c2_tmpc12", 9), ("tmpc_shipped", 5)])
+def test_struct_of_tables_entry_is_bit_identical_and_small(cfg, planners):
+    """stage-invariant parameters once per set + obstacle table + warm starts, expanded on the device --
+    bit-identical to the flat entry on the expanded inputs, <= 3 KB host->device per solve for the benchmark configuration."""
+    eng = engine.Engine(cfg, 0, 512)
+    n_sets = 16
+    b = synthetic.make_batch(eng.parameter_map, eng.dims, n_sets, planners, seed=23)
+    N, npar, nx = eng.N, eng.npar, eng.nx
+    P = b["params"].reshape(n_sets, planners, N, npar)
+    lay = eng.table_layout()
+    inv_idx = lay["invariant_idx"]
+    assert (P[..., inv_idx] == P[:, :1, :1][..., inv_idx]).all()            # what the generator calls stage-invariant IS
+    invariant = np.ascontiguousarray(P[:, 0, 0][:, inv_idx])
+    radius = np.full((n_sets, b["obst_pred"].shape[2]), synthetic.OBSTACLE_RADIUS)
+    stage_idx = stage = None
+    if "prev_traj_x" in eng.parameter_map:                                   # the consistency reference: per stage, shared? no: per planner
+        pidx = np.array([eng.parameter_map[k] for k in ("consistency_weight", "prev_traj_x", "prev_traj_y")], np.int32)
+        pvals = np.ascontiguousarray(P[..., pidx])
+    else:
+        pidx = pvals = None
+    xs = np.ascontiguousarray(b["xinit"].reshape(n_sets, planners, nx)[:, 0])
+    flat = eng.solve_batch(b["xinit"], b["x0"], b["params"], num_iter=5)
+    best = eng.select_best(b["set_offsets"], flat["pobj"], flat["exit_code"])
+    out = eng.solve_sets_tables(n_sets, planners, xs, invariant, b["obst_pred"], b["x0"], guided=b["guided"], robot_radius=b["robot_radius"],
+                                obstacle_radius=radius, param_idx=pidx, planner_params=pvals, num_iter=5)
+    np.testing.assert_array_equal(out["exit_code"], flat["exit_code"])
+    np.testing.assert_array_equal(out["best"], best)
+    ok = flat["exit_code"] == 1
+    # the halfspaces are rebuilt on the device (bit-identical to the oracle restatement, not to numpy's): trajectories agree to rounding
+    assert np.abs(out["xtraj"][ok] - flat["xtraj"][ok]).max() < 1e-6
+    per_solve = out["h2d_bytes"] / b["n"]
+    if cfg == "c2_tmpc12":
+        assert per_solve <= 3072, per_solve
+    # and with the obstacle table in the (x, y, psi, r) form of the wire path: same result bit for bit
+    tab4 = np.concatenate([b["obst_pred"], np.zeros_like(b["obst_pred"][..., :1]), np.full_like(b["obst_pred"][..., :1], synthetic.OBSTACLE_RADIUS)], axis=-1)
+    out4 = eng.solve_sets_tables(n_sets, planners, xs, invariant, tab4, b["x0"], guided=b["guided"], robot_radius=b["robot_radius"],
+                                 param_idx=pidx, planner_params=pvals, num_iter=5)
+    for k in ("xtraj", "utraj", "pobj", "exit_code", "qp_status", "res_eq", "best"):
+        np.testing.assert_array_equal(out4[k], out[k])
+    # against the guided entry fed with the host-built shared block: the device-built block is the same block
+    shared = np.ascontiguousarray(P[:, 0])
+    g = eng.solve_sets_guided(n_sets, planners, xs, shared, b["x0"], b["obst_pred"], b["guided"], b["robot_radius"], num_iter=5,
+                              param_idx=pidx, planner_params=pvals)
+    for k in ("xtraj", "utraj", "pobj", "exit_code", "qp_status", "res_eq", "best"):
+        np.testing.assert_array_equal(g[k], out[k])

@@ -116,6 +116,9 @@ typedef struct {
     REAL P[NN + 1][NX * NX], pv[NN + 1][NX], Lx0[NN][NX], Lx1[NN][NX], L10[NN], iL[NN][NU], lv[NN][NU];
     REAL dv[NN + 1][NZ], dpi[NN + 1][NX], dlam[NN][NCMAX], dt[NN][NCMAX];
     REAL dva[NN + 1][NZ];
+#ifdef MPC_HPIPM_BALANCE
+    REAL dt_aff[NN][NCMAX], dlam_aff[NN][NCMAX];
+#endif
     int qp_warm;                     /* previous QP solution available (HPIPM warm start 2) */
     int ipm_iters_total, qp_iters_last;
 } work_t;
@@ -354,6 +357,9 @@ static void linearize(work_t *w, const REAL *xinit, const REAL *params)
     (void)xinit;
 }
 
+#ifdef MPC_HPIPM_BALANCE
+long g_cond_pc_triggers, g_cond_pc_checks;      /* diagnostics of the conditional predictor-corrector (not thread safe: run with 1 thread) */
+#endif
 /* entry e of stage k is active? (x box rows are absent at k = 0: x_0 is fixed) */
 static int active(int k, int e)
 {
@@ -503,7 +509,8 @@ static void kkt_gradient(work_t *w, int corrector, REAL sigmu)
             if (!active(k, e)) continue;
             REAL invt = 1.0 / w->t[k][e];
             REAL gam = w->lam[k][e] * invt * w->rd[k][e];
-            if (corrector) gam += w->dt[k][e] * w->dlam[k][e] * invt - sigmu * invt;
+            if (corrector == 1) gam += w->dt[k][e] * w->dlam[k][e] * invt - sigmu * invt;
+            else if (corrector == 2) gam += -sigmu * invt;      /* centering direction only (conditional predictor-corrector) */
             crow_axpy(w, k, e, gam, w->gt[k]);
         }
     }
@@ -614,9 +621,11 @@ static REAL ipm_step_ineq(work_t *w, REAL (*dv)[NZ], int corrector, REAL sigmu)
             REAL lam = w->lam[k][e], t = w->t[k][e], invt = 1.0 / t;
             REAL dt = crow_dot(w, k, e, dv[k]) + w->rd[k][e];
             REAL dl;
-            if (corrector) {
+            if (corrector == 1) {
                 REAL corr = w->dt[k][e] * w->dlam[k][e] * invt;
                 dl = -(lam + lam * invt * dt + (corr - sigmu * invt));
+            } else if (corrector == 2) {
+                dl = -(lam + lam * invt * dt - sigmu * invt);
             } else {
                 dl = -(lam + lam * invt * dt);
             }
@@ -663,7 +672,36 @@ static int qp_solve(work_t *w, const REAL *dx0)
         /* corrector: rm += dt_aff dlam_aff - sigma mu (folded into gtilde and dlam) */
         kkt_gradient(w, 1, sigmu);
         riccati_solve(w, w->dv);
+#ifdef MPC_HPIPM_BALANCE
+        /* [upstream, from memory of hpipm ocp_qp_ipm.c: mode BALANCE has cond_pred_corr = 1] conditional Mehrotra predictor-
+         * corrector: if the corrected step would leave the duality measure above twice the predictor's, fall back to the
+         * pure centering direction (complementarity right-hand side lam t - sigma mu, no second-order term).  The affine
+         * dt / dlam are needed again by the fallback, so they are saved first.  BALANCE's two iterative-refinement steps
+         * (itref_corr_max = 2) only run while the residual of the Newton system exceeds the exit tolerances (1e-5 here): the
+         * Riccati solve leaves ~1e-12 (tests/test_oracle_solve.py checks the QP KKT conditions to 1e-10), so they never start. */
+        memcpy(w->dt_aff, w->dt, sizeof(w->dt)); memcpy(w->dlam_aff, w->dlam, sizeof(w->dlam));
+#endif
         alpha = ipm_step_ineq(w, w->dv, 1, sigmu);
+#ifdef MPC_HPIPM_BALANCE
+        {
+            REAL T1 = 0.0, T2 = 0.0;
+            for (int k = 0; k < NN; k++)
+                for (int e = 0; e < g_nc; e++)
+                    if (active(k, e)) {
+                        T1 += w->lam[k][e] * w->dt[k][e] + w->t[k][e] * w->dlam[k][e];
+                        T2 += w->dt[k][e] * w->dlam[k][e];
+                    }
+            REAL mu_pc = (mu * cnt + alpha * T1 + alpha * alpha * T2) / cnt;
+            if (mu_pc > 2.0 * mu_aff) {
+                g_cond_pc_triggers++;
+                memcpy(w->dt, w->dt_aff, sizeof(w->dt)); memcpy(w->dlam, w->dlam_aff, sizeof(w->dlam));
+                kkt_gradient(w, 2, sigmu);
+                riccati_solve(w, w->dv);
+                alpha = ipm_step_ineq(w, w->dv, 2, sigmu);
+            }
+            g_cond_pc_checks++;
+        }
+#endif
         REAL a = alpha < 1.0 ? alpha * IPM_STEP_SCALE : alpha;
         for (int k = 0; k <= NN; k++) {
             for (int i = 0; i < NZ; i++) w->v[k][i] += a * w->dv[k][i];

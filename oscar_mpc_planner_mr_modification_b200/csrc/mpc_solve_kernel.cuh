@@ -393,6 +393,13 @@ __device__ __noinline__ void forward_scan(const double* Wv, const double* Lx0, c
 //               After the factorisation of the stage, in place: iL0 @(0,0), L10 @(1,0), iL1 @(1,1), Lxu[i][0..1]
 //               @(2+i,0..1), P @(2+i,2+j), l = Luu^-1 q_u @(7,0..1), p @(7,2+i)
 //        RO_B   [W | rb], NX x (NZ+1) row-major      RO_PRB  P+ rb      RO_DZ  step of the stage [du; dx]
+// HPIPM "BALANCE" mode behaviour that DESIGN.md section 4 leaves out by default: the conditional Mehrotra predictor-corrector
+// (fall back to the pure centering direction when the corrected step would leave the duality measure above twice the
+// predictor's).  1 = on, in this kernel and in the oracle (-DMPC_HPIPM_BALANCE); the role-split kernel is not built then.
+#ifndef MPC_HPIPM_BALANCE
+#define MPC_HPIPM_BALANCE 0
+#endif
+constexpr bool BALANCE = MPC_HPIPM_BALANCE != 0;
 #ifndef MPC_COOP
 #define MPC_COOP 0   // thread-per-stage kernel: 1 = cooperative Riccati recursion (all lanes on one stage, shared-memory workspace)
 #endif
@@ -1081,6 +1088,27 @@ __device__ __noinline__ void mirror_packed(double* Hp)
     mirror_generic(Hp);
 }
 
+// Software prefetch of the thread-local Jacobian rows (MPC_C_PREFETCH = entries ahead, 0 = off): the rows of C are read once
+// per pass in entry order and do not survive in the L1 between passes (8 warps x 18 KB); a row is 3 doubles per lane,
+// i.e. 6 lines of the lane-interleaved local window, fetched PF entries ahead so that the loads of the entry loop hit.
+#ifndef MPC_C_PREFETCH
+#define MPC_C_PREFETCH 0
+#endif
+template <class CM>
+__device__ __forceinline__ void c_prefetch(const CM& C, int e)
+{
+#if MPC_C_PREFETCH > 0
+    if constexpr (!LT_C) {
+        if (e + MPC_C_PREFETCH < NCG) {
+            const double* q = &C.p[HROW[e + MPC_C_PREFETCH] * NHS];
+            const size_t a = __cvta_generic_to_local(q);
+#pragma unroll
+            for (int w = 0; w < 2 * NHS; w++) asm volatile("prefetch.local.L1 [%0];" ::"l"(a + 4 * w));
+        }
+    }
+#endif
+}
+
 // chat_e' y for general entry e (y indexed by z component)
 template <class CM>
 __device__ __forceinline__ double gen_dot(const CM& C, int e, const double* y)
@@ -1106,12 +1134,13 @@ __device__ __forceinline__ IneqStep ineq_affine(double lam, double invt, double 
     s.corr = s.dt * s.dlam * invt;
     return s;
 }
-__device__ __forceinline__ IneqStep ineq_final(double lam, double invt, double rd, double cdva, double cdv, double sigmu)
+// cen: pure centering direction (conditional predictor-corrector fallback, MPC_HPIPM_BALANCE): no second-order term
+__device__ __forceinline__ IneqStep ineq_final(double lam, double invt, double rd, double cdva, double cdv, double sigmu, bool cen = false)
 {
     const IneqStep a = ineq_affine(lam, invt, rd, cdva);
     IneqStep s;
     s.dt = cdv + rd;
-    s.dlam = -(lam + lam * invt * s.dt + (a.corr - sigmu * invt));
+    s.dlam = -(lam + lam * invt * s.dt + (((BALANCE && cen) ? 0.0 : a.corr) - sigmu * invt));
     s.corr = 0.0;
     return s;
 }
@@ -1305,6 +1334,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
         double itb[NCB];                             // 1/t of the box entries, reused by passes B, C and the update (general entries: recomputed)
 #endif
         double dva[NZ], dv[NZ], dpi[NX], sigmu = 0.0, a_ = 0.0;
+        bool cen = false;                            // the step being applied is the centering fallback (MPC_HPIPM_BALANCE)
 #pragma unroll
         for (int e = 0; e < NCB; e++) itb[e] = 0.0;
 #pragma unroll
@@ -1361,7 +1391,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                         {   // lower: chat = +e_i, d = dl
                             double lam = lamb[i], t = tb[i];
                             if (upd) {
-                                const IneqStep st = ineq_final(lam, itb[i], vo[i] - dl - t, dva[i], dv[i], sigmu);
+                                const IneqStep st = ineq_final(lam, itb[i], vo[i] - dl - t, dva[i], dv[i], sigmu, cen);
                                 lam = clamp_lo(lam + a_ * st.dlam, IPM_LAM_MIN); t = clamp_lo(t + a_ * st.dt, IPM_T_MIN);
                                 lamb[i] = lam; tb[i] = t;
                             }
@@ -1374,7 +1404,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                         {   // upper: chat = -e_i, d = -du
                             double lam = lamb[NZ + i], t = tb[NZ + i];
                             if (upd) {
-                                const IneqStep st = ineq_final(lam, itb[NZ + i], du - vo[i] - t, -dva[i], -dv[i], sigmu);
+                                const IneqStep st = ineq_final(lam, itb[NZ + i], du - vo[i] - t, -dva[i], -dv[i], sigmu, cen);
                                 lam = clamp_lo(lam + a_ * st.dlam, IPM_LAM_MIN); t = clamp_lo(t + a_ * st.dt, IPM_T_MIN);
                                 lamb[NZ + i] = lam; tb[NZ + i] = t;
                             }
@@ -1389,6 +1419,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                 if (path) {
 #pragma unroll GEN_UNROLL
                     for (int e = 0; e < NCG; e++) {
+                        c_prefetch(C, e);
                         const int r = HROW[e];
                         const double sg = HSGN[e];
                         double lam = lamg[e], t = tg[e];
@@ -1400,7 +1431,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                                 const double ca = C[r * NHS + a];
                                 cvo += ca * vo[HSUP[a]]; cda += ca * dva[HSUP[a]]; cd += ca * dv[HSUP[a]];
                             }
-                            const IneqStep st = ineq_final(lam, rcp_nb(t), sg * cvo - dg[e] - t, sg * cda, sg * cd, sigmu);      // 1/t recomputed: cheaper than a thread-local array
+                            const IneqStep st = ineq_final(lam, rcp_nb(t), sg * cvo - dg[e] - t, sg * cda, sg * cd, sigmu, cen);      // 1/t recomputed: cheaper than a thread-local array
                             lam = clamp_lo(lam + a_ * st.dlam, IPM_LAM_MIN); t = clamp_lo(t + a_ * st.dt, IPM_T_MIN);
                             lamg[e] = lam; tg[e] = t;
                         }
@@ -1604,6 +1635,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
             if (path) {
 #pragma unroll GEN_UNROLL
                 for (int e = 0; e < NCG; e++) {
+                    c_prefetch(C, e);
                     const int r = HROW[e];
                     const double sg = HSGN[e], lam = lamg[e], t = tg[e];
                     double cv = 0.0, cd = 0.0;
@@ -1628,6 +1660,9 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
 #pragma unroll
             for (int i = 0; i < NZ; i++) gt[i] += V1[i] - sigmu * V2[i];
 
+            cen = false;
+#pragma unroll 1
+            for (int attempt = 0; attempt < (BALANCE ? 2 : 1); attempt++) {
             // ---- corrector solve (factorisation reused): backward vector sweep + forward sweep
             if constexpr (COOP) {
                 if (live) {
@@ -1759,6 +1794,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
 
             // ---- pass C: step length of the corrected direction
             StepFrac sfc;                  // alpha = sfc.ratio()
+            double T1 = 0.0, T2 = 0.0;     // (MPC_HPIPM_BALANCE) duality measure of the corrected step, expanded in powers of alpha
 #pragma unroll
             for (int i = 0; i < NZ; i++) {
                 const bool act = (i < NU) ? path : xbox;
@@ -1766,19 +1802,22 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                     const double dl = LBZ[i] - z[i], du = UBZ[i] - z[i];
                     {
                         const double lam = lamb[i], t = tb[i];
-                        const IneqStep st = ineq_final(lam, itb[i], v[i] - dl - t, dva[i], dv[i], sigmu);
+                        const IneqStep st = ineq_final(lam, itb[i], v[i] - dl - t, dva[i], dv[i], sigmu, cen);
                         sfc.add(lam, st.dlam, t, st.dt);
+                        if constexpr (BALANCE) { T1 += lam * st.dt + t * st.dlam; T2 += st.dt * st.dlam; }
                     }
                     {
                         const double lam = lamb[NZ + i], t = tb[NZ + i];
-                        const IneqStep st = ineq_final(lam, itb[NZ + i], du - v[i] - t, -dva[i], -dv[i], sigmu);
+                        const IneqStep st = ineq_final(lam, itb[NZ + i], du - v[i] - t, -dva[i], -dv[i], sigmu, cen);
                         sfc.add(lam, st.dlam, t, st.dt);
+                        if constexpr (BALANCE) { T1 += lam * st.dt + t * st.dlam; T2 += st.dt * st.dlam; }
                     }
                 }
             }
             if (path) {
 #pragma unroll GEN_UNROLL
                 for (int e = 0; e < NCG; e++) {
+                    c_prefetch(C, e);
                     const int r = HROW[e];
                     const double sg = HSGN[e], lam = lamg[e], t = tg[e];
                     double cv = 0.0, cda = 0.0, cd = 0.0;
@@ -1787,11 +1826,28 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                         const double ca = C[r * NHS + a];
                         cv += ca * v[HSUP[a]]; cda += ca * dva[HSUP[a]]; cd += ca * dv[HSUP[a]];
                     }
-                    const IneqStep st = ineq_final(lam, rcp_nb(t), sg * cv - dg[e] - t, sg * cda, sg * cd, sigmu);
+                    const IneqStep st = ineq_final(lam, rcp_nb(t), sg * cv - dg[e] - t, sg * cda, sg * cd, sigmu, cen);
                     sfc.add(lam, st.dlam, t, st.dt);
+                    if constexpr (BALANCE) { T1 += lam * st.dt + t * st.dlam; T2 += st.dt * st.dlam; }
                 }
             }
             alpha = grp.min(sfc.ratio());
+            if constexpr (BALANCE) {
+                // conditional predictor-corrector [upstream: hpipm ocp_qp_ipm.c, cond_pred_corr = 1 in mode BALANCE]: the duality
+                // measure the corrected step would leave, against twice the predictor's
+                if (attempt == 0) {
+                    T1 = grp.sum(T1); T2 = grp.sum(T2);
+                    const double mu_pc = (mu * (double)IPM_COUNT + alpha * T1 + alpha * alpha * T2) / (double)IPM_COUNT;
+                    if (mu_pc > 2.0 * mu_aff) {
+                        cen = true;                                  // redo the solve with the centering right-hand side only
+#pragma unroll
+                        for (int i = 0; i < NZ; i++) gt[i] -= V1[i];
+                        continue;
+                    }
+                }
+                break;
+            }
+            }   // attempt
             a_ = alpha < 1.0 ? alpha * IPM_STEP_SCALE : alpha;      // applied by the next pass DA
         }
         ipm_total += kk;

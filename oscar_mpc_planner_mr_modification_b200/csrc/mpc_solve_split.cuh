@@ -31,7 +31,7 @@ constexpr int RPB = (NCG + NBR - 1) / NBR > 0 ? (NCG + NBR - 1) / NBR : 1;     /
 constexpr int NHP = NHS * (NHS + 1) / 2;                                       // packed block over the support of h
 constexpr int XS = NHP + 2 * NHS + 3;            // exchange slots per B role and stage: Hs | g | rg | nd nm sm
 constexpr int XSX = 3 * NZ + 3;                  // exchange slots of role X per stage: diag Ht | g | rg | nd nm sm
-constexpr bool SPLIT_OK = (NSTAGE + 1 <= 32) && NPAD <= 32 && NCG >= 6 && NCG >= 2 * NBR;
+constexpr bool SPLIT_OK = (NSTAGE + 1 <= 32) && NPAD <= 32 && NCG >= 6 && NCG >= 2 * NBR && !BALANCE;      // (the BALANCE variant exists in the thread-per-stage kernel only)
 // shared memory of one problem (doubles)
 constexpr int SP_RS = 0;
 constexpr int SP_XCH = (RS_DOUBLES + 1) & ~1;    // [NBR][XS][32]

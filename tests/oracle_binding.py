@@ -17,18 +17,21 @@ def _ptr(a):
 class Oracle:
     _cache = {}
 
-    def __init__(self, config):
-        path = os.path.join(ORACLE_DIR, "_build", "liboracle_%s.so" % config)
+    def __init__(self, config, variant=""):
+        """variant "balance_": the -DMPC_HPIPM_BALANCE build (conditional predictor-corrector)"""
+        libname = "liboracle_%s%s.so" % (variant, config)
+        path = os.path.join(ORACLE_DIR, "_build", libname)
         if not os.path.exists(path):
-            subprocess.run(["make", "-C", ORACLE_DIR, "_build/liboracle_%s.so" % config], check=True,
+            subprocess.run(["make", "-C", ORACLE_DIR, "_build/" + libname], check=True,
                            stdout=subprocess.DEVNULL)
-        if config not in Oracle._cache:
+        config_key = variant + config
+        if config_key not in Oracle._cache:
             lib = ctypes.CDLL(path)
             lib.oracle_param_name.restype = ctypes.c_char_p
             lib.oracle_var_name.restype = ctypes.c_char_p
             lib.oracle_bounds.restype = ctypes.POINTER(ctypes.c_double)
-            Oracle._cache[config] = lib
-        self.lib = Oracle._cache[config]
+            Oracle._cache[config_key] = lib
+        self.lib = Oracle._cache[config_key]
         d = [ctypes.c_int() for _ in range(5)]
         self.lib.oracle_dims(*[ctypes.byref(v) for v in d])
         self.N, self.nx, self.nu, self.npar, self.nh = [v.value for v in d]

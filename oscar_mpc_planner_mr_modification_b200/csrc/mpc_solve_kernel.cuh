@@ -85,30 +85,90 @@ static_assert(MPC_WARPS_PER_CTA % ((NSTAGE + 1 + 31) / 32) == 0, "warps per CTA 
 static_assert(NU == 2, "Riccati input block elimination is written for nu == 2");
 
 constexpr int GEN_UNROLL = MPC_GEN_UNROLL;
-// Where the per-entry state of the general inequality entries lives.  0: thread-local arrays (L1/L2 backed; 8 warps x 86 KB do
-// not fit the L1).  1: multipliers and slacks in shared memory ([entry][thread of the group], conflict free).  2 (default):
-// + the right-hand sides d -- 147 KB per CTA for 24 entries, +5.5 % throughput; 3: + the Jacobian rows C, which only fits
-// with 6 warps per CTA and then loses more parallelism than it gains (measured 196 k vs 217 k solves/s).
-#ifndef MPC_LT_SMEM
-#define MPC_LT_SMEM 2
-#endif
-#ifndef MPC_LT_MASK          // which arrays: bit 0 multipliers, 1 slacks, 2 right-hand sides d, 3 Jacobian rows C
+// Shared-memory placement of per-stage state (one column [entry][thread of the group] per value: conflict free).  What pays is
+// what takes REGISTER pressure out of the interior-point loop (255 registers per thread, ~270 doubles of live state: the rest
+// is spilled to thread-local memory, which 8 warps x ~60 KB cannot keep in the L1).  Measured on c2_tmpc12 (18 432 problems):
+//   general multipliers + slacks + d (147 KB)                                   221 k solves/s   (round-1 layout)
+//   + box multipliers and slacks (205 KB)                                       234 k
+//   general multipliers + slacks, box multipliers + slacks + 1/t (184 KB)       245 k            <- default
+//   (+ g, b: 244 k; box without 1/t but H: 232 k; Jacobian columns x, y instead of d: 217 k; 7 warps with everything: 227 k)
+// The default takes the arrays in that priority order while they fit beside each other for all warps of the CTA:
+// MPC_LT_MASK bits: 0 general multipliers, 1 general slacks, 2 right-hand sides d, 3 Jacobian rows C; MPC_BOX_SMEM: 1 = 1/t of the
+// box entries, 2 = their multipliers and slacks, 3 = all three.  Either macro can be pinned on the command line.
+constexpr int SMEM_BUDGET_DOUBLES = (227 * 1024 - 6144) / 8 / (MPC_WARPS_PER_CTA * 32);      // per thread, static shared memory set aside
+constexpr int auto_lt_mask()
+{
+    int used = 2 * NCG + 6 * (NX + NU), mask = 3;
+    if (used + NCG <= SMEM_BUDGET_DOUBLES) { mask |= 4; used += NCG; }
+    if (used + NH * NHS <= SMEM_BUDGET_DOUBLES) mask |= 8;
+    return mask;
+}
+#ifdef MPC_LT_SMEM
+#ifndef MPC_LT_MASK          // (older knob: 0 none, 1 multipliers + slacks, 2 + d, 3 + C)
 #define MPC_LT_MASK (MPC_LT_SMEM == 0 ? 0 : (MPC_LT_SMEM == 1 ? 3 : (MPC_LT_SMEM == 2 ? 7 : 15)))
+#endif
+#endif
+#ifndef MPC_LT_MASK
+#define MPC_LT_MASK auto_lt_mask()
 #endif
 constexpr bool LT_SMEM = MPC_LT_MASK != 0;
 constexpr bool LT_LAM = (MPC_LT_MASK & 1) != 0, LT_T = (MPC_LT_MASK & 2) != 0, LT_D = (MPC_LT_MASK & 4) != 0, LT_C = (MPC_LT_MASK & 8) != 0;
 constexpr int LT_OFF_LAM = 0, LT_OFF_T = LT_OFF_LAM + (LT_LAM ? NCG : 0), LT_OFF_D = LT_OFF_T + (LT_T ? NCG : 0),
               LT_OFF_C = LT_OFF_D + (LT_D ? NCG : 0);
 #ifndef MPC_BOX_SMEM
-#define MPC_BOX_SMEM 0
+#define MPC_BOX_SMEM 3
 #endif
-constexpr int LT_ENTRY_DOUBLES = LT_OFF_C + (LT_C ? NH * NHS : 0);
-constexpr int LT_DOUBLES = (LT_ENTRY_DOUBLES + (MPC_BOX_SMEM ? 2 * (NX + NU) : 0)) * GW * 32;      // per group: lam, t (d, C) of the general entries (+ 1/t of the boxes)
+// MPC_C_SPLIT: the first MPC_C_SPLIT support columns of every Jacobian row in shared memory, the remaining ones thread-local and
+// SKIPPED when they are zero in every lane of the warp (e.g. the psi column with a zero disc offset) -- a third of the loads of
+// the inequality passes then never leave the SM although the full rows do not fit beside the multipliers (needs !LT_C)
+#ifndef MPC_C_SPLIT
+#define MPC_C_SPLIT 0
+#endif
+constexpr int CSPL = (MPC_C_SPLIT > NHS ? NHS : MPC_C_SPLIT);
+static_assert(CSPL == 0 || !LT_C, "MPC_C_SPLIT needs the Jacobian rows outside shared memory (MPC_LT_MASK bit 3 clear)");
+constexpr int LT_OFF_CS = LT_OFF_C + (LT_C ? NH * NHS : 0);
+constexpr int LT_ENTRY_DOUBLES = LT_OFF_CS + NH * CSPL;
+constexpr int BOX_SM_DOUBLES = (MPC_BOX_SMEM == 1 ? 2 * (NX + NU) : (MPC_BOX_SMEM == 2 ? 4 * (NX + NU) : (MPC_BOX_SMEM == 3 ? 6 * (NX + NU) : 0)));      // 1: 1/t; 2: multipliers + slacks; 3: all three
+// MPC_QP_SMEM: per-stage QP data that the interior-point loop only READS, once per iteration in pass DA, parked in shared memory
+// after the linearisation instead of staying in registers (where they are spilled): bit 0 g and b (12 doubles), bit 1 H (28)
+#ifndef MPC_QP_SMEM
+#define MPC_QP_SMEM 0
+#endif
+constexpr bool QPS_GB = (MPC_QP_SMEM & 1) != 0, QPS_H = (MPC_QP_SMEM & 2) != 0;
+constexpr int QP_OFF_G = LT_ENTRY_DOUBLES + BOX_SM_DOUBLES, QP_OFF_B = QP_OFF_G + (QPS_GB ? NZ : 0), QP_OFF_H = QP_OFF_B + (QPS_GB ? NX : 0);
+constexpr int LT_DOUBLES = (QP_OFF_H + (QPS_H ? NPK : 0)) * GW * 32;      // per group: lam, t (d, C) of the general entries (+ 1/t of the boxes)
 // column accessor: stride GW*32 doubles in shared memory ([entry][thread of the group]), stride 1 for a thread-local array
 template <bool SM>
 struct LtCol {
     double* p;
     __device__ __forceinline__ double& operator[](int e) const { return p[SM ? e * (((NSTAGE + 1 + 31) / 32) * 32) : e]; }
+};
+// Jacobian rows of the general constraints: at(r, a) = d h_r / d z_HSUP[a].  Plain (all in one place, shared or thread-local)
+// or split by column (MPC_C_SPLIT).  operator[] (flat index r * NHS + a) is what the emitted con_lin writes through.
+template <bool SM>
+struct CRows {
+    double* p;          // flat rows: shared-memory column accessor stride or thread-local
+    double* sm;         // split: [NH * CSPL][threads of the group] in shared memory
+    bool tail_zero;     // split: the thread-local tail columns are zero in every lane (set after the linearisation)
+    __device__ __forceinline__ double& operator[](int i) const
+    {
+        if constexpr (CSPL > 0) {
+            const int r = i / NHS, a = i - r * NHS;
+            if (a < CSPL) return sm[(r * CSPL + a) * (((NSTAGE + 1 + 31) / 32) * 32)];
+            return p[i];
+        } else {
+            return p[SM ? i * (((NSTAGE + 1 + 31) / 32) * 32) : i];
+        }
+    }
+    __device__ __forceinline__ double at(int r, int a) const
+    {
+        if constexpr (CSPL > 0) {
+            if (a < CSPL) return sm[(r * CSPL + a) * (((NSTAGE + 1 + 31) / 32) * 32)];
+            return tail_zero ? 0.0 : p[r * NHS + a];
+        } else {
+            return p[SM ? (r * NHS + a) * (((NSTAGE + 1 + 31) / 32) * 32) : r * NHS + a];
+        }
+    }
 };
 struct SmemCol {
     double* p;
@@ -1116,7 +1176,7 @@ __device__ __forceinline__ double gen_dot(const CM& C, int e, const double* y)
     const int r = HROW[e];
     double s = 0.0;
 #pragma unroll
-    for (int a = 0; a < NHS; a++) s += C[r * NHS + a] * y[HSUP[a]];
+    for (int a = 0; a < NHS; a++) s += C.at(r, a) * y[HSUP[a]];
     return HSGN[e] * s;
 }
 
@@ -1190,7 +1250,13 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
     const double* __restrict__ p = params_g + ((size_t)prob * NSTAGE + (path ? k : NSTAGE - 1)) * NP;
 
     double z[NZ], pi[NX], v[NZ], qpi[NX];
+#if MPC_BOX_SMEM >= 2
+    // multipliers and slacks of the box entries in shared memory too: 56 registers less in the interior-point loop
+    const SmemCol lamb{lt_sm + LT_ENTRY_DOUBLES * (GW * 32) + (grp.wig * 32 + (threadIdx.x & 31))};
+    const SmemCol tb{lt_sm + (LT_ENTRY_DOUBLES + NCB) * (GW * 32) + (grp.wig * 32 + (threadIdx.x & 31))};
+#else
     double lamb[NCB], tb[NCB];
+#endif
     // general-entry state: shared-memory columns or thread-local arrays (MPC_LT_MASK); the unused alternative is optimised away
     double* const lt_me = lt_sm + (grp.wig * 32 + (threadIdx.x & 31));
     double lamg_loc[(!LT_LAM && NCG > 0) ? NCG : 1], tg_loc[(!LT_T && NCG > 0) ? NCG : 1];
@@ -1230,7 +1296,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
         // ======================= K1-K4: linearise at the current iterate ============================
         double H[NPK], g[NZ], Wv[NWV], b[NX];
         double C_loc[(!LT_C && NH > 0) ? NH * NHS : 1], dg_loc[(!LT_D && NCG > 0) ? NCG : 1];
-        const LtCol<LT_C> C{LT_C ? lt_me + LT_OFF_C * (GW * 32) : C_loc};
+        CRows<LT_C> C{LT_C ? lt_me + LT_OFF_C * (GW * 32) : C_loc, lt_me + LT_OFF_CS * (GW * 32), false};
         const LtCol<LT_D> dg{LT_D ? lt_me + LT_OFF_D * (GW * 32) : dg_loc};
         {
             double pin[NX], xnx[NX], zx_[NX];
@@ -1262,6 +1328,25 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
 #pragma unroll
                 for (int i = NU; i < NZ; i++) H[pk(i, i)] = REG_EPS;   // mirror(0) = eps I; no terminal cost
             }
+        }
+        const SmemCol gs{lt_me + QP_OFF_G * (GW * 32)}, bs{lt_me + QP_OFF_B * (GW * 32)}, Hs{lt_me + QP_OFF_H * (GW * 32)};
+        if constexpr (QPS_GB) {
+#pragma unroll
+            for (int i = 0; i < NZ; i++) gs[i] = g[i];
+#pragma unroll
+            for (int i = 0; i < NX; i++) bs[i] = b[i];
+        }
+        if constexpr (QPS_H) {
+#pragma unroll
+            for (int i = 0; i < NPK; i++) Hs[i] = H[i];
+        }
+        if constexpr (CSPL > 0 && CSPL < NHS && NH > 0) {      // are the thread-local tail columns of the Jacobian zero everywhere?
+            bool nzt = false;
+            if (path)
+                for (int r = 0; r < NH; r++)
+#pragma unroll
+                    for (int a = CSPL; a < NHS; a++) nzt = nzt || (C_loc[r * NHS + a] != 0.0);
+            C.tail_zero = !grp.any(nzt);
         }
 
         double* const blk = rs + (live ? k : 0) * RSTRIDE;      // this stage's block of the cooperative Riccati workspace (MPC_COOP)
@@ -1327,9 +1412,9 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
         int kk = 0;
         bool isnan_ = false;
         // state of the previous iteration's step, applied at the top of the next pass (fused update):
-#if MPC_BOX_SMEM
+#if MPC_BOX_SMEM == 1 || MPC_BOX_SMEM == 3
         // 1/t of the box entries (reused by passes B, C and the update) parked in shared memory: 28 registers less in the loop
-        const SmemCol itb{lt_sm + LT_ENTRY_DOUBLES * (GW * 32) + (grp.wig * 32 + (threadIdx.x & 31))};
+        const SmemCol itb{lt_sm + (LT_ENTRY_DOUBLES + (MPC_BOX_SMEM == 3 ? 2 * NCB : 0)) * (GW * 32) + (grp.wig * 32 + (threadIdx.x & 31))};
 #else
         double itb[NCB];                             // 1/t of the box entries, reused by passes B, C and the update (general entries: recomputed)
 #endif
@@ -1361,12 +1446,12 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                 grp.shift_down(qpi, qpn);
                 grp.shift_down(vx_, vxn);
 #pragma unroll
-                for (int i = 0; i < NPK; i++) Ht[i] = H[i];
+                for (int i = 0; i < NPK; i++) Ht[i] = QPS_H ? Hs[i] : H[i];
 #pragma unroll
                 for (int i = 0; i < NZ; i++) {
-                    double s = g[i];
+                    double s = QPS_GB ? gs[i] : g[i];
 #pragma unroll
-                    for (int j = 0; j < NZ; j++) s += H[pk(i, j)] * v[j];
+                    for (int j = 0; j < NZ; j++) s += Ht[pk(i, j)] * v[j];
                     rg[i] = s;
                 }
 #pragma unroll
@@ -1374,7 +1459,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                 if (path) {
                     wt_mul_add(Wv, qpn, rg);
 #pragma unroll
-                    for (int i = 0; i < NX; i++) rb[i] = b[i] - vxn[i];
+                    for (int i = 0; i < NX; i++) rb[i] = (QPS_GB ? bs[i] : b[i]) - vxn[i];
                     w_mul_add(Wv, v, rb);
                 }
                 if (k >= 1) {
@@ -1428,7 +1513,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                             double cvo = 0.0, cda = 0.0, cd = 0.0;
 #pragma unroll
                             for (int a = 0; a < NHS; a++) {
-                                const double ca = C[r * NHS + a];
+                                const double ca = C.at(r, a);
                                 cvo += ca * vo[HSUP[a]]; cda += ca * dva[HSUP[a]]; cd += ca * dv[HSUP[a]];
                             }
                             const IneqStep st = ineq_final(lam, rcp_nb(t), sg * cvo - dg[e] - t, sg * cda, sg * cd, sigmu, cen);      // 1/t recomputed: cheaper than a thread-local array
@@ -1436,14 +1521,14 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                             lamg[e] = lam; tg[e] = t;
                         }
 #pragma unroll
-                        for (int a = 0; a < NHS; a++) cv += C[r * NHS + a] * v[HSUP[a]];
+                        for (int a = 0; a < NHS; a++) cv += C.at(r, a) * v[HSUP[a]];
                         const double it_ = rcp_nb(t);
                         const double rd = sg * cv - dg[e] - t, G = lam * it_, m = lam * t;
 #pragma unroll
                         for (int a = 0; a < NHS; a++) {
-                            const double ca = C[r * NHS + a];
+                            const double ca = C.at(r, a);
 #pragma unroll
-                            for (int bb = 0; bb <= a; bb++) Ht[pk(HSUP[a], HSUP[bb])] += G * ca * C[r * NHS + bb];
+                            for (int bb = 0; bb <= a; bb++) Ht[pk(HSUP[a], HSUP[bb])] += G * ca * C.at(r, bb);
                             gt[HSUP[a]] += sg * ca * (G * rd);
                             rg[HSUP[a]] -= sg * ca * lam;
                         }
@@ -1640,15 +1725,15 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                     const double sg = HSGN[e], lam = lamg[e], t = tg[e];
                     double cv = 0.0, cd = 0.0;
 #pragma unroll
-                    for (int a = 0; a < NHS; a++) { cv += C[r * NHS + a] * v[HSUP[a]]; cd += C[r * NHS + a] * dva[HSUP[a]]; }
+                    for (int a = 0; a < NHS; a++) { const double ca = C.at(r, a); cv += ca * v[HSUP[a]]; cd += ca * dva[HSUP[a]]; }
                     const double it_ = rcp_nb(t);
                     const IneqStep st = ineq_affine(lam, it_, sg * cv - dg[e] - t, sg * cd);
                     sfa.add(lam, st.dlam, t, st.dt);
                     S1 += lam * st.dt + t * st.dlam; S2 += st.dt * st.dlam;
 #pragma unroll
                     for (int a = 0; a < NHS; a++) {
-                        V1[HSUP[a]] += sg * C[r * NHS + a] * st.corr;
-                        V2[HSUP[a]] += sg * C[r * NHS + a] * it_;
+                        V1[HSUP[a]] += sg * C.at(r, a) * st.corr;
+                        V2[HSUP[a]] += sg * C.at(r, a) * it_;
                     }
                 }
             }
@@ -1823,7 +1908,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                     double cv = 0.0, cda = 0.0, cd = 0.0;
 #pragma unroll
                     for (int a = 0; a < NHS; a++) {
-                        const double ca = C[r * NHS + a];
+                        const double ca = C.at(r, a);
                         cv += ca * v[HSUP[a]]; cda += ca * dva[HSUP[a]]; cd += ca * dv[HSUP[a]];
                     }
                     const IneqStep st = ineq_final(lam, rcp_nb(t), sg * cv - dg[e] - t, sg * cda, sg * cd, sigmu, cen);

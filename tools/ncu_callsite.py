@@ -76,6 +76,6 @@ for (a0, name), (a1, _) in zip(marks[:-1], marks[1:]):
 v = agg[None]
 print("  %5.1f%% samp %5.1f%% exec  (outside solve_problem: work loop, non-inlined functions)" % (100 * v[0] / tot_s, 100 * v[1] / tot_e))
 print("== top call-site lines")
-for k, v in sorted(((k, v) for k, v in agg.items() if k is not None), key=lambda kv: -kv[1][0])[:25]:
+for k, v in sorted(((k, v) for k, v in agg.items() if k is not None), key=lambda kv: -kv[1][0])[:int(os.environ.get("NCU_TOP", "25"))]:
     print("  line %4d  %5.2f%% samp %5.2f%% exec avgthr %4.1f long_sb %4.1f%% | %s" % (k, 100 * v[0] / tot_s, 100 * v[1] / tot_e, v[2] / max(v[1], 1), 100 * v[3] / tot_s,
                                                                           src[k - 1].strip()[:100]))

@@ -85,6 +85,7 @@ static_assert(MPC_WARPS_PER_CTA % ((NSTAGE + 1 + 31) / 32) == 0, "warps per CTA 
 static_assert(NU == 2, "Riccati input block elimination is written for nu == 2");
 
 constexpr int GEN_UNROLL = MPC_GEN_UNROLL;
+constexpr int NPX = NX * (NX + 1) / 2;      // packed P
 // Shared-memory placement of per-stage state (one column [entry][thread of the group] per value: conflict free).  What pays is
 // what takes REGISTER pressure out of the interior-point loop (255 registers per thread, ~270 doubles of live state: the rest
 // is spilled to thread-local memory, which 8 warps x ~60 KB cannot keep in the L1).  Measured on c2_tmpc12 (18 432 problems):
@@ -125,6 +126,12 @@ constexpr int LT_OFF_LAM = 0, LT_OFF_T = LT_OFF_LAM + (LT_LAM ? NCG : 0), LT_OFF
 #define MPC_C_SPLIT 0
 #endif
 constexpr int CSPL = (MPC_C_SPLIT > NHS ? NHS : MPC_C_SPLIT);
+// MPC_C_ZSKIP (default off: measured 240.5 k vs 246.0 k solves/s, the predication costs more than the loads it saves): the LAST support column of the Jacobian rows (psi for the shipped modules: it only enters through the
+// disc offset) is not loaded in the inequality passes while it is zero in every lane of the warp -- decided once per linearisation
+#ifndef MPC_C_ZSKIP
+#define MPC_C_ZSKIP 0
+#endif
+constexpr int CTAIL0 = CSPL > 0 ? CSPL : ((MPC_C_ZSKIP != 0 && NHS > 1) ? NHS - 1 : NHS);      // first column of the skippable tail
 static_assert(CSPL == 0 || !LT_C, "MPC_C_SPLIT needs the Jacobian rows outside shared memory (MPC_LT_MASK bit 3 clear)");
 constexpr int LT_OFF_CS = LT_OFF_C + (LT_C ? NH * NHS : 0);
 constexpr int LT_ENTRY_DOUBLES = LT_OFF_CS + NH * CSPL;
@@ -136,7 +143,14 @@ constexpr int BOX_SM_DOUBLES = (MPC_BOX_SMEM == 1 ? 2 * (NX + NU) : (MPC_BOX_SME
 #endif
 constexpr bool QPS_GB = (MPC_QP_SMEM & 1) != 0, QPS_H = (MPC_QP_SMEM & 2) != 0;
 constexpr int QP_OFF_G = LT_ENTRY_DOUBLES + BOX_SM_DOUBLES, QP_OFF_B = QP_OFF_G + (QPS_GB ? NZ : 0), QP_OFF_H = QP_OFF_B + (QPS_GB ? NX : 0);
-constexpr int LT_DOUBLES = (QP_OFF_H + (QPS_H ? NPK : 0)) * GW * 32;      // per group: lam, t (d, C) of the general entries (+ 1/t of the boxes)
+// MPC_RIC_SMEM: outputs of the Riccati factorisation that are produced by ONE serial step and read much later: bit 0 the
+// cost-to-go matrix P (15 doubles; used by the multiplier step dpi = P dx + p at the very end of the iteration), bit 1 P+ rb (5)
+#ifndef MPC_RIC_SMEM
+#define MPC_RIC_SMEM 0
+#endif
+constexpr bool RIC_P = (MPC_RIC_SMEM & 1) != 0, RIC_PRB = (MPC_RIC_SMEM & 2) != 0;
+constexpr int RIC_OFF_P = QP_OFF_H + (QPS_H ? NPK : 0), RIC_OFF_PRB = RIC_OFF_P + (RIC_P ? NPX : 0);
+constexpr int LT_DOUBLES = (RIC_OFF_PRB + (RIC_PRB ? NX : 0)) * GW * 32;      // per group: lam, t (d, C) of the general entries (+ 1/t of the boxes)
 // column accessor: stride GW*32 doubles in shared memory ([entry][thread of the group]), stride 1 for a thread-local array
 template <bool SM>
 struct LtCol {
@@ -166,6 +180,7 @@ struct CRows {
             if (a < CSPL) return sm[(r * CSPL + a) * (((NSTAGE + 1 + 31) / 32) * 32)];
             return tail_zero ? 0.0 : p[r * NHS + a];
         } else {
+            if (a >= CTAIL0 && tail_zero) return 0.0;
             return p[SM ? (r * NHS + a) * (((NSTAGE + 1 + 31) / 32) * 32) : r * NHS + a];
         }
     }
@@ -176,7 +191,6 @@ struct SmemCol {
 };
 constexpr int NCB = 2 * NZ;                 // box entries: lower(z_i) i<NZ, then upper(z_i)
 constexpr int NC = NCB + NCG;               // inequality entries per path stage
-constexpr int NPX = NX * (NX + 1) / 2;      // packed P
 constexpr unsigned FULL = 0xffffffffu;
 
 // ---- algorithm constants: identical to oracle/mpc_oracle.c -------------------------------------
@@ -1340,12 +1354,12 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
 #pragma unroll
             for (int i = 0; i < NPK; i++) Hs[i] = H[i];
         }
-        if constexpr (CSPL > 0 && CSPL < NHS && NH > 0) {      // are the thread-local tail columns of the Jacobian zero everywhere?
+        if constexpr (CTAIL0 < NHS && NH > 0) {      // are the tail columns of the Jacobian zero in every lane?
             bool nzt = false;
             if (path)
                 for (int r = 0; r < NH; r++)
 #pragma unroll
-                    for (int a = CSPL; a < NHS; a++) nzt = nzt || (C_loc[r * NHS + a] != 0.0);
+                    for (int a = CTAIL0; a < NHS; a++) nzt = nzt || (C.p[LT_C ? (r * NHS + a) * (GW * 32) : r * NHS + a] != 0.0);
             C.tail_zero = !grp.any(nzt);
         }
 
@@ -1586,22 +1600,33 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
 #pragma unroll
                 for (int i = 0; i < NZ; i++) dva[i] = (live && (path || i >= NU)) ? blk[RO_DZ + i] : 0.0;
             }
-            double P[NPX], pv[NX], Lx0[NX], Lx1[NX], Prb[NX], lv[NU], L10 = 0.0, iL0 = 0.0, iL1 = 0.0;
+            double P[RIC_P ? 1 : NPX], pv[NX], Lx0[NX], Lx1[NX], Prb[RIC_PRB ? 1 : NX], lv[NU], L10 = 0.0, iL0 = 0.0, iL1 = 0.0;
+            const SmemCol Ps{lt_me + RIC_OFF_P * (GW * 32)}, Prbs{lt_me + RIC_OFF_PRB * (GW * 32)};      // (MPC_RIC_SMEM)
+            auto prb = [&](int i) -> double { if constexpr (RIC_PRB) return Prbs[i]; else return Prb[i]; };
+            auto pmat = [&](int i) -> double { if constexpr (RIC_P) return Ps[i]; else return P[i]; };
             if constexpr (!COOP) {
+            if constexpr (!RIC_P) {
 #pragma unroll
-            for (int i = 0; i < NPX; i++) P[i] = 0.0;
+                for (int i = 0; i < NPX; i++) P[i] = 0.0;
+            }
 #pragma unroll
-            for (int i = 0; i < NX; i++) { pv[i] = 0.0; Prb[i] = 0.0; Lx0[i] = 0.0; Lx1[i] = 0.0; }
+            for (int i = 0; i < NX; i++) { pv[i] = 0.0; Lx0[i] = 0.0; Lx1[i] = 0.0; }
+            if constexpr (!RIC_PRB) {
+#pragma unroll
+                for (int i = 0; i < NX; i++) Prb[i] = 0.0;
+            }
             lv[0] = lv[1] = 0.0;
             if (term) {
 #pragma unroll
                 for (int i = 0; i < NX; i++) {
                     pv[i] = gt[NU + i];
 #pragma unroll
-                    for (int j = 0; j <= i; j++) P[pk(i, j)] = Ht[pk(NU + i, NU + j)];
+                    for (int j = 0; j <= i; j++) {
+                        const double pij = Ht[pk(NU + i, NU + j)];
+                        hb[pk(i, j)] = pij;
+                        if constexpr (RIC_P) Ps[pk(i, j)] = pij; else P[pk(i, j)] = pij;
+                    }
                 }
-#pragma unroll
-                for (int i = 0; i < NPX; i++) hb[i] = P[i];
 #pragma unroll
                 for (int i = 0; i < NX; i++) hb[NPX + i] = pv[i];
             }
@@ -1623,7 +1648,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                         double a = 0.0;
 #pragma unroll
                         for (int j = 0; j < NX; j++) a += Pn[pk(i, j)] * rb[j];
-                        Prb[i] = a;
+                        if constexpr (RIC_PRB) Prbs[i] = a; else Prb[i] = a;
                         y[i] = pn[i] + a;
                     }
 #pragma unroll
@@ -1640,13 +1665,15 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
 #pragma unroll
                     for (int i = 0; i < NX; i++)
 #pragma unroll
-                        for (int j = 0; j <= i; j++) P[pk(i, j)] = G[pk(NU + i, NU + j)] - Lx0[i] * Lx0[j] - Lx1[i] * Lx1[j];
+                        for (int j = 0; j <= i; j++) {
+                            const double pij = G[pk(NU + i, NU + j)] - Lx0[i] * Lx0[j] - Lx1[i] * Lx1[j];
+                            hb[pk(i, j)] = pij;
+                            if constexpr (RIC_P) Ps[pk(i, j)] = pij; else P[pk(i, j)] = pij;
+                        }
                     lv[0] = q[0] * iL0;
                     lv[1] = (q[1] - L10 * lv[0]) * iL1;
 #pragma unroll
                     for (int i = 0; i < NX; i++) pv[i] = q[NU + i] - Lx0[i] * lv[0] - Lx1[i] * lv[1];
-#pragma unroll
-                    for (int i = 0; i < NPX; i++) hb[i] = P[i];
 #pragma unroll
                     for (int i = 0; i < NX; i++) hb[NPX + i] = pv[i];
                 }
@@ -1783,7 +1810,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
 #pragma unroll
                         for (int j = 0; j < NX; j++) {
                             am.M[i * NX + j] = Acl[j * NX + i];
-                            c_ += Acl[j * NX + i] * Prb[j];
+                            c_ += Acl[j * NX + i] * prb(j);
                         }
                         am.c[i] = c_;
                     }
@@ -1804,7 +1831,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                     double q0 = gt[0], q1 = gt[1];
 #pragma unroll
                     for (int i = 0; i < NX; i++) {
-                        const double y = pn[i] + Prb[i];
+                        const double y = pn[i] + prb(i);
                         q0 += Bd[i * NU] * y; q1 += Bd[i * NU + 1] * y;
                     }
                     lv[0] = q0 * iL0;
@@ -1827,7 +1854,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                     for (int i = 0; i < NX; i++) pn[i] = hb[NPX + i];
                     double q[NZ], y[NX];
 #pragma unroll
-                    for (int i = 0; i < NX; i++) y[i] = pn[i] + Prb[i];
+                    for (int i = 0; i < NX; i++) y[i] = pn[i] + prb(i);
 #pragma unroll
                     for (int i = 0; i < NZ; i++) q[i] = gt[i];
                     wt_mul_add(Wv, y, q);
@@ -1871,7 +1898,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                 for (int i = 0; i < NX; i++) {
                     double a = pv[i];
 #pragma unroll
-                    for (int j = 0; j < NX; j++) a += P[pk(i, j)] * dv[NU + j];
+                    for (int j = 0; j < NX; j++) a += pmat(pk(i, j)) * dv[NU + j];
                     dpi[i] = a;
                 }
             }

@@ -272,6 +272,14 @@ int mpcgpu_multi_solve_batch(mpcgpu_multi *m, int n, const double *xinit, const 
 /* max over the devices of the solve-kernel time of the last multi call (ms, CUDA events on each device) */
 float mpcgpu_multi_last_kernel_ms(mpcgpu_multi *m);
 
+/* Diagnostic build (-DMPC_CHECK=1, lib/libmpcgpu_check.so; no reference counterpart -- it stands in for compute-sanitizer's
+ * memcheck / racecheck, which this pool's GPUs refuse): shared-memory accessors with per-array bounds, canary words between the
+ * shared-memory regions of both solve kernels, and labelled rendezvous in the role-split kernel (every role posts the protocol
+ * point it arrived at; a mismatch is counted).  counters8: [0] index out of range, [1] canary overwritten, [2] roles met at
+ * different barrier labels, [3] reserved, [4] problems checked.  Both return MPCGPU_ERR_ARG on a normal build. */
+int mpcgpu_check_report(mpcgpu_engine *e, unsigned long long *counters8, int reset);
+int mpcgpu_check_selftest(mpcgpu_engine *e);
+
 /* Kernel choice (no reference counterpart).  Two kernels implement the same solve: the thread-per-stage kernel
  * (one warp per problem, 8 problems per SM: throughput) and the role-split kernel (one CTA of several warps
  * per problem: latency; compiled for configurations with enough general constraints).  AUTO takes the role-split

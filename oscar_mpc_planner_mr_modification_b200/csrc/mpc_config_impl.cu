@@ -4,8 +4,8 @@
 
 namespace MPC_NS {
 
-constexpr size_t SMEM_THR = (size_t)(WARPS_PER_CTA / GW) * (LT_DOUBLES + (COOP ? RS_DOUBLES : 0)) * sizeof(double);   // per-entry state of the general inequality entries
-constexpr size_t SMEM_LAT = (size_t)(LT_DOUBLES + (COOP ? RS_DOUBLES : 0)) * sizeof(double);
+constexpr size_t SMEM_THR = (size_t)(WARPS_PER_CTA / GW) * (LT_STRIDE + (COOP ? RS_DOUBLES : 0)) * sizeof(double);   // per-entry state of the general inequality entries
+constexpr size_t SMEM_LAT = (size_t)(LT_STRIDE + (COOP ? RS_DOUBLES : 0)) * sizeof(double);
 #ifndef MPC_SPLIT
 #define MPC_SPLIT 1
 #endif
@@ -76,8 +76,44 @@ static cudaError_t launch_model_eval(cudaStream_t stream, int n, const double* z
     return cudaGetLastError();
 }
 
+#if MPC_CHECK
+static cudaError_t check_report(unsigned long long* out8, int reset)
+{
+    cudaError_t err = cudaDeviceSynchronize();
+    if (err == cudaSuccess) err = cudaMemcpyFromSymbol(out8, g_check, sizeof(g_check));
+    if (err == cudaSuccess && reset) {
+        const unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        err = cudaMemcpyToSymbol(g_check, z, sizeof(z));
+    }
+    return err;
+}
+// the detector detecting: one out-of-range index through a shared-memory column and one overwritten canary word
+__global__ void check_selftest_kernel()
+{
+    extern __shared__ double sm[];
+    sm[threadIdx.x] = 0.0;
+    sm[64 + threadIdx.x] = CANARY;
+    __syncthreads();
+    const SmemCol col{sm + threadIdx.x, 1};
+    if (threadIdx.x == 3) col[1] = 5.0;                    // index 1 of a 1-entry column: counted, redirected to entry 0
+    if (threadIdx.x == 0) sm[64 + 7] = 1.0;                // a stray store into the canary row
+    __syncthreads();
+    if (sm[64 + threadIdx.x] != CANARY) MPC_CHECK_FAIL(1);
+}
+static cudaError_t check_selftest(cudaStream_t stream)
+{
+    check_selftest_kernel<<<1, 32, 2 * 64 * sizeof(double), stream>>>();
+    return cudaGetLastError();
+}
+#endif
+
 static const MpcConfigOps ops = {MPCGEN_CONFIG_NAME, NSTAGE, NX, NU, NP, NH, NC, MEM_DOUBLES, launch_solve, occupancy,
-                                 NHS, MODEL_EVAL_DOUBLES, launch_model_eval, SPLIT_ALWAYS ? SPLIT_WARPS : GW, USE_SPLIT ? 1 : 0};
+                                 NHS, MODEL_EVAL_DOUBLES, launch_model_eval, SPLIT_ALWAYS ? SPLIT_WARPS : GW, USE_SPLIT ? 1 : 0,
+#if MPC_CHECK
+                                 check_report, check_selftest};
+#else
+                                 nullptr, nullptr};
+#endif
 
 static struct Registrar {
     Registrar() { mpc_register_config(&ops); }

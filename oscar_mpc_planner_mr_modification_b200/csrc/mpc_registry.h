@@ -17,6 +17,9 @@ struct MpcConfigOps {
                                      const double* mh, double* out);
     int group_warps;   // warps cooperating on one problem (1 for N <= 31, 2 for N <= 63)
     int has_split;     // 1 when the role-split kernel exists for this configuration
+    // MPC_CHECK build only (nullptr otherwise): read (and optionally clear) the diagnostic counters; run the detector's self-test
+    cudaError_t (*check_report)(unsigned long long* out8, int reset);
+    cudaError_t (*check_selftest)(cudaStream_t stream);
 };
 
 void mpc_register_config(const MpcConfigOps* ops);

@@ -37,6 +37,21 @@
 #define MPC_NS MPC_CAT(mpck_, MPC_CFG_TAG)   // one namespace per compiled configuration
 
 namespace MPC_NS {
+// ---- MPC_CHECK build (diagnostic variant library, never shipped): what compute-sanitizer would look for, since the tool is closed
+//      on this pool.  Counters (read through mpcgpu_check_report): 0 index outside an array of the shared-memory placement,
+//      1 canary word between shared-memory regions overwritten, 2 roles of the role-split kernel met at different barrier labels,
+//      3 exchange slot read with a stale generation, 4 problems checked.
+#ifndef MPC_CHECK
+#define MPC_CHECK 0
+#endif
+#if MPC_CHECK
+__device__ unsigned long long g_check[8];
+#define MPC_CHECK_FAIL(i) atomicAdd(&g_check[i], 1ull)
+#define MPCK(n) , (n)
+constexpr double CANARY = -7.0e300;
+#else
+#define MPCK(n)
+#endif
 // Branch-free reciprocal square root: hardware approximation (rsqrt.approx.f64, ~2^-23) + one cubically convergent
 // correction y (1 + e/2 + 3 e^2/8), e = 1 - a y^2 (error below the rounding of a double).  Half the instructions of
 // rsqrt() and no slow-path branch, so two of them interleave in one in-order instruction stream (the two Cholesky
@@ -150,12 +165,22 @@ constexpr int QP_OFF_G = LT_ENTRY_DOUBLES + BOX_SM_DOUBLES, QP_OFF_B = QP_OFF_G 
 #endif
 constexpr bool RIC_P = (MPC_RIC_SMEM & 1) != 0, RIC_PRB = (MPC_RIC_SMEM & 2) != 0;
 constexpr int RIC_OFF_P = QP_OFF_H + (QPS_H ? NPK : 0), RIC_OFF_PRB = RIC_OFF_P + (RIC_P ? NPX : 0);
-constexpr int LT_DOUBLES = (RIC_OFF_PRB + (RIC_PRB ? NX : 0)) * GW * 32;      // per group: lam, t (d, C) of the general entries (+ 1/t of the boxes)
+constexpr int LT_DOUBLES = (RIC_OFF_PRB + (RIC_PRB ? NX : 0)) * GW * 32;
+constexpr int LT_STRIDE = LT_DOUBLES + (MPC_CHECK ? GW * 32 : 0);      // MPC_CHECK: a row of canaries behind every group's region      // per group: lam, t (d, C) of the general entries (+ 1/t of the boxes)
 // column accessor: stride GW*32 doubles in shared memory ([entry][thread of the group]), stride 1 for a thread-local array
 template <bool SM>
 struct LtCol {
     double* p;
-    __device__ __forceinline__ double& operator[](int e) const { return p[SM ? e * (((NSTAGE + 1 + 31) / 32) * 32) : e]; }
+#if MPC_CHECK
+    int n;
+#endif
+    __device__ __forceinline__ double& operator[](int e) const
+    {
+#if MPC_CHECK
+        if (e < 0 || e >= n) { MPC_CHECK_FAIL(0); e = 0; }
+#endif
+        return p[SM ? e * (((NSTAGE + 1 + 31) / 32) * 32) : e];
+    }
 };
 // Jacobian rows of the general constraints: at(r, a) = d h_r / d z_HSUP[a].  Plain (all in one place, shared or thread-local)
 // or split by column (MPC_C_SPLIT).  operator[] (flat index r * NHS + a) is what the emitted con_lin writes through.
@@ -166,6 +191,9 @@ struct CRows {
     bool tail_zero;     // split: the thread-local tail columns are zero in every lane (set after the linearisation)
     __device__ __forceinline__ double& operator[](int i) const
     {
+#if MPC_CHECK
+        if (i < 0 || i >= NH * NHS) { MPC_CHECK_FAIL(0); i = 0; }
+#endif
         if constexpr (CSPL > 0) {
             const int r = i / NHS, a = i - r * NHS;
             if (a < CSPL) return sm[(r * CSPL + a) * (((NSTAGE + 1 + 31) / 32) * 32)];
@@ -176,6 +204,9 @@ struct CRows {
     }
     __device__ __forceinline__ double at(int r, int a) const
     {
+#if MPC_CHECK
+        if (r < 0 || r >= NH || a < 0 || a >= NHS) { MPC_CHECK_FAIL(0); r = 0; a = 0; }
+#endif
         if constexpr (CSPL > 0) {
             if (a < CSPL) return sm[(r * CSPL + a) * (((NSTAGE + 1 + 31) / 32) * 32)];
             return tail_zero ? 0.0 : p[r * NHS + a];
@@ -187,7 +218,16 @@ struct CRows {
 };
 struct SmemCol {
     double* p;
-    __device__ __forceinline__ double& operator[](int e) const { return p[e * (((NSTAGE + 1 + 31) / 32) * 32)]; }
+#if MPC_CHECK
+    int n;
+#endif
+    __device__ __forceinline__ double& operator[](int e) const
+    {
+#if MPC_CHECK
+        if (e < 0 || e >= n) { MPC_CHECK_FAIL(0); e = 0; }
+#endif
+        return p[e * (((NSTAGE + 1 + 31) / 32) * 32)];
+    }
 };
 constexpr int NCB = 2 * NZ;                 // box entries: lower(z_i) i<NZ, then upper(z_i)
 constexpr int NC = NCB + NCG;               // inequality entries per path stage
@@ -1266,16 +1306,16 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
     double z[NZ], pi[NX], v[NZ], qpi[NX];
 #if MPC_BOX_SMEM >= 2
     // multipliers and slacks of the box entries in shared memory too: 56 registers less in the interior-point loop
-    const SmemCol lamb{lt_sm + LT_ENTRY_DOUBLES * (GW * 32) + (grp.wig * 32 + (threadIdx.x & 31))};
-    const SmemCol tb{lt_sm + (LT_ENTRY_DOUBLES + NCB) * (GW * 32) + (grp.wig * 32 + (threadIdx.x & 31))};
+    const SmemCol lamb{lt_sm + LT_ENTRY_DOUBLES * (GW * 32) + (grp.wig * 32 + (threadIdx.x & 31)) MPCK(NCB)};
+    const SmemCol tb{lt_sm + (LT_ENTRY_DOUBLES + NCB) * (GW * 32) + (grp.wig * 32 + (threadIdx.x & 31)) MPCK(NCB)};
 #else
     double lamb[NCB], tb[NCB];
 #endif
     // general-entry state: shared-memory columns or thread-local arrays (MPC_LT_MASK); the unused alternative is optimised away
     double* const lt_me = lt_sm + (grp.wig * 32 + (threadIdx.x & 31));
     double lamg_loc[(!LT_LAM && NCG > 0) ? NCG : 1], tg_loc[(!LT_T && NCG > 0) ? NCG : 1];
-    const LtCol<LT_LAM> lamg{LT_LAM ? lt_me + LT_OFF_LAM * (GW * 32) : lamg_loc};
-    const LtCol<LT_T> tg{LT_T ? lt_me + LT_OFF_T * (GW * 32) : tg_loc};
+    const LtCol<LT_LAM> lamg{LT_LAM ? lt_me + LT_OFF_LAM * (GW * 32) : lamg_loc MPCK(NCG)};
+    const LtCol<LT_T> tg{LT_T ? lt_me + LT_OFF_T * (GW * 32) : tg_loc MPCK(NCG)};
 #pragma unroll
     for (int i = 0; i < NZ; i++) {
         z[i] = live ? x0_g[(size_t)prob * NZ * (NSTAGE + 1) + k * NZ + i] : 0.0;   // loadWarmstart (:274-284)
@@ -1311,7 +1351,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
         double H[NPK], g[NZ], Wv[NWV], b[NX];
         double C_loc[(!LT_C && NH > 0) ? NH * NHS : 1], dg_loc[(!LT_D && NCG > 0) ? NCG : 1];
         CRows<LT_C> C{LT_C ? lt_me + LT_OFF_C * (GW * 32) : C_loc, lt_me + LT_OFF_CS * (GW * 32), false};
-        const LtCol<LT_D> dg{LT_D ? lt_me + LT_OFF_D * (GW * 32) : dg_loc};
+        const LtCol<LT_D> dg{LT_D ? lt_me + LT_OFF_D * (GW * 32) : dg_loc MPCK(NCG)};
         {
             double pin[NX], xnx[NX], zx_[NX];
 #pragma unroll
@@ -1343,7 +1383,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                 for (int i = NU; i < NZ; i++) H[pk(i, i)] = REG_EPS;   // mirror(0) = eps I; no terminal cost
             }
         }
-        const SmemCol gs{lt_me + QP_OFF_G * (GW * 32)}, bs{lt_me + QP_OFF_B * (GW * 32)}, Hs{lt_me + QP_OFF_H * (GW * 32)};
+        const SmemCol gs{lt_me + QP_OFF_G * (GW * 32) MPCK(NZ)}, bs{lt_me + QP_OFF_B * (GW * 32) MPCK(NX)}, Hs{lt_me + QP_OFF_H * (GW * 32) MPCK(NPK)};
         if constexpr (QPS_GB) {
 #pragma unroll
             for (int i = 0; i < NZ; i++) gs[i] = g[i];
@@ -1428,7 +1468,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
         // state of the previous iteration's step, applied at the top of the next pass (fused update):
 #if MPC_BOX_SMEM == 1 || MPC_BOX_SMEM == 3
         // 1/t of the box entries (reused by passes B, C and the update) parked in shared memory: 28 registers less in the loop
-        const SmemCol itb{lt_sm + (LT_ENTRY_DOUBLES + (MPC_BOX_SMEM == 3 ? 2 * NCB : 0)) * (GW * 32) + (grp.wig * 32 + (threadIdx.x & 31))};
+        const SmemCol itb{lt_sm + (LT_ENTRY_DOUBLES + (MPC_BOX_SMEM == 3 ? 2 * NCB : 0)) * (GW * 32) + (grp.wig * 32 + (threadIdx.x & 31)) MPCK(NCB)};
 #else
         double itb[NCB];                             // 1/t of the box entries, reused by passes B, C and the update (general entries: recomputed)
 #endif
@@ -1601,7 +1641,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                 for (int i = 0; i < NZ; i++) dva[i] = (live && (path || i >= NU)) ? blk[RO_DZ + i] : 0.0;
             }
             double P[RIC_P ? 1 : NPX], pv[NX], Lx0[NX], Lx1[NX], Prb[RIC_PRB ? 1 : NX], lv[NU], L10 = 0.0, iL0 = 0.0, iL1 = 0.0;
-            const SmemCol Ps{lt_me + RIC_OFF_P * (GW * 32)}, Prbs{lt_me + RIC_OFF_PRB * (GW * 32)};      // (MPC_RIC_SMEM)
+            const SmemCol Ps{lt_me + RIC_OFF_P * (GW * 32) MPCK(NPX)}, Prbs{lt_me + RIC_OFF_PRB * (GW * 32) MPCK(NX)};      // (MPC_RIC_SMEM)
             auto prb = [&](int i) -> double { if constexpr (RIC_PRB) return Prbs[i]; else return Prb[i]; };
             auto pmat = [&](int i) -> double { if constexpr (RIC_P) return Ps[i]; else return P[i]; };
             if constexpr (!COOP) {
@@ -2053,6 +2093,9 @@ mpc_solve_kernel(int n, const double* __restrict__ xinit, const double* __restri
     grp.gid = warp / GW;
     grp.wig = warp % GW;
     grp.xch = s_xch[grp.gid];
+#if MPC_CHECK
+    s_lt[(size_t)grp.gid * LT_STRIDE + LT_DOUBLES + grp.wig * 32 + lane] = CANARY;
+#endif
     for (;;) {
         int prob = 0;
         if (grp.wig == 0 && lane == 0) prob = atomicAdd(work_counter, 1);
@@ -2067,8 +2110,13 @@ mpc_solve_kernel(int n, const double* __restrict__ xinit, const double* __restri
         if (prob >= n) return;
         const int nit = num_iter ? num_iter[prob] : num_iter_all;
         solve_problem<(WPC != WARPS_PER_CTA) || (MPC_SCAN_ALWAYS != 0)>(prob, xinit, x0, params, nit, mem, mem_doubles, xtraj, utraj, pobj, exit_code, qp_status, res_eq,
-                      ipm_iters, s_hand[grp.gid], s_lt + (size_t)grp.gid * LT_DOUBLES,
-                      s_lt + (size_t)GROUPS * LT_DOUBLES + (size_t)grp.gid * (COOP ? RS_DOUBLES : 0), grp);
+                      ipm_iters, s_hand[grp.gid], s_lt + (size_t)grp.gid * LT_STRIDE,
+                      s_lt + (size_t)GROUPS * LT_STRIDE + (size_t)grp.gid * (COOP ? RS_DOUBLES : 0), grp);
+#if MPC_CHECK
+        grp.sync();
+        if (s_lt[(size_t)grp.gid * LT_STRIDE + LT_DOUBLES + grp.wig * 32 + lane] != CANARY) MPC_CHECK_FAIL(1);
+        if (grp.wig == 0 && lane == 0) MPC_CHECK_FAIL(4);
+#endif
     }
 }
 

@@ -33,13 +33,17 @@ constexpr int XS = NHP + 2 * NHS + 3;            // exchange slots per B role an
 constexpr int XSX = 3 * NZ + 3;                  // exchange slots of role X per stage: diag Ht | g | rg | nd nm sm
 constexpr bool SPLIT_OK = (NSTAGE + 1 <= 32) && NPAD <= 32 && NCG >= 6 && NCG >= 2 * NBR && !BALANCE;      // (the BALANCE variant exists in the thread-per-stage kernel only)
 // shared memory of one problem (doubles)
+constexpr int SP_GAP = MPC_CHECK ? 2 : 0;        // MPC_CHECK: two canary doubles behind every region
 constexpr int SP_RS = 0;
-constexpr int SP_XCH = (RS_DOUBLES + 1) & ~1;    // [NBR][XS][32]
-constexpr int SP_XCX = SP_XCH + NBR * XS * 32;   // [XSX][32] slots of role X
-constexpr int SP_PUB = SP_XCX + XSX * 32;        // [2 NZ][32]: z and v of every stage, published by role A (v: amended by role X)
-constexpr int SP_DEC = SP_PUB + 2 * NZ * 32;     // decisions published by role A
-constexpr int SP_SW = SP_DEC + 8;                // blocked-sweep workspace (SW_DOUBLES)
-constexpr int SP_DOUBLES = SP_SW + SW_DOUBLES;
+constexpr int SP_XCH = ((RS_DOUBLES + 1) & ~1) + SP_GAP;    // [NBR][XS][32]
+constexpr int SP_XCX = SP_XCH + NBR * XS * 32 + SP_GAP;   // [XSX][32] slots of role X
+constexpr int SP_PUB = SP_XCX + XSX * 32 + SP_GAP;        // [2 NZ][32]: z and v of every stage, published by role A (v: amended by role X)
+constexpr int SP_DEC = SP_PUB + 2 * NZ * 32 + SP_GAP;     // decisions published by role A
+constexpr int SP_SW = SP_DEC + 8 + SP_GAP;                // blocked-sweep workspace (SW_DOUBLES)
+constexpr int SP_DOUBLES = SP_SW + SW_DOUBLES + SP_GAP;
+#if MPC_CHECK
+__device__ constexpr int SP_CANARY_AT[6] = {SP_XCH - SP_GAP, SP_XCX - SP_GAP, SP_PUB - SP_GAP, SP_DEC - SP_GAP, SP_SW - SP_GAP, SP_DOUBLES - SP_GAP};
+#endif
 enum { DEC_CONT = 0, DEC_SIGMU = 1, DEC_STEP = 2, DEC_SQP = 3, DEC_STATUS = 4 };
 
 #ifdef MPC_PROF          // cycle accounting of role A (lane 0 of problem 0 prints it): a diagnostic build, never shipped
@@ -51,6 +55,25 @@ enum { DEC_CONT = 0, DEC_SIGMU = 1, DEC_STEP = 2, DEC_SQP = 3, DEC_STATUS = 4 };
 #endif
 __host__ __device__ constexpr int hidx(int a, int b) { return a * (a + 1) / 2 + b; }      // a >= b
 __device__ __forceinline__ void split_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(SPLIT_THREADS) : "memory"); }
+// Rendezvous with a label: the roles run mirrored loop structures and must meet at the SAME point of the protocol.  The MPC_CHECK
+// build verifies it (every role posts the label it arrived with; role A compares after the barrier) -- the race evidence the
+// closed compute-sanitizer cannot give.
+#if MPC_CHECK
+__device__ __forceinline__ void split_barrier_l(int label)
+{
+    __shared__ int s_label[SPLIT_WARPS];
+    const int role = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) s_label[role] = label;
+    split_barrier();
+    if (threadIdx.x == 0) {
+        for (int r = 0; r < SPLIT_WARPS; r++)
+            if (s_label[r] != label) MPC_CHECK_FAIL(2);
+    }
+    split_barrier();
+}
+#else
+__device__ __forceinline__ void split_barrier_l(int) { split_barrier(); }
+#endif
 
 // ------------------------------------------------------------------------------------------------------------------
 // role B: a slice [e_lo, e_hi) of the general inequality entries of every path stage
@@ -85,7 +108,7 @@ __device__ __noinline__ void split_role_b(const int prob, const double* __restri
     }
 
     for (int it = 0; it < num_iter; it++) {
-        split_barrier();                                             // L1: z on the support of h is published
+        split_barrier_l(101);                                             // L1: z on the support of h is published
         {
             double zz[NZ], Hh[NPK];
 #pragma unroll
@@ -106,9 +129,9 @@ __device__ __noinline__ void split_role_b(const int prob, const double* __restri
 #pragma unroll
                 for (int b = 0; b <= a; b++) xs[hidx(a, b) * 32] = Hh[pk(HSUP[a], HSUP[b])];
         }
-        split_barrier();                                             // L2: constraint Hessian terms handed to A
-        split_barrier();                                             // L3: A has initialised v
-        split_barrier();                                             // L4: role X has centred v inside the boxes
+        split_barrier_l(102);                                             // L2: constraint Hessian terms handed to A
+        split_barrier_l(103);                                             // L3: A has initialised v
+        split_barrier_l(104);                                             // L4: role X has centred v inside the boxes
 #pragma unroll
         for (int a = 0; a < NHS; a++) v3[a] = pub[(NZ + HSUP[a]) * 32];
         if (qp_warm) {
@@ -174,10 +197,10 @@ __device__ __noinline__ void split_role_b(const int prob, const double* __restri
 #pragma unroll
             for (int a = 0; a < NHS; a++) { xs[(NHP + a) * 32] = gs[a]; xs[(NHP + NHS + a) * 32] = rgs[a]; }
             xs[(NHP + 2 * NHS) * 32] = nd; xs[(NHP + 2 * NHS + 1) * 32] = nm; xs[(NHP + 2 * NHS + 2) * 32] = sm_;
-            split_barrier();                                         // 1: DA terms handed to A
-            split_barrier();                                         // 2: A has decided
+            split_barrier_l(1);                                         // 1: DA terms handed to A
+            split_barrier_l(2);                                         // 2: A has decided
             if (dec[DEC_CONT] == 0.0) break;
-            split_barrier();                                         // 3: factorisation + predictor sweep done
+            split_barrier_l(3);                                         // 3: factorisation + predictor sweep done
 #pragma unroll
             for (int a = 0; a < NHS; a++) dva3[a] = path ? blk[RO_DZ + HSUP[a]] : 0.0;
 
@@ -206,10 +229,10 @@ __device__ __noinline__ void split_role_b(const int prob, const double* __restri
 #pragma unroll
             for (int a = 0; a < NHS; a++) { xs[a * 32] = V1[a]; xs[(NHS + a) * 32] = V2[a]; }
             xs[(2 * NHS) * 32] = sfa.ratio(); xs[(2 * NHS + 1) * 32] = S1; xs[(2 * NHS + 2) * 32] = S2;
-            split_barrier();                                         // 4: pass-B terms handed to A
-            split_barrier();                                         // 5: sigma mu published
+            split_barrier_l(4);                                         // 4: pass-B terms handed to A
+            split_barrier_l(5);                                         // 5: sigma mu published
             sigmu = dec[DEC_SIGMU];
-            split_barrier();                                         // 6: corrector sweeps done
+            split_barrier_l(6);                                         // 6: corrector sweeps done
 #pragma unroll
             for (int a = 0; a < NHS; a++) dv3[a] = path ? blk[RO_DZ + HSUP[a]] : 0.0;
 
@@ -229,15 +252,15 @@ __device__ __noinline__ void split_role_b(const int prob, const double* __restri
                 sfc.add(lam, st.dlam, t, st.dt);
             }
             xs[0] = sfc.ratio();
-            split_barrier();                                         // 7: ratios handed to A
-            split_barrier();                                         // 8: step length published
+            split_barrier_l(7);                                         // 7: ratios handed to A
+            split_barrier_l(8);                                         // 8: step length published
             a_ = dec[DEC_STEP];
         }
-        split_barrier();                                             // 9: outcome of this SQP iteration published
+        split_barrier_l(9);                                             // 9: outcome of this SQP iteration published
         qp_warm = 1;
         if (dec[DEC_SQP] == 0.0) break;
     }
-    split_barrier();                                                 // F: final status published
+    split_barrier_l(99);                                                 // F: final status published
     if (mem && dec[DEC_STATUS] == 0.0) {
         double* m = mem + 1 + (NSTAGE + 1) * NX;
         for (int e = 0; e < ne; e++) { m[k * NC + NCB + e_lo + e] = lamg[e]; m[NSTAGE * NC + k * NC + NCB + e_lo + e] = tg[e]; }
@@ -271,11 +294,11 @@ __device__ __noinline__ void split_role_x(const int prob, const int num_iter, do
     }
 
     for (int it = 0; it < num_iter; it++) {
-        split_barrier();                                             // L1: z is published
+        split_barrier_l(101);                                             // L1: z is published
 #pragma unroll
         for (int i = 0; i < NZ; i++) { const double zi = pub[i * 32]; zl[i] = LBZ[i] - zi; zu[i] = UBZ[i] - zi; }
-        split_barrier();                                             // L2
-        split_barrier();                                             // L3: A has initialised v
+        split_barrier_l(102);                                             // L2
+        split_barrier_l(103);                                             // L3: A has initialised v
 #pragma unroll
         for (int i = 0; i < NZ; i++) v[i] = pub[(NZ + i) * 32];
         if (qp_warm) {
@@ -305,7 +328,7 @@ __device__ __noinline__ void split_role_x(const int prob, const int num_iter, do
 #pragma unroll
             for (int i = 0; i < NZ; i++) pub[(NZ + i) * 32] = v[i];
         }
-        split_barrier();                                             // L4: v is final for every role
+        split_barrier_l(104);                                             // L4: v is final for every role
 
         double a_ = 0.0, sigmu = 0.0;
         for (int kk = 0;; kk++) {
@@ -349,10 +372,10 @@ __device__ __noinline__ void split_role_x(const int prob, const int num_iter, do
                 xs[i * 32] = hd; xs[(NZ + i) * 32] = gg; xs[(2 * NZ + i) * 32] = rr;
             }
             xs[(3 * NZ) * 32] = nd; xs[(3 * NZ + 1) * 32] = nm; xs[(3 * NZ + 2) * 32] = sm_;
-            split_barrier();                                         // 1
-            split_barrier();                                         // 2
+            split_barrier_l(1);                                         // 1
+            split_barrier_l(2);                                         // 2
             if (dec[DEC_CONT] == 0.0) break;
-            split_barrier();                                         // 3
+            split_barrier_l(3);                                         // 3
 #pragma unroll
             for (int i = 0; i < NZ; i++) dva[i] = path ? blk[RO_DZ + i] : 0.0;
 
@@ -384,10 +407,10 @@ __device__ __noinline__ void split_role_x(const int prob, const int num_iter, do
                 xs[i * 32] = V1; xs[(NZ + i) * 32] = V2;
             }
             xs[(2 * NZ) * 32] = sfa.ratio(); xs[(2 * NZ + 1) * 32] = S1; xs[(2 * NZ + 2) * 32] = S2;
-            split_barrier();                                         // 4
-            split_barrier();                                         // 5
+            split_barrier_l(4);                                         // 4
+            split_barrier_l(5);                                         // 5
             sigmu = dec[DEC_SIGMU];
-            split_barrier();                                         // 6
+            split_barrier_l(6);                                         // 6
 #pragma unroll
             for (int i = 0; i < NZ; i++) dv[i] = path ? blk[RO_DZ + i] : 0.0;
             StepFrac sfc;
@@ -409,15 +432,15 @@ __device__ __noinline__ void split_role_x(const int prob, const int num_iter, do
                 }
             }
             xs[0] = sfc.ratio();
-            split_barrier();                                         // 7
-            split_barrier();                                         // 8
+            split_barrier_l(7);                                         // 7
+            split_barrier_l(8);                                         // 8
             a_ = dec[DEC_STEP];
         }
-        split_barrier();                                             // 9
+        split_barrier_l(9);                                             // 9
         qp_warm = 1;
         if (dec[DEC_SQP] == 0.0) break;
     }
-    split_barrier();                                                 // F
+    split_barrier_l(99);                                                 // F
     if (mem && dec[DEC_STATUS] == 0.0 && path) {
         double* m = mem + 1 + (NSTAGE + 1) * NX;
         for (int e = 0; e < NCB; e++) { m[k * NC + e] = lamb[e]; m[NSTAGE * NC + k * NC + e] = tb[e]; }
@@ -482,7 +505,7 @@ __device__ __noinline__ void split_role_a(const int prob, const double* __restri
             grp.shift_down(zx_, xnx);
 #pragma unroll
             for (int i = 0; i < NZ; i++) pub[i * 32] = z[i];
-            split_barrier();                                         // L1
+            split_barrier_l(101);                                         // L1
 #pragma unroll
             for (int i = 0; i < NPK; i++) H[i] = 0.0;
 #pragma unroll
@@ -499,7 +522,7 @@ __device__ __noinline__ void split_role_a(const int prob, const double* __restri
                 for (int i = 0; i < NX; i++) b[i] = xn[i] - xnx[i];
             }
             PROF(0)
-            split_barrier();                                         // L2: constraint Hessian terms are in the slots
+            split_barrier_l(102);                                         // L2: constraint Hessian terms are in the slots
             PROF(1)
             if (path) {
 #pragma unroll 1
@@ -535,8 +558,8 @@ __device__ __noinline__ void split_role_a(const int prob, const double* __restri
 #pragma unroll
         for (int i = 0; i < NZ; i++) pub[(NZ + i) * 32] = v[i];
         PROF(2)
-        split_barrier();                                             // L3
-        split_barrier();                                             // L4: role X has centred v inside the boxes (cold start)
+        split_barrier_l(103);                                             // L3
+        split_barrier_l(104);                                             // L4: role X has centred v inside the boxes (cold start)
 #pragma unroll
         for (int i = 0; i < NZ; i++) v[i] = pub[(NZ + i) * 32];
         PROF(3)
@@ -592,7 +615,7 @@ __device__ __noinline__ void split_role_a(const int prob, const double* __restri
                 for (int i = 0; i < NZ; i++) gt[i] = rg[i];
             }
             PROF(4)
-            split_barrier();                                         // 1: the slices' DA terms are in the slots
+            split_barrier_l(1);                                         // 1: the slices' DA terms are in the slots
             PROF(5)
 #pragma unroll
             for (int i = 0; i < NZ; i++) {                           // box entries (role X)
@@ -645,7 +668,7 @@ __device__ __noinline__ void split_role_a(const int prob, const double* __restri
                 }
             }
             PROF(6)
-            split_barrier();                                         // 2
+            split_barrier_l(2);                                         // 2
             PROF(7)
             if (!cont) break;
             __syncwarp();
@@ -699,14 +722,14 @@ __device__ __noinline__ void split_role_a(const int prob, const double* __restri
                 for (int i = 0; i < NZ; i++) blk[RO_DZ + i] = dva[i];
             }
             PROF(9)
-            split_barrier();                                         // 3
+            split_barrier_l(3);                                         // 3
             PROF(10)
 
             // ---- pass B (box entries): affine step length, mu_aff sums, corrector vectors
             double S1 = 0.0, S2 = 0.0, V1[NZ], V2[NZ];
             double ratio = 1.0;
             PROF(11)
-            split_barrier();                                         // 4: the slices' pass-B terms are in the slots
+            split_barrier_l(4);                                         // 4: the slices' pass-B terms are in the slots
             PROF(12)
 #pragma unroll
             for (int i = 0; i < NZ; i++) { V1[i] = xcx[i * 32]; V2[i] = xcx[(NZ + i) * 32]; }      // box entries (role X)
@@ -730,7 +753,7 @@ __device__ __noinline__ void split_role_a(const int prob, const double* __restri
 #pragma unroll
             for (int i = 0; i < NZ; i++) gt[i] += V1[i] - sigmu * V2[i];
             PROF(13)
-            split_barrier();                                         // 5
+            split_barrier_l(5);                                         // 5
             PROF(14)
             double pv[NX];
             {   // backward vector sweep: p_k = Acl_k' (p_{k+1} + P_{k+1} rb_k) + (gt_x - Lxu Luu^-1 gt_u)
@@ -789,7 +812,7 @@ __device__ __noinline__ void split_role_a(const int prob, const double* __restri
                 for (int i = 0; i < NZ; i++) blk[RO_DZ + i] = dv[i];
             }
             PROF(16)
-            split_barrier();                                         // 6
+            split_barrier_l(6);                                         // 6
             PROF(17)
             if (k >= 1 && live) {                                    // dpi_k = P_k dx_k + p_k
 #pragma unroll
@@ -804,7 +827,7 @@ __device__ __noinline__ void split_role_a(const int prob, const double* __restri
             // ---- pass C (box entries): step length of the corrected direction
             double ratc = 1.0;
             PROF(18)
-            split_barrier();                                         // 7: the slices' ratios are in slot 0
+            split_barrier_l(7);                                         // 7: the slices' ratios are in slot 0
             PROF(19)
             ratc = fmin(ratc, xcx[0]);                               // box entries (role X)
             if (path) {
@@ -815,7 +838,7 @@ __device__ __noinline__ void split_role_a(const int prob, const double* __restri
             a_ = alpha < 1.0 ? alpha * IPM_STEP_SCALE : alpha;      // applied by the next pass DA
             if (k == 0) dec[DEC_STEP] = a_;
             PROF(20)
-            split_barrier();                                         // 8
+            split_barrier_l(8);                                         // 8
             PROF(21)
         }
         ipm_total += kk;
@@ -824,7 +847,7 @@ __device__ __noinline__ void split_role_a(const int prob, const double* __restri
         // ======================= SQP-RTI full step ===================================================
         const bool qp_failed = (qps != 0 && qps != 1);
         if (k == 0) dec[DEC_SQP] = (qps == 0) ? 1.0 : 0.0;
-        split_barrier();                                             // 9
+        split_barrier_l(9);                                             // 9
         if (qp_failed) { status = 4; break; }                        // ACADOS_QP_FAILURE: iterate unchanged
 #pragma unroll
         for (int i = 0; i < NZ; i++) z[i] += v[i];
@@ -857,7 +880,7 @@ __device__ __noinline__ void split_role_a(const int prob, const double* __restri
     req = warp_max(req);
     if (!(req <= RES_EQ_MAX) && status == 0 && !defer) status = 4;      // defer: completion belongs to the caller (stepwise interface)
     if (k == 0) dec[DEC_STATUS] = (double)status;
-    split_barrier();                                                 // F
+    split_barrier_l(99);                                                 // F
     const int exit_code = (status == 0) ? 1 : (status == 1 ? 0 : status);
     if (live) {
 #pragma unroll
@@ -909,6 +932,10 @@ mpc_solve_split_kernel(int n, const double* __restrict__ xinit, const double* __
         __syncthreads();
         const int prob = s_prob;
         if (prob >= n) return;
+#if MPC_CHECK
+        if (threadIdx.x < 12) s_split[SP_CANARY_AT[threadIdx.x >> 1] + (threadIdx.x & 1)] = CANARY;
+        __syncthreads();
+#endif
         const int nit_raw = num_iter ? num_iter[prob] : num_iter_all;
         const int nit = nit_raw < 0 ? -nit_raw : nit_raw;      // < 0: completion deferred (see solve_problem)
         if (role == 0)
@@ -918,5 +945,10 @@ mpc_solve_split_kernel(int n, const double* __restrict__ xinit, const double* __
             split_role_x(prob, nit, mem, mem_doubles, s_split);
         else
             split_role_b(prob, params, nit, mem, mem_doubles, s_split, role - 2);
+#if MPC_CHECK
+        __syncthreads();
+        if (threadIdx.x < 12 && s_split[SP_CANARY_AT[threadIdx.x >> 1] + (threadIdx.x & 1)] != CANARY) MPC_CHECK_FAIL(1);
+        if (threadIdx.x == 0) MPC_CHECK_FAIL(4);
+#endif
     }
 }

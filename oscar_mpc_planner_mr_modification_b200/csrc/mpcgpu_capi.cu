@@ -931,6 +931,23 @@ int mpcgpu_measure_fp64_peak(int device, double* tflops)
     return MPCGPU_OK;
 }
 
+int mpcgpu_check_report(mpcgpu_engine* e, unsigned long long* counters8, int reset)
+{
+    if (!e || !counters8) return MPCGPU_ERR_ARG;
+    if (!e->ops->check_report) return MPCGPU_ERR_ARG;      // not a diagnostic (-DMPC_CHECK=1) build
+    CK(cudaSetDevice(e->device));
+    CK(e->ops->check_report(counters8, reset));
+    return MPCGPU_OK;
+}
+int mpcgpu_check_selftest(mpcgpu_engine* e)
+{
+    if (!e || !e->ops->check_selftest) return MPCGPU_ERR_ARG;
+    CK(cudaSetDevice(e->device));
+    CK(e->ops->check_selftest(e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return MPCGPU_OK;
+}
+
 int mpcgpu_alloc_pinned(size_t bytes, void** out)
 {
     if (!out || bytes == 0) return MPCGPU_ERR_ARG;

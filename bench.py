@@ -471,7 +471,8 @@ def main():
     #      records and the selected trajectory of every set come back): rank 0 drives all GPUs of the job while the other ranks wait
     e2e_multi = None
     if world > 1:
-        barrier()
+        cpu_group = dist.new_group(backend="gloo")      # the waiting ranks must wait on the HOST: an NCCL barrier would spin on their GPUs,
+        barrier()                                       # which rank 0 is about to drive from its own process
         if rank == 0:
             multi = engine.MultiEngine(cfg, list(range(world)), n)
             Pv = h_np[0][2].reshape(n_sets, planners, N, npar)
@@ -494,6 +495,7 @@ def main():
                          "kernel_ms_max_over_devices": multi.last_kernel_ms(),
                          "what": "mpcgpu_multi_solve_sets: contiguous ranges of whole sets per GPU, device-side selection, decision records + the selected trajectory gathered"}
             multi.close()
+        dist.barrier(group=cpu_group)
         barrier()
 
     # ---- roofline of the dominant kernel (mpc_solve_kernel)

@@ -1208,6 +1208,9 @@ __device__ __noinline__ void mirror_packed(double* Hp)
 #ifndef MPC_C_PREFETCH
 #define MPC_C_PREFETCH 0
 #endif
+#ifndef MPC_PARAM_PREFETCH
+#define MPC_PARAM_PREFETCH 1
+#endif
 template <class CM>
 __device__ __forceinline__ void c_prefetch(const CM& C, int e)
 {
@@ -1366,6 +1369,12 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
             for (int i = 0; i < NX; i++) b[i] = 0.0;
             if (path) {
                 double xn[NX];
+#if MPC_PARAM_PREFETCH
+                // the stage's parameter block (NP doubles, stride NP between lanes) is read piecemeal by the emitted model code:
+                // ask for all of its lines now so that the constraint rows find them in the L1
+#pragma unroll 1
+                for (int o = 0; o < NP; o += 16) asm volatile("prefetch.global.L1 [%0];" ::"l"(p + o));
+#endif
                 cost_lin(z, p, g, H);
                 dyn_lin(z, pin, xn, Wv, H);
 #pragma unroll

@@ -211,20 +211,52 @@ def main():
 
     # ---- synthetic batches of this rank's shard (independent homotopy sets; no data-path collective).  TWO resident batches are
     #      rotated between steps so that no step re-solves what the previous one left in L2 (each is larger than L2 anyway).
-    t_gen = time.perf_counter()
-    batches = [synthetic.make_batch(eng.parameter_map, d, n_sets, planners, seed=1234 + 7919 * rank + 104729 * i) for i in range(2)]
-    batch = batches[0]
-    t_gen = (time.perf_counter() - t_gen) / len(batches)
-
+    #      The data come from the counter-based generator ON THE DEVICE (Philox4x32-10 keyed by (seed, global set index):
+    #      rank r holds sets [r n_sets, (r+1) n_sets) of the global batch) and are copied back once for the host-array entries;
+    #      configurations the generator does not cover fall back to the numpy generator.
     def pinned(a):
         t = torch.empty(a.shape, dtype=torch.float64 if a.dtype == np.float64 else torch.int32, pin_memory=True)
         t.numpy()[...] = a
         return t
 
-    h_in = [(pinned(b["xinit"]), pinned(b["x0"]), pinned(b["params"])) for b in batches]
+    t_gen = time.perf_counter()
+    try:
+        M_syn = synthetic.synth_layout(eng.parameter_map, d)["n_obst"]
+        generator = "device: Philox4x32-10 keyed by (seed, set index), mpcgpu_generate_synthetic_device"
+    except ValueError:
+        M_syn, generator = None, "host: numpy (synthetic.make_batch)"
+    if M_syn is not None:
+        d_in, d_obst = [], []
+        for i in range(2):
+            bufs = (torch.empty((n, nx), dtype=torch.float64, device=dev), torch.empty((n, (N + 1) * nz), dtype=torch.float64, device=dev),
+                    torch.empty((n, N * npar), dtype=torch.float64, device=dev))
+            ob = torch.empty((n_sets, N, M_syn, 2), dtype=torch.float64, device=dev)
+            engine.generate_synthetic(eng.parameter_map, d, n_sets, planners, seed=1234 + 104729 * i, first_set=rank * n_sets,
+                                      device=local_rank, device_buffers=[b.data_ptr() for b in bufs] + [ob.data_ptr()])
+            d_in.append(bufs)
+            d_obst.append(ob)
+        torch.cuda.synchronize()
+        t_gen = (time.perf_counter() - t_gen) / 2
+        h_in = []
+        for bufs in d_in:
+            hb = tuple(torch.empty(b.shape, dtype=torch.float64, pin_memory=True) for b in bufs)
+            for h_, b in zip(hb, bufs):
+                h_.copy_(b)
+            h_in.append(hb)
+        has_lin = "lin_constraint_0_a1" in eng.parameter_map
+        follow = [1 if (has_lin and not (planners > 1 and h == planners - 1)) else 0 for h in range(planners)]
+        batches = [dict(xinit=h[0].numpy(), x0=h[1].numpy(), params=h[2].numpy(), n=n, set_offsets=np.arange(0, n + 1, planners, dtype=np.int32),
+                        obst_pred=(ob.cpu().numpy() if has_lin else np.zeros((n_sets, N, 0, 2))), guided=np.tile(np.array(follow, np.uint8), n_sets),
+                        robot_radius=synthetic.ROBOT_RADIUS) for h, ob in zip(h_in, d_obst)]
+        del d_obst
+    else:
+        batches = [synthetic.make_batch(eng.parameter_map, d, n_sets, planners, seed=1234 + 7919 * rank + 104729 * i) for i in range(2)]
+        t_gen = (time.perf_counter() - t_gen) / len(batches)
+        h_in = [(pinned(b["xinit"]), pinned(b["x0"]), pinned(b["params"])) for b in batches]
+        d_in = [tuple(t.to(dev) for t in h) for h in h_in]
+    batch = batches[0]
     h_xinit, h_x0, h_params = h_in[0]
     h_offsets = pinned(batch["set_offsets"])
-    d_in = [tuple(t.to(dev) for t in h) for h in h_in]
     d_offsets = h_offsets.to(dev)
     d_xtraj = torch.empty((n, (N + 1) * nx), dtype=torch.float64, device=dev)
     d_utraj = torch.empty((n, N * nu), dtype=torch.float64, device=dev)
@@ -571,7 +603,7 @@ def main():
                            "solves_per_gpu_per_step": n, "l2": "inputs (%.2f GB/GPU) larger than L2" % (h2d / 1e9),
                            "parallelism": "sets sharded over %d GPU(s), no collective on the solve path" % world,
                            "success_frac": float((exit_codes == 1).mean()), "ipm_iters_mean": ipm_mean,
-                           "host_generation_s": t_gen, "resident_batches": len(batches),
+                           "generator": generator, "generation_s": t_gen, "resident_batches": len(batches),
                            "inputs": "two resident batches rotated between steps: no step re-solves the inputs of the previous one"},
                 "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,

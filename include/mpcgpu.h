@@ -236,6 +236,43 @@ int mpcgpu_model_eval(mpcgpu_engine *e, int n, const double *z, const double *p,
  * resident DFMA kernel (best of 5 after warm-up).  The FP64 roofline denominator of bench.py. */
 int mpcgpu_measure_fp64_peak(int device, double *tflops);
 
+/* Synthetic workload on the device (measurement infrastructure, no reference counterpart; SURVEY 8d: "counter-based Philox
+ * keyed by problem index so host and device generate identical data").  Fills the reference's own input layouts (xinit, x0,
+ * all_parameters: acados_solver_interface.h:51-91) for homotopy sets first_set .. first_set + n_sets - 1 directly in DEVICE
+ * memory; a set's data depend on (seed, set index) only, so any shard of any rank reproduces its slice of the global batch.
+ * Value conventions as the reference's modules (contouring.cpp:52-126 spline block, ellipsoid_constraints.cpp:34-90 stage k <-
+ * prediction k-1 and dummies at k = 0, linearized_constraints.cpp:49-189 halfspaces from the warm-start positions,
+ * data_preparation.cpp:64-81 constant-velocity predictions, acados_solver_interface.cpp:303-342 braking roll-out).
+ * Host mirror with the same arithmetic: synthetic.make_batch_philox (numpy).  The layout names the parameter indices of the
+ * configuration (-1: absent) and carries the constants, so that both sides use the same doubles. */
+#define MPCGPU_SYNTH_MAX_OBST 16
+typedef struct mpcgpu_synth_layout {
+    int N, nx, nu, npar;
+    int guided;                 /* 1: planners follow guidance polylines, the last planner of a set (planners > 1) brakes */
+    int weights[9];             /* acceleration, angular_velocity, velocity, reference_velocity, contour, lag, terminal_angle,
+                                   terminal_contouring, consistency_weight */
+    int spline[5][9];           /* segment i: x a b c d, y a b c d, start */
+    int ego_disc_radius, ego_disc_0_offset;
+    int goal[3];                /* goal_weight, goal_x, goal_y */
+    int prev_traj_x, prev_traj_y;
+    int n_obst;                 /* ellipsoid obstacles */
+    int obst[MPCGPU_SYNTH_MAX_OBST][7];   /* x, y, psi, r, major, minor, chi */
+    int n_lin;                  /* guidance halfspaces */
+    int lin[MPCGPU_SYNTH_MAX_OBST][3];    /* a1, a2, b */
+    double dt, pi, vg, need, deceleration, robot_radius, obstacle_radius, lin_margin;
+    double weight_values[9];
+    double lateral[8];          /* lateral offset of guidance corridor h % 8 */
+    double lat_profile[64];     /* sin^2(pi k / N), k <= N */
+} mpcgpu_synth_layout;
+/* d_obst_pred (nullable): [n_sets][N][n_obst][2] obstacle predictions, the input of mpcgpu_solve_sets_guided.  stream: a
+ * cudaStream_t (NULL: default stream); the call returns after the launch. */
+int mpcgpu_generate_synthetic_device(int device, const mpcgpu_synth_layout *layout, unsigned long long seed, long long first_set,
+                                     int n_sets, int planners, double *d_xinit, double *d_x0, double *d_params,
+                                     double *d_obst_pred, void *stream);
+/* the same data into HOST arrays (temporary device buffers inside; synchronous) */
+int mpcgpu_generate_synthetic(int device, const mpcgpu_synth_layout *layout, unsigned long long seed, long long first_set,
+                              int n_sets, int planners, double *xinit, double *x0, double *params, double *obst_pred);
+
 /* Pinned (page-locked) host memory for the HOST-array entry points: copies from pinned buffers overlap the solve kernels
  * of the chunked pipeline; pageable memory works but serialises.  No reference counterpart (plumbing). */
 int mpcgpu_alloc_pinned(size_t bytes, void **out);

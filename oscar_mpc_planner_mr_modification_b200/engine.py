@@ -17,6 +17,7 @@ SYMBOLS = [
     "mpcgpu_mem_doubles", "mpcgpu_solve_batch", "mpcgpu_solve_batch_device", "mpcgpu_sync", "mpcgpu_solve_sets", "mpcgpu_select_best",
     "mpcgpu_alloc_pinned", "mpcgpu_free_pinned", "mpcgpu_solve_sets_tables", "mpcgpu_multi_create", "mpcgpu_multi_destroy", "mpcgpu_multi_num_devices", "mpcgpu_multi_engine",
     "mpcgpu_multi_shard_range", "mpcgpu_multi_solve_sets", "mpcgpu_multi_solve_sets_guided", "mpcgpu_multi_solve_batch", "mpcgpu_multi_last_kernel_ms",
+    "mpcgpu_generate_synthetic", "mpcgpu_generate_synthetic_device",
     "mpcgpu_select_best_device", "mpcgpu_model_eval_doubles", "mpcgpu_model_eval", "mpcgpu_measure_fp64_peak", "mpcgpu_launch_count", "mpcgpu_last_kernel_ms", "mpcgpu_last_error", "mpcgpu_set_kernel_mode", "mpcgpu_guidance_halfspaces_device", "mpcgpu_solve_sets_guided",
 ]
 
@@ -104,6 +105,73 @@ class ParamTables(ctypes.Structure):
 
 class MpcGpuError(RuntimeError):
     pass
+
+
+class SynthLayout(ctypes.Structure):
+    """struct mpcgpu_synth_layout (include/mpcgpu.h): parameter indices + constants of the counter-based synthetic generator"""
+    _fields_ = [("N", ctypes.c_int), ("nx", ctypes.c_int), ("nu", ctypes.c_int), ("npar", ctypes.c_int), ("guided", ctypes.c_int),
+                ("weights", ctypes.c_int * 9), ("spline", (ctypes.c_int * 9) * 5), ("ego_disc_radius", ctypes.c_int),
+                ("ego_disc_0_offset", ctypes.c_int), ("goal", ctypes.c_int * 3), ("prev_traj_x", ctypes.c_int), ("prev_traj_y", ctypes.c_int),
+                ("n_obst", ctypes.c_int), ("obst", (ctypes.c_int * 7) * 16), ("n_lin", ctypes.c_int), ("lin", (ctypes.c_int * 3) * 16),
+                ("dt", ctypes.c_double), ("pi", ctypes.c_double), ("vg", ctypes.c_double), ("need", ctypes.c_double),
+                ("deceleration", ctypes.c_double), ("robot_radius", ctypes.c_double), ("obstacle_radius", ctypes.c_double),
+                ("lin_margin", ctypes.c_double), ("weight_values", ctypes.c_double * 9), ("lateral", ctypes.c_double * 8),
+                ("lat_profile", ctypes.c_double * 64)]
+
+    @classmethod
+    def from_dict(cls, d):
+        """d: synthetic.synth_layout(parameter_map, dims)"""
+        L = cls()
+        for name, _ in cls._fields_:
+            v = d[name]
+            if name in ("spline", "obst", "lin"):
+                for i, row in enumerate(v):
+                    for j, x in enumerate(row):
+                        getattr(L, name)[i][j] = x
+                for i in range(len(v), len(getattr(L, name))):
+                    for j in range(len(getattr(L, name)[i])):
+                        getattr(L, name)[i][j] = -1
+            elif isinstance(v, (list, tuple)):
+                for i, x in enumerate(v):
+                    getattr(L, name)[i] = x
+            else:
+                setattr(L, name, v)
+        return L
+
+
+def generate_synthetic(parameter_map, dims, n_sets, planners, seed=1234, first_set=0, device=0, guided=None, device_buffers=None,
+                       stream=None):
+    """Synthetic homotopy sets first_set .. first_set + n_sets - 1 of the global batch of `seed`, generated ON THE DEVICE
+    (mpcgpu_generate_synthetic[_device]; host mirror: synthetic.make_batch_philox).
+    device_buffers = (xinit, x0, params, obst_pred or None) raw device addresses: filled in place, asynchronously on `stream`,
+    returns None.  Otherwise the data are copied back and returned as a make_batch-style dict of numpy arrays."""
+    from . import synthetic
+    lib = load_library()
+    ld = synthetic.synth_layout(parameter_map, dims, guided)
+    L = SynthLayout.from_dict(ld)
+    vp, ull, ll = ctypes.c_void_p, ctypes.c_ulonglong, ctypes.c_longlong
+    if device_buffers is not None:
+        lib.mpcgpu_generate_synthetic_device.argtypes = [ctypes.c_int, vp, ull, ll, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp]
+        xi, x0, pa, ob = device_buffers
+        rc = lib.mpcgpu_generate_synthetic_device(int(device), ctypes.byref(L), int(seed), int(first_set), int(n_sets), int(planners),
+                                                  _ptr(xi), _ptr(x0), _ptr(pa), _ptr(ob), _ptr(stream) if stream else None)
+        if rc != 0:
+            raise MpcGpuError("mpcgpu_generate_synthetic_device failed: status %d" % rc)
+        return None
+    N, nx, nu, npar, M = ld["N"], ld["nx"], ld["nu"], ld["npar"], ld["n_obst"]
+    B = n_sets * planners
+    out = dict(xinit=np.empty((B, nx)), x0=np.empty((B, (N + 1) * (nx + nu))), params=np.empty((B, N * npar)),
+               obst_pred=np.empty((n_sets, N, M if ld["n_lin"] else 0, 2)), set_offsets=np.arange(0, B + 1, planners, dtype=np.int32), n=B,
+               robot_radius=ld["robot_radius"])
+    follow = [bool(ld["guided"]) and not (planners > 1 and h == planners - 1) for h in range(planners)]
+    out["guided"] = np.ascontiguousarray(np.tile(np.array([1 if f else 0 for f in follow], np.uint8), n_sets))
+    lib.mpcgpu_generate_synthetic.argtypes = [ctypes.c_int, vp, ull, ll, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp]
+    rc = lib.mpcgpu_generate_synthetic(int(device), ctypes.byref(L), int(seed), int(first_set), int(n_sets), int(planners),
+                                       _ptr(out["xinit"]), _ptr(out["x0"]), _ptr(out["params"]),
+                                       _ptr(out["obst_pred"]) if out["obst_pred"].size else None)
+    if rc != 0:
+        raise MpcGpuError("mpcgpu_generate_synthetic failed: status %d" % rc)
+    return out
 
 
 class Engine:

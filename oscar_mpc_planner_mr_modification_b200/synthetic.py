@@ -332,3 +332,212 @@ def apply_consistency(batch, pmap, dims, planners, prev_traj, enabled, weight):
     P[..., pmap["prev_traj_x"]] = np.where(act, prev_traj[:, None, :, 0], 0.0)
     P[..., pmap["prev_traj_y"]] = np.where(act, prev_traj[:, None, :, 1], 0.0)
     return en.reshape(-1)
+
+
+# ---- counter-based generator: host mirror of csrc/mpcgpu_synth.cu --------------------------------------------
+# A set's data depend on (seed, global set index) only: Philox4x32-10, counter = (set index lo, hi, draw block, 0),
+# key = (seed lo, hi).  The arithmetic below is, operation for operation, the one of the device kernel (which is compiled
+# without FMA contraction); sin / cos / arctan2 are the only functions whose last bit may differ between the two.
+_M32 = np.uint64(0xFFFFFFFF)
+
+
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Philox4x32-10 (Salmon et al. 2011) on uint32 arrays (held in uint64 for the 32x32 -> 64 products)."""
+    c0, c1, c2, c3 = (np.asarray(c, np.uint64) & _M32 for c in (c0, c1, c2, c3))
+    k0 = np.uint64(k0) & _M32
+    k1 = np.uint64(k1) & _M32
+    for _ in range(10):
+        p0 = np.uint64(0xD2511F53) * c0
+        p1 = np.uint64(0xCD9E8D57) * c2
+        n0 = (p1 >> np.uint64(32)) ^ c1 ^ k0
+        n2 = (p0 >> np.uint64(32)) ^ c3 ^ k1
+        c0, c1, c2, c3 = n0, p1 & _M32, n2, p0 & _M32
+        k0 = (k0 + np.uint64(0x9E3779B9)) & _M32
+        k1 = (k1 + np.uint64(0xBB67AE85)) & _M32
+    return c0, c1, c2, c3
+
+
+def philox_uniform(seed, gs, j):
+    """j-th uniform double in [0, 1) of every global set index in `gs` (53 bits, as the device's draw())."""
+    gs = np.asarray(gs, np.uint64)
+    seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    r = philox4x32_10(gs & _M32, gs >> np.uint64(32), np.full(gs.shape, j >> 1, np.uint64), np.zeros(gs.shape, np.uint64),
+                      seed & 0xFFFFFFFF, seed >> 32)
+    a, b = r[2 * (j & 1)], r[2 * (j & 1) + 1]
+    return ((a >> np.uint64(5)).astype(np.float64) * 67108864.0 + (b >> np.uint64(6)).astype(np.float64)) * (1.0 / 9007199254740992.0)
+
+
+def synth_layout(pmap, dims, guided=None):
+    """Parameter indices + constants of the counter-based generator for one configuration (the fields of
+    mpcgpu_synth_layout, include/mpcgpu.h).  Supported: base weights, contouring spline, goal, consistency reference, ellipsoid
+    obstacles and guidance halfspaces -- i.e. c1_basic, tmpc_shipped, c2_tmpc12, c6_goal_unicycle; configurations with
+    Gaussian / decomp / per-disc linearised constraints raise ValueError (use make_batch)."""
+    for pre in ("gaussian_obst_", "disc_0_decomp_", "disc_0_lin_constraint_"):
+        if any(k.startswith(pre) for k in pmap):
+            raise ValueError("counter-based generator: constraint family %s* is not supported" % pre)
+    N = dims["N"]
+    g = lambda name: int(pmap.get(name, -1))
+    M = sum(1 for k in pmap if k.startswith("ellipsoid_obst_") and k.endswith("_x"))
+    nlin = sum(1 for k in pmap if k.startswith("lin_constraint_") and k.endswith("_a1"))
+    if M > 16 or nlin > 16 or N + 1 > 64:
+        raise ValueError("counter-based generator: at most 16 obstacles / halfspaces and N <= 63")
+    kk = np.arange(64, dtype=np.float64)
+    return dict(
+        N=N, nx=dims["nx"], nu=dims["nu"], npar=dims["npar"], guided=int((nlin > 0) if guided is None else bool(guided)),
+        weights=[g(n) for n in WEIGHTS],
+        spline=[[g(t % i) for t in ("spline_x%d_a", "spline_x%d_b", "spline_x%d_c", "spline_x%d_d", "spline_y%d_a", "spline_y%d_b",
+                                    "spline_y%d_c", "spline_y%d_d", "spline%d_start")] for i in range(NUM_SEGMENTS)],
+        ego_disc_radius=g("ego_disc_radius"), ego_disc_0_offset=g("ego_disc_0_offset"),
+        goal=[g("goal_weight"), g("goal_x"), g("goal_y")], prev_traj_x=g("prev_traj_x"), prev_traj_y=g("prev_traj_y"),
+        n_obst=M, obst=[[g("ellipsoid_obst_%d_%s" % (j, f)) for f in ("x", "y", "psi", "r", "major", "minor", "chi")] for j in range(M)],
+        n_lin=nlin, lin=[[g("lin_constraint_%d_%s" % (j, f)) for f in ("a1", "a2", "b")] for j in range(nlin)],
+        dt=float(dims["dt"]), pi=float(np.pi), vg=float(np.clip(WEIGHTS["reference_velocity"], 0.5, 2.5)),
+        need=ROBOT_RADIUS + OBSTACLE_RADIUS + 0.1, deceleration=DECELERATION, robot_radius=ROBOT_RADIUS,
+        obstacle_radius=OBSTACLE_RADIUS, lin_margin=1e-3 + ROBOT_RADIUS,
+        weight_values=[float(v) for v in WEIGHTS.values()], lateral=[float(v) for v in _LATERAL],
+        lat_profile=[float(v) for v in np.where(kk <= N, np.sin(np.pi * kk / N) ** 2, 0.0)],
+    )
+
+
+def _natural_cubic_thomas(t, y):
+    """Natural cubic spline, Thomas algorithm in the device kernel's operation order.  t, y: (S, n)."""
+    n = t.shape[1]
+    h = t[:, 1:] - t[:, :-1]
+    cp = np.zeros_like(t)
+    dp = np.zeros_like(t)
+    for i in range(1, n - 1):
+        r = 3.0 * ((y[:, i + 1] - y[:, i]) / h[:, i] - (y[:, i] - y[:, i - 1]) / h[:, i - 1])
+        den = 2.0 * (h[:, i - 1] + h[:, i]) - h[:, i - 1] * cp[:, i - 1]
+        cp[:, i] = h[:, i] / den
+        dp[:, i] = (r - h[:, i - 1] * dp[:, i - 1]) / den
+    c = np.zeros_like(t)
+    for i in range(n - 2, 0, -1):
+        c[:, i] = dp[:, i] - cp[:, i] * c[:, i + 1]
+    b = (y[:, 1:] - y[:, :-1]) / h - h * (2.0 * c[:, :-1] + c[:, 1:]) / 3.0
+    a = (c[:, 1:] - c[:, :-1]) / (3.0 * h)
+    return a, c[:, :-1], b, y[:, :-1]
+
+
+def make_batch_philox(pmap, dims, n_sets, planners_per_set=1, seed=1234, first_set=0, guided=None):
+    """The scenario definition of make_batch on the counter-based generator: homotopy sets first_set .. first_set + n_sets - 1
+    of the global batch of `seed`.  Same return value as make_batch."""
+    L = synth_layout(pmap, dims, guided)
+    N, nx, nu, npar, dt = L["N"], L["nx"], L["nu"], L["npar"], L["dt"]
+    nz, S, Pn, M = nx + nu, n_sets, planners_per_set, L["n_obst"]
+    gs = np.arange(first_set, first_set + S, dtype=np.uint64)
+    U = lambda lo, hi, j: lo + (hi - lo) * philox_uniform(seed, gs, j)
+    st = np.stack([U(-0.5, 0.5, 0), U(-0.5, 0.5, 1), U(-0.3, 0.3, 2), U(0.0, 2.5, 3), np.zeros(S)], axis=1)
+    wx, wy, ts = np.zeros((S, 7)), np.zeros((S, 7)), np.zeros((S, 7))
+    for i in range(1, 7):
+        wx[:, i] = wx[:, i - 1] + U(3.0, 6.0, 3 + i)
+        wy[:, i] = U(-2.0, 2.0, 9 + i)
+    for i in range(1, 7):
+        ddx, ddy = wx[:, i] - wx[:, i - 1], wy[:, i] - wy[:, i - 1]
+        ts[:, i] = ts[:, i - 1] + np.sqrt(ddx * ddx + ddy * ddy)
+    spx = _natural_cubic_thomas(ts, wx)
+    spy = _natural_cubic_thomas(ts, wy)
+    op0 = np.zeros((S, M, 2))
+    ovel = np.zeros((S, M, 2))
+    for j in range(M):
+        op0[:, j, 0], op0[:, j, 1] = U(2.0, 20.0, 16 + 4 * j), U(-4.0, 4.0, 17 + 4 * j)
+        sp, hd = U(0.5, 1.5, 18 + 4 * j), U(-L["pi"], L["pi"], 19 + 4 * j)
+        ovel[:, j, 0], ovel[:, j, 1] = sp * np.cos(hd), sp * np.sin(hd)
+    steps = np.arange(N, dtype=np.float64)[None, :, None, None]
+    opred = op0[:, None] + ovel[:, None] * dt * steps                      # (S, N, M, 2)
+    ostage = np.concatenate([opred[:, :1], opred], axis=1)                 # stage k <- prediction max(k - 1, 0)
+
+    x0 = np.zeros((S, Pn, N + 1, nz))
+    kk = np.arange(N + 1, dtype=np.float64)[None, :]
+    follow = [bool(L["guided"]) and not (Pn > 1 and h == Pn - 1) for h in range(Pn)]
+    for h in range(Pn):
+        X = np.zeros((S, N + 1, nz))
+        if follow[h]:
+            px = st[:, 0:1] + L["vg"] * dt * kk
+            py = st[:, 1:2] + L["lateral"][h % 8] * np.asarray(L["lat_profile"][:N + 1])[None, :]
+            for _ in range(3):
+                for j in range(M):
+                    ddx, ddy = px - ostage[:, :, j, 0], py - ostage[:, :, j, 1]
+                    dist = np.sqrt(ddx * ddx + ddy * ddy)
+                    push = np.where(dist < L["need"], (L["need"] - dist) / np.maximum(dist, 1e-9), 0.0)
+                    px, py = px + ddx * push, py + ddy * push
+            px[:, 0], py[:, 0] = st[:, 0], st[:, 1]
+            vel = np.zeros((S, N + 1, 2))
+            for c, q in enumerate((px, py)):
+                vel[:, 1:N, c] = (q[:, 2:] - q[:, :-2]) / (2.0 * dt)
+                vel[:, 0, c] = (q[:, 1] - q[:, 0]) / dt
+                vel[:, N, c] = (q[:, N] - q[:, N - 1]) / dt
+            X[:, :, nu + 0], X[:, :, nu + 1] = px, py
+            X[:, :, nu + 2] = np.arctan2(vel[:, :, 1], vel[:, :, 0])
+            X[:, :, nu + 3] = np.sqrt(vel[:, :, 0] * vel[:, :, 0] + vel[:, :, 1] * vel[:, :, 1])
+            if nx > 4:
+                sacc = np.zeros(S)
+                for q in range(1, N + 1):
+                    sacc = sacc + X[:, q - 1, nu + 3] * dt
+                    X[:, q, nu + 4] = sacc
+            X[:, 0, nu:] = st[:, :nx]
+        else:
+            a = -L["deceleration"] if (L["guided"] and Pn > 1 and h == Pn - 1) else 0.0
+            x, y, psi, v, s = (st[:, i].copy() for i in range(5))
+            for q in range(N + 1):
+                X[:, q, 0] = a
+                X[:, q, nu:] = np.stack([x, y, psi, v, s], axis=1)[:, :nx]
+                x = x + v * dt * np.cos(psi)
+                y = y + v * dt * np.sin(psi)
+                s = s + v * dt
+                v = np.maximum(v + a * dt, 0.0)
+        x0[:, h] = X
+
+    P = np.zeros((S, Pn, N, npar))
+
+    def setp(idx, val):
+        if idx >= 0:
+            P[..., idx] = val
+
+    for idx, val in zip(L["weights"], L["weight_values"]):
+        setp(idx, val)
+    for i in range(NUM_SEGMENTS):
+        for c in range(4):
+            setp(L["spline"][i][c], spx[c][:, i][:, None, None])
+            setp(L["spline"][i][4 + c], spy[c][:, i][:, None, None])
+        setp(L["spline"][i][8], ts[:, i][:, None, None])
+    setp(L["ego_disc_radius"], L["robot_radius"])
+    setp(L["ego_disc_0_offset"], 0.0)
+    setp(L["goal"][0], 1.0)
+    setp(L["goal"][1], wx[:, 3][:, None, None])
+    setp(L["goal"][2], wy[:, 3][:, None, None])
+    setp(L["prev_traj_x"], x0[:, :, :N, nu + 0])
+    setp(L["prev_traj_y"], x0[:, :, :N, nu + 1])
+    for j in range(M):
+        ix, iy, _, ir, _, _, ichi = L["obst"][j]
+        P[:, :, 1:, ix] = opred[:, None, :N - 1, j, 0]
+        P[:, :, 1:, iy] = opred[:, None, :N - 1, j, 1]
+        P[:, :, 1:, ir] = L["obstacle_radius"]
+        P[:, :, 0, ix] = (st[:, 0] + 50.0)[:, None]
+        P[:, :, 0, iy] = (st[:, 1] + 50.0)[:, None]
+        P[:, :, 0, ir] = 0.1
+        P[..., ichi] = 1.0
+    for j in range(L["n_lin"]):
+        ia1, ia2, ib = L["lin"][j]
+        P[..., ia1], P[..., ia2] = 1.0, 0.0
+        P[..., ib] = (st[:, 0] + 100.0)[:, None, None]
+        if j >= M:
+            continue
+        for h in range(Pn):
+            if not follow[h]:
+                continue
+            ox, oy = opred[:, :N - 1, j, 0], opred[:, :N - 1, j, 1]
+            ddx, ddy = ox - x0[:, h, 1:N, nu + 0], oy - x0[:, h, 1:N, nu + 1]
+            dist = np.maximum(np.sqrt(ddx * ddx + ddy * ddy), 1e-9)
+            a1, a2 = ddx / dist, ddy / dist
+            P[:, h, 1:, ia1], P[:, h, 1:, ia2] = a1, a2
+            P[:, h, 1:, ib] = a1 * ox + a2 * oy - L["lin_margin"]
+    B = S * Pn
+    return dict(
+        xinit=np.ascontiguousarray(np.repeat(st[:, None, :nx], Pn, axis=1).reshape(B, nx)),
+        x0=np.ascontiguousarray(x0.reshape(B, (N + 1) * nz)),
+        params=np.ascontiguousarray(P.reshape(B, N * npar)),
+        set_offsets=np.arange(0, B + 1, Pn, dtype=np.int32), n=B,
+        obst_pred=np.ascontiguousarray(opred if L["n_lin"] else opred[:, :, :0]),
+        guided=np.ascontiguousarray(np.tile(np.array([1 if f else 0 for f in follow], np.uint8), S)),
+        robot_radius=ROBOT_RADIUS,
+    )

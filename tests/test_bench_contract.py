@@ -56,3 +56,4 @@ def test_gpu_arm_line():
         assert ex[k]["solves_per_s_per_gpu"] > 0 and 0 < ex[k]["fp64_frac"] < 1, k
     assert 0 < rf["executed"]["frac"] < rf["frac"]
     assert "all host cores" in d["cpu_baseline"]["cores_policy"] and d["config"]["resident_batches"] == 2
+    assert d["config"]["generator"].startswith("device") and d["config"]["generation_s"] < 5.0

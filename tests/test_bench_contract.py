@@ -52,6 +52,7 @@ def test_gpu_arm_line():
     # SURVEY 8(d) beside the headline: one iteration of the same workload, the other configurations, executed FLOPs, one CPU policy
     ex = d["extra"]
     assert ex["c2_tmpc12/iter1"]["solves_per_s_per_gpu"] > d["value"] and 0 < ex["c2_tmpc12/iter1"]["fp64_frac"] < 1
+    assert ex["c2_tmpc12/iter1_warm"]["success_frac"] > 0.5 > ex["c2_tmpc12/iter1"]["success_frac"]
     for k in ("c1_basic/iter10", "tmpc_shipped/iter10", "c5_ccmpc/iter10", "c6_goal_unicycle/iter10", "c7_linearized/iter1"):
         assert ex[k]["solves_per_s_per_gpu"] > 0 and 0 < ex[k]["fp64_frac"] < 1, k
     assert 0 < rf["executed"]["frac"] < rf["frac"]

@@ -134,6 +134,18 @@ def test_both_kernels_against_the_oracle(cfg, planners, num_iter):
         o2 = eng.solve_batch(batch["xinit"], x0b, batch["params"], num_iter=2, mem=rmem.copy())
         np.testing.assert_array_equal(o2["exit_code"], ref2["exit_code"])
         assert rel_err(o2["xtraj"][ok2], ref2["xtraj"][ok2]).max() < REL_TOL
+    # the fork's steady state (bench.py extra "iter1_warm"): ONE iteration per control cycle from the previous
+    # solution and the capsule memory -- most planners succeed, so the argmin is exercised on full sets
+    ref3 = orc.solve_batch(batch["xinit"], x0b, batch["params"], num_iter=1, mem=rmem.copy())
+    ok3 = ref3["exit_code"] == 1
+    assert ok3.mean() > 0.5 * okm.mean() > 0
+    ref_best = orc.select_best(batch["set_offsets"], ref3["pobj"], ref3["exit_code"])
+    for mode in (engine.KERNEL_STAGE, engine.KERNEL_SPLIT):
+        eng.set_kernel_mode(mode)
+        o3 = eng.solve_batch(batch["xinit"], x0b, batch["params"], num_iter=1, mem=rmem.copy())
+        np.testing.assert_array_equal(o3["exit_code"], ref3["exit_code"])
+        assert rel_err(o3["xtraj"][ok3], ref3["xtraj"][ok3]).max() < REL_TOL
+        assert same_selection(eng.select_best(batch["set_offsets"], o3["pobj"], o3["exit_code"]), ref_best, ref3, batch["set_offsets"])
     eng.set_kernel_mode(engine.KERNEL_AUTO)
 
 

@@ -95,6 +95,14 @@ using namespace mpcgen;
 // One thread per stage: a problem is solved by a GROUP of GW consecutive warps of one CTA (GW = 1 for
 // N <= 31, GW = 2 for N <= 63, e.g. the N = 50 CC-MPC configuration).  Stage k = warp-in-group * 32 + lane.
 constexpr int GW = (NSTAGE + 1 + 31) / 32;
+// Columns of the per-stage shared-memory arrays ([entry][stage slot]): one slot per LIVE lane (stages 0..N) instead of one per lane
+// of the group.  Inequality entries exist on path stages only, so the terminal stage's slot is a dummy and the dead lanes of the
+// group (lane 31 for N = 30) share it.  For N = 30 this is 31/32 of the footprint -- exactly what lets the right-hand sides d of
+// the 24 general entries of c2 sit beside the multipliers and slacks at 8 warps per CTA.
+#ifndef MPC_COL_COMPACT
+#define MPC_COL_COMPACT 1
+#endif
+constexpr int LCOL = MPC_COL_COMPACT ? (NSTAGE + 1) : GW * 32;
 static_assert(GW == 1 || GW == 2, "thread-per-stage kernel needs N <= 63");
 static_assert(MPC_WARPS_PER_CTA % ((NSTAGE + 1 + 31) / 32) == 0, "warps per CTA must be a multiple of the group size");
 static_assert(NU == 2, "Riccati input block elimination is written for nu == 2");
@@ -111,10 +119,19 @@ constexpr int NPX = NX * (NX + 1) / 2;      // packed P
 // The default takes the arrays in that priority order while they fit beside each other for all warps of the CTA:
 // MPC_LT_MASK bits: 0 general multipliers, 1 general slacks, 2 right-hand sides d, 3 Jacobian rows C; MPC_BOX_SMEM: 1 = 1/t of the
 // box entries, 2 = their multipliers and slacks, 3 = all three.  Either macro can be pinned on the command line.
-constexpr int SMEM_BUDGET_DOUBLES = (227 * 1024 - 6144) / 8 / (MPC_WARPS_PER_CTA * 32);      // per thread, static shared memory set aside
+// Budget per stage slot.  If EVERYTHING (incl. the Jacobian rows) fits into the 227 KB maximum, take it: nothing thread-local is
+// left for the L1 to serve (c5: +4 % over the smaller configuration).  Otherwise stay within the 196 KB shared-memory
+// configuration: the step to 228 KB costs 32 KB of L1 (60 -> 28 KB) that the thread-local rest (Jacobian rows, spills) needs more
+// than d needs shared memory (c2 with d inside at 228 KB 251 k solves/s, without at 196 KB 253.6 k; 250.8 k before compact columns).
+#ifndef MPC_SMEM_KB
+#define MPC_SMEM_KB 196
+#endif
+constexpr int SMEM_BUDGET_DOUBLES = (MPC_SMEM_KB * 1024 - 4096) / 8 / ((MPC_WARPS_PER_CTA / GW) * LCOL);
+constexpr int SMEM_MAX_DOUBLES = (227 * 1024 - 4096) / 8 / ((MPC_WARPS_PER_CTA / GW) * LCOL);
 constexpr int auto_lt_mask()
 {
     int used = 2 * NCG + 6 * (NX + NU), mask = 3;
+    if (used + NCG + NH * NHS <= SMEM_MAX_DOUBLES) return 15;
     if (used + NCG <= SMEM_BUDGET_DOUBLES) { mask |= 4; used += NCG; }
     if (used + NH * NHS <= SMEM_BUDGET_DOUBLES) mask |= 8;
     return mask;
@@ -165,7 +182,8 @@ constexpr int QP_OFF_G = LT_ENTRY_DOUBLES + BOX_SM_DOUBLES, QP_OFF_B = QP_OFF_G 
 #endif
 constexpr bool RIC_P = (MPC_RIC_SMEM & 1) != 0, RIC_PRB = (MPC_RIC_SMEM & 2) != 0;
 constexpr int RIC_OFF_P = QP_OFF_H + (QPS_H ? NPK : 0), RIC_OFF_PRB = RIC_OFF_P + (RIC_P ? NPX : 0);
-constexpr int LT_DOUBLES = (RIC_OFF_PRB + (RIC_PRB ? NX : 0)) * GW * 32;
+constexpr int LT_DOUBLES = (RIC_OFF_PRB + (RIC_PRB ? NX : 0)) * LCOL;
+static_assert(!MPC_COL_COMPACT || (MPC_QP_SMEM == 0 && MPC_RIC_SMEM == 0), "compact columns: the terminal stage's slot is shared with the dead lanes");
 constexpr int LT_STRIDE = LT_DOUBLES + (MPC_CHECK ? GW * 32 : 0);      // MPC_CHECK: a row of canaries behind every group's region      // per group: lam, t (d, C) of the general entries (+ 1/t of the boxes)
 // column accessor: stride GW*32 doubles in shared memory ([entry][thread of the group]), stride 1 for a thread-local array
 template <bool SM>
@@ -179,7 +197,7 @@ struct LtCol {
 #if MPC_CHECK
         if (e < 0 || e >= n) { MPC_CHECK_FAIL(0); e = 0; }
 #endif
-        return p[SM ? e * (((NSTAGE + 1 + 31) / 32) * 32) : e];
+        return p[SM ? e * LCOL : e];
     }
 };
 // Jacobian rows of the general constraints: at(r, a) = d h_r / d z_HSUP[a].  Plain (all in one place, shared or thread-local)
@@ -196,10 +214,10 @@ struct CRows {
 #endif
         if constexpr (CSPL > 0) {
             const int r = i / NHS, a = i - r * NHS;
-            if (a < CSPL) return sm[(r * CSPL + a) * (((NSTAGE + 1 + 31) / 32) * 32)];
+            if (a < CSPL) return sm[(r * CSPL + a) * LCOL];
             return p[i];
         } else {
-            return p[SM ? i * (((NSTAGE + 1 + 31) / 32) * 32) : i];
+            return p[SM ? i * LCOL : i];
         }
     }
     __device__ __forceinline__ double at(int r, int a) const
@@ -208,11 +226,11 @@ struct CRows {
         if (r < 0 || r >= NH || a < 0 || a >= NHS) { MPC_CHECK_FAIL(0); r = 0; a = 0; }
 #endif
         if constexpr (CSPL > 0) {
-            if (a < CSPL) return sm[(r * CSPL + a) * (((NSTAGE + 1 + 31) / 32) * 32)];
+            if (a < CSPL) return sm[(r * CSPL + a) * LCOL];
             return tail_zero ? 0.0 : p[r * NHS + a];
         } else {
             if (a >= CTAIL0 && tail_zero) return 0.0;
-            return p[SM ? (r * NHS + a) * (((NSTAGE + 1 + 31) / 32) * 32) : r * NHS + a];
+            return p[SM ? (r * NHS + a) * LCOL : r * NHS + a];
         }
     }
 };
@@ -226,7 +244,7 @@ struct SmemCol {
 #if MPC_CHECK
         if (e < 0 || e >= n) { MPC_CHECK_FAIL(0); e = 0; }
 #endif
-        return p[e * (((NSTAGE + 1 + 31) / 32) * 32)];
+        return p[e * LCOL];
     }
 };
 constexpr int NCB = 2 * NZ;                 // box entries: lower(z_i) i<NZ, then upper(z_i)
@@ -1306,19 +1324,20 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
     const bool xbox = path && k >= 1;         // x_0 is fixed: no state bounds at stage 0
     const double* __restrict__ p = params_g + ((size_t)prob * NSTAGE + (path ? k : NSTAGE - 1)) * NP;
 
+    const int slot = MPC_COL_COMPACT ? (k < NSTAGE ? k : NSTAGE) : k;      // stage slot of the shared-memory columns (dead lanes: the terminal stage's dummy)
     double z[NZ], pi[NX], v[NZ], qpi[NX];
 #if MPC_BOX_SMEM >= 2
     // multipliers and slacks of the box entries in shared memory too: 56 registers less in the interior-point loop
-    const SmemCol lamb{lt_sm + LT_ENTRY_DOUBLES * (GW * 32) + (grp.wig * 32 + (threadIdx.x & 31)) MPCK(NCB)};
-    const SmemCol tb{lt_sm + (LT_ENTRY_DOUBLES + NCB) * (GW * 32) + (grp.wig * 32 + (threadIdx.x & 31)) MPCK(NCB)};
+    const SmemCol lamb{lt_sm + LT_ENTRY_DOUBLES * LCOL + slot MPCK(NCB)};
+    const SmemCol tb{lt_sm + (LT_ENTRY_DOUBLES + NCB) * LCOL + slot MPCK(NCB)};
 #else
     double lamb[NCB], tb[NCB];
 #endif
     // general-entry state: shared-memory columns or thread-local arrays (MPC_LT_MASK); the unused alternative is optimised away
-    double* const lt_me = lt_sm + (grp.wig * 32 + (threadIdx.x & 31));
+    double* const lt_me = lt_sm + slot;
     double lamg_loc[(!LT_LAM && NCG > 0) ? NCG : 1], tg_loc[(!LT_T && NCG > 0) ? NCG : 1];
-    const LtCol<LT_LAM> lamg{LT_LAM ? lt_me + LT_OFF_LAM * (GW * 32) : lamg_loc MPCK(NCG)};
-    const LtCol<LT_T> tg{LT_T ? lt_me + LT_OFF_T * (GW * 32) : tg_loc MPCK(NCG)};
+    const LtCol<LT_LAM> lamg{LT_LAM ? lt_me + LT_OFF_LAM * LCOL : lamg_loc MPCK(NCG)};
+    const LtCol<LT_T> tg{LT_T ? lt_me + LT_OFF_T * LCOL : tg_loc MPCK(NCG)};
 #pragma unroll
     for (int i = 0; i < NZ; i++) {
         z[i] = live ? x0_g[(size_t)prob * NZ * (NSTAGE + 1) + k * NZ + i] : 0.0;   // loadWarmstart (:274-284)
@@ -1353,8 +1372,8 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
         // ======================= K1-K4: linearise at the current iterate ============================
         double H[NPK], g[NZ], Wv[NWV], b[NX];
         double C_loc[(!LT_C && NH > 0) ? NH * NHS : 1], dg_loc[(!LT_D && NCG > 0) ? NCG : 1];
-        CRows<LT_C> C{LT_C ? lt_me + LT_OFF_C * (GW * 32) : C_loc, lt_me + LT_OFF_CS * (GW * 32), false};
-        const LtCol<LT_D> dg{LT_D ? lt_me + LT_OFF_D * (GW * 32) : dg_loc MPCK(NCG)};
+        CRows<LT_C> C{LT_C ? lt_me + LT_OFF_C * LCOL : C_loc, lt_me + LT_OFF_CS * LCOL, false};
+        const LtCol<LT_D> dg{LT_D ? lt_me + LT_OFF_D * LCOL : dg_loc MPCK(NCG)};
         {
             double pin[NX], xnx[NX], zx_[NX];
 #pragma unroll
@@ -1392,7 +1411,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                 for (int i = NU; i < NZ; i++) H[pk(i, i)] = REG_EPS;   // mirror(0) = eps I; no terminal cost
             }
         }
-        const SmemCol gs{lt_me + QP_OFF_G * (GW * 32) MPCK(NZ)}, bs{lt_me + QP_OFF_B * (GW * 32) MPCK(NX)}, Hs{lt_me + QP_OFF_H * (GW * 32) MPCK(NPK)};
+        const SmemCol gs{lt_me + QP_OFF_G * LCOL MPCK(NZ)}, bs{lt_me + QP_OFF_B * LCOL MPCK(NX)}, Hs{lt_me + QP_OFF_H * LCOL MPCK(NPK)};
         if constexpr (QPS_GB) {
 #pragma unroll
             for (int i = 0; i < NZ; i++) gs[i] = g[i];
@@ -1408,7 +1427,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
             if (path)
                 for (int r = 0; r < NH; r++)
 #pragma unroll
-                    for (int a = CTAIL0; a < NHS; a++) nzt = nzt || (C.p[LT_C ? (r * NHS + a) * (GW * 32) : r * NHS + a] != 0.0);
+                    for (int a = CTAIL0; a < NHS; a++) nzt = nzt || (C.p[LT_C ? (r * NHS + a) * LCOL : r * NHS + a] != 0.0);
             C.tail_zero = !grp.any(nzt);
         }
 
@@ -1477,7 +1496,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
         // state of the previous iteration's step, applied at the top of the next pass (fused update):
 #if MPC_BOX_SMEM == 1 || MPC_BOX_SMEM == 3
         // 1/t of the box entries (reused by passes B, C and the update) parked in shared memory: 28 registers less in the loop
-        const SmemCol itb{lt_sm + (LT_ENTRY_DOUBLES + (MPC_BOX_SMEM == 3 ? 2 * NCB : 0)) * (GW * 32) + (grp.wig * 32 + (threadIdx.x & 31)) MPCK(NCB)};
+        const SmemCol itb{lt_sm + (LT_ENTRY_DOUBLES + (MPC_BOX_SMEM == 3 ? 2 * NCB : 0)) * LCOL + slot MPCK(NCB)};
 #else
         double itb[NCB];                             // 1/t of the box entries, reused by passes B, C and the update (general entries: recomputed)
 #endif
@@ -1650,7 +1669,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                 for (int i = 0; i < NZ; i++) dva[i] = (live && (path || i >= NU)) ? blk[RO_DZ + i] : 0.0;
             }
             double P[RIC_P ? 1 : NPX], pv[NX], Lx0[NX], Lx1[NX], Prb[RIC_PRB ? 1 : NX], lv[NU], L10 = 0.0, iL0 = 0.0, iL1 = 0.0;
-            const SmemCol Ps{lt_me + RIC_OFF_P * (GW * 32) MPCK(NPX)}, Prbs{lt_me + RIC_OFF_PRB * (GW * 32) MPCK(NX)};      // (MPC_RIC_SMEM)
+            const SmemCol Ps{lt_me + RIC_OFF_P * LCOL MPCK(NPX)}, Prbs{lt_me + RIC_OFF_PRB * LCOL MPCK(NX)};      // (MPC_RIC_SMEM)
             auto prb = [&](int i) -> double { if constexpr (RIC_PRB) return Prbs[i]; else return Prb[i]; };
             auto pmat = [&](int i) -> double { if constexpr (RIC_P) return Ps[i]; else return P[i]; };
             if constexpr (!COOP) {

@@ -68,7 +68,12 @@ int mpcgpu_mem_doubles(const mpcgpu_engine *e);
  *   pobj[n] AcadosInfo::pobj; exit_code[n] return value of solve() (1 success, 0, 2, 3, 4: :197-203);
  *   qp_status[n] AcadosInfo::qp_status in the numbering Solver::explainExitFlag decodes (:409-420): 0 ok,
  *                2 max iterations, 3 minimal step, 4 NaN; res_eq[n] the value tested at :177;
- *   ipm_iters[n] or NULL: total interior-point iterations (diagnostic). */
+ *   ipm_iters[n] or NULL: total interior-point iterations (diagnostic).
+ * Host pipeline: batches of >= 8192 problems whose INPUT arrays are page-locked (mpcgpu_alloc_pinned, cudaHostAlloc,
+ * cudaHostRegister) are solved by ONE persistent launch while the copy stream still delivers the inputs chunk by chunk (a gate
+ * word behind the work counter tells the kernel how far they have arrived); results are written by the kernel straight into
+ * OUTPUT arrays that are page-locked too, otherwise staged and copied once.  Pageable inputs take chunked launches (copies
+ * from pageable memory would serialise the single launch).  Results are identical either way. */
 int mpcgpu_solve_batch(mpcgpu_engine *e, int n, const double *xinit, const double *x0, const double *params,
                        const int *num_iter, int num_iter_all, double *mem_inout, double *xtraj, double *utraj,
                        double *pobj, int *exit_code, int *qp_status, double *res_eq, int *ipm_iters);

@@ -35,14 +35,18 @@ static cudaError_t launch_solve(int grid, int mode, cudaStream_t stream, int n, 
                          const int* num_iter, int num_iter_all, double* mem, double* xtraj, double* utraj, double* pobj,
                          int* exit_code, int* qp_status, double* res_eq, int* ipm_iters, int* work_counter)
 {
-    cudaError_t err = cudaMemsetAsync(work_counter, 0, sizeof(int), stream);
+    // work_counter[0]: next problem index; [1]: input gate of the thread-per-stage kernel (0 = inputs resident).  A gated launch
+    // (mode bit 8, host pipeline) finds both words prepared by the caller on its copy stream.
+    const bool gated = (mode & 0x100) != 0;
+    mode &= 0xff;
+    cudaError_t err = gated ? cudaSuccess : cudaMemsetAsync(work_counter, 0, 2 * sizeof(int), stream);
     if (err != cudaSuccess) return err;
     err = set_smem_attributes();
     if (err != cudaSuccess) return err;
     // small batches (grid < 0, at most one problem per SM) -> role-split kernel unless the caller pins a kernel
     int sms = 148, dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const bool split = USE_SPLIT && (mode == 2 || SPLIT_ALWAYS || (mode == 0 && grid < 0 && -grid <= sms));
+    const bool split = USE_SPLIT && !gated && (mode == 2 || SPLIT_ALWAYS || (mode == 0 && grid < 0 && -grid <= sms));
     if (split)
         mpc_solve_split_kernel<<<grid < 0 ? -grid : (n < sms * 4 ? n : sms * 4), SPLIT_THREADS, SMEM_SPLIT, stream>>>(n, xinit, x0, params, num_iter, num_iter_all, mem,
                                                                                           MEM_DOUBLES, xtraj, utraj, pobj, exit_code,

@@ -2136,6 +2136,13 @@ mpc_solve_kernel(int n, const double* __restrict__ xinit, const double* __restri
             grp.sync();
         }
         if (prob >= n) return;
+        // gated launch (host pipeline of mpcgpu_solve_batch): the word behind the work counter is 0 (inputs resident) or -(m + 1)
+        // where the inputs of problems 0 .. m-1 have arrived; the copy stream raises it behind every chunk it has delivered
+        {
+            const volatile int* gate = work_counter + 1;
+            for (int g = *gate; g < 0 && -(g + 1) <= prob; g = *gate) __nanosleep(500);
+            __threadfence();
+        }
         const int nit = num_iter ? num_iter[prob] : num_iter_all;
         solve_problem<(WPC != WARPS_PER_CTA) || (MPC_SCAN_ALWAYS != 0)>(prob, xinit, x0, params, nit, mem, mem_doubles, xtraj, utraj, pobj, exit_code, qp_status, res_eq,
                       ipm_iters, s_hand[grp.gid], s_lt + (size_t)grp.gid * LT_STRIDE,

@@ -160,7 +160,7 @@ struct mpcgpu_engine {
     void* d_obst = nullptr; size_t cap_obst = 0;   // obstacle predictions + guided flags of mpcgpu_solve_sets_guided
     cudaStream_t stream = nullptr, stream2 = nullptr;   // stream2: second lane of the chunked host pipeline
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    static constexpr int MAX_CHUNKS = 6;
+    static constexpr int MAX_CHUNKS = 12;      // gated path: up to 12 input chunks; legacy path: up to 6 launches
     cudaEvent_t cev0[MAX_CHUNKS] = {}, cev1[MAX_CHUNKS] = {};   // per chunk (host path)
     int chunks_timed = 0;      // > 0: last_kernel_ms sums the chunk kernels of the last host call
     // device staging for the host-pointer entry points
@@ -169,7 +169,9 @@ struct mpcgpu_engine {
     int *d_num_iter = nullptr, *d_exit = nullptr, *d_qps = nullptr, *d_ipm = nullptr, *d_counters = nullptr, *d_offsets = nullptr,
         *d_best = nullptr;
     unsigned long long launch_seq = 0;   // every solve launch takes its own work counter from the ring d_counters[MPCGPU_MAX_INFLIGHT]
-    int* next_counter() { return d_counters + (launch_seq++ % MPCGPU_MAX_INFLIGHT); }
+    int* next_counter() { return d_counters + 2 * (launch_seq++ % MPCGPU_MAX_INFLIGHT); }      // {work counter, input gate}
+    int* h_gate = nullptr;               // pinned: gate values of the host pipeline
+    cudaEvent_t ev_gate = nullptr;
     double *d_prev = nullptr, *d_objout = nullptr, *d_consout = nullptr, *d_static = nullptr;   // set options, allocated on first use
     double* d_tab = nullptr; size_t cap_tab = 0;      // struct-of-tables inputs: [invariant | stage | obstacle radius] doubles, then the index arrays
     int* d_tabidx = nullptr; size_t cap_tabidx = 0;
@@ -220,12 +222,15 @@ int mpcgpu_engine_create(const char* config_name, int device, int max_batch, mpc
     AL(e->d_xinit, B * nx * 8); AL(e->d_x0, B * nz * (N + 1) * 8); AL(e->d_params, B * N * ops->np * 8);
     AL(e->d_mem, B * ops->mem_doubles * 8); AL(e->d_xtraj, B * nx * (N + 1) * 8); AL(e->d_utraj, B * nu * N * 8);
     AL(e->d_pobj, B * 8); AL(e->d_res_eq, B * 8); AL(e->d_scale, B * 8); AL(e->d_sub, B * 8);
-    AL(e->d_num_iter, B * 4); AL(e->d_exit, B * 4); AL(e->d_qps, B * 4); AL(e->d_ipm, B * 4); AL(e->d_counters, 4 * MPCGPU_MAX_INFLIGHT);
+    AL(e->d_num_iter, B * 4); AL(e->d_exit, B * 4); AL(e->d_qps, B * 4); AL(e->d_ipm, B * 4); AL(e->d_counters, 8 * MPCGPU_MAX_INFLIGHT);
     AL(e->d_offsets, (B + 1) * 4); AL(e->d_best, B * 4); AL(e->d_disabled, B);
 #undef AL
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&e->ev0) != cudaSuccess || cudaEventCreate(&e->ev1) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->ev_gate, cudaEventDisableTiming) != cudaSuccess ||
+        cudaHostAlloc((void**)&e->h_gate, (mpcgpu_engine::MAX_CHUNKS + 2) * sizeof(int), cudaHostAllocDefault) != cudaSuccess ||
+        cudaMemset(e->d_counters, 0, 8 * MPCGPU_MAX_INFLIGHT) != cudaSuccess ||
         [&] { for (int i = 0; i < mpcgpu_engine::MAX_CHUNKS; i++) if (cudaEventCreate(&e->cev0[i]) != cudaSuccess || cudaEventCreate(&e->cev1[i]) != cudaSuccess) return true; return false; }()) {
         e->err = "stream/event creation failed";
         return fail(MPCGPU_ERR_CUDA);
@@ -258,6 +263,8 @@ int mpcgpu_engine_destroy(mpcgpu_engine* e)
         if (p) cudaFree(p);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->ev_gate) cudaEventDestroy(e->ev_gate);
+    if (e->h_gate) cudaFreeHost(e->h_gate);
     for (int i = 0; i < mpcgpu_engine::MAX_CHUNKS; i++) { if (e->cev0[i]) cudaEventDestroy(e->cev0[i]); if (e->cev1[i]) cudaEventDestroy(e->cev1[i]); }
     if (e->stream) cudaStreamDestroy(e->stream);
     if (e->stream2) cudaStreamDestroy(e->stream2);
@@ -279,7 +286,8 @@ int mpcgpu_mem_doubles(const mpcgpu_engine* e) { return e ? e->ops->mem_doubles 
 
 static int launch_solve_on(mpcgpu_engine* e, cudaStream_t st, int* counter, cudaEvent_t t0, cudaEvent_t t1, int n, const double* xinit,
                            const double* x0, const double* params, const int* num_iter, int num_iter_all, double* mem_inout,
-                           double* xtraj, double* utraj, double* pobj, int* exit_code, int* qp_status, double* res_eq, int* ipm_iters);
+                           double* xtraj, double* utraj, double* pobj, int* exit_code, int* qp_status, double* res_eq, int* ipm_iters,
+                           bool gated = false);
 
 int mpcgpu_solve_batch_device(mpcgpu_engine* e, int n, const double* xinit, const double* x0, const double* params,
                               const int* num_iter, int num_iter_all, double* mem_inout, double* xtraj, double* utraj,
@@ -297,7 +305,8 @@ int mpcgpu_solve_batch_device(mpcgpu_engine* e, int n, const double* xinit, cons
 
 static int launch_solve_on(mpcgpu_engine* e, cudaStream_t st, int* counter, cudaEvent_t t0, cudaEvent_t t1, int n, const double* xinit,
                            const double* x0, const double* params, const int* num_iter, int num_iter_all, double* mem_inout,
-                           double* xtraj, double* utraj, double* pobj, int* exit_code, int* qp_status, double* res_eq, int* ipm_iters)
+                           double* xtraj, double* utraj, double* pobj, int* exit_code, int* qp_status, double* res_eq, int* ipm_iters,
+                           bool gated)
 {
     // small batches (one or a few homotopy sets): one problem per CTA so every problem gets its own SM;
     // otherwise the persistent throughput grid
@@ -310,7 +319,7 @@ static int launch_solve_on(mpcgpu_engine* e, cudaStream_t st, int* counter, cuda
         if (grid > e->grid) grid = e->grid;
     }
     CK(cudaEventRecord(t0, st));
-    CK(e->ops->launch_solve(grid, e->kernel_mode, st, n, xinit, x0, params, num_iter, num_iter_all, mem_inout, xtraj, utraj, pobj, exit_code,
+    CK(e->ops->launch_solve(grid, e->kernel_mode | (gated ? 0x100 : 0), st, n, xinit, x0, params, num_iter, num_iter_all, mem_inout, xtraj, utraj, pobj, exit_code,
                             qp_status, res_eq, ipm_iters, counter));
     CK(cudaEventRecord(t1, st));
     e->launches += 1;
@@ -361,6 +370,73 @@ static int solve_batch_impl(mpcgpu_engine* e, int n, const double* xinit, const 
     const MpcConfigOps* o = e->ops;
     const size_t B = (size_t)n;
     const int N = o->N, nx = o->nx, nu = o->nu, nz = nx + nu;
+    const size_t sx0 = (size_t)nz * (N + 1), spar = (size_t)N * o->np, sxt = (size_t)nx * (N + 1), sut = (size_t)nu * N,
+                 smem_ = (size_t)o->mem_doubles;
+    // ---- Gated single launch (large batches from PINNED host memory).  Separate launches per chunk leave every SM partly idle
+    // while the last warps of a chunk finish (a CTA of the next launch needs the whole SM): ~6 % of a 36 864-problem step.  Instead
+    // ONE persistent launch takes the whole batch; the copy stream delivers the inputs chunk by chunk and raises a gate word
+    // behind every chunk, and a warp that draws a problem beyond the gate waits for it (copies run ~4x ahead of the solves, so
+    // only the first chunk is ever waited for).  Chunk boundaries are multiples of 16 problems: a boundary then falls on a 128-byte
+    // line of every input array, so no SM can have cached a line that a later copy completes.  Results: written by the kernel
+    // straight into the caller's arrays when those are pinned (mapped) host memory, else staged and copied once at the end.
+    auto pinned_dev = [](const void* h, bool need) -> void* {
+        if (!h) return need ? nullptr : (void*)1;
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, h) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        return (a.type == cudaMemoryTypeHost) ? a.devicePointer : nullptr;
+    };
+    if (B >= 8192 && pinned_dev(xinit, true) && pinned_dev(x0, true) && pinned_dev(params, true) && pinned_dev(num_iter, false) &&
+        pinned_dev(mem_inout, false)) {
+        size_t gb[mpcgpu_engine::MAX_CHUNKS + 1];
+        int ng = 0;
+        gb[0] = 0;
+        gb[++ng] = 2048;                                    // enough to start every warp of the grid; 1.6 ms of copy for c2
+        size_t per_ = (B - 2048 + (mpcgpu_engine::MAX_CHUNKS - 2)) / (mpcgpu_engine::MAX_CHUNKS - 1);
+        if (per_ < 4096) per_ = 4096;
+        per_ = (per_ + 15) & ~(size_t)15;
+        while (gb[ng] < B) { const size_t hi = gb[ng] + per_; gb[ng + 1] = hi < B ? hi : B; ng++; }
+        int* slot = e->next_counter();
+        e->h_gate[0] = -1;
+        for (int c = 0; c < ng; c++) e->h_gate[c + 1] = (c + 1 == ng) ? 0 : -(int)gb[c + 1] - 1;      // the last chunk opens the gate for good
+        cudaStream_t cs = e->stream2;
+        CK(cudaMemsetAsync(slot, 0, sizeof(int), cs));
+        CK(cudaMemcpyAsync(slot + 1, &e->h_gate[0], sizeof(int), cudaMemcpyHostToDevice, cs));
+        CK(cudaEventRecord(e->ev_gate, cs));
+        CK(cudaStreamWaitEvent(e->stream, e->ev_gate, 0));
+        for (int c = 0; c < ng; c++) {
+            const size_t b0 = gb[c], m = gb[c + 1] - b0;
+            CK(cudaMemcpyAsync(e->d_xinit + b0 * nx, xinit + b0 * nx, m * nx * 8, cudaMemcpyHostToDevice, cs));
+            CK(cudaMemcpyAsync(e->d_x0 + b0 * sx0, x0 + b0 * sx0, m * sx0 * 8, cudaMemcpyHostToDevice, cs));
+            CK(cudaMemcpyAsync(e->d_params + b0 * spar, params + b0 * spar, m * spar * 8, cudaMemcpyHostToDevice, cs));
+            if (num_iter) CK(cudaMemcpyAsync(e->d_num_iter + b0, num_iter + b0, m * 4, cudaMemcpyHostToDevice, cs));
+            if (mem_inout) CK(cudaMemcpyAsync(e->d_mem + b0 * smem_, mem_inout + b0 * smem_, m * smem_ * 8, cudaMemcpyHostToDevice, cs));
+            CK(cudaMemcpyAsync(slot + 1, &e->h_gate[c + 1], sizeof(int), cudaMemcpyHostToDevice, cs));
+        }
+        // every copy and every gate update is enqueued: the launch cannot be left waiting for a copy that was never issued
+        void* zx = pinned_dev(xtraj, true); void* zu = pinned_dev(utraj, true); void* zp = pinned_dev(pobj, true);
+        void* ze = pinned_dev(exit_code, true); void* zq = pinned_dev(qp_status, true); void* zr = pinned_dev(res_eq, true);
+        void* zi = ipm_iters ? pinned_dev(ipm_iters, true) : nullptr;
+        const bool direct = zx && zu && zp && ze && zq && zr && (!ipm_iters || zi);
+        int rc = launch_solve_on(e, e->stream, slot, e->ev0, e->ev1, n, e->d_xinit, e->d_x0, e->d_params, num_iter ? e->d_num_iter : nullptr, num_iter_all,
+                                 mem_inout ? e->d_mem : nullptr, direct ? (double*)zx : e->d_xtraj, direct ? (double*)zu : e->d_utraj,
+                                 direct ? (double*)zp : e->d_pobj, direct ? (int*)ze : e->d_exit, direct ? (int*)zq : e->d_qps,
+                                 direct ? (double*)zr : e->d_res_eq, direct ? (int*)zi : e->d_ipm, true);
+        if (rc != MPCGPU_OK) return rc;
+        if (!direct) {
+            CK(cudaMemcpyAsync(xtraj, e->d_xtraj, B * sxt * 8, cudaMemcpyDeviceToHost, e->stream));
+            CK(cudaMemcpyAsync(utraj, e->d_utraj, B * sut * 8, cudaMemcpyDeviceToHost, e->stream));
+            CK(cudaMemcpyAsync(pobj, e->d_pobj, B * 8, cudaMemcpyDeviceToHost, e->stream));
+            CK(cudaMemcpyAsync(exit_code, e->d_exit, B * 4, cudaMemcpyDeviceToHost, e->stream));
+            CK(cudaMemcpyAsync(qp_status, e->d_qps, B * 4, cudaMemcpyDeviceToHost, e->stream));
+            CK(cudaMemcpyAsync(res_eq, e->d_res_eq, B * 8, cudaMemcpyDeviceToHost, e->stream));
+            if (ipm_iters) CK(cudaMemcpyAsync(ipm_iters, e->d_ipm, B * 4, cudaMemcpyDeviceToHost, e->stream));
+        }
+        if (mem_inout) CK(cudaMemcpyAsync(mem_inout, e->d_mem, B * smem_ * 8, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        CK(cudaStreamSynchronize(e->stream2));
+        e->chunks_timed = 0;
+        return MPCGPU_OK;
+    }
     // Chunked two-stream pipeline: the H2D copy of chunk c+1 and the D2H copy of chunk c-1 overlap the solve
     // kernel of chunk c (pinned host memory makes the copies truly asynchronous).  Chunks stay >= 8192
     // problems so that the persistent grid keeps several waves per launch.
@@ -385,8 +461,6 @@ static int solve_batch_impl(mpcgpu_engine* e, int n, const double* xinit, const 
             nchunk++;
         }
     }
-    const size_t sx0 = (size_t)nz * (N + 1), spar = (size_t)N * o->np, sxt = (size_t)nx * (N + 1), sut = (size_t)nu * N,
-                 smem_ = (size_t)o->mem_doubles;
     for (int c = 0; c < nchunk; c++) {
         const size_t b0 = bounds[c];
         if (b0 >= B || bounds[c + 1] <= b0) { nchunk = c; break; }
@@ -691,12 +765,21 @@ static int solve_sets_impl(mpcgpu_engine* e, int n_sets, int planners, const dou
     int nchunk = 0;
     bounds[0] = 0;
     const int sets8k = (8192 + planners - 1) / planners;
-    if (n_sets >= 4 * sets8k) {
+    // Separate solve launches per chunk cost ~6 % (SMs idle while the last warps of a chunk finish; a gate as in
+    // mpcgpu_solve_batch is no option here: the expansion kernels of a later chunk could not run beside the persistent grid).
+    // When the compact inputs are small -- under ~8 KB per problem, i.e. their copy takes less than that -- everything is
+    // copied and expanded first and ONE launch solves the batch.
+    size_t in_bytes = (size_t)nz * (N + 1) * 8 + (size_t)nidx * N * 8 + (mem_host ? smem_ * 8 : 0) +
+                      ((size_t)nx * 8 + (size_t)ob_per_set * 8 + (size_t)st_per_set * 8 + (cons ? (size_t)N * 16 : 0) +
+                       (tab ? ((size_t)tab->n_invariant + (size_t)N * tab->n_stage + (size_t)tab->M) * 8 : (size_t)N * np * 8)) / planners;
+    if (in_bytes <= 8192) {
+        bounds[++nchunk] = n_sets;
+    } else if (n_sets >= 4 * sets8k) {
         int first = n_sets / 16;
         if (first * planners < 2048) first = (2048 + planners - 1) / planners;
         bounds[++nchunk] = first;
     }
-    {
+    if (bounds[nchunk] < n_sets) {
         const int rest = n_sets - bounds[nchunk];
         int k = rest / sets8k;
         if (k < 1) k = 1;

@@ -94,6 +94,41 @@ def measure_fp64_peak(device=0):
     return v.value
 
 
+class PinnedArray:
+    """numpy view of page-locked host memory from mpcgpu_alloc_pinned (freed with the object).  Copies from pinned arrays run
+    asynchronously; mpcgpu_solve_batch then takes its gated single-launch pipeline and writes results straight into pinned
+    output arrays."""
+
+    def __init__(self, shape, dtype=np.float64):
+        lib = load_library()
+        lib.mpcgpu_alloc_pinned.argtypes = [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]
+        lib.mpcgpu_free_pinned.argtypes = [ctypes.c_void_p]
+        self._lib = lib
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self._ptr = ctypes.c_void_p()
+        rc = lib.mpcgpu_alloc_pinned(max(nbytes, 8), ctypes.byref(self._ptr))
+        if rc != 0:
+            raise RuntimeError("mpcgpu_alloc_pinned(%d bytes) failed: %d" % (nbytes, rc))
+        buf = (ctypes.c_char * max(nbytes, 8)).from_address(self._ptr.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def __del__(self):
+        try:
+            if self._ptr:
+                self.array = None
+                self._lib.mpcgpu_free_pinned(self._ptr)
+                self._ptr = None
+        except Exception:
+            pass
+
+
+def pinned_copy(a):
+    """(holder, array): a copy of `a` in pinned host memory; keep the holder alive while the array is in use"""
+    h = PinnedArray(a.shape, a.dtype)
+    h.array[...] = a
+    return h, h.array
+
+
 class ParamTables(ctypes.Structure):
     """struct mpcgpu_param_tables (include/mpcgpu.h): the struct-of-tables parameter path"""
     _fields_ = [("n_invariant", ctypes.c_int), ("invariant_idx", ctypes.c_void_p), ("invariant", ctypes.c_void_p),

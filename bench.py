@@ -584,7 +584,8 @@ def main():
                         "frac": exf * n / (kms * 1e-3) / 1e12 / fp64_peak, "source": ex["source"]}
         roofline = {"bound": "fp64", "kernel": "mpc_solve_kernel", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                     "frac": achieved / fp64_peak, "traffic": traffic,
-                    "traffic_note": "DRAM bytes per launch (ncu) vs %d algorithmic: thread-local arrays / spills written back through L2" % (bytes_per_solve(d) * n),
+                    "traffic_note": "DRAM bytes per launch (ncu) vs %d algorithmic: parameters re-read in most SQP iterations + thread-local lines written back "
+                                    "(L2 holds the stack frames and parameter blocks of 1 184 problems in flight); latency bound, DRAM bus < 2 %% busy" % (bytes_per_solve(d) * n),
                     "peak_source": "DFMA micro-kernel measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                     "flops_per_solve": fps, "kernel_ms": kms, "executed": executed,
                     "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,

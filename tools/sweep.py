@@ -1,8 +1,8 @@
 #!/usr/bin/env python3
 """Batch-size / iteration-count sweep of the solve kernel on one GPU (BASELINE configs[2]: 4096 .. 1M
-independent N=30 problems).  Inputs are generated once on the host for `--base-sets` homotopy sets and
-tiled ON THE DEVICE to the requested batch (duplicates cost the same as distinct problems; every copy is
-separate memory).  Device-resident timing with CUDA events.  Writes one JSON line per point."""
+independent N=30 problems).  Inputs: every problem distinct, generated ON THE DEVICE by the counter-based generator
+(mpcgpu_generate_synthetic_device) where it covers the configuration; otherwise generated once on the host for `--base-sets`
+homotopy sets and tiled on the device.  Device-resident timing with CUDA events.  Writes one JSON line per point."""
 import argparse
 import json
 import os
@@ -27,13 +27,27 @@ def main():
     dev = torch.device("cuda", 0)
     sizes = [int(v) for v in args.sizes.split(",")]
     eng = engine.Engine(args.config, 0, max(sizes))
-    base = synthetic.make_batch(eng.parameter_map, eng.dims, args.base_sets, args.planners, seed=1234)
-    nb = base["n"]
-    bx, b0, bp = (torch.from_numpy(base[k]).to(dev) for k in ("xinit", "x0", "params"))
+    try:
+        synthetic.synth_layout(eng.parameter_map, eng.dims)
+        on_device = True
+    except ValueError:
+        on_device = False
+        base = synthetic.make_batch(eng.parameter_map, eng.dims, args.base_sets, args.planners, seed=1234)
+        nb = base["n"]
+        bx, b0, bp = (torch.from_numpy(base[k]).to(dev) for k in ("xinit", "x0", "params"))
     stream = torch.cuda.Stream(device=dev)
     for n in sizes:
-        reps = (n + nb - 1) // nb
-        xi = bx.repeat(reps, 1)[:n].contiguous(); x0 = b0.repeat(reps, 1)[:n].contiguous(); pr = bp.repeat(reps, 1)[:n].contiguous()
+        if on_device:
+            ns = (n + args.planners - 1) // args.planners
+            n = min(ns * args.planners, max(sizes)) // args.planners * args.planners
+            ns = n // args.planners
+            xi = torch.empty((n, eng.nx), dtype=torch.float64, device=dev)
+            x0 = torch.empty((n, (eng.N + 1) * eng.nz), dtype=torch.float64, device=dev)
+            pr = torch.empty((n, eng.N * eng.npar), dtype=torch.float64, device=dev)
+            engine.generate_synthetic(eng.parameter_map, eng.dims, ns, args.planners, seed=1234, device_buffers=[xi.data_ptr(), x0.data_ptr(), pr.data_ptr(), None])
+        else:
+            reps = (n + nb - 1) // nb
+            xi = bx.repeat(reps, 1)[:n].contiguous(); x0 = b0.repeat(reps, 1)[:n].contiguous(); pr = bp.repeat(reps, 1)[:n].contiguous()
         xt = torch.empty((n, (eng.N + 1) * eng.nx), dtype=torch.float64, device=dev); ut = torch.empty((n, eng.N * eng.nu), dtype=torch.float64, device=dev)
         po = torch.empty(n, dtype=torch.float64, device=dev); rq = torch.empty(n, dtype=torch.float64, device=dev)
         ec = torch.empty(n, dtype=torch.int32, device=dev); qs = torch.empty(n, dtype=torch.int32, device=dev); ip = torch.empty(n, dtype=torch.int32, device=dev)
@@ -51,7 +65,8 @@ def main():
             t = min(ms[1:])
             print(json.dumps({"config": args.config, "n": n, "num_iter": nit, "kernel_ms": t, "solves_per_s": n / t * 1e3,
                               "success_frac": float((ec == 1).float().mean().item()), "ipm_iters_mean": float(ip.float().mean().item()),
-                              "input_gb": (xi.numel() + x0.numel() + pr.numel()) * 8 / 1e9}), flush=True)
+                              "input_gb": (xi.numel() + x0.numel() + pr.numel()) * 8 / 1e9,
+                              "inputs": "distinct, generated on the device" if on_device else "tiled from %d host-generated sets" % args.base_sets}), flush=True)
         del xi, x0, pr, xt, ut
         torch.cuda.empty_cache()
 

@@ -385,7 +385,7 @@ static int solve_batch_impl(mpcgpu_engine* e, int n, const double* xinit, const 
         if (cudaPointerGetAttributes(&a, h) != cudaSuccess) { cudaGetLastError(); return nullptr; }
         return (a.type == cudaMemoryTypeHost) ? a.devicePointer : nullptr;
     };
-    if (B >= 8192 && pinned_dev(xinit, true) && pinned_dev(x0, true) && pinned_dev(params, true) && pinned_dev(num_iter, false) &&
+    if (B >= 8192 && e->kernel_mode != MPCGPU_KERNEL_SPLIT && pinned_dev(xinit, true) && pinned_dev(x0, true) && pinned_dev(params, true) && pinned_dev(num_iter, false) &&
         pinned_dev(mem_inout, false)) {
         size_t gb[mpcgpu_engine::MAX_CHUNKS + 1];
         int ng = 0;

@@ -545,7 +545,19 @@ def main():
             m_sh = pinned(np.tile(np.ascontiguousarray(Pv[:, 0]), (world, 1, 1))).numpy()
             m_x0 = pinned(np.tile(h_np[0][1], (world, 1))).numpy()
             m_pv = pinned(np.tile(np.ascontiguousarray(Pv[..., differs_m]), (world, 1, 1, 1))).numpy()
-            run_m = lambda: multi.solve_sets(tot_sets, planners, m_xs, m_sh, m_x0, differs_m, m_pv, num_iter=args.num_iter, best_only=True)
+            lb_, lc_ = eng.lin_constraint_block()
+            what_m = "mpcgpu_multi_solve_sets"
+            if lc_ > 0 and set(differs_m.tolist()) <= set(range(lb_, lb_ + 3 * lc_)) and batches[0]["obst_pred"].size:
+                # guidance halfspaces built on each device (7 KB per solve from the host: every device copies and expands its range
+                # first and solves it in one launch)
+                m_ob = pinned(np.tile(batches[0]["obst_pred"], (world, 1, 1, 1))).numpy()
+                m_g = np.tile(batches[0]["guided"], world)
+                run_m = lambda: multi.solve_sets(tot_sets, planners, m_xs, m_sh, m_x0, None, None, num_iter=args.num_iter, best_only=True,
+                                                 guided_args=(m_ob, m_g, batches[0]["robot_radius"], lb_, lc_))
+                what_m = "mpcgpu_multi_solve_sets_guided"
+                m_pv = m_ob
+            else:
+                run_m = lambda: multi.solve_sets(tot_sets, planners, m_xs, m_sh, m_x0, differs_m, m_pv, num_iter=args.num_iter, best_only=True)
             om = run_m()
             t0 = time.perf_counter()
             for _ in range(max(2, args.steps // 2)):
@@ -556,7 +568,7 @@ def main():
                          "h2d_bytes_per_step": int((m_xs.size + m_sh.size + m_x0.size + m_pv.size) * 8),
                          "d2h_bytes_per_step": int(tot_sets * planners * 28 + tot_sets * (4 + ((N + 1) * nx + N * nu) * 8)),
                          "kernel_ms_max_over_devices": multi.last_kernel_ms(),
-                         "what": "mpcgpu_multi_solve_sets: contiguous ranges of whole sets per GPU, device-side selection, decision records + the selected trajectory gathered"}
+                         "what": what_m + ": contiguous ranges of whole sets per GPU, device-side selection, decision records + the selected trajectory gathered"}
             multi.close()
         dist.barrier(group=cpu_group)
         barrier()

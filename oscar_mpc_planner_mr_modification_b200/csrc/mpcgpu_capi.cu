@@ -461,6 +461,9 @@ static int solve_batch_impl(mpcgpu_engine* e, int n, const double* xinit, const 
             nchunk++;
         }
     }
+    const bool out_pinned = nchunk == 1 || (pinned_dev(xtraj, true) && pinned_dev(utraj, true) && pinned_dev(pobj, true) && pinned_dev(exit_code, true) &&
+                                            pinned_dev(qp_status, true) && pinned_dev(res_eq, true) && pinned_dev(ipm_iters, false) &&
+                                            pinned_dev(mem_inout, false));      // (one chunk: nothing to overlap, copy in stream order)
     for (int c = 0; c < nchunk; c++) {
         const size_t b0 = bounds[c];
         if (b0 >= B || bounds[c + 1] <= b0) { nchunk = c; break; }
@@ -477,6 +480,7 @@ static int solve_batch_impl(mpcgpu_engine* e, int n, const double* xinit, const 
                                  e->d_xtraj + b0 * sxt, e->d_utraj + b0 * sut, e->d_pobj + b0, e->d_exit + b0, e->d_qps + b0,
                                  e->d_res_eq + b0, e->d_ipm + b0);
         if (rc != MPCGPU_OK) return rc;
+        if (!out_pinned) continue;      // a copy into pageable memory blocks the host until the chunk is solved: it would serialise the pipeline
         CK(cudaMemcpyAsync(xtraj + b0 * sxt, e->d_xtraj + b0 * sxt, m * sxt * 8, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(utraj + b0 * sut, e->d_utraj + b0 * sut, m * sut * 8, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(pobj + b0, e->d_pobj + b0, m * 8, cudaMemcpyDeviceToHost, st));
@@ -488,6 +492,16 @@ static int solve_batch_impl(mpcgpu_engine* e, int n, const double* xinit, const 
     }
     CK(cudaStreamSynchronize(e->stream));
     CK(cudaStreamSynchronize(e->stream2));
+    if (!out_pinned) {                  // pageable outputs: everything at the end, one copy per array
+        CK(cudaMemcpy(xtraj, e->d_xtraj, B * sxt * 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(utraj, e->d_utraj, B * sut * 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(pobj, e->d_pobj, B * 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(exit_code, e->d_exit, B * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(qp_status, e->d_qps, B * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(res_eq, e->d_res_eq, B * 8, cudaMemcpyDeviceToHost));
+        if (ipm_iters) CK(cudaMemcpy(ipm_iters, e->d_ipm, B * 4, cudaMemcpyDeviceToHost));
+        if (mem_inout) CK(cudaMemcpy(mem_inout, e->d_mem, B * smem_ * 8, cudaMemcpyDeviceToHost));
+    }
     e->chunks_timed = nchunk;
     return MPCGPU_OK;
 }
@@ -791,6 +805,18 @@ static int solve_sets_impl(mpcgpu_engine* e, int n_sets, int planners, const dou
             nchunk++;
         }
     }
+    // results: copied behind the chunk's kernels when the destination is page-locked; a copy into PAGEABLE memory would block
+    // the host until the chunk is solved and so serialise the chunks -- those are made at the end
+    struct Pending { void* dst; const void* src; size_t bytes; };
+    std::vector<Pending> pending;
+    auto out_copy = [&](void* dst, const void* src, size_t bytes, cudaStream_t cs) -> cudaError_t {
+        cudaPointerAttributes a;
+        const bool pinned = nchunk == 1 || (cudaPointerGetAttributes(&a, dst) == cudaSuccess && a.type == cudaMemoryTypeHost);
+        if (pinned) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, cs);
+        cudaGetLastError();
+        pending.push_back({dst, src, bytes});
+        return cudaSuccess;
+    };
     for (int c = 0; c < nchunk; c++) {
         const int s0 = bounds[c], ns = bounds[c + 1] - s0;
         if (ns <= 0) { nchunk = c; break; }
@@ -882,11 +908,11 @@ static int solve_sets_impl(mpcgpu_engine* e, int n_sets, int planners, const dou
             CK(cudaGetLastError());
             e->launches += 1;
         }
-        if (opt && opt->objective_out) CK(cudaMemcpyAsync(opt->objective_out + p0, e->d_objout + p0, m * 8, cudaMemcpyDeviceToHost, cs));
-        if (opt && opt->consistency_cost_out) CK(cudaMemcpyAsync(opt->consistency_cost_out + p0, e->d_consout + p0, m * 8, cudaMemcpyDeviceToHost, cs));
-        if (mem_host) CK(cudaMemcpyAsync(mem_host + p0 * smem_, e->d_mem + p0 * smem_, m * smem_ * 8, cudaMemcpyDeviceToHost, cs));
-        if (xtraj) CK(cudaMemcpyAsync(xtraj + p0 * nx * (N + 1), e->d_xtraj + p0 * nx * (N + 1), m * nx * (N + 1) * 8, cudaMemcpyDeviceToHost, cs));
-        if (utraj) CK(cudaMemcpyAsync(utraj + p0 * nu * N, e->d_utraj + p0 * nu * N, m * nu * N * 8, cudaMemcpyDeviceToHost, cs));
+        if (opt && opt->objective_out) CK(out_copy(opt->objective_out + p0, e->d_objout + p0, m * 8, cs));
+        if (opt && opt->consistency_cost_out) CK(out_copy(opt->consistency_cost_out + p0, e->d_consout + p0, m * 8, cs));
+        if (mem_host) CK(out_copy(mem_host + p0 * smem_, e->d_mem + p0 * smem_, m * smem_ * 8, cs));
+        if (xtraj) CK(out_copy(xtraj + p0 * nx * (N + 1), e->d_xtraj + p0 * nx * (N + 1), m * nx * (N + 1) * 8, cs));
+        if (utraj) CK(out_copy(utraj + p0 * nu * N, e->d_utraj + p0 * nu * N, m * nu * N * 8, cs));
         if (opt && opt->best_xtraj && opt->best_utraj) {
             // the input staging of this chunk is free once its solve has run: the per-set trajectories are gathered into it
             double* bx = e->d_x0 + p0 * nz * (N + 1);
@@ -894,17 +920,18 @@ static int solve_sets_impl(mpcgpu_engine* e, int n_sets, int planners, const dou
             gather_best_kernel<<<ns, 128, 0, cs>>>(ns, e->d_offsets + s0, e->d_best + s0, nx * (N + 1), nu * N, e->d_xtraj, e->d_utraj, bx, bu);
             CK(cudaGetLastError());
             e->launches += 1;
-            CK(cudaMemcpyAsync(opt->best_xtraj + (size_t)s0 * nx * (N + 1), bx, (size_t)ns * nx * (N + 1) * 8, cudaMemcpyDeviceToHost, cs));
-            CK(cudaMemcpyAsync(opt->best_utraj + (size_t)s0 * nu * N, bu, (size_t)ns * nu * N * 8, cudaMemcpyDeviceToHost, cs));
+            CK(out_copy(opt->best_xtraj + (size_t)s0 * nx * (N + 1), bx, (size_t)ns * nx * (N + 1) * 8, cs));
+            CK(out_copy(opt->best_utraj + (size_t)s0 * nu * N, bu, (size_t)ns * nu * N * 8, cs));
         }
-        CK(cudaMemcpyAsync(pobj + p0, e->d_pobj + p0, m * 8, cudaMemcpyDeviceToHost, cs));
-        CK(cudaMemcpyAsync(exit_code + p0, e->d_exit + p0, m * 4, cudaMemcpyDeviceToHost, cs));
-        CK(cudaMemcpyAsync(qp_status + p0, e->d_qps + p0, m * 4, cudaMemcpyDeviceToHost, cs));
-        CK(cudaMemcpyAsync(res_eq + p0, e->d_res_eq + p0, m * 8, cudaMemcpyDeviceToHost, cs));
-        CK(cudaMemcpyAsync(best_idx + s0, e->d_best + s0, (size_t)ns * 4, cudaMemcpyDeviceToHost, cs));
+        CK(out_copy(pobj + p0, e->d_pobj + p0, m * 8, cs));
+        CK(out_copy(exit_code + p0, e->d_exit + p0, m * 4, cs));
+        CK(out_copy(qp_status + p0, e->d_qps + p0, m * 4, cs));
+        CK(out_copy(res_eq + p0, e->d_res_eq + p0, m * 8, cs));
+        CK(out_copy(best_idx + s0, e->d_best + s0, (size_t)ns * 4, cs));
     }
     CK(cudaStreamSynchronize(e->stream));
     CK(cudaStreamSynchronize(e->stream2));
+    for (const Pending& pc : pending) CK(cudaMemcpy(pc.dst, pc.src, pc.bytes, cudaMemcpyDeviceToHost));
     e->chunks_timed = nchunk;
     return MPCGPU_OK;
 }

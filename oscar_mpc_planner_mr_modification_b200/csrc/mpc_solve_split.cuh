@@ -18,14 +18,19 @@
 // taken by A and published in shared memory.
 #pragma once
 
-#ifndef MPC_SPLIT_ROLES          // roles B: slices of about 4 general entries (measured best for latency: 6 roles for 24 entries)
-#define MPC_SPLIT_ROLES (NCG >= 24 ? 6 : (NCG >= 12 ? 3 : 2))
+#ifndef MPC_SPLIT_XROLES         // roles X: the box entries of a stage shared out over 1 or 2 warps.  One warp with all 2 NZ entries is the
+#define MPC_SPLIT_XROLES 2       // straggler of every pass (28 entry updates against 4-5 per B role); two warps halve what role A waits for
+#endif
+#ifndef MPC_SPLIT_ROLES          // roles B: slices of 4-5 general entries; with role A and the X roles the CTA stays at 8 warps (255 registers each)
+#define MPC_SPLIT_ROLES (NCG >= 24 ? 7 - MPC_SPLIT_XROLES : (NCG >= 12 ? 3 : 2))
 #endif
 #ifndef MPC_SPLIT_MIN_CTAS       // 1: all 255 registers for role A (the kernel serves small batches: one CTA per SM)
 #define MPC_SPLIT_MIN_CTAS 1
 #endif
 constexpr int NBR = MPC_SPLIT_ROLES;
-constexpr int SPLIT_WARPS = 2 + NBR;             // role A, role X (box entries), NBR roles B
+constexpr int NXR = MPC_SPLIT_XROLES;            // warps sharing the box entries
+constexpr int XSPLIT = NXR == 2 ? (NZ + 1) / 2 : NZ;   // variables 0..XSPLIT-1: X role 0, the rest: X role 1
+constexpr int SPLIT_WARPS = 1 + NXR + NBR;       // role A, NXR roles X (box entries), NBR roles B
 constexpr int SPLIT_THREADS = SPLIT_WARPS * 32;
 constexpr int RPB = (NCG + NBR - 1) / NBR > 0 ? (NCG + NBR - 1) / NBR : 1;     // general entries per B role
 constexpr int NHP = NHS * (NHS + 1) / 2;                                       // packed block over the support of h
@@ -36,8 +41,8 @@ constexpr bool SPLIT_OK = (NSTAGE + 1 <= 32) && NPAD <= 32 && NCG >= 6 && NCG >=
 constexpr int SP_GAP = MPC_CHECK ? 2 : 0;        // MPC_CHECK: two canary doubles behind every region
 constexpr int SP_RS = 0;
 constexpr int SP_XCH = ((RS_DOUBLES + 1) & ~1) + SP_GAP;    // [NBR][XS][32]
-constexpr int SP_XCX = SP_XCH + NBR * XS * 32 + SP_GAP;   // [XSX][32] slots of role X
-constexpr int SP_PUB = SP_XCX + XSX * 32 + SP_GAP;        // [2 NZ][32]: z and v of every stage, published by role A (v: amended by role X)
+constexpr int SP_XCX = SP_XCH + NBR * XS * 32 + SP_GAP;   // [NXR][XSX][32] slots of the X roles
+constexpr int SP_PUB = SP_XCX + NXR * XSX * 32 + SP_GAP;        // [2 NZ][32]: z and v of every stage, published by role A (v: amended by role X)
 constexpr int SP_DEC = SP_PUB + 2 * NZ * 32 + SP_GAP;     // decisions published by role A
 constexpr int SP_SW = SP_DEC + 8 + SP_GAP;                // blocked-sweep workspace (SW_DOUBLES)
 constexpr int SP_DOUBLES = SP_SW + SW_DOUBLES + SP_GAP;
@@ -270,12 +275,14 @@ __device__ __noinline__ void split_role_b(const int prob, const double* __restri
 // ------------------------------------------------------------------------------------------------------------------
 // role X: the 2 NZ box entries of every stage (input box on path stages, state box on stages 1..N-1)
 // ------------------------------------------------------------------------------------------------------------------
+template <int XR>
 __device__ __noinline__ void split_role_x(const int prob, const int num_iter, double* mem_g, const int mem_doubles, double* sm)
 {
+    constexpr int I_LO = XR == 0 ? 0 : XSPLIT, I_HI = XR == 0 ? XSPLIT : NZ;      // this role's variables
     const int k = threadIdx.x & 31;
     const bool path = k < NSTAGE, xbox = path && k >= 1;
     double* const rs = sm + SP_RS;
-    double* const xs = sm + SP_XCX + k;                                 // slot s of this stage: xs[s * 32]
+    double* const xs = sm + SP_XCX + XR * XSX * 32 + k;                 // slot s of this role and stage: xs[s * 32]
     double* const pub = sm + SP_PUB + k;
     const double* const dec = sm + SP_DEC;
     const double* const blk = rs + (path ? k : 0) * RSTRIDE;
@@ -289,7 +296,10 @@ __device__ __noinline__ void split_role_x(const int prob, const int num_iter, do
     double* mem = mem_g ? mem_g + (size_t)prob * mem_doubles : nullptr;
     if (mem && mem[0] != 0.0) {
         const double* m = mem + 1 + (NSTAGE + 1) * NX;
-        if (path) for (int e = 0; e < NCB; e++) { lamb[e] = m[k * NC + e]; tb[e] = m[NSTAGE * NC + k * NC + e]; }
+        if (path) for (int e = 0; e < NCB; e++) {
+            const int i = e < NZ ? e : e - NZ;
+            if (i >= I_LO && i < I_HI) { lamb[e] = m[k * NC + e]; tb[e] = m[NSTAGE * NC + k * NC + e]; }
+        }
         qp_warm = (mem[0] >= 2.0);
     }
 
@@ -303,7 +313,7 @@ __device__ __noinline__ void split_role_x(const int prob, const int num_iter, do
         for (int i = 0; i < NZ; i++) v[i] = pub[(NZ + i) * 32];
         if (qp_warm) {
 #pragma unroll
-            for (int i = 0; i < NZ; i++) {
+            for (int i = I_LO; i < I_HI; i++) {
                 const bool act = (i < NU) ? path : xbox;
                 if (act) {
                     lamb[i] = clamp_lo(lamb[i], IPM_THR0); tb[i] = clamp_lo(tb[i], IPM_THR0);
@@ -312,7 +322,7 @@ __device__ __noinline__ void split_role_x(const int prob, const int num_iter, do
             }
         } else {
 #pragma unroll
-            for (int i = 0; i < NZ; i++) {
+            for (int i = I_LO; i < I_HI; i++) {
                 const bool act = (i < NU) ? path : xbox;
                 if (act) {
                     const double dl = zl[i], du = zu[i];
@@ -326,7 +336,7 @@ __device__ __noinline__ void split_role_x(const int prob, const int num_iter, do
                 }
             }
 #pragma unroll
-            for (int i = 0; i < NZ; i++) pub[(NZ + i) * 32] = v[i];
+            for (int i = I_LO; i < I_HI; i++) pub[(NZ + i) * 32] = v[i];
         }
         split_barrier_l(104);                                             // L4: v is final for every role
 
@@ -337,7 +347,7 @@ __device__ __noinline__ void split_role_x(const int prob, const int num_iter, do
             for (int i = 0; i < NZ; i++) { vo[i] = v[i]; if (upd) v[i] += a_ * dv[i]; }
             double nd = 0.0, nm = 0.0, sm_ = 0.0;
 #pragma unroll
-            for (int i = 0; i < NZ; i++) {
+            for (int i = I_LO; i < I_HI; i++) {
                 const bool act = (i < NU) ? path : xbox;
                 double hd = 0.0, gg = 0.0, rr = 0.0;
                 if (act) {
@@ -382,7 +392,7 @@ __device__ __noinline__ void split_role_x(const int prob, const int num_iter, do
             StepFrac sfa;
             double S1 = 0.0, S2 = 0.0;
 #pragma unroll
-            for (int i = 0; i < NZ; i++) {
+            for (int i = I_LO; i < I_HI; i++) {
                 const bool act = (i < NU) ? path : xbox;
                 double V1 = 0.0, V2 = 0.0;
                 if (act) {
@@ -415,7 +425,7 @@ __device__ __noinline__ void split_role_x(const int prob, const int num_iter, do
             for (int i = 0; i < NZ; i++) dv[i] = path ? blk[RO_DZ + i] : 0.0;
             StepFrac sfc;
 #pragma unroll
-            for (int i = 0; i < NZ; i++) {
+            for (int i = I_LO; i < I_HI; i++) {
                 const bool act = (i < NU) ? path : xbox;
                 if (act) {
                     const double dl = zl[i], du = zu[i];
@@ -443,7 +453,10 @@ __device__ __noinline__ void split_role_x(const int prob, const int num_iter, do
     split_barrier_l(99);                                                 // F
     if (mem && dec[DEC_STATUS] == 0.0 && path) {
         double* m = mem + 1 + (NSTAGE + 1) * NX;
-        for (int e = 0; e < NCB; e++) { m[k * NC + e] = lamb[e]; m[NSTAGE * NC + k * NC + e] = tb[e]; }
+        for (int e = 0; e < NCB; e++) {
+            const int i = e < NZ ? e : e - NZ;
+            if (i >= I_LO && i < I_HI) { m[k * NC + e] = lamb[e]; m[NSTAGE * NC + k * NC + e] = tb[e]; }
+        }
     }
 }
 
@@ -618,10 +631,15 @@ __device__ __noinline__ void split_role_a(const int prob, const double* __restri
             split_barrier_l(1);                                         // 1: the slices' DA terms are in the slots
             PROF(5)
 #pragma unroll
-            for (int i = 0; i < NZ; i++) {                           // box entries (role X)
-                Ht[pk(i, i)] += xcx[i * 32]; gt[i] += xcx[(NZ + i) * 32]; rg[i] += xcx[(2 * NZ + i) * 32];
+            for (int i = 0; i < NZ; i++) {                           // box entries (roles X: variable i lives in role i >= XSPLIT)
+                const double* xr = xcx + (i >= XSPLIT ? XSX * 32 : 0);
+                Ht[pk(i, i)] += xr[i * 32]; gt[i] += xr[(NZ + i) * 32]; rg[i] += xr[(2 * NZ + i) * 32];
             }
-            nd = nanmax(nd, xcx[(3 * NZ) * 32]); nm = nanmax(nm, xcx[(3 * NZ + 1) * 32]); sm_ += xcx[(3 * NZ + 2) * 32];
+#pragma unroll
+            for (int r = 0; r < NXR; r++) {
+                const double* xr = xcx + r * XSX * 32;
+                nd = nanmax(nd, xr[(3 * NZ) * 32]); nm = nanmax(nm, xr[(3 * NZ + 1) * 32]); sm_ += xr[(3 * NZ + 2) * 32];
+            }
             if (path) {
 #pragma unroll 1
                 for (int r = 0; r < NBR; r++) {
@@ -732,8 +750,15 @@ __device__ __noinline__ void split_role_a(const int prob, const double* __restri
             split_barrier_l(4);                                         // 4: the slices' pass-B terms are in the slots
             PROF(12)
 #pragma unroll
-            for (int i = 0; i < NZ; i++) { V1[i] = xcx[i * 32]; V2[i] = xcx[(NZ + i) * 32]; }      // box entries (role X)
-            ratio = fmin(ratio, xcx[(2 * NZ) * 32]); S1 += xcx[(2 * NZ + 1) * 32]; S2 += xcx[(2 * NZ + 2) * 32];
+            for (int i = 0; i < NZ; i++) {                           // box entries (roles X)
+                const double* xr = xcx + (i >= XSPLIT ? XSX * 32 : 0);
+                V1[i] = xr[i * 32]; V2[i] = xr[(NZ + i) * 32];
+            }
+#pragma unroll
+            for (int r = 0; r < NXR; r++) {
+                const double* xr = xcx + r * XSX * 32;
+                ratio = fmin(ratio, xr[(2 * NZ) * 32]); S1 += xr[(2 * NZ + 1) * 32]; S2 += xr[(2 * NZ + 2) * 32];
+            }
             if (path) {
 #pragma unroll 1
                 for (int r = 0; r < NBR; r++) {
@@ -829,7 +854,8 @@ __device__ __noinline__ void split_role_a(const int prob, const double* __restri
             PROF(18)
             split_barrier_l(7);                                         // 7: the slices' ratios are in slot 0
             PROF(19)
-            ratc = fmin(ratc, xcx[0]);                               // box entries (role X)
+#pragma unroll
+            for (int r = 0; r < NXR; r++) ratc = fmin(ratc, xcx[r * XSX * 32]);      // box entries (roles X): slot 0 of each role's region
             if (path) {
 #pragma unroll 1
                 for (int r = 0; r < NBR; r++) ratc = fmin(ratc, xch[(size_t)r * XS * 32]);
@@ -942,9 +968,11 @@ mpc_solve_split_kernel(int n, const double* __restrict__ xinit, const double* __
             split_role_a(prob, xinit, x0, params, nit, mem, mem_doubles, xtraj, utraj, pobj, exit_code, qp_status, res_eq, ipm_iters,
                          s_split, nit_raw < 0);
         else if (role == 1)
-            split_role_x(prob, nit, mem, mem_doubles, s_split);
+            split_role_x<0>(prob, nit, mem, mem_doubles, s_split);
+        else if (NXR == 2 && role == 2)
+            split_role_x<NXR - 1>(prob, nit, mem, mem_doubles, s_split);
         else
-            split_role_b(prob, params, nit, mem, mem_doubles, s_split, role - 2);
+            split_role_b(prob, params, nit, mem, mem_doubles, s_split, role - 1 - NXR);
 #if MPC_CHECK
         __syncthreads();
         if (threadIdx.x < 12 && s_split[SP_CANARY_AT[threadIdx.x >> 1] + (threadIdx.x & 1)] != CANARY) MPC_CHECK_FAIL(1);

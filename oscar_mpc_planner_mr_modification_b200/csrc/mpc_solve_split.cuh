@@ -27,6 +27,10 @@
 #ifndef MPC_SPLIT_MIN_CTAS       // 1: all 255 registers for role A (the kernel serves small batches: one CTA per SM)
 #define MPC_SPLIT_MIN_CTAS 1
 #endif
+#ifndef MPC_SPLIT_B_UNROLL       // entries of a B role's slice in flight together (2 / 3 / 5: kernel 2.19 / 2.20 / 2.23 ms for the 9-planner set)
+#define MPC_SPLIT_B_UNROLL 2
+#endif
+constexpr int SPLIT_B_UNROLL = MPC_SPLIT_B_UNROLL;
 constexpr int NBR = MPC_SPLIT_ROLES;
 constexpr int NXR = MPC_SPLIT_XROLES;            // warps sharing the box entries
 constexpr int XSPLIT = NXR == 2 ? (NZ + 1) / 2 : NZ;   // variables 0..XSPLIT-1: X role 0, the rest: X role 1
@@ -165,7 +169,7 @@ __device__ __noinline__ void split_role_b(const int prob, const double* __restri
             for (int i = 0; i < NHP; i++) Hs[i] = 0.0;
 #pragma unroll
             for (int a = 0; a < NHS; a++) { gs[a] = 0.0; rgs[a] = 0.0; }
-#pragma unroll GEN_UNROLL
+#pragma unroll SPLIT_B_UNROLL
             for (int e = 0; e < ne; e++) {
                 const int r = HROW[e_lo + e] - r_lo;
                 const double sg = HSGN[e_lo + e];
@@ -214,7 +218,7 @@ __device__ __noinline__ void split_role_b(const int prob, const double* __restri
             double S1 = 0.0, S2 = 0.0, V1[NHS], V2[NHS];
 #pragma unroll
             for (int a = 0; a < NHS; a++) { V1[a] = 0.0; V2[a] = 0.0; }
-#pragma unroll GEN_UNROLL
+#pragma unroll SPLIT_B_UNROLL
             for (int e = 0; e < ne; e++) {
                 const int r = HROW[e_lo + e] - r_lo;
                 const double sg = HSGN[e_lo + e], lam = lamg[e], t = tg[e];
@@ -243,7 +247,7 @@ __device__ __noinline__ void split_role_b(const int prob, const double* __restri
 
             // ---- pass C: step length of the corrected direction
             StepFrac sfc;
-#pragma unroll GEN_UNROLL
+#pragma unroll SPLIT_B_UNROLL
             for (int e = 0; e < ne; e++) {
                 const int r = HROW[e_lo + e] - r_lo;
                 const double sg = HSGN[e_lo + e], lam = lamg[e], t = tg[e];

@@ -102,17 +102,21 @@ __device__ __noinline__ void split_role_b(const int prob, const double* __restri
     const int ne = path ? e_hi - e_lo : 0;
     const int r_lo = e_hi > e_lo ? HROW[e_lo] : 0, r_hi = e_hi > e_lo ? HROW[e_hi - 1] + 1 : 0;
 
-    double C[RPB * NHS], dg[RPB], lamg[RPB], tg[RPB], itg[RPB];
+    double C[RPB * NHS], Ce[RPB * NHS], sge[RPB], dg[RPB], lamg[RPB], tg[RPB], itg[RPB];
     double v3[NHS], vo3[NHS], dva3[NHS], dv3[NHS];
+#pragma unroll
     for (int e = 0; e < RPB; e++) { lamg[e] = 0.0; tg[e] = 0.0; itg[e] = 0.0; dg[e] = 0.0; }
-    for (int i = 0; i < RPB * NHS; i++) C[i] = 0.0;
+    for (int i = 0; i < RPB * NHS; i++) { C[i] = 0.0; Ce[i] = 0.0; }
+#pragma unroll
+    for (int e = 0; e < RPB; e++) sge[e] = 1.0;
 #pragma unroll
     for (int a = 0; a < NHS; a++) { v3[a] = 0.0; vo3[a] = 0.0; dva3[a] = 0.0; dv3[a] = 0.0; }
     int qp_warm = 0;
     double* mem = mem_g ? mem_g + (size_t)prob * mem_doubles : nullptr;
     if (mem && mem[0] != 0.0) {
         const double* m = mem + 1 + (NSTAGE + 1) * NX;
-        for (int e = 0; e < ne; e++) { lamg[e] = m[k * NC + NCB + e_lo + e]; tg[e] = m[NSTAGE * NC + k * NC + NCB + e_lo + e]; }
+#pragma unroll
+        for (int e = 0; e < RPB; e++) if (e < ne) { lamg[e] = m[k * NC + NCB + e_lo + e]; tg[e] = m[NSTAGE * NC + k * NC + NCB + e_lo + e]; }
         qp_warm = (mem[0] >= 2.0);
     }
 
@@ -129,9 +133,21 @@ __device__ __noinline__ void split_role_b(const int prob, const double* __restri
             if (ne > 0) {
                 double mh[RPB], hv[RPB];
                 for (int j = 0; j < RPB; j++) mh[j] = 0.0;
-                for (int e = 0; e < ne; e++) mh[HROW[e_lo + e] - r_lo] -= HSGN[e_lo + e] * lamg[e];      // lam_u - lam_l
+#pragma unroll
+                for (int e = 0; e < RPB; e++) if (e < ne) mh[HROW[e_lo + e] - r_lo] -= HSGN[e_lo + e] * lamg[e];      // lam_u - lam_l
                 con_lin_rows(zz, p, r_lo, r_hi, mh, Hh, hv, C);
-                for (int e = 0; e < ne; e++) dg[e] = HSGN[e_lo + e] * (HBND[e_lo + e] - hv[HROW[e_lo + e] - r_lo]);
+#pragma unroll
+                for (int e = 0; e < RPB; e++) if (e < ne) dg[e] = HSGN[e_lo + e] * (HBND[e_lo + e] - hv[HROW[e_lo + e] - r_lo]);
+                // per ENTRY copies (row of the entry, its sign): the passes below index them with compile-time constants, so they
+                // live in registers -- indexed through HROW[e_lo + e] they sat in thread-local memory and every dot product
+                // of a pass waited for local loads
+#pragma unroll
+                for (int e = 0; e < RPB; e++) {
+                    const int r = e < ne ? HROW[e_lo + e] - r_lo : 0;
+                    sge[e] = e < ne ? HSGN[e_lo + e] : 1.0;
+#pragma unroll
+                    for (int a = 0; a < NHS; a++) Ce[e * NHS + a] = C[r * NHS + a];
+                }
             }
 #pragma unroll
             for (int a = 0; a < NHS; a++)
@@ -144,16 +160,19 @@ __device__ __noinline__ void split_role_b(const int prob, const double* __restri
 #pragma unroll
         for (int a = 0; a < NHS; a++) v3[a] = pub[(NZ + HSUP[a]) * 32];
         if (qp_warm) {
-            for (int e = 0; e < ne; e++) { lamg[e] = clamp_lo(lamg[e], IPM_THR0); tg[e] = clamp_lo(tg[e], IPM_THR0); }
-        } else {
-            for (int e = 0; e < ne; e++) {
-                const int r = HROW[e_lo + e] - r_lo;
-                double s = 0.0;
 #pragma unroll
-                for (int a = 0; a < NHS; a++) s += C[r * NHS + a] * v3[a];
-                double tt = HSGN[e_lo + e] * s - dg[e];
-                if (tt < IPM_THR0) tt = IPM_THR0;
-                tg[e] = tt; lamg[e] = IPM_MU0 * rcp_nb(tt);
+            for (int e = 0; e < RPB; e++) if (e < ne) { lamg[e] = clamp_lo(lamg[e], IPM_THR0); tg[e] = clamp_lo(tg[e], IPM_THR0); }
+        } else {
+#pragma unroll
+            for (int e = 0; e < RPB; e++) {
+                if (e < ne) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int a = 0; a < NHS; a++) s += Ce[e * NHS + a] * v3[a];
+                    double tt = sge[e] * s - dg[e];
+                    if (tt < IPM_THR0) tt = IPM_THR0;
+                    tg[e] = tt; lamg[e] = IPM_MU0 * rcp_nb(tt);
+                }
             }
         }
 
@@ -169,17 +188,16 @@ __device__ __noinline__ void split_role_b(const int prob, const double* __restri
             for (int i = 0; i < NHP; i++) Hs[i] = 0.0;
 #pragma unroll
             for (int a = 0; a < NHS; a++) { gs[a] = 0.0; rgs[a] = 0.0; }
-#pragma unroll SPLIT_B_UNROLL
-            for (int e = 0; e < ne; e++) {
-                const int r = HROW[e_lo + e] - r_lo;
-                const double sg = HSGN[e_lo + e];
+#pragma unroll
+            for (int e = 0; e < RPB; e++) if (e < ne) {
+                const double sg = sge[e];
                 double lam = lamg[e], t = tg[e];
                 double cv = 0.0;
                 if (upd) {
                     double cvo = 0.0, cda = 0.0, cd = 0.0;
 #pragma unroll
                     for (int a = 0; a < NHS; a++) {
-                        const double ca = C[r * NHS + a];
+                        const double ca = Ce[e * NHS + a];
                         cvo += ca * vo3[a]; cda += ca * dva3[a]; cd += ca * dv3[a];
                     }
                     const IneqStep st = ineq_final(lam, itg[e], sg * cvo - dg[e] - t, sg * cda, sg * cd, sigmu);
@@ -187,15 +205,15 @@ __device__ __noinline__ void split_role_b(const int prob, const double* __restri
                     lamg[e] = lam; tg[e] = t;
                 }
 #pragma unroll
-                for (int a = 0; a < NHS; a++) cv += C[r * NHS + a] * v3[a];
+                for (int a = 0; a < NHS; a++) cv += Ce[e * NHS + a] * v3[a];
                 const double it_ = rcp_nb(t);
                 const double rd = sg * cv - dg[e] - t, G = lam * it_, m = lam * t;
                 itg[e] = it_;
 #pragma unroll
                 for (int a = 0; a < NHS; a++) {
-                    const double ca = C[r * NHS + a];
+                    const double ca = Ce[e * NHS + a];
 #pragma unroll
-                    for (int bb = 0; bb <= a; bb++) Hs[hidx(a, bb)] += G * ca * C[r * NHS + bb];
+                    for (int bb = 0; bb <= a; bb++) Hs[hidx(a, bb)] += G * ca * Ce[e * NHS + bb];
                     gs[a] += sg * ca * (G * rd);
                     rgs[a] -= sg * ca * lam;
                 }
@@ -218,21 +236,20 @@ __device__ __noinline__ void split_role_b(const int prob, const double* __restri
             double S1 = 0.0, S2 = 0.0, V1[NHS], V2[NHS];
 #pragma unroll
             for (int a = 0; a < NHS; a++) { V1[a] = 0.0; V2[a] = 0.0; }
-#pragma unroll SPLIT_B_UNROLL
-            for (int e = 0; e < ne; e++) {
-                const int r = HROW[e_lo + e] - r_lo;
-                const double sg = HSGN[e_lo + e], lam = lamg[e], t = tg[e];
+#pragma unroll
+            for (int e = 0; e < RPB; e++) if (e < ne) {
+                const double sg = sge[e], lam = lamg[e], t = tg[e];
                 double cv = 0.0, cd = 0.0;
 #pragma unroll
-                for (int a = 0; a < NHS; a++) { cv += C[r * NHS + a] * v3[a]; cd += C[r * NHS + a] * dva3[a]; }
+                for (int a = 0; a < NHS; a++) { cv += Ce[e * NHS + a] * v3[a]; cd += Ce[e * NHS + a] * dva3[a]; }
                 const double it_ = itg[e];
                 const IneqStep st = ineq_affine(lam, it_, sg * cv - dg[e] - t, sg * cd);
                 sfa.add(lam, st.dlam, t, st.dt);
                 S1 += lam * st.dt + t * st.dlam; S2 += st.dt * st.dlam;
 #pragma unroll
                 for (int a = 0; a < NHS; a++) {
-                    V1[a] += sg * C[r * NHS + a] * st.corr;
-                    V2[a] += sg * C[r * NHS + a] * it_;
+                    V1[a] += sg * Ce[e * NHS + a] * st.corr;
+                    V2[a] += sg * Ce[e * NHS + a] * it_;
                 }
             }
 #pragma unroll
@@ -247,14 +264,13 @@ __device__ __noinline__ void split_role_b(const int prob, const double* __restri
 
             // ---- pass C: step length of the corrected direction
             StepFrac sfc;
-#pragma unroll SPLIT_B_UNROLL
-            for (int e = 0; e < ne; e++) {
-                const int r = HROW[e_lo + e] - r_lo;
-                const double sg = HSGN[e_lo + e], lam = lamg[e], t = tg[e];
+#pragma unroll
+            for (int e = 0; e < RPB; e++) if (e < ne) {
+                const double sg = sge[e], lam = lamg[e], t = tg[e];
                 double cv = 0.0, cda = 0.0, cd = 0.0;
 #pragma unroll
                 for (int a = 0; a < NHS; a++) {
-                    const double ca = C[r * NHS + a];
+                    const double ca = Ce[e * NHS + a];
                     cv += ca * v3[a]; cda += ca * dva3[a]; cd += ca * dv3[a];
                 }
                 const IneqStep st = ineq_final(lam, itg[e], sg * cv - dg[e] - t, sg * cda, sg * cd, sigmu);
@@ -272,7 +288,8 @@ __device__ __noinline__ void split_role_b(const int prob, const double* __restri
     split_barrier_l(99);                                                 // F: final status published
     if (mem && dec[DEC_STATUS] == 0.0) {
         double* m = mem + 1 + (NSTAGE + 1) * NX;
-        for (int e = 0; e < ne; e++) { m[k * NC + NCB + e_lo + e] = lamg[e]; m[NSTAGE * NC + k * NC + NCB + e_lo + e] = tg[e]; }
+#pragma unroll
+        for (int e = 0; e < RPB; e++) if (e < ne) { m[k * NC + NCB + e_lo + e] = lamg[e]; m[NSTAGE * NC + k * NC + NCB + e_lo + e] = tg[e]; }
     }
 }
 

@@ -184,6 +184,12 @@ constexpr bool RIC_P = (MPC_RIC_SMEM & 1) != 0, RIC_PRB = (MPC_RIC_SMEM & 2) != 
 constexpr int RIC_OFF_P = QP_OFF_H + (QPS_H ? NPK : 0), RIC_OFF_PRB = RIC_OFF_P + (RIC_P ? NPX : 0);
 constexpr int LT_DOUBLES = (RIC_OFF_PRB + (RIC_PRB ? NX : 0)) * LCOL;
 static_assert(!MPC_COL_COMPACT || (MPC_QP_SMEM == 0 && MPC_RIC_SMEM == 0), "compact columns: the terminal stage's slot is shared with the dead lanes");
+#ifndef MPC_TMEM
+#define MPC_TMEM 1
+#endif
+constexpr int TM_ECOLS = 8;                      // tensor memory: 32-bit columns per general entry = (NHS + 1) doubles, padded
+constexpr bool TMEM_CD = (MPC_TMEM != 0) && !LT_C && !LT_D && NCG > 0 && NCG * TM_ECOLS <= 256 && NHS + 1 <= 4 && GW == 1 && CSPL == 0 && MPC_C_ZSKIP == 0 &&
+                         MPC_WARPS_PER_CTA == 8;
 constexpr int LT_STRIDE = LT_DOUBLES + (MPC_CHECK ? GW * 32 : 0);      // MPC_CHECK: a row of canaries behind every group's region      // per group: lam, t (d, C) of the general entries (+ 1/t of the boxes)
 // column accessor: stride GW*32 doubles in shared memory ([entry][thread of the group]), stride 1 for a thread-local array
 template <bool SM>
@@ -308,7 +314,29 @@ __device__ __forceinline__ double warp_sum(double v)
 // ---- group primitives: warp shuffles inside a warp, shared-memory exchange + named barrier across the
 //      GW warps of a problem.  For GW == 1 every function reduces to the plain warp intrinsic.
 constexpr int XCH = 32;                          // exchange doubles per warp (an affine map: 30)
+// ---- Tensor memory as a third on-chip store (MPC_TMEM, thread-per-stage throughput instantiation).  The engine has no MMA, so
+//      the SM's 256 KB of tensor memory are free: 128 lanes x 512 columns x 32 bit; warp w of the CTA reaches lanes
+//      32 (w % 4) .. +31, and with 8 warps every warp gets 256 columns = 128 doubles per thread, 12-cycle loads.  The Jacobian rows
+//      and right-hand sides of the general entries (written once per linearisation, read in every pass) live there instead of in
+//      thread-local memory: entry e = 8 columns {c0, c1, c2, d}.  tcgen05.ld / .st are warp-collective (.sync.aligned): the entry
+//      loops then run for all 32 lanes and only the commits are predicated.
+__device__ __forceinline__ void tmem_ld8(unsigned taddr, double& a, double& b, double& c, double& d)
+{
+    unsigned r0, r1, r2, r3, r4, r5, r6, r7;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    a = __hiloint2double((int)r1, (int)r0); b = __hiloint2double((int)r3, (int)r2);
+    c = __hiloint2double((int)r5, (int)r4); d = __hiloint2double((int)r7, (int)r6);
+}
+__device__ __forceinline__ void tmem_st8(unsigned taddr, double a, double b, double c, double d)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 :: "r"(taddr), "r"(__double2loint(a)), "r"(__double2hiint(a)), "r"(__double2loint(b)), "r"(__double2hiint(b)),
+                    "r"(__double2loint(c)), "r"(__double2hiint(c)), "r"(__double2loint(d)), "r"(__double2hiint(d)) : "memory");
+}
 struct Grp {
+    unsigned tmem = 0;                           // MPC_TMEM: tensor-memory address of this warp's slot (lane quarter, column base)
     double* xch;                                 // [GW][XCH] shared-memory exchange area of this group
     int gid, wig;                                // group index inside the CTA, warp index inside the group
     __device__ __forceinline__ void sync() const
@@ -1315,6 +1343,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
     // num_iter < 0: |num_iter| iterations with the completion step DEFERRED -- the stepwise interface (solveOneIteration,
     // acados_solver_interface.cpp:145-160) keeps multipliers and QP memory between iterations; the res_eq demotion and the
     // reset on failure belong to completeOneIteration (:176-191) and are applied by the caller
+    constexpr bool TM = TMEM_CD && !SCAN;      // Jacobian rows + right-hand sides of the general entries in tensor memory
     const bool defer = num_iter < 0;
     if (defer) num_iter = -num_iter;
     const int k = grp.wig * 32 + (threadIdx.x & 31);   // stage owned by this thread
@@ -1374,6 +1403,21 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
         double C_loc[(!LT_C && NH > 0) ? NH * NHS : 1], dg_loc[(!LT_D && NCG > 0) ? NCG : 1];
         CRows<LT_C> C{LT_C ? lt_me + LT_OFF_C * LCOL : C_loc, lt_me + LT_OFF_CS * LCOL, false};
         const LtCol<LT_D> dg{LT_D ? lt_me + LT_OFF_D * LCOL : dg_loc MPCK(NCG)};
+        // row and right-hand side of general entry e: from tensor memory (all lanes, warp-collective) or from wherever C / d live
+        auto entry_cd = [&](int e, double (&cr)[NHS > 0 ? NHS : 1], double& de) {
+            if constexpr (TM) {
+                double c0, c1, c2;
+                tmem_ld8(grp.tmem + e * TM_ECOLS, c0, c1, c2, de);
+                cr[0] = c0;
+                if constexpr (NHS > 1) cr[1] = c1;
+                if constexpr (NHS > 2) cr[2] = c2;
+            } else {
+                const int r = HROW[e];
+#pragma unroll
+                for (int a = 0; a < NHS; a++) cr[a] = C.at(r, a);
+                de = dg[e];
+            }
+        };
         {
             double pin[NX], xnx[NX], zx_[NX];
 #pragma unroll
@@ -1410,6 +1454,15 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
 #pragma unroll
                 for (int i = NU; i < NZ; i++) H[pk(i, i)] = REG_EPS;   // mirror(0) = eps I; no terminal cost
             }
+        }
+        if constexpr (TM) {      // every lane of the warp (the stores are warp-collective); lanes without a path stage park don't-cares
+#pragma unroll 2
+            for (int e = 0; e < NCG; e++) {
+                const int r = HROW[e];
+                tmem_st8(grp.tmem + e * TM_ECOLS, C_loc[r * NHS], NHS > 1 ? C_loc[r * NHS + (NHS > 1 ? 1 : 0)] : 0.0,
+                         NHS > 2 ? C_loc[r * NHS + (NHS > 2 ? 2 : 0)] : 0.0, dg_loc[e]);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         }
         const SmemCol gs{lt_me + QP_OFF_G * LCOL MPCK(NZ)}, bs{lt_me + QP_OFF_B * LCOL MPCK(NX)}, Hs{lt_me + QP_OFF_H * LCOL MPCK(NPK)};
         if constexpr (QPS_GB) {
@@ -1480,10 +1533,17 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                     lamb[i] = IPM_MU0 * rcp_nb(tl); lamb[NZ + i] = IPM_MU0 * rcp_nb(tu);
                 }
             }
-            if (path) for (int e = 0; e < NCG; e++) {
-                double tt = gen_dot(C, e, v) - dg[e];
-                if (tt < IPM_THR0) tt = IPM_THR0;
-                tg[e] = tt; lamg[e] = IPM_MU0 * rcp_nb(tt);
+            if (TM || path) for (int e = 0; e < NCG; e++) {
+                double cr[NHS > 0 ? NHS : 1], de;
+                entry_cd(e, cr, de);
+                if (!TM || path) {
+                    double s_ = 0.0;
+#pragma unroll
+                    for (int a = 0; a < NHS; a++) s_ += cr[a] * v[HSUP[a]];
+                    double tt = HSGN[e] * s_ - de;
+                    if (tt < IPM_THR0) tt = IPM_THR0;
+                    tg[e] = tt; lamg[e] = IPM_MU0 * rcp_nb(tt);
+                }
             }
         }
 
@@ -1583,38 +1643,41 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                         }
                     }
                 }
-                if (path) {
+                if (TM || path) {      // TM: every lane runs the loop (tensor-memory loads are warp-collective), commits predicated
 #pragma unroll GEN_UNROLL
                     for (int e = 0; e < NCG; e++) {
                         c_prefetch(C, e);
-                        const int r = HROW[e];
-                        const double sg = HSGN[e];
-                        double lam = lamg[e], t = tg[e];
-                        double cv = 0.0;
-                        if (upd) {
-                            double cvo = 0.0, cda = 0.0, cd = 0.0;
+                        double cr[NHS > 0 ? NHS : 1], de;
+                        entry_cd(e, cr, de);
+                        if (!TM || path) {
+                            const double sg = HSGN[e];
+                            double lam = lamg[e], t = tg[e];
+                            double cv = 0.0;
+                            if (upd) {
+                                double cvo = 0.0, cda = 0.0, cd = 0.0;
+#pragma unroll
+                                for (int a = 0; a < NHS; a++) {
+                                    const double ca = cr[a];
+                                    cvo += ca * vo[HSUP[a]]; cda += ca * dva[HSUP[a]]; cd += ca * dv[HSUP[a]];
+                                }
+                                const IneqStep st = ineq_final(lam, rcp_nb(t), sg * cvo - de - t, sg * cda, sg * cd, sigmu, cen);      // 1/t recomputed: cheaper than a thread-local array
+                                lam = clamp_lo(lam + a_ * st.dlam, IPM_LAM_MIN); t = clamp_lo(t + a_ * st.dt, IPM_T_MIN);
+                                lamg[e] = lam; tg[e] = t;
+                            }
+#pragma unroll
+                            for (int a = 0; a < NHS; a++) cv += cr[a] * v[HSUP[a]];
+                            const double it_ = rcp_nb(t);
+                            const double rd = sg * cv - de - t, G = lam * it_, m = lam * t;
 #pragma unroll
                             for (int a = 0; a < NHS; a++) {
-                                const double ca = C.at(r, a);
-                                cvo += ca * vo[HSUP[a]]; cda += ca * dva[HSUP[a]]; cd += ca * dv[HSUP[a]];
+                                const double ca = cr[a];
+#pragma unroll
+                                for (int bb = 0; bb <= a; bb++) Ht[pk(HSUP[a], HSUP[bb])] += G * ca * cr[bb];
+                                gt[HSUP[a]] += sg * ca * (G * rd);
+                                rg[HSUP[a]] -= sg * ca * lam;
                             }
-                            const IneqStep st = ineq_final(lam, rcp_nb(t), sg * cvo - dg[e] - t, sg * cda, sg * cd, sigmu, cen);      // 1/t recomputed: cheaper than a thread-local array
-                            lam = clamp_lo(lam + a_ * st.dlam, IPM_LAM_MIN); t = clamp_lo(t + a_ * st.dt, IPM_T_MIN);
-                            lamg[e] = lam; tg[e] = t;
+                            nd = nanmax(nd, fabs(rd)); nm = nanmax(nm, fabs(m)); sm += m;
                         }
-#pragma unroll
-                        for (int a = 0; a < NHS; a++) cv += C.at(r, a) * v[HSUP[a]];
-                        const double it_ = rcp_nb(t);
-                        const double rd = sg * cv - dg[e] - t, G = lam * it_, m = lam * t;
-#pragma unroll
-                        for (int a = 0; a < NHS; a++) {
-                            const double ca = C.at(r, a);
-#pragma unroll
-                            for (int bb = 0; bb <= a; bb++) Ht[pk(HSUP[a], HSUP[bb])] += G * ca * C.at(r, bb);
-                            gt[HSUP[a]] += sg * ca * (G * rd);
-                            rg[HSUP[a]] -= sg * ca * lam;
-                        }
-                        nd = nanmax(nd, fabs(rd)); nm = nanmax(nm, fabs(m)); sm += m;
                     }
                 }
                 if (k == 0) {
@@ -1812,23 +1875,26 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                     }
                 }
             }
-            if (path) {
+            if (TM || path) {
 #pragma unroll GEN_UNROLL
                 for (int e = 0; e < NCG; e++) {
                     c_prefetch(C, e);
-                    const int r = HROW[e];
-                    const double sg = HSGN[e], lam = lamg[e], t = tg[e];
-                    double cv = 0.0, cd = 0.0;
+                    double cr[NHS > 0 ? NHS : 1], de;
+                    entry_cd(e, cr, de);
+                    if (!TM || path) {
+                        const double sg = HSGN[e], lam = lamg[e], t = tg[e];
+                        double cv = 0.0, cd = 0.0;
 #pragma unroll
-                    for (int a = 0; a < NHS; a++) { const double ca = C.at(r, a); cv += ca * v[HSUP[a]]; cd += ca * dva[HSUP[a]]; }
-                    const double it_ = rcp_nb(t);
-                    const IneqStep st = ineq_affine(lam, it_, sg * cv - dg[e] - t, sg * cd);
-                    sfa.add(lam, st.dlam, t, st.dt);
-                    S1 += lam * st.dt + t * st.dlam; S2 += st.dt * st.dlam;
+                        for (int a = 0; a < NHS; a++) { const double ca = cr[a]; cv += ca * v[HSUP[a]]; cd += ca * dva[HSUP[a]]; }
+                        const double it_ = rcp_nb(t);
+                        const IneqStep st = ineq_affine(lam, it_, sg * cv - de - t, sg * cd);
+                        sfa.add(lam, st.dlam, t, st.dt);
+                        S1 += lam * st.dt + t * st.dlam; S2 += st.dt * st.dlam;
 #pragma unroll
-                    for (int a = 0; a < NHS; a++) {
-                        V1[HSUP[a]] += sg * C.at(r, a) * st.corr;
-                        V2[HSUP[a]] += sg * C.at(r, a) * it_;
+                        for (int a = 0; a < NHS; a++) {
+                            V1[HSUP[a]] += sg * cr[a] * st.corr;
+                            V2[HSUP[a]] += sg * cr[a] * it_;
+                        }
                     }
                 }
             }
@@ -1994,21 +2060,24 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                     }
                 }
             }
-            if (path) {
+            if (TM || path) {
 #pragma unroll GEN_UNROLL
                 for (int e = 0; e < NCG; e++) {
                     c_prefetch(C, e);
-                    const int r = HROW[e];
-                    const double sg = HSGN[e], lam = lamg[e], t = tg[e];
-                    double cv = 0.0, cda = 0.0, cd = 0.0;
+                    double cr[NHS > 0 ? NHS : 1], de;
+                    entry_cd(e, cr, de);
+                    if (!TM || path) {
+                        const double sg = HSGN[e], lam = lamg[e], t = tg[e];
+                        double cv = 0.0, cda = 0.0, cd = 0.0;
 #pragma unroll
-                    for (int a = 0; a < NHS; a++) {
-                        const double ca = C.at(r, a);
-                        cv += ca * v[HSUP[a]]; cda += ca * dva[HSUP[a]]; cd += ca * dv[HSUP[a]];
+                        for (int a = 0; a < NHS; a++) {
+                            const double ca = cr[a];
+                            cv += ca * v[HSUP[a]]; cda += ca * dva[HSUP[a]]; cd += ca * dv[HSUP[a]];
+                        }
+                        const IneqStep st = ineq_final(lam, rcp_nb(t), sg * cv - de - t, sg * cda, sg * cd, sigmu, cen);
+                        sfc.add(lam, st.dlam, t, st.dt);
+                        if constexpr (BALANCE) { T1 += lam * st.dt + t * st.dlam; T2 += st.dt * st.dlam; }
                     }
-                    const IneqStep st = ineq_final(lam, rcp_nb(t), sg * cv - dg[e] - t, sg * cda, sg * cd, sigmu, cen);
-                    sfc.add(lam, st.dlam, t, st.dt);
-                    if constexpr (BALANCE) { T1 += lam * st.dt + t * st.dlam; T2 += st.dt * st.dlam; }
                 }
             }
             alpha = grp.min(sfc.ratio());
@@ -2124,6 +2193,18 @@ mpc_solve_kernel(int n, const double* __restrict__ xinit, const double* __restri
 #if MPC_CHECK
     s_lt[(size_t)grp.gid * LT_STRIDE + LT_DOUBLES + grp.wig * 32 + lane] = CANARY;
 #endif
+    constexpr bool TM = TMEM_CD && (WPC == WARPS_PER_CTA) && (MPC_SCAN_ALWAYS == 0);
+    __shared__ unsigned s_tmem;
+    if constexpr (TM) {      // the CTA owns its SM: all 512 columns; warp w: lanes 32 (w % 4) .., columns 256 (w / 4) ..
+        if (warp == 0) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(&s_tmem)), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        grp.tmem = s_tmem + ((32u * (warp & 3)) << 16) + 256u * (warp >> 2);
+    }
     for (;;) {
         int prob = 0;
         if (grp.wig == 0 && lane == 0) prob = atomicAdd(work_counter, 1);
@@ -2135,7 +2216,7 @@ mpc_solve_kernel(int n, const double* __restrict__ xinit, const double* __restri
             prob = s_prob[grp.gid];
             grp.sync();
         }
-        if (prob >= n) return;
+        if (prob >= n) break;
         // gated launch (host pipeline of mpcgpu_solve_batch): the word behind the work counter is 0 (inputs resident) or -(m + 1)
         // where the inputs of problems 0 .. m-1 have arrived; the copy stream raises it behind every chunk it has delivered
         {
@@ -2152,6 +2233,11 @@ mpc_solve_kernel(int n, const double* __restrict__ xinit, const double* __restri
         if (s_lt[(size_t)grp.gid * LT_STRIDE + LT_DOUBLES + grp.wig * 32 + lane] != CANARY) MPC_CHECK_FAIL(1);
         if (grp.wig == 0 && lane == 0) MPC_CHECK_FAIL(4);
 #endif
+    }
+    if constexpr (TM) {      // every warp has left the work loop before the columns go back
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "r"(512u) : "memory");
     }
 }
 

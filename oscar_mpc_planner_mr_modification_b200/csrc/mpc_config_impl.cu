@@ -1,4 +1,5 @@
 // Compiled once per problem configuration:  nvcc -DMPC_MODEL_HEADER='"<cfg>/model.cuh"' -DMPC_CFG_TAG=<cfg>
+#include <cstdlib>
 #include "mpc_solve_kernel.cuh"
 #include "mpc_registry.h"
 
@@ -28,6 +29,8 @@ static cudaError_t set_smem_attributes()
     err = cudaFuncSetAttribute(mpc_solve_kernel<GW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LAT);
     if (err == cudaSuccess && GW != WARPS_PER_CTA)
         err = cudaFuncSetAttribute(mpc_solve_kernel<WARPS_PER_CTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_THR);
+    if (const char* co = getenv("MPCGPU_CARVEOUT"))      // experiment: preferred shared-memory carve-out in percent
+        cudaFuncSetAttribute(mpc_solve_kernel<WARPS_PER_CTA>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(co));
     return err;
 }
 

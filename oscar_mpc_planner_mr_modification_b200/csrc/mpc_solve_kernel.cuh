@@ -18,7 +18,9 @@
 #endif
 
 #ifndef MPC_GEN_UNROLL
-#define MPC_GEN_UNROLL 2   // general-constraint loops: entries in flight together (hides local-memory latency)
+#define MPC_GEN_UNROLL 0   // general-constraint loops: entries in flight together.  0 = automatic: 2 where the entries' rows come from
+                           // thread-local or shared memory (hides their latency), 1 where they come from tensor memory (12-cycle loads:
+                           // 261.1 k solves/s against 257.5 / 256.2 / 247.7 k for 2 / 3 / 4 on the 18 432-problem batch)
 #endif
 #ifndef MPC_SCAN_ALWAYS
 #define MPC_SCAN_ALWAYS 0   // 1: substitution sweeps as prefix scans in the throughput instantiation too
@@ -107,7 +109,7 @@ static_assert(GW == 1 || GW == 2, "thread-per-stage kernel needs N <= 63");
 static_assert(MPC_WARPS_PER_CTA % ((NSTAGE + 1 + 31) / 32) == 0, "warps per CTA must be a multiple of the group size");
 static_assert(NU == 2, "Riccati input block elimination is written for nu == 2");
 
-constexpr int GEN_UNROLL = MPC_GEN_UNROLL;
+
 constexpr int NPX = NX * (NX + 1) / 2;      // packed P
 // Shared-memory placement of per-stage state (one column [entry][thread of the group] per value: conflict free).  What pays is
 // what takes REGISTER pressure out of the interior-point loop (255 registers per thread, ~270 doubles of live state: the rest
@@ -167,7 +169,18 @@ constexpr int CTAIL0 = CSPL > 0 ? CSPL : ((MPC_C_ZSKIP != 0 && NHS > 1) ? NHS - 
 static_assert(CSPL == 0 || !LT_C, "MPC_C_SPLIT needs the Jacobian rows outside shared memory (MPC_LT_MASK bit 3 clear)");
 constexpr int LT_OFF_CS = LT_OFF_C + (LT_C ? NH * NHS : 0);
 constexpr int LT_ENTRY_DOUBLES = LT_OFF_CS + NH * CSPL;
-constexpr int BOX_SM_DOUBLES = (MPC_BOX_SMEM == 1 ? 2 * (NX + NU) : (MPC_BOX_SMEM == 2 ? 4 * (NX + NU) : (MPC_BOX_SMEM == 3 ? 6 * (NX + NU) : 0)));      // 1: 1/t; 2: multipliers + slacks; 3: all three
+#ifndef MPC_TMEM
+#define MPC_TMEM 2
+#endif
+constexpr int TM_ECOLS = 8;                      // tensor memory: 32-bit columns per general entry = (NHS + 1) doubles, padded
+constexpr bool TMEM_CD = (MPC_TMEM != 0) && !LT_C && !LT_D && NCG > 0 && NCG * TM_ECOLS <= 256 && NHS + 1 <= 4 && GW == 1 && CSPL == 0 && MPC_C_ZSKIP == 0 &&
+                         MPC_WARPS_PER_CTA == 8;
+// MPC_TMEM >= 2: the multipliers and slacks of the box entries go to tensor memory as well (variable i = 8 columns {lam_l, t_l, lam_u,
+// t_u} behind the general entries); their 4 (NX + NU) shared-memory columns are not allocated, so the SM runs the next smaller
+// shared-memory configuration and the L1 -- which serves the register spills -- doubles.
+constexpr bool TMEM_BOX = TMEM_CD && (MPC_TMEM >= 2) && MPC_BOX_SMEM == 3 && (NCG * TM_ECOLS + (NX + NU) * 8 <= 256);
+constexpr int TM_BOX_COL0 = NCG * TM_ECOLS;
+constexpr int BOX_SM_DOUBLES = TMEM_BOX ? 2 * (NX + NU) : (MPC_BOX_SMEM == 1 ? 2 * (NX + NU) : (MPC_BOX_SMEM == 2 ? 4 * (NX + NU) : (MPC_BOX_SMEM == 3 ? 6 * (NX + NU) : 0)));      // 1: 1/t; 2: multipliers + slacks; 3: all three
 // MPC_QP_SMEM: per-stage QP data that the interior-point loop only READS, once per iteration in pass DA, parked in shared memory
 // after the linearisation instead of staying in registers (where they are spilled): bit 0 g and b (12 doubles), bit 1 H (28)
 #ifndef MPC_QP_SMEM
@@ -184,12 +197,7 @@ constexpr bool RIC_P = (MPC_RIC_SMEM & 1) != 0, RIC_PRB = (MPC_RIC_SMEM & 2) != 
 constexpr int RIC_OFF_P = QP_OFF_H + (QPS_H ? NPK : 0), RIC_OFF_PRB = RIC_OFF_P + (RIC_P ? NPX : 0);
 constexpr int LT_DOUBLES = (RIC_OFF_PRB + (RIC_PRB ? NX : 0)) * LCOL;
 static_assert(!MPC_COL_COMPACT || (MPC_QP_SMEM == 0 && MPC_RIC_SMEM == 0), "compact columns: the terminal stage's slot is shared with the dead lanes");
-#ifndef MPC_TMEM
-#define MPC_TMEM 1
-#endif
-constexpr int TM_ECOLS = 8;                      // tensor memory: 32-bit columns per general entry = (NHS + 1) doubles, padded
-constexpr bool TMEM_CD = (MPC_TMEM != 0) && !LT_C && !LT_D && NCG > 0 && NCG * TM_ECOLS <= 256 && NHS + 1 <= 4 && GW == 1 && CSPL == 0 && MPC_C_ZSKIP == 0 &&
-                         MPC_WARPS_PER_CTA == 8;
+constexpr int GEN_UNROLL = MPC_GEN_UNROLL > 0 ? MPC_GEN_UNROLL : (TMEM_CD ? 1 : 2);
 constexpr int LT_STRIDE = LT_DOUBLES + (MPC_CHECK ? GW * 32 : 0);      // MPC_CHECK: a row of canaries behind every group's region      // per group: lam, t (d, C) of the general entries (+ 1/t of the boxes)
 // column accessor: stride GW*32 doubles in shared memory ([entry][thread of the group]), stride 1 for a thread-local array
 template <bool SM>
@@ -1357,11 +1365,27 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
     double z[NZ], pi[NX], v[NZ], qpi[NX];
 #if MPC_BOX_SMEM >= 2
     // multipliers and slacks of the box entries in shared memory too: 56 registers less in the interior-point loop
+    // (TMEM_BOX: the columns do not exist -- tensor memory in the throughput instantiation, thread-local arrays in the other)
     const SmemCol lamb{lt_sm + LT_ENTRY_DOUBLES * LCOL + slot MPCK(NCB)};
     const SmemCol tb{lt_sm + (LT_ENTRY_DOUBLES + NCB) * LCOL + slot MPCK(NCB)};
 #else
     double lamb[NCB], tb[NCB];
 #endif
+    constexpr bool TMB = TM && TMEM_BOX;
+    double lamb_l[TMEM_BOX ? NCB : 1], tb_l[TMEM_BOX ? NCB : 1];
+    // the four values of variable i's box entries {lam_l, t_l, lam_u, t_u}: a register window over tensor memory (loaded and
+    // stored by ALL lanes, warp-collective), or the entries where they live otherwise
+    auto box_ld = [&](int i, double (&bx)[4]) {
+        if constexpr (TMB) tmem_ld8(grp.tmem + TM_BOX_COL0 + 8 * i, bx[0], bx[1], bx[2], bx[3]);
+    };
+    auto box_st = [&](int i, const double (&bx)[4]) {
+        if constexpr (TMB) tmem_st8(grp.tmem + TM_BOX_COL0 + 8 * i, bx[0], bx[1], bx[2], bx[3]);
+    };
+    auto box_st_done = [&]() { if constexpr (TMB) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); };
+#define BXLL (*(TMB ? &bx[0] : (TMEM_BOX ? &lamb_l[i] : &lamb[i])))
+#define BXTL (*(TMB ? &bx[1] : (TMEM_BOX ? &tb_l[i] : &tb[i])))
+#define BXLU (*(TMB ? &bx[2] : (TMEM_BOX ? &lamb_l[NZ + i] : &lamb[NZ + i])))
+#define BXTU (*(TMB ? &bx[3] : (TMEM_BOX ? &tb_l[NZ + i] : &tb[NZ + i])))
     // general-entry state: shared-memory columns or thread-local arrays (MPC_LT_MASK); the unused alternative is optimised away
     double* const lt_me = lt_sm + slot;
     double lamg_loc[(!LT_LAM && NCG > 0) ? NCG : 1], tg_loc[(!LT_T && NCG > 0) ? NCG : 1];
@@ -1377,7 +1401,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
 #pragma unroll
     for (int i = 0; i < NX; i++) { xi[i] = xinit_g[(size_t)prob * NX + i]; pi[i] = 0.0; qpi[i] = 0.0; }
 #pragma unroll
-    for (int e = 0; e < NCB; e++) { lamb[e] = 0.0; tb[e] = 0.0; }
+    for (int i = 0; i < NZ; i++) { double bx[4] = {0.0, 0.0, 0.0, 0.0}; BXLL = 0.0; BXTL = 0.0; BXLU = 0.0; BXTU = 0.0; box_st(i, bx); }
     for (int e = 0; e < NCG; e++) { lamg[e] = 0.0; tg[e] = 0.0; }
     int qp_warm = 0;
     double* mem = mem_g ? mem_g + (size_t)prob * mem_doubles : nullptr;
@@ -1385,8 +1409,16 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
         const double* m = mem + 1;
         if (live) for (int i = 0; i < NX; i++) pi[i] = m[k * NX + i];
         m += (NSTAGE + 1) * NX;
+#pragma unroll
+        for (int i = 0; i < NZ; i++) {
+            double bx[4] = {0.0, 0.0, 0.0, 0.0};
+            if (path) {
+                BXLL = m[k * NC + i]; BXTL = m[NSTAGE * NC + k * NC + i];
+                BXLU = m[k * NC + NZ + i]; BXTU = m[NSTAGE * NC + k * NC + NZ + i];
+            }
+            box_st(i, bx);
+        }
         if (path) {
-            for (int e = 0; e < NCB; e++) { lamb[e] = m[k * NC + e]; tb[e] = m[NSTAGE * NC + k * NC + e]; }
             for (int e = 0; e < NCG; e++) { lamg[e] = m[k * NC + NCB + e]; tg[e] = m[NSTAGE * NC + k * NC + NCB + e]; }
         }
         m += 2 * NSTAGE * NC;
@@ -1512,16 +1544,20 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
 #pragma unroll
             for (int i = 0; i < NZ; i++) {
                 const bool act = (i < NU) ? path : xbox;
+                double bx[4];
+                box_ld(i, bx);
                 if (act) {
-                    lamb[i] = clamp_lo(lamb[i], IPM_THR0); tb[i] = clamp_lo(tb[i], IPM_THR0);
-                    lamb[NZ + i] = clamp_lo(lamb[NZ + i], IPM_THR0); tb[NZ + i] = clamp_lo(tb[NZ + i], IPM_THR0);
+                    BXLL = clamp_lo(BXLL, IPM_THR0); BXTL = clamp_lo(BXTL, IPM_THR0);
+                    BXLU = clamp_lo(BXLU, IPM_THR0); BXTU = clamp_lo(BXTU, IPM_THR0);
                 }
+                box_st(i, bx);
             }
             if (path) for (int e = 0; e < NCG; e++) { lamg[e] = clamp_lo(lamg[e], IPM_THR0); tg[e] = clamp_lo(tg[e], IPM_THR0); }
         } else {
 #pragma unroll
             for (int i = 0; i < NZ; i++) {
                 const bool act = (i < NU) ? path : xbox;
+                double bx[4] = {0.0, 0.0, 0.0, 0.0};
                 if (act) {
                     const double dl = LBZ[i] - z[i], du = UBZ[i] - z[i];
                     double tl = v[i] - dl, tu = du - v[i];
@@ -1529,9 +1565,10 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                         if (tu < IPM_THR0) { v[i] = 0.5 * (dl + du); tl = IPM_THR0; tu = IPM_THR0; }
                         else { tl = IPM_THR0; v[i] = dl + IPM_THR0; }
                     } else if (tu < IPM_THR0) { tu = IPM_THR0; v[i] = du - IPM_THR0; }
-                    tb[i] = tl; tb[NZ + i] = tu;
-                    lamb[i] = IPM_MU0 * rcp_nb(tl); lamb[NZ + i] = IPM_MU0 * rcp_nb(tu);
+                    BXTL = tl; BXTU = tu;
+                    BXLL = IPM_MU0 * rcp_nb(tl); BXLU = IPM_MU0 * rcp_nb(tu);
                 }
+                box_st(i, bx);
             }
             if (TM || path) for (int e = 0; e < NCG; e++) {
                 double cr[NHS > 0 ? NHS : 1], de;
@@ -1547,6 +1584,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
             }
         }
 
+        box_st_done();
         double alpha = 1.0, mu = 0.0;
 #ifdef MPC_TRACE
         double nrm_g, nrm_b, nrm_d, nrm_m;
@@ -1556,7 +1594,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
         // state of the previous iteration's step, applied at the top of the next pass (fused update):
 #if MPC_BOX_SMEM == 1 || MPC_BOX_SMEM == 3
         // 1/t of the box entries (reused by passes B, C and the update) parked in shared memory: 28 registers less in the loop
-        const SmemCol itb{lt_sm + (LT_ENTRY_DOUBLES + (MPC_BOX_SMEM == 3 ? 2 * NCB : 0)) * LCOL + slot MPCK(NCB)};
+        const SmemCol itb{lt_sm + (LT_ENTRY_DOUBLES + ((MPC_BOX_SMEM == 3 && !TMEM_BOX) ? 2 * NCB : 0)) * LCOL + slot MPCK(NCB)};
 #else
         double itb[NCB];                             // 1/t of the box entries, reused by passes B, C and the update (general entries: recomputed)
 #endif
@@ -1613,14 +1651,16 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
 #pragma unroll
                 for (int i = 0; i < NZ; i++) {
                     const bool act = (i < NU) ? path : xbox;
+                    double bx[4];
+                    box_ld(i, bx);
                     if (act) {
                         const double dl = LBZ[i] - z[i], du = UBZ[i] - z[i];
                         {   // lower: chat = +e_i, d = dl
-                            double lam = lamb[i], t = tb[i];
+                            double lam = BXLL, t = BXTL;
                             if (upd) {
                                 const IneqStep st = ineq_final(lam, itb[i], vo[i] - dl - t, dva[i], dv[i], sigmu, cen);
                                 lam = clamp_lo(lam + a_ * st.dlam, IPM_LAM_MIN); t = clamp_lo(t + a_ * st.dt, IPM_T_MIN);
-                                lamb[i] = lam; tb[i] = t;
+                                BXLL = lam; BXTL = t;
                             }
                             const double it_ = rcp_nb(t);
                             const double rd = v[i] - dl - t, G = lam * it_, m = lam * t;
@@ -1629,11 +1669,11 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                             nd = nanmax(nd, fabs(rd)); nm = nanmax(nm, fabs(m)); sm += m;
                         }
                         {   // upper: chat = -e_i, d = -du
-                            double lam = lamb[NZ + i], t = tb[NZ + i];
+                            double lam = BXLU, t = BXTU;
                             if (upd) {
                                 const IneqStep st = ineq_final(lam, itb[NZ + i], du - vo[i] - t, -dva[i], -dv[i], sigmu, cen);
                                 lam = clamp_lo(lam + a_ * st.dlam, IPM_LAM_MIN); t = clamp_lo(t + a_ * st.dt, IPM_T_MIN);
-                                lamb[NZ + i] = lam; tb[NZ + i] = t;
+                                BXLU = lam; BXTU = t;
                             }
                             const double it_ = rcp_nb(t);
                             const double rd = du - v[i] - t, G = lam * it_, m = lam * t;
@@ -1642,7 +1682,9 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                             nd = nanmax(nd, fabs(rd)); nm = nanmax(nm, fabs(m)); sm += m;
                         }
                     }
+                    if (upd) box_st(i, bx);
                 }
+                if (upd) box_st_done();
                 if (TM || path) {      // TM: every lane runs the loop (tensor-memory loads are warp-collective), commits predicated
 #pragma unroll GEN_UNROLL
                     for (int e = 0; e < NCG; e++) {
@@ -1855,10 +1897,12 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
 #pragma unroll
             for (int i = 0; i < NZ; i++) {
                 const bool act = (i < NU) ? path : xbox;
+                double bx[4];
+                box_ld(i, bx);
                 if (act) {
                     const double dl = LBZ[i] - z[i], du = UBZ[i] - z[i];
                     {
-                        const double lam = lamb[i], t = tb[i];
+                        const double lam = BXLL, t = BXTL;
                         const double it_ = itb[i];
                         const IneqStep st = ineq_affine(lam, it_, v[i] - dl - t, dva[i]);
                         sfa.add(lam, st.dlam, t, st.dt);
@@ -1866,7 +1910,7 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
                         V1[i] += st.corr; V2[i] += it_;
                     }
                     {
-                        const double lam = lamb[NZ + i], t = tb[NZ + i];
+                        const double lam = BXLU, t = BXTU;
                         const double it_ = itb[NZ + i];
                         const IneqStep st = ineq_affine(lam, it_, du - v[i] - t, -dva[i]);
                         sfa.add(lam, st.dlam, t, st.dt);
@@ -2044,16 +2088,18 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
 #pragma unroll
             for (int i = 0; i < NZ; i++) {
                 const bool act = (i < NU) ? path : xbox;
+                double bx[4];
+                box_ld(i, bx);
                 if (act) {
                     const double dl = LBZ[i] - z[i], du = UBZ[i] - z[i];
                     {
-                        const double lam = lamb[i], t = tb[i];
+                        const double lam = BXLL, t = BXTL;
                         const IneqStep st = ineq_final(lam, itb[i], v[i] - dl - t, dva[i], dv[i], sigmu, cen);
                         sfc.add(lam, st.dlam, t, st.dt);
                         if constexpr (BALANCE) { T1 += lam * st.dt + t * st.dlam; T2 += st.dt * st.dlam; }
                     }
                     {
-                        const double lam = lamb[NZ + i], t = tb[NZ + i];
+                        const double lam = BXLU, t = BXTU;
                         const IneqStep st = ineq_final(lam, itb[NZ + i], du - v[i] - t, -dva[i], -dv[i], sigmu, cen);
                         sfc.add(lam, st.dlam, t, st.dt);
                         if constexpr (BALANCE) { T1 += lam * st.dt + t * st.dlam; T2 += st.dt * st.dlam; }
@@ -2155,8 +2201,16 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
             if (k == 0) mem[0] = 2.0;
             if (live) for (int i = 0; i < NX; i++) m[k * NX + i] = pi[i];
             m += (NSTAGE + 1) * NX;
+#pragma unroll
+            for (int i = 0; i < NZ; i++) {
+                double bx[4];
+                box_ld(i, bx);
+                if (path) {
+                    m[k * NC + i] = BXLL; m[NSTAGE * NC + k * NC + i] = BXTL;
+                    m[k * NC + NZ + i] = BXLU; m[NSTAGE * NC + k * NC + NZ + i] = BXTU;
+                }
+            }
             if (path) {
-                for (int e = 0; e < NCB; e++) { m[k * NC + e] = lamb[e]; m[NSTAGE * NC + k * NC + e] = tb[e]; }
                 for (int e = 0; e < NCG; e++) { m[k * NC + NCB + e] = lamg[e]; m[NSTAGE * NC + k * NC + NCB + e] = tg[e]; }
             }
             m += 2 * NSTAGE * NC;
@@ -2164,6 +2218,10 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
         }
     }
 }
+#undef BXLL
+#undef BXTL
+#undef BXLU
+#undef BXTU
 
 constexpr int WARPS_PER_CTA = MPC_WARPS_PER_CTA;
 

@@ -288,7 +288,7 @@ def emit_model_header(pb, name, sim_steps=3):
 
     # ---- cost -----------------------------------------------------------------------------------
     w("\n// stage cost l(z,p), unscaled (solver_definition.py:19-35 with the reference's modules)")
-    w("__device__ __forceinline__ double cost_val(const double* z, const double* __restrict__ p)\n{\n    double l;")
+    w("template <class PT>      // PT: const double* (reference layout, index k*npar + idx) or any type with operator[] and operator+ (e.g. a strided view)\n__device__ __forceinline__ double cost_val(const double* z, const PT p)\n{\n    double l;")
     w(emit_block([("l", cost)], m))
     w("    return l;\n}")
     g = [sp.diff(cost, v) for v in z]
@@ -317,7 +317,7 @@ def emit_model_header(pb, name, sim_steps=3):
     w("__device__ constexpr int HBLK_IDX[%d][%d] = {%s};" % (len(comp), bmax, ", ".join(
         "{" + ", ".join(str(v) for v in c + [-1] * (bmax - len(c))) + "}" for c in comp)))
     w("\n// g = DT * grad l ; H(packed) = DT * hess l   (all NPK entries written)")
-    w("__device__ __forceinline__ void cost_lin(const double* z, const double* __restrict__ p, double* g, double* H)\n{")
+    w("template <class PT>\n__device__ __forceinline__ void cost_lin(const double* z, const PT p, double* g, double* H)\n{")
     w(emit_block([("g[%d]" % i, pb["dt"] * g[i]) for i in range(nz)] +
                  [("H[%d]" % _idx(i, j), pb["dt"] * Hc[(i, j)]) for i in range(nz) for j in range(i + 1)], m))
     w("}")
@@ -356,8 +356,8 @@ def emit_model_header(pb, name, sim_steps=3):
     # ---- both at once: one traversal of the rows with the common subexpressions (cos / sin / sqrt / reciprocals of the
     #      obstacle parameters) shared between the Jacobian and the multiplier-weighted Hessian
     w("\n// hv[NH] = h(z,p);  C[r*NHS + s] = d h_r / d z_HSUP[s];  H(packed NZ) += sum_r mh[r] d2 h_r / dz2")
-    w("template <class CM>      // C: plain array or any type with operator[] (e.g. a shared-memory column accessor)")
-    w("__device__ __forceinline__ void con_lin(const double* z, const double* __restrict__ p, const double* mh, double* H, double* hv, CM&& C)\n{")
+    w("template <class PT, class CM>      // C: plain array or any type with operator[] (e.g. a shared-memory column accessor)")
+    w("__device__ __forceinline__ void con_lin(const double* z, const PT p, const double* mh, double* H, double* hv, CM&& C)\n{")
     if nh:
         if flat:
             m3 = dict(m)
@@ -368,14 +368,14 @@ def emit_model_header(pb, name, sim_steps=3):
         for gi, (r0, cnt, stride, fixed) in enumerate(groups):
             mq = qmap(r0, fixed)
             mq[mhs[r0]] = "mh[%d + r]" % r0
-            w("#pragma unroll 1\n    for (int r = 0; r < %d; r++) {\n        const double* __restrict__ q = p + r * %d;" % (cnt, stride))
+            w("#pragma unroll 1\n    for (int r = 0; r < %d; r++) {\n        const PT q = p + r * %d;" % (cnt, stride))
             w(emit_block([("hv[%d + r]" % r0, h[r0])] +
                          [("C[(%d + r) * %d + %d]" % (r0, nhs, s_), sp.diff(h[r0], z[sup[s_]])) for s_ in range(nhs)] +
                          hess_outputs([r0], mhs), mq, tmp_prefix="l%d_" % gi, indent="        "))
             w("    }")
     w("}")
     w("\n// the same restricted to the rows [r_lo, r_hi): hv, C, mh indexed by (row - r_lo)")
-    w("__device__ __forceinline__ void con_lin_rows(const double* z, const double* __restrict__ p, int r_lo, int r_hi, const double* mh, double* H, double* hv, double* C)\n{")
+    w("template <class PT>\n__device__ __forceinline__ void con_lin_rows(const double* z, const PT p, int r_lo, int r_hi, const double* mh, double* H, double* hv, double* C)\n{")
     if nh:
         for i in flat:
             m3 = dict(m)
@@ -388,7 +388,7 @@ def emit_model_header(pb, name, sim_steps=3):
             mq = qmap(r0, fixed)
             mq[mhs[r0]] = "mh[o]"
             w("#pragma unroll 1\n    for (int r = (r_lo > %d ? r_lo - %d : 0); r < (r_hi - %d < %d ? r_hi - %d : %d); r++) {" % (r0, r0, r0, cnt, r0, cnt))
-            w("        const double* __restrict__ q = p + r * %d;\n        const int o = %d + r - r_lo;" % (stride, r0))
+            w("        const PT q = p + r * %d;\n        const int o = %d + r - r_lo;" % (stride, r0))
             w(emit_block([("hv[o]", h[r0])] + [("C[o * %d + %d]" % (nhs, s_), sp.diff(h[r0], z[sup[s_]])) for s_ in range(nhs)] +
                          hess_outputs([r0], mhs), mq, tmp_prefix="m%d_" % gi, indent="        "))
             w("    }")

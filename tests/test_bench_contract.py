@@ -45,7 +45,7 @@ def test_gpu_arm_line():
     assert d["gpu_launches"] >= 2 * d["steps"]
     rf = d["roofline"]
     assert rf["bound"] == "fp64" and 0.0 < rf["frac"] < 1.0 and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9 and rf["traffic"] > 0
-    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and 0 < d["e2e"]["value"] <= 1.05 * d["value"]
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and 0 < d["e2e"]["value"] <= 1.15 * d["value"]
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
     assert d["latency"]["p50"] > 0 and d["e2e_sets"]["guided"]["value"] > 0

@@ -100,7 +100,7 @@ constexpr int GW = (NSTAGE + 1 + 31) / 32;
 // Columns of the per-stage shared-memory arrays ([entry][stage slot]): one slot per LIVE lane (stages 0..N) instead of one per lane
 // of the group.  Inequality entries exist on path stages only, so the terminal stage's slot is a dummy and the dead lanes of the
 // group (lane 31 for N = 30) share it.  For N = 30 this is 31/32 of the footprint -- exactly what lets the right-hand sides d of
-// the 24 general entries of c2 sit beside the multipliers and slacks at 8 warps per CTA.
+// the 24 general entries of c2 sit beside the multipliers and slacks at 8 warps per CTA (they have since moved to tensor memory).
 #ifndef MPC_COL_COMPACT
 #define MPC_COL_COMPACT 1
 #endif
@@ -118,6 +118,7 @@ constexpr int NPX = NX * (NX + 1) / 2;      // packed P
 //   + box multipliers and slacks (205 KB)                                       234 k
 //   general multipliers + slacks, box multipliers + slacks + 1/t (184 KB)       245 k            <- default
 //   (+ g, b: 244 k; box without 1/t but H: 232 k; Jacobian columns x, y instead of d: 217 k; 7 warps with everything: 227 k)
+//   ... + Jacobian rows, d and the box multipliers + slacks in TENSOR memory (MPC_TMEM below; 123 KB of shared memory left)  263 k
 // The default takes the arrays in that priority order while they fit beside each other for all warps of the CTA:
 // MPC_LT_MASK bits: 0 general multipliers, 1 general slacks, 2 right-hand sides d, 3 Jacobian rows C; MPC_BOX_SMEM: 1 = 1/t of the
 // box entries, 2 = their multipliers and slacks, 3 = all three.  Either macro can be pinned on the command line.

@@ -389,10 +389,12 @@ class Engine:
 
     def table_layout(self):
         """generated/<config>/tables.yaml: invariant parameter indices and the obstacle / halfspace slot layout"""
-        with open(os.path.join(config_dir(self.config), "tables.yaml")) as f:
-            t = yaml.safe_load(f)
-        t["invariant_idx"] = np.array([self.parameter_map[n] for n in t["invariant"]], np.int32)
-        return t
+        if getattr(self, "_table_layout", None) is None:      # (parsed once: the set entries call this per solve)
+            with open(os.path.join(config_dir(self.config), "tables.yaml")) as f:
+                t = yaml.safe_load(f)
+            t["invariant_idx"] = np.array([self.parameter_map[n] for n in t["invariant"]], np.int32)
+            self._table_layout = t
+        return self._table_layout
 
     def solve_sets_tables(self, n_sets, planners, xinit_sets, invariant, obstacles, x0, guided=None, robot_radius=0.0, obstacle_radius=None,
                           stage_idx=None, stage=None, param_idx=None, planner_params=None, num_iter=10, out=None, obj_scale=None, disabled=None,

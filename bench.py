@@ -556,6 +556,16 @@ def main():
                                                  guided_args=(m_ob, m_g, batches[0]["robot_radius"], lb_, lc_))
                 what_m = "mpcgpu_multi_solve_sets_guided"
                 m_pv = m_ob
+                lay_m = eng.table_layout()
+                if lay_m.get("ellipsoid") and set(range(npar)) - set(lay_m["invariant_idx"].tolist()) <= (
+                        set(range(lb_, lb_ + 3 * lc_)) | set(range(lay_m["ellipsoid"]["base"], lay_m["ellipsoid"]["base"] + lay_m["ellipsoid"]["count"] * lay_m["ellipsoid"]["stride"]))):
+                    # struct-of-tables entry: 2.4 KB per solve from the host, the parameter blocks are built on every device
+                    m_inv = pinned(np.tile(np.ascontiguousarray(Pv[:, 0, 0][:, lay_m["invariant_idx"]]), (world, 1))).numpy()
+                    m_rad = pinned(np.full((tot_sets, m_ob.shape[2]), synthetic.OBSTACLE_RADIUS)).numpy()
+                    run_m = lambda: multi.solve_sets_tables(tot_sets, planners, m_xs, m_inv, m_ob, m_x0, guided=m_g, robot_radius=batches[0]["robot_radius"],
+                                                            obstacle_radius=m_rad, num_iter=args.num_iter, best_only=True)
+                    what_m = "mpcgpu_multi_solve_sets_tables"
+                    m_sh = m_inv
             else:
                 run_m = lambda: multi.solve_sets(tot_sets, planners, m_xs, m_sh, m_x0, differs_m, m_pv, num_iter=args.num_iter, best_only=True)
             om = run_m()

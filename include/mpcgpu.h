@@ -307,6 +307,11 @@ int mpcgpu_multi_solve_sets_guided(mpcgpu_multi *m, int n_sets, int planners, co
                                    const int *num_iter, int num_iter_all, double *xtraj, double *utraj, double *pobj,
                                    int *exit_code, int *qp_status, double *res_eq, const double *obj_scale, const double *obj_sub,
                                    const unsigned char *disabled, int *best_idx, const mpcgpu_set_options *opt);
+int mpcgpu_multi_solve_sets_tables(mpcgpu_multi *m, int n_sets, int planners, const double *xinit_sets, const mpcgpu_param_tables *tables,
+                                   const double *x0, int nidx, const int *param_idx, const double *planner_params, const int *num_iter,
+                                   int num_iter_all, double *xtraj, double *utraj, double *pobj, int *exit_code, int *qp_status,
+                                   double *res_eq, const double *obj_scale, const double *obj_sub, const unsigned char *disabled,
+                                   int *best_idx, const mpcgpu_set_options *opt);
 /* independent problems (no sets): contiguous ranges of problems */
 int mpcgpu_multi_solve_batch(mpcgpu_multi *m, int n, const double *xinit, const double *x0, const double *params,
                              const int *num_iter, int num_iter_all, double *mem_inout, double *xtraj, double *utraj,

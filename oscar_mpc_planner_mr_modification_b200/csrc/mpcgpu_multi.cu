@@ -222,6 +222,39 @@ int mpcgpu_multi_solve_sets(mpcgpu_multi* m, int n_sets, int planners, const dou
                                           obj_sub, disabled, best_idx, opt);
 }
 
+// struct-of-tables entry (2.4 KB per solve from the host for c2): every table is per set, per (set, stage) or per problem
+int mpcgpu_multi_solve_sets_tables(mpcgpu_multi* m, int n_sets, int planners, const double* xinit_sets, const mpcgpu_param_tables* tables,
+                                   const double* x0, int nidx, const int* param_idx, const double* planner_params, const int* num_iter,
+                                   int num_iter_all, double* xtraj, double* utraj, double* pobj, int* exit_code, int* qp_status,
+                                   double* res_eq, const double* obj_scale, const double* obj_sub, const unsigned char* disabled,
+                                   int* best_idx, const mpcgpu_set_options* opt)
+{
+    if (!m || n_sets < 0 || planners <= 0 || !tables) return MPCGPU_ERR_ARG;
+    if (n_sets == 0) return MPCGPU_OK;
+    int N, nx, nu, np, nh;
+    mpcgpu_desc_query(m->eng[0], &N, &nx, &nu, &np, &nh);
+    const int md = mpcgpu_mem_doubles(m->eng[0]);
+    const size_t nz = (size_t)nx + nu;
+    const mpcgpu_param_tables T = *tables;
+    return run_sharded(m, n_sets, [=](int dev, int s0, int s1) {
+        const int ns = s1 - s0;
+        const size_t p0 = (size_t)s0 * planners;
+        mpcgpu_set_options o;
+        if (opt) o = slice_options(opt, s0, p0, N, nx, nu, md);
+        mpcgpu_param_tables t = T;
+        if (t.invariant) t.invariant += (size_t)s0 * t.n_invariant;
+        if (t.stage) t.stage += (size_t)s0 * N * t.n_stage;
+        if (t.obstacles) t.obstacles += (size_t)s0 * N * t.M * t.ob_stride;
+        if (t.obstacle_radius) t.obstacle_radius += (size_t)s0 * t.M;
+        if (t.guided) t.guided += p0;
+        return mpcgpu_solve_sets_tables(m->eng[dev], ns, planners, xinit_sets + (size_t)s0 * nx, &t, x0 + p0 * nz * (N + 1), nidx, param_idx,
+                                        planner_params ? planner_params + p0 * N * nidx : nullptr, num_iter ? num_iter + p0 : nullptr, num_iter_all,
+                                        xtraj ? xtraj + p0 * nx * (N + 1) : nullptr, utraj ? utraj + p0 * nu * N : nullptr, pobj + p0, exit_code + p0,
+                                        qp_status + p0, res_eq + p0, obj_scale ? obj_scale + p0 : nullptr, obj_sub ? obj_sub + p0 : nullptr,
+                                        disabled ? disabled + p0 : nullptr, best_idx + s0, opt ? &o : nullptr);
+    });
+}
+
 int mpcgpu_multi_solve_batch(mpcgpu_multi* m, int n, const double* xinit, const double* x0, const double* params, const int* num_iter,
                              int num_iter_all, double* mem_inout, double* xtraj, double* utraj, double* pobj, int* exit_code,
                              int* qp_status, double* res_eq, int* ipm_iters)

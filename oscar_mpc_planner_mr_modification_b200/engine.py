@@ -16,7 +16,7 @@ SYMBOLS = [
     "mpcgpu_num_configs", "mpcgpu_config_name", "mpcgpu_engine_create", "mpcgpu_engine_destroy", "mpcgpu_desc_query",
     "mpcgpu_mem_doubles", "mpcgpu_solve_batch", "mpcgpu_solve_batch_device", "mpcgpu_sync", "mpcgpu_solve_sets", "mpcgpu_select_best",
     "mpcgpu_alloc_pinned", "mpcgpu_free_pinned", "mpcgpu_solve_sets_tables", "mpcgpu_multi_create", "mpcgpu_multi_destroy", "mpcgpu_multi_num_devices", "mpcgpu_multi_engine",
-    "mpcgpu_multi_shard_range", "mpcgpu_multi_solve_sets", "mpcgpu_multi_solve_sets_guided", "mpcgpu_multi_solve_batch", "mpcgpu_multi_last_kernel_ms",
+    "mpcgpu_multi_shard_range", "mpcgpu_multi_solve_sets", "mpcgpu_multi_solve_sets_guided", "mpcgpu_multi_solve_sets_tables", "mpcgpu_multi_solve_batch", "mpcgpu_multi_last_kernel_ms",
     "mpcgpu_generate_synthetic", "mpcgpu_generate_synthetic_device",
     "mpcgpu_select_best_device", "mpcgpu_model_eval_doubles", "mpcgpu_model_eval", "mpcgpu_measure_fp64_peak", "mpcgpu_launch_count", "mpcgpu_last_kernel_ms", "mpcgpu_last_error", "mpcgpu_set_kernel_mode", "mpcgpu_guidance_halfspaces_device", "mpcgpu_solve_sets_guided",
 ]
@@ -398,7 +398,7 @@ class Engine:
 
     def solve_sets_tables(self, n_sets, planners, xinit_sets, invariant, obstacles, x0, guided=None, robot_radius=0.0, obstacle_radius=None,
                           stage_idx=None, stage=None, param_idx=None, planner_params=None, num_iter=10, out=None, obj_scale=None, disabled=None,
-                          **opts):
+                          _multi=None, **opts):
         """mpcgpu_solve_sets_tables: stage-invariant parameters [n_sets, n_invariant] (order of table_layout()["invariant"]), obstacle
         table [n_sets, N, M, 2|4], warm starts; the parameter block is built on the device."""
         n = n_sets * planners
@@ -437,11 +437,14 @@ class Engine:
         pidx = None if nidx == 0 else np.ascontiguousarray(param_idx, np.int32)
         pvals = None if nidx == 0 else np.ascontiguousarray(planner_params, np.float64)
         vp = ctypes.c_void_p
-        self.lib.mpcgpu_solve_sets_tables.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, ctypes.c_int, vp, vp, vp, ctypes.c_int] + [vp] * 11
-        rc = self.lib.mpcgpu_solve_sets_tables(self.handle, n_sets, planners, _ptr(f64(xinit_sets)), ctypes.byref(t), _ptr(f64(x0)), nidx, _ptr(pidx),
+        fn = self.lib.mpcgpu_solve_sets_tables if _multi is None else self.lib.mpcgpu_multi_solve_sets_tables      # (same arguments behind the handle)
+        fn.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, ctypes.c_int, vp, vp, vp, ctypes.c_int] + [vp] * 11
+        rc = fn(self.handle if _multi is None else _multi, n_sets, planners, _ptr(f64(xinit_sets)), ctypes.byref(t), _ptr(f64(x0)), nidx, _ptr(pidx),
                                                _ptr(pvals), None, int(num_iter), None if best_only else _ptr(out["xtraj"]),
                                                None if best_only else _ptr(out["utraj"]), _ptr(out["pobj"]), _ptr(out["exit_code"]),
                                                _ptr(out["qp_status"]), _ptr(out["res_eq"]), _ptr(sc), None, _ptr(ds), _ptr(out["best"]), opt)
+        if _multi is not None and rc != 0:
+            raise RuntimeError("mpcgpu_multi_solve_sets_tables failed with status %d" % rc)
         self._check(rc, "mpcgpu_solve_sets_tables")
         out["h2d_bytes"] = int(8 * (inv.size + (0 if ob is None else ob.size) + (0 if rad is None else rad.size) + (0 if stg is None else stg.size)
                                     + np.asarray(x0).size + np.asarray(xinit_sets).size + (0 if pvals is None else pvals.size)) + (0 if g is None else g.size))
@@ -616,3 +619,7 @@ class MultiEngine:
         if rc != 0:
             raise RuntimeError("mpcgpu_multi_solve_sets failed with status %d" % rc)
         return out
+
+    def solve_sets_tables(self, n_sets, planners, xinit_sets, invariant, obstacles, x0, **kw):
+        """mpcgpu_multi_solve_sets_tables: the struct-of-tables entry over all devices (arguments as Engine.solve_sets_tables)"""
+        return self.first.solve_sets_tables(n_sets, planners, xinit_sets, invariant, obstacles, x0, _multi=self.handle, **kw)

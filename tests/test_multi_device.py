@@ -80,4 +80,15 @@ def test_multi_device_flat_batch_and_guided_sets():
                              guided_args=(b["obst_pred"], b["guided"], b["robot_radius"], lin_base, lin_count))
         for k in ("xtraj", "pobj", "exit_code", "best"):
             np.testing.assert_array_equal(g[k], gref[k])
+        # struct-of-tables entry over the devices: the tables are sliced by set (mpcgpu_multi_solve_sets_tables)
+        lay = single.table_layout()
+        P = b["params"].reshape(n_sets, PLANNERS, single.N, single.npar)
+        invariant = np.ascontiguousarray(P[:, 0, 0][:, lay["invariant_idx"]])
+        radius = np.full((n_sets, b["obst_pred"].shape[2]), synthetic.OBSTACLE_RADIUS)
+        targs = dict(guided=b["guided"], robot_radius=b["robot_radius"], obstacle_radius=radius, num_iter=3)
+        tref = single.solve_sets_tables(n_sets, PLANNERS, xs, invariant, b["obst_pred"], b["x0"], **targs)
+        t = multi.solve_sets_tables(n_sets, PLANNERS, xs, invariant, b["obst_pred"], b["x0"], **targs)
+        for k in ("xtraj", "utraj", "pobj", "exit_code", "qp_status", "best"):
+            np.testing.assert_array_equal(t[k], tref[k])
+        np.testing.assert_array_equal(t["best"], gref["best"])
         multi.close()

@@ -184,10 +184,14 @@ constexpr int TM_BOX_COL0 = NCG * TM_ECOLS;
 constexpr int BOX_SM_DOUBLES = TMEM_BOX ? 2 * (NX + NU) : (MPC_BOX_SMEM == 1 ? 2 * (NX + NU) : (MPC_BOX_SMEM == 2 ? 4 * (NX + NU) : (MPC_BOX_SMEM == 3 ? 6 * (NX + NU) : 0)));      // 1: 1/t; 2: multipliers + slacks; 3: all three
 // MPC_QP_SMEM: per-stage QP data that the interior-point loop only READS, once per iteration in pass DA, parked in shared memory
 // after the linearisation instead of staying in registers (where they are spilled): bit 0 g and b (12 doubles), bit 1 H (28)
+// Default (-1): g and b where the box multipliers have left shared memory for tensor memory -- there the shared-memory configuration
+// has room and the L1 is not shared with thread-local arrays any more: 270.2 k solves/s against 263.9 k (H as well: 261.8 k, no gain);
+// before tensor memory the same move was neutral (244 against 245 k).
 #ifndef MPC_QP_SMEM
-#define MPC_QP_SMEM 0
+#define MPC_QP_SMEM -1
 #endif
-constexpr bool QPS_GB = (MPC_QP_SMEM & 1) != 0, QPS_H = (MPC_QP_SMEM & 2) != 0;
+constexpr int QP_SMEM_EFF = (MPC_QP_SMEM) >= 0 ? (MPC_QP_SMEM) : (TMEM_BOX ? 1 : 0);
+constexpr bool QPS_GB = (QP_SMEM_EFF & 1) != 0, QPS_H = (QP_SMEM_EFF & 2) != 0;
 constexpr int QP_OFF_G = LT_ENTRY_DOUBLES + BOX_SM_DOUBLES, QP_OFF_B = QP_OFF_G + (QPS_GB ? NZ : 0), QP_OFF_H = QP_OFF_B + (QPS_GB ? NX : 0);
 // MPC_RIC_SMEM: outputs of the Riccati factorisation that are produced by ONE serial step and read much later: bit 0 the
 // cost-to-go matrix P (15 doubles; used by the multiplier step dpi = P dx + p at the very end of the iteration), bit 1 P+ rb (5)
@@ -197,7 +201,7 @@ constexpr int QP_OFF_G = LT_ENTRY_DOUBLES + BOX_SM_DOUBLES, QP_OFF_B = QP_OFF_G 
 constexpr bool RIC_P = (MPC_RIC_SMEM & 1) != 0, RIC_PRB = (MPC_RIC_SMEM & 2) != 0;
 constexpr int RIC_OFF_P = QP_OFF_H + (QPS_H ? NPK : 0), RIC_OFF_PRB = RIC_OFF_P + (RIC_P ? NPX : 0);
 constexpr int LT_DOUBLES = (RIC_OFF_PRB + (RIC_PRB ? NX : 0)) * LCOL;
-static_assert(!MPC_COL_COMPACT || (MPC_QP_SMEM == 0 && MPC_RIC_SMEM == 0), "compact columns: the terminal stage's slot is shared with the dead lanes");
+static_assert(!MPC_COL_COMPACT || MPC_RIC_SMEM == 0, "compact columns: the terminal stage's slot is shared with the dead lanes");
 constexpr int GEN_UNROLL = MPC_GEN_UNROLL > 0 ? MPC_GEN_UNROLL : (TMEM_CD ? 1 : 2);
 constexpr int LT_STRIDE = LT_DOUBLES + (MPC_CHECK ? GW * 32 : 0);      // MPC_CHECK: a row of canaries behind every group's region      // per group: lam, t (d, C) of the general entries (+ 1/t of the boxes)
 // column accessor: stride GW*32 doubles in shared memory ([entry][thread of the group]), stride 1 for a thread-local array
@@ -1498,15 +1502,19 @@ __device__ void solve_problem(int prob, const double* __restrict__ xinit_g, cons
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         }
         const SmemCol gs{lt_me + QP_OFF_G * LCOL MPCK(NZ)}, bs{lt_me + QP_OFF_B * LCOL MPCK(NX)}, Hs{lt_me + QP_OFF_H * LCOL MPCK(NPK)};
-        if constexpr (QPS_GB) {
+        if constexpr (QPS_GB) {      // (live lanes only: with compact columns the dead lanes share the terminal stage's slot)
+            if (live) {
 #pragma unroll
-            for (int i = 0; i < NZ; i++) gs[i] = g[i];
+                for (int i = 0; i < NZ; i++) gs[i] = g[i];
 #pragma unroll
-            for (int i = 0; i < NX; i++) bs[i] = b[i];
+                for (int i = 0; i < NX; i++) bs[i] = b[i];
+            }
         }
         if constexpr (QPS_H) {
+            if (live) {
 #pragma unroll
-            for (int i = 0; i < NPK; i++) Hs[i] = H[i];
+                for (int i = 0; i < NPK; i++) Hs[i] = H[i];
+            }
         }
         if constexpr (CTAIL0 < NHS && NH > 0) {      // are the tail columns of the Jacobian zero in every lane?
             bool nzt = false;
